@@ -1,0 +1,170 @@
+"""Pins the CPU oracle (oracle/aerobulk_oracle.c) to the reference.
+
+Primary pin: doc/ex_ab.dat, the reference's own captured output at the
+`aerobulk_model` boundary (tests/golden/ex_ab.json, parsed verbatim by
+tests/golden/make_golden.py).  Secondary: SURVEY.md Appendix B (independent
+transcription, 16 digits) and the stale README toy table (3 digits).
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import ALGOS, OracleSession, lib, turb_noskin
+
+RT0 = 273.15
+SKIN_ALGOS = ("coare3p0", "coare3p6", "ecmwf")
+
+
+def _load(golden_dir, name):
+    with open(os.path.join(golden_dir, name)) as f:
+        return json.load(f)
+
+
+def _printed_tol(s: str, value: float) -> float:
+    """Tolerance of a value printed by gfortran as REAL(x,4): half a unit of the last
+    printed digit plus one float32 rounding of the value."""
+    mant, _, exp = s.upper().partition("E")
+    decimals = len(mant.split(".")[1]) if "." in mant else 0
+    last = 10.0 ** (-decimals + (int(exp) if exp else 0))
+    return 0.5 * last + abs(value) * 2.0 ** -23
+
+
+def _run_example(algo, inp, nb_iter=None, legacy_visc=False, U=None, V=None):
+    L = lib()
+    L.abo_debug_coare3p0_visc_at_tzu(1 if legacy_visc else 0)
+    try:
+        s = OracleSession()
+        sst = np.array(inp["sst_C"]) + RT0
+        t = np.array(inp["t_zt_C"]) + RT0
+        q = np.array(inp["q_zt"])
+        U = np.array(inp["U_zu"] if U is None else U, dtype=float)
+        V = np.array(inp["V_zu"] if V is None else V, dtype=float)
+        slp = np.array(inp["slp"])
+        kw = dict(Niter=inp["nb_iter"] if nb_iter is None else nb_iter)
+        if algo in SKIN_ALGOS:
+            kw.update(l_use_skin=True, rad_sw=np.array(inp["rad_sw"]), rad_lw=np.array(inp["rad_lw"]))
+        return s.model(1, 1, algo, inp["zt"], inp["zu"], sst, t, q, U, V, slp, **kw)
+    finally:
+        L.abo_debug_coare3p0_visc_at_tzu(0)
+
+
+@pytest.mark.parametrize("algo", ["coare3p6", "ecmwf", "ncar", "andreas", "coare3p0"])
+def test_ex_ab_dat_every_printed_digit(golden_dir, algo):
+    g = _load(golden_dir, "ex_ab.json")
+    # doc/ex_ab.dat predates mod_blk_coare3p0.f90:237 (visc_air(t_zu) -> visc_air(theta_zt)); the
+    # test-only knob restores that single line so the COARE 3.0 rows pin the rest of that path.
+    o = _run_example(algo, g["inputs"], legacy_visc=(algo == "coare3p0"))
+    ga = g["algos"][algo]
+    checks = [("QH", o["QH"]), ("QL", o["QL"]), ("Evap_mm_day", o["Evap"] * 3600.0 * 24.0),
+              ("Tau_x", o["Tau_x"]), ("Tau_y", o["Tau_y"])]
+    if algo in SKIN_ALGOS:
+        checks.append(("SSST_C", o["T_s"] - RT0))
+    for key, got in checks:
+        for k in range(2):
+            ref, s = ga[key][k], ga[key + "_str"][k]
+            assert abs(got[k] - ref) <= _printed_tol(s, ref), (algo, key, k, got[k], s)
+
+
+def test_ex_ab_dat_theta(golden_dir):
+    g = _load(golden_dir, "ex_ab.json")
+    L = lib()
+    for k in range(2):
+        th = L.abo_theta_from_z_P0_T_q(2.0, 101000.0, g["inputs"]["t_zt_C"][k] + RT0, 0.012) - RT0
+        s = g["algos"]["ncar"]["theta_zt_C_str"][k]
+        assert abs(th - float(s)) <= _printed_tol(s, float(s))
+
+
+def test_coare3p0_drift_is_the_documented_one_line(golden_dir):
+    """Current source (visc_air(theta_zt)) differs from the stale file by 5e-5..3e-4 relative."""
+    g = _load(golden_dir, "ex_ab.json")
+    o = _run_example("coare3p0", g["inputs"])
+    ref = np.array(g["algos"]["coare3p0"]["QH"])
+    rel = np.abs(o["QH"] - ref) / np.abs(ref)
+    assert np.all(rel > 1e-5) and np.all(rel < 5e-4), rel
+
+
+def test_survey_b1_b2(golden_dir):
+    k = _load(golden_dir, "survey_kat.json")
+    g = _load(golden_dir, "ex_ab.json")
+    for tab, nb, U, V in (("B1", 50, [5.0, 5.0], [0.0, 0.0]), ("B2", 5, [4.0, 4.0], [9.0, 9.0])):
+        cache = {}
+        for row in k[tab]:
+            algo = row["algo"]
+            if algo not in cache:
+                cache[algo] = _run_example(algo, g["inputs"], nb_iter=nb, U=U, V=V)
+            o = cache[algo]
+            idx = 0 if row["T_air_C"] == 20.0 else 1
+            for key in ("QL", "QH", "Tau_x", "Tau_y", "Evap", "T_s"):
+                if key not in row or row[key] is None:
+                    continue
+                got = o[key][idx] if key in o else g["inputs"]["sst_C"][idx] + RT0
+                assert got == pytest.approx(row[key], rel=2e-12, abs=1e-300), (tab, algo, key)
+
+
+def test_survey_b3_warm_layer_series(golden_dir):
+    """24-step warm-layer integration through aerobulk_model semantics (quirks 1-3 of SURVEY 8a)."""
+    k = _load(golden_dir, "survey_kat.json")
+    cases = sorted({(r["algo"], r["nb_iter"]) for r in k["B3"]})
+    for algo, nb in cases:
+        s = OracleSession()
+        one = lambda v: np.array([[v]], dtype=float)
+        want = {r["jt"]: r for r in k["B3"] if r["algo"] == algo and r["nb_iter"] == nb}
+        for jt in range(1, 25):
+            rsw = max(0.0, 900.0 * math.sin(math.pi * (jt - 6) / 12.0))
+            o = s.model(jt, 24, algo, 2.0, 10.0, one(301.15), one(300.15), one(0.018), one(3.0), one(1.0), one(101000.0),
+                        Niter=nb, l_use_skin=True, rad_sw=one(rsw), rad_lw=one(400.0))
+            if jt in want:
+                r = want[jt]
+                for key in ("T_s", "QL", "QH"):
+                    assert o[key][0, 0] == pytest.approx(r[key], rel=1e-11), (algo, nb, jt, key)
+                if jt < 24:  # state is deallocated at jt == Nt
+                    names = ("dT_wl", "Hz_wl", "Qnt_ac", "Tau_ac")
+                    for which, name in enumerate(names):
+                        if r.get(name) is None:
+                            continue
+                        st = s.state(which, 1)
+                        if st is None:
+                            assert algo == "ecmwf" and which >= 2
+                            continue
+                        assert st[0] == pytest.approx(r[name], rel=1e-10, abs=1e-15), (algo, nb, jt, name)
+
+
+def test_survey_b4_blocks_and_psi(golden_dir):
+    k = _load(golden_dir, "survey_kat.json")
+    L = lib()
+    b = k["B4_blocks"]
+    assert L.abo_e_sat(295.15) == pytest.approx(b["e_sat_295p15"], rel=1e-15)
+    assert L.abo_q_sat(295.15, 101000.0) == pytest.approx(b["q_sat_295p15_101000"], rel=1e-15)
+    assert L.abo_theta_from_z_P0_T_q(2.0, 101000.0, 293.15, 0.012) == pytest.approx(b["theta_2_101000_293p15_0p012"], rel=1e-15)
+    cols = {"ncar": "ncar", "coare": "coare3p6", "ecmwf": "ecmwf", "andreas": "andreas"}
+    for row in k["B4_psi"]:
+        for c, algo in cols.items():
+            assert L.abo_psi_m(ALGOS[algo], row["zeta"]) == pytest.approx(row[f"ψm {c}"], rel=1e-13, abs=1e-15)
+            assert L.abo_psi_h(ALGOS[algo], row["zeta"]) == pytest.approx(row[f"ψh {c}"], rel=1e-13, abs=1e-15)
+    # SIGN(0.5,+0.) = +0.5 selects the stable branch of psi_coare at zeta=0 (mod_common_coare.f90:248-252)
+    assert L.abo_psi_m(ALGOS["coare3p0"], 0.0) == pytest.approx(-4.524e-3, abs=1e-12)
+
+
+def test_readme_toy_table_coarse(golden_dir):
+    """README.md:188-211 (stale by ~1e-3): coarse known answer for Cd, u*, L, QL, QH, tau."""
+    t = _load(golden_dir, "readme_toy.json")
+    L = lib()
+    sst, tair, q, U, slp = 22.0 + RT0, 20.0 + RT0, 0.012, 5.0, 101000.0
+    ssq = 0.98 * L.abo_q_sat(sst, slp)
+    tha = L.abo_theta_from_z_P0_T_q(2.0, slp, tair, q)
+    for i, algo in enumerate(t["algos"]):
+        o = turb_noskin(algo, 20, 2.0, 10.0, sst, tha, ssq, q, U)
+        assert 1e3 * o["Cd"] == pytest.approx(t["rows"]["C_D"][i], rel=2e-3)
+        assert 1e3 * o["Ce"] == pytest.approx(t["rows"]["C_E"][i], rel=2e-3)
+        assert 1e3 * o["Ch"] == pytest.approx(t["rows"]["C_H"][i], rel=2e-3)
+        assert o["us"] == pytest.approx(t["rows"]["u*"][i], rel=2e-3)
+        assert o["L"] == pytest.approx(t["rows"]["L"][i], rel=5e-3)
+        s = OracleSession()
+        one = lambda v: np.array([v], dtype=float)
+        r = s.model(1, 1, algo, 2.0, 10.0, one(sst), one(tair), one(q), one(U), one(0.0), one(slp), Niter=20)
+        assert r["QL"][0] == pytest.approx(t["rows"]["QL"][i], rel=3e-3)
+        assert r["QH"][0] == pytest.approx(t["rows"]["QH"][i], rel=3e-3)
+        assert 1e3 * r["Tau_x"][0] == pytest.approx(t["rows"]["Wind stress"][i], rel=3e-3)
