@@ -1,0 +1,776 @@
+// ab_api.cu -- host side of libaerobulk_gpu.so: the AEROBULK_MODEL session
+// (reference src/mod_aerobulk.f90:24-269 + the SAVEd globals of src/mod_const.f90:22-33
+// and the warm-layer module arrays of src/mod_skin_coare.f90:31-36 /
+// src/mod_skin_ecmwf.f90:52-55) and the C ABI declared in include/aerobulk_gpu.h.
+//
+// Data layout in HBM: every field is one contiguous FP64 array of Ni*Nj points in the
+// caller's (Fortran, column-major) order; a row block j0..j1 is the byte range
+// [j0*Ni*8, j1*Ni*8) of each field, so chunks and shards are plain pointer offsets.
+// Host-array calls stage through 8 input + 6 output device arrays (grow-only) and are
+// pipelined in row-block chunks over three streams (H2D | kernel | D2H).
+// Warm-layer state never leaves the device between jt==1 and jt==nitend.
+// the library is built with -fvisibility=hidden: only the declared C ABI is exported
+#pragma GCC visibility push(default)
+#include "../../include/aerobulk_gpu.h"
+#pragma GCC visibility pop
+
+#include <cuda_runtime.h>
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "ab_kernels.cuh"
+
+namespace {
+
+constexpr int MAX_CHUNKS = 8;
+constexpr long long MIN_CHUNK_POINTS = 1 << 17;
+
+struct Session {
+    // ---- module globals of mod_const.f90:22-33
+    int nb_iter = 5;
+    int nitend = 1;
+    bool l_use_skin_schemes = false;
+    int ihum = 0;   // 0 'sh', 1 'dp', 2 'rh'
+    double rdt = 3600.;
+    double gdept = 1.;
+    // ---- plumbing
+    int device = -1;
+    bool device_ready = false;
+    cudaStream_t own_stream = nullptr, user_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+    bool use_user_stream = false;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {}, ev_all_in = nullptr;
+    int error_mode = 0;
+    int verbose = 1;
+    char errmsg[1024] = {0};
+    int errcode = 0;
+    bool preinit_done = false;
+    // ---- warm-layer state (device)
+    long long n_coare = 0, n_ecmwf = 0;
+    double *c_state[4] = {nullptr, nullptr, nullptr, nullptr};   // dT_wl, Hz_wl, Qnt_ac, Tau_ac
+    double *e_dT_wl = nullptr;
+    // ---- staging for host-array calls
+    long long cap = 0;
+    double *d_in[8] = {}, *d_out[6] = {};
+    // ---- statistics + deferred wind-stress flag
+    double *d_partials = nullptr, *d_stats = nullptr;
+    unsigned long long *d_bad = nullptr, *h_bad = nullptr;   // h_bad: pinned
+    bool bad_pending = false;
+    int last_Ni = 0;
+    const double *last_taux = nullptr, *last_tauy = nullptr;   // device pointers of the last launch
+    long launches = 0;
+};
+
+Session g;
+std::mutex g_mu;
+
+const char *HUM_NAMES[3] = {"sh", "dp", "rh"};
+
+// ---------------------------------------------------------------------------
+// errors: ctl_stop semantics (mod_const.f90:238-278) or return codes
+// ---------------------------------------------------------------------------
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g.errmsg, sizeof(g.errmsg), fmt, ap);
+    va_end(ap);
+    g.errcode = code;
+    if (g.error_mode == 0) {
+        printf(" *** E R R O R :  \n %s\n\n", g.errmsg);
+        fflush(stdout);
+        exit(1);
+    }
+    return code;
+}
+
+#define CUDA_TRY(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(AEROBULK_GPU_ERR_CUDA, "CUDA error '%s' at %s:%d (%s)", cudaGetErrorString(e__), \
+                        __FILE__, __LINE__, #call);                                                 \
+    } while (0)
+
+cudaStream_t compute_stream() { return g.use_user_stream ? g.user_stream : g.own_stream; }
+
+int ensure_device()
+{
+    if (g.device_ready) {
+        CUDA_TRY(cudaSetDevice(g.device));
+        return 0;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(AEROBULK_GPU_ERR_CUDA, "no CUDA device available (%s): libaerobulk_gpu has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (g.device < 0) {
+        const char *env = getenv("AEROBULK_GPU_DEVICE");
+        if (!env) env = getenv("LOCAL_RANK");
+        g.device = env ? (atoi(env) % count) : 0;
+    }
+    if (g.device >= count) return fail(AEROBULK_GPU_ERR_CUDA, "device %d requested but only %d visible", g.device, count);
+    CUDA_TRY(cudaSetDevice(g.device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g.in_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g.out_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < MAX_CHUNKS; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&g.ev_in[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&g.ev_k[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&g.ev_all_in, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&g.d_partials, sizeof(double) * abk::NSTATS * abk::stats_max_blocks()));
+    CUDA_TRY(cudaMalloc(&g.d_stats, sizeof(double) * abk::NSTATS));
+    CUDA_TRY(cudaMalloc(&g.d_bad, sizeof(unsigned long long)));
+    CUDA_TRY(cudaHostAlloc(&g.h_bad, sizeof(unsigned long long), cudaHostAllocDefault));
+    *g.h_bad = ~0ull;
+    CUDA_TRY(cudaMemset(g.d_bad, 0xFF, sizeof(unsigned long long)));
+    g.device_ready = true;
+    return 0;
+}
+
+void free_coare_state()
+{
+    for (int k = 0; k < 4; ++k) {
+        if (g.c_state[k]) cudaFree(g.c_state[k]);
+        g.c_state[k] = nullptr;
+    }
+    g.n_coare = 0;
+}
+void free_ecmwf_state()
+{
+    if (g.e_dT_wl) cudaFree(g.e_dT_wl);
+    g.e_dT_wl = nullptr;
+    g.n_ecmwf = 0;
+}
+
+int ensure_staging(long long n)
+{
+    if (n <= g.cap) return 0;
+    for (int k = 0; k < 8; ++k) {
+        if (g.d_in[k]) cudaFree(g.d_in[k]);
+        g.d_in[k] = nullptr;
+    }
+    for (int k = 0; k < 6; ++k) {
+        if (g.d_out[k]) cudaFree(g.d_out[k]);
+        g.d_out[k] = nullptr;
+    }
+    g.cap = 0;
+    for (int k = 0; k < 8; ++k) CUDA_TRY(cudaMalloc(&g.d_in[k], sizeof(double) * (size_t)n));
+    for (int k = 0; k < 6; ++k) CUDA_TRY(cudaMalloc(&g.d_out[k], sizeof(double) * (size_t)n));
+    g.cap = n;
+    return 0;
+}
+
+int algo_id(const char *calgo)
+{
+    if (!strcmp(calgo, "coare3p0")) return abd::COARE3P0;
+    if (!strcmp(calgo, "coare3p6")) return abd::COARE3P6;
+    if (!strcmp(calgo, "ncar")) return abd::NCAR;
+    if (!strcmp(calgo, "ecmwf")) return abd::ECMWF;
+    if (!strcmp(calgo, "andreas")) return abd::ANDREAS;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// AEROBULK_INIT from field statistics (mod_aerobulk.f90:24-160)
+// ---------------------------------------------------------------------------
+struct FieldCheck {
+    const char *name, *unit;
+    double zmin, zmax;
+};
+// order of the statistics vector: sst t_air slp u10 v10 wnd hum rad_sw(=rad_lw) rad_lw
+const FieldCheck CHECKS[9] = {
+    {"sst", "K", 270., 320.},      {"t_air", "K", 180., 330.},   {"slp", "Pa", 80000., 110000.},
+    {"u10", "m/s", -50., 50.},     {"v10", "m/s", -50., 50.},    {"wnd", "m/s", 0., 50.},
+    {"hum", "kg/kg", 0., 0.},      {"rad_sw", "W/m^2", 0., 1500.}, {"rad_lw", "W/m^2", 0., 750.}};
+
+int check_units(const char *name, const char *unit, double zmin, double zmax, const double *st5, double np)
+{
+    // check_unit_consistency, mod_phymbl.f90:1851-1954
+    const double zmean = st5[0] / np;
+    const bool bad = (st5[2] > zmax) || (st5[1] < zmin) || (zmean < zmin) || (zmean > zmax);
+    if (bad)
+        return fail(AEROBULK_GPU_ERR_UNITS,
+                    "*** ERROR (check_unit_consistency@mod_phymbl): field `%s` does not seem to be in %s !\n"
+                    " min value = %10.3E max value = %10.3E mean value = %10.3E",
+                    name, unit, st5[3], st5[4], zmean);
+    return 0;
+}
+
+int init_from_stats(int Nt, const char *calgo, bool lskin, bool lsrad, const double *st, int Ni, int Nj)
+{
+    if (g.verbose) {
+        printf(" \n ===================================================================\n");
+        printf("                    ----- AeroBulk_init -----\n \n");
+        printf("     *** Bulk parameterization to be used => \"%s\"\n", calgo);
+    }
+    if (lskin) {
+        if (!(strncmp(calgo, "coar", 4) == 0 || strcmp(calgo, "ecmwf") == 0))
+            return fail(AEROBULK_GPU_ERR_SKIN_ALGO,
+                        "AEROBULK_INIT => Only `COARE*` and `ECMWF` algorithms support cool-skin & warm/layer schemes");
+        if (!lsrad)
+            return fail(AEROBULK_GPU_ERR_SKIN_NORAD,
+                        "AEROBULK_INIT => provide SW and LW rad. input if you want to use skin schemes");
+        g.l_use_skin_schemes = true;   // :74 -- sticky
+        if (g.verbose) printf("        ==> will use the Cool-skin & Warm-layer scheme of `%s` !\n", calgo);
+    } else if (g.verbose) {
+        printf("     *** Cool-skin & Warm-layer schemes will NOT be used!\n");
+    }
+    g.nitend = Nt;   // :99
+    if (g.verbose) {
+        if (Ni > 0) printf("     *** Computational domain shape: Ni x Nj = %05d x %05d\n", Ni, Nj);
+        printf("     *** Number of time records that will be treated: %11d\n", g.nitend);
+        printf("     *** Number of iterations in bulk algos: nb_iter  = %4d\n", g.nb_iter);
+        printf("     *** Filling the `mask` array...\n");
+    }
+    const double np = st[0], ntot = st[1];
+    if (np == ntot) {
+        if (g.verbose) printf("         ==> no points need to be masked! :)\n");
+    } else if (np > 0.) {
+        if (g.verbose) printf("         ==> number of points to mask: %.0f (out of %.0f)\n", ntot - np, ntot);
+    } else {
+        return fail(AEROBULK_GPU_ERR_ALL_MASKED, "the whole domain is masked!\n check unit consistency of input fields");
+    }
+    // type_of_humidity, mod_phymbl.f90:1957-2007
+    const double *h = st + 2 + 5 * 6;
+    const double zmean = h[0] / np, zmin = h[1], zmax = h[2];
+    const char *ln;
+    if (zmean >= 0. && zmean < 0.08 && zmin >= 0. && zmax < 0.08) { g.ihum = 0; ln = "specific humidity [kg/kg]"; }
+    else if (zmean >= 150. && zmean < 330. && zmin >= 150. && zmax < 330.) { g.ihum = 1; ln = "dew-point temperature [K]"; }
+    else if (zmean >= 0. && zmean <= 100. && zmin >= 0. && zmax <= 100.) { g.ihum = 2; ln = "relative humidity [%]"; }
+    else
+        return fail(AEROBULK_GPU_ERR_HUMIDITY,
+                    "ERROR: type_of_humidity()@mod_aerobulk_compute => un-identified humidity type!\n"
+                    "   ==> we could not identify the humidity type based on the mean, min & max of the field:\n"
+                    "     * mean = %g\n     * min  = %g\n     * max  = %g", zmean, zmin, zmax);
+    if (g.verbose) printf("     *** Type of prescribed air humidity  `%s`\n", ln);
+
+    for (int f = 0; f < (lsrad ? 9 : 7); ++f) {
+        FieldCheck c = CHECKS[f];
+        if (f == 6) {
+            // check_unit_consistency(ctype_humidity, pha): note the reference's unit label is 'kg/kg' for all three
+            c.unit = "kg/kg";
+            if (g.ihum == 0) { c.name = "sh"; c.zmin = 0.; c.zmax = 0.08; }
+            else if (g.ihum == 1) { c.name = "dp"; c.zmin = 150.; c.zmax = 330.; }
+            else { c.name = "rh"; c.zmin = 0.; c.zmax = 100.; }
+        }
+        int rc = check_units(c.name, c.unit, c.zmin, c.zmax, st + 2 + 5 * f, np);
+        if (rc) return rc;
+    }
+    if (g.verbose) {
+        printf(" ===================================================================\n");
+        fflush(stdout);
+    }
+    return 0;
+}
+
+int local_stats(long long n, const double *sst, const double *t_zt, const double *hum, const double *U,
+                const double *V, const double *slp, const double *rad_lw, cudaStream_t s, double *host_stats)
+{
+    abk::StatsArgs a;
+    a.sst = sst; a.t_zt = t_zt; a.hum_zt = hum; a.U_zu = U; a.V_zu = V; a.slp = slp; a.rad_lw = rad_lw;
+    a.n = n;
+    a.partials = g.d_partials;
+    a.out = g.d_stats;
+    long long want = (n + 255) / 256;
+    int nblocks = (int)(want < 1 ? 1 : (want > abk::stats_max_blocks() ? abk::stats_max_blocks() : want));
+    CUDA_TRY(abk::launch_stats(a, nblocks, s));
+    g.launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(host_stats, g.d_stats, sizeof(double) * abk::NSTATS, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+abd::Uniform make_uniform(double zt, double zu)
+{
+    abd::Uniform u;
+    u.zt = zt;
+    u.zu = zu;
+    u.log_zt = log(zt);
+    u.log_zu = log(zu);
+    u.log_ztu = log(zt / zu);
+    u.log_zu10 = log(zu / 10.);
+    u.log_10 = log(10.);
+    const double zz0 = 0.0001;
+    u.fg_c_a = 0.035 * log(10. / zz0) / log(zu / zz0);        // mod_common_coare.f90:107
+    const double zc_b = 0.004 * 600. * 1.2 * 1.2 * 1.2;         // :108
+    u.fg_1_o_Ribcu = -zc_b / zu;                               // :140
+    u.rdt = g.rdt;
+    u.gdept = g.gdept;
+    u.nb_iter = g.nb_iter;
+    u.isd = 12;   // aerobulk_compute passes isecday_utc=12 (seconds), mod_aerobulk_compute.f90:136,146
+    return u;
+}
+
+// reports a wind stress > 10 N/m^2 found by earlier launches (mod_phymbl.f90:1250-1253)
+int check_bad_flag(const double *h_taux, const double *h_tauy)
+{
+    if (!g.bad_pending) return 0;
+    g.bad_pending = false;
+    const unsigned long long bad = *g.h_bad;
+    if (bad == ~0ull) return 0;
+    *g.h_bad = ~0ull;
+    cudaMemset(g.d_bad, 0xFF, sizeof(unsigned long long));
+    double tx = 0., ty = 0.;
+    if (h_taux && h_tauy) {
+        tx = h_taux[bad];
+        ty = h_tauy[bad];
+    } else if (g.last_taux && g.last_tauy) {
+        cudaMemcpy(&tx, g.last_taux + bad, sizeof(double), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&ty, g.last_tauy + bad, sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    const int Ni = g.last_Ni > 0 ? g.last_Ni : 1;
+    return fail(AEROBULK_GPU_ERR_TAU,
+                "BULK_FORMULA_VCTR()@mod_phymbl: wind stress too strong!\n  => %8.2f N/m^2 ! At ji, jj = %04lld, %04lld",
+                sqrt(tx * tx + ty * ty), (long long)(bad % Ni) + 1, (long long)(bad / Ni) + 1);
+}
+
+// ---------------------------------------------------------------------------
+// AEROBULK_MODEL (mod_aerobulk.f90:176-269) + aerobulk_compute dispatch
+// ---------------------------------------------------------------------------
+int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, double zu, int Ni, int Nj,
+               const double *sst, const double *t_zt, const double *hum_zt, const double *U_zu,
+               const double *V_zu, const double *slp, double *QL, double *QH, double *Tau_x, double *Tau_y,
+               double *Evap, const int *Niter, const int *l_use_skin, const double *rad_sw,
+               const double *rad_lw, double *T_s)
+{
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!calgo || !sst || !t_zt || !hum_zt || !U_zu || !V_zu || !slp || !QL || !QH || !Tau_x || !Tau_y || !Evap)
+        return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_model: NULL mandatory argument");
+    if (Ni < 0 || Nj < 0) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_model: negative shape %d x %d", Ni, Nj);
+
+    if (Niter) g.nb_iter = *Niter;   // :236 sticky
+    const bool lskin = l_use_skin ? (*l_use_skin != 0) : false;
+    const bool lsrad = (rad_sw != nullptr) && (rad_lw != nullptr);
+    if (jt < 1) return fail(AEROBULK_GPU_ERR_JT, "AEROBULK_MODEL => jt < 1 !??\n we are in a Fortran world here...");
+
+    int rc = ensure_device();
+    if (rc) return rc;
+    const long long n = (long long)Ni * (long long)Nj;
+    cudaStream_t cs = compute_stream();
+
+    // a pending deferred error from earlier asynchronous launches surfaces first
+    if (g.bad_pending) {
+        CUDA_TRY(cudaStreamSynchronize(cs));
+        rc = check_bad_flag(nullptr, nullptr);
+        if (rc) return rc;
+    }
+
+    const double *in_h[8] = {sst, t_zt, hum_zt, U_zu, V_zu, slp, lsrad ? rad_sw : nullptr, lsrad ? rad_lw : nullptr};
+    const double *in_d[8];
+    double *out_h[6] = {QL, QH, Tau_x, Tau_y, Evap, lsrad ? T_s : nullptr};
+    double *out_d[6];
+    const size_t bytes = sizeof(double) * (size_t)n;
+
+    // chunk plan (row blocks of the flattened array, multiples of the block size)
+    int nchunks = 1;
+    if (!device_ptrs) {
+        nchunks = (int)(n / MIN_CHUNK_POINTS);
+        nchunks = nchunks < 1 ? 1 : (nchunks > MAX_CHUNKS ? MAX_CHUNKS : nchunks);
+    }
+    long long cstart[MAX_CHUNKS + 1];
+    {
+        const long long per = ((n + nchunks - 1) / nchunks + 127) / 128 * 128;
+        for (int c = 0; c <= nchunks; ++c) {
+            long long s0 = (long long)c * per;
+            cstart[c] = s0 > n ? n : s0;
+        }
+        cstart[nchunks] = n;
+    }
+
+    if (device_ptrs) {
+        for (int k = 0; k < 8; ++k) in_d[k] = in_h[k];
+        for (int k = 0; k < 6; ++k) out_d[k] = out_h[k];
+    } else {
+        rc = ensure_staging(n);
+        if (rc) return rc;
+        for (int k = 0; k < 8; ++k) in_d[k] = in_h[k] ? g.d_in[k] : nullptr;
+        for (int k = 0; k < 6; ++k) out_d[k] = out_h[k] ? g.d_out[k] : nullptr;
+        // H2D, chunk by chunk, on the copy-in stream
+        for (int c = 0; c < nchunks; ++c) {
+            const long long s0 = cstart[c], len = cstart[c + 1] - s0;
+            for (int k = 0; k < 8 && len > 0; ++k)
+                if (in_h[k])
+                    CUDA_TRY(cudaMemcpyAsync(g.d_in[k] + s0, in_h[k] + s0, sizeof(double) * (size_t)len,
+                                             cudaMemcpyHostToDevice, g.in_stream));
+            CUDA_TRY(cudaEventRecord(g.ev_in[c], g.in_stream));
+        }
+    }
+
+    // ---- jt == 1: AEROBULK_INIT (needs global field statistics before any flux is computed)
+    if (jt == 1) {
+        if (g.preinit_done) {
+            g.preinit_done = false;   // aerobulk_gpu_init_from_stats() already ran the global init
+        } else {
+            double st[abk::NSTATS];
+            if (!device_ptrs) CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_in[nchunks - 1], 0));
+            if (n > 0) {
+                // :248 -- prsw=rad_lw: rad_lw is checked against both radiation ranges, rad_sw never
+                rc = local_stats(n, in_d[0], in_d[1], in_d[2], in_d[3], in_d[4], in_d[5], lsrad ? in_d[7] : nullptr, cs, st);
+                if (rc) return rc;
+            } else {
+                memset(st, 0, sizeof(st));
+            }
+            rc = init_from_stats(Nt, calgo, lskin, lsrad, st, Ni, Nj);
+            if (rc) return rc;
+        }
+    }
+
+    // ---- aerobulk_compute (mod_aerobulk_compute.f90:22-213)
+    const int ialgo = algo_id(calgo);
+    if (!ialgo)
+        return fail(AEROBULK_GPU_ERR_ALGO, "ERROR: mod_aerobulk_compute.f90 => bulk algorithm %s is unknown!!!", calgo);
+    const bool skin_algo = (ialgo == abd::COARE3P0 || ialgo == abd::COARE3P6 || ialgo == abd::ECMWF);
+    const bool use_skin = g.l_use_skin_schemes && skin_algo;
+    if (use_skin && !lsrad)
+        return fail(AEROBULK_GPU_ERR_SKIN_NORAD,
+                    "skin schemes are active (l_use_skin_schemes is sticky, mod_aerobulk.f90:74) but rad_sw/rad_lw are absent");
+
+    // kt == nit000 -> *_INIT allocates the warm-layer state (mod_blk_coare3p6.f90:250,68-95; mod_blk_ecmwf.f90:189)
+    if (use_skin && jt == 1) {
+        if (ialgo == abd::ECMWF) {
+            if (g.n_ecmwf) return fail(AEROBULK_GPU_ERR_STATE, " ECMWF_INIT => allocation of dT_wl & Hz_wl failed!");
+            if (n > 0) CUDA_TRY(cudaMalloc(&g.e_dT_wl, bytes));
+            g.n_ecmwf = n;
+        } else {
+            if (g.n_coare)
+                return fail(AEROBULK_GPU_ERR_STATE, " COARE_INIT => allocation of Tau_ac, Qnt_ac, dT_wl & Hz_wl failed!");
+            for (int k = 0; k < 4 && n > 0; ++k) CUDA_TRY(cudaMalloc(&g.c_state[k], bytes));
+            g.n_coare = n;
+        }
+    }
+    if (use_skin) {
+        const long long have = (ialgo == abd::ECMWF) ? g.n_ecmwf : g.n_coare;
+        if (have != n || (jt > 1 && have == 0 && n > 0))
+            return fail(AEROBULK_GPU_ERR_STATE, "warm-layer state missing or of another size at jt=%d (no jt==1 call for this session?)", jt);
+    }
+
+    abk::FluxArgs a;
+    memset(&a, 0, sizeof(a));
+    a.u = make_uniform(zt, zu);
+    a.ihum = g.ihum;
+    a.first_step = (jt == 1);
+    a.bad_index = g.d_bad;
+    const bool zteq = fabs(zu - zt) < 0.01;
+
+    for (int c = 0; c < nchunks; ++c) {
+        const long long s0 = cstart[c], len = cstart[c + 1] - s0;
+        if (len <= 0) continue;
+        a.sst = in_d[0] + s0; a.t_zt = in_d[1] + s0; a.hum_zt = in_d[2] + s0;
+        a.U_zu = in_d[3] + s0; a.V_zu = in_d[4] + s0; a.slp = in_d[5] + s0;
+        a.rad_sw = in_d[6] ? in_d[6] + s0 : nullptr;
+        a.rad_lw = in_d[7] ? in_d[7] + s0 : nullptr;
+        a.lon = nullptr;
+        a.QL = out_d[0] + s0; a.QH = out_d[1] + s0; a.Tau_x = out_d[2] + s0; a.Tau_y = out_d[3] + s0;
+        a.Evap = out_d[4] + s0;
+        a.T_s = out_d[5] ? out_d[5] + s0 : nullptr;
+        if (use_skin) {
+            if (ialgo == abd::ECMWF) {
+                a.dT_wl = g.e_dT_wl + s0;
+            } else {
+                a.dT_wl = g.c_state[0] + s0; a.Hz_wl = g.c_state[1] + s0;
+                a.Qnt_ac = g.c_state[2] + s0; a.Tau_ac = g.c_state[3] + s0;
+            }
+        }
+        a.n = len;
+        a.index_offset = s0;
+        if (!device_ptrs) CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_in[c], 0));
+        CUDA_TRY(abk::launch_flux(ialgo, use_skin, zteq, a, cs));
+        g.launches += 1;
+        if (!device_ptrs) {
+            CUDA_TRY(cudaEventRecord(g.ev_k[c], cs));
+            CUDA_TRY(cudaStreamWaitEvent(g.out_stream, g.ev_k[c], 0));
+            for (int k = 0; k < 6; ++k)
+                if (out_h[k])
+                    CUDA_TRY(cudaMemcpyAsync(out_h[k] + s0, g.d_out[k] + s0, sizeof(double) * (size_t)len,
+                                             cudaMemcpyDeviceToHost, g.out_stream));
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(g.h_bad, g.d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs));
+    g.bad_pending = true;
+    g.last_Ni = Ni;
+    g.last_taux = out_d[2];
+    g.last_tauy = out_d[3];
+
+    const bool last = (jt == g.nitend);
+    if (!device_ptrs || last || jt == 1) {
+        CUDA_TRY(cudaStreamSynchronize(cs));
+        if (!device_ptrs) CUDA_TRY(cudaStreamSynchronize(g.out_stream));
+        rc = check_bad_flag(device_ptrs ? nullptr : Tau_x, device_ptrs ? nullptr : Tau_y);
+    }
+
+    // kt == nitend -> *_EXIT frees the state (mod_blk_coare3p6.f90:411); jt == Nt -> AEROBULK_BYE (:267)
+    if (use_skin && last) {
+        if (ialgo == abd::ECMWF) free_ecmwf_state();
+        else free_coare_state();
+    }
+    if (rc) return rc;
+    if (jt == Nt && g.verbose) {
+        printf(" ===================================================================\n");
+        printf("                    ----- AeroBulk_bye -----\n");
+        printf(" ===================================================================\n \n");
+        fflush(stdout);
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int aerobulk_gpu_model(int jt, int Nt, const char *calgo, double zt, double zu, int Ni, int Nj, const double *sst,
+                       const double *t_zt, const double *hum_zt, const double *U_zu, const double *V_zu,
+                       const double *slp, double *QL, double *QH, double *Tau_x, double *Tau_y, double *Evap,
+                       const int *Niter, const int *l_use_skin, const double *rad_sw, const double *rad_lw, double *T_s)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return model_impl(false, jt, Nt, calgo, zt, zu, Ni, Nj, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y,
+                      Evap, Niter, l_use_skin, rad_sw, rad_lw, T_s);
+}
+
+int aerobulk_gpu_model_device(int jt, int Nt, const char *calgo, double zt, double zu, int Ni, int Nj,
+                              const double *sst, const double *t_zt, const double *hum_zt, const double *U_zu,
+                              const double *V_zu, const double *slp, double *QL, double *QH, double *Tau_x,
+                              double *Tau_y, double *Evap, const int *Niter, const int *l_use_skin,
+                              const double *rad_sw, const double *rad_lw, double *T_s)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return model_impl(true, jt, Nt, calgo, zt, zu, Ni, Nj, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y,
+                      Evap, Niter, l_use_skin, rad_sw, rad_lw, T_s);
+}
+
+static void copy_algo(char *dst, size_t cap, const char *calgo, int l)
+{
+    size_t n = (l < 0) ? 0 : (size_t)l;
+    if (n >= cap) n = cap - 1;
+    memcpy(dst, calgo, n);
+    dst[n] = 0;
+    // TRIM(): the Fortran side compares the blank-trimmed string
+    while (n > 0 && dst[n - 1] == ' ') dst[--n] = 0;
+}
+
+void aerobulk_cxx_skin(const int *jt, const int *Nt, const char *calgo, const double *zt, const double *zu,
+                       const double *sst, const double *t_zt, const double *hum_zt, const double *U_zu,
+                       const double *V_zu, const double *slp, double *QL, double *QH, double *Tau_x, double *Tau_y,
+                       double *Evap, const int *Niter, const bool *l_skin, const double *rad_sw, const double *rad_lw,
+                       double *T_s, const int *l, const int *m)
+{
+    char algo[64];
+    copy_algo(algo, sizeof(algo), calgo, *l);
+    const int lskin = (*(const unsigned char *)l_skin) != 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    model_impl(false, *jt, *Nt, algo, *zt, *zu, *m, 1, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y, Evap,
+               Niter, &lskin, rad_sw, rad_lw, T_s);
+}
+
+void aerobulk_cxx_no_skin(const int *jt, const int *Nt, const char *calgo, const double *zt, const double *zu,
+                          const double *sst, const double *t_zt, const double *hum_zt, const double *U_zu,
+                          const double *V_zu, const double *slp, double *QL, double *QH, double *Tau_x,
+                          double *Tau_y, double *Evap, const int *Niter, const int *l, const int *m)
+{
+    char algo[64];
+    copy_algo(algo, sizeof(algo), calgo, *l);
+    std::lock_guard<std::mutex> lk(g_mu);
+    model_impl(false, *jt, *Nt, algo, *zt, *zu, *m, 1, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y, Evap,
+               Niter, nullptr, nullptr, nullptr, nullptr);
+}
+
+int aerobulk_gpu_synchronize(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.device_ready) return 0;
+    CUDA_TRY(cudaSetDevice(g.device));
+    CUDA_TRY(cudaStreamSynchronize(compute_stream()));
+    CUDA_TRY(cudaStreamSynchronize(g.out_stream));
+    return check_bad_flag(nullptr, nullptr);
+}
+
+int aerobulk_gpu_init_local_stats(int Ni, int Nj, const double *sst, const double *t_zt, const double *hum_zt,
+                                  const double *U_zu, const double *V_zu, const double *slp, const double *rad_lw,
+                                  double *stats)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!stats || !sst || !t_zt || !hum_zt || !U_zu || !V_zu || !slp) return fail(AEROBULK_GPU_ERR_ARG, "init_local_stats: NULL argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const long long n = (long long)Ni * Nj;
+    if (n <= 0) {
+        for (int k = 0; k < abk::NSTATS; ++k) {
+            const int op = aerobulk_gpu_stats_reduce_op(k);
+            stats[k] = op == 0 ? 0. : op == 1 ? 1.79769313486231570e308 : -1.79769313486231570e308;
+        }
+        return 0;
+    }
+    return local_stats(n, sst, t_zt, hum_zt, U_zu, V_zu, slp, rad_lw, compute_stream(), stats);
+}
+
+int aerobulk_gpu_stats_reduce_op(int i)
+{
+    if (i < 2 || i >= 2 + 5 * abk::NFIELDS) return 0;
+    const int r = (i - 2) % 5;
+    return (r == 0) ? 0 : (r == 1 || r == 3) ? 1 : 2;
+}
+
+int aerobulk_gpu_init_from_stats(int Nt, const char *calgo, const int *l_use_skin, int have_rad, const double *stats)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!calgo || !stats) return fail(AEROBULK_GPU_ERR_ARG, "init_from_stats: NULL argument");
+    const bool lskin = l_use_skin ? (*l_use_skin != 0) : false;
+    int rc = init_from_stats(Nt, calgo, lskin, have_rad != 0, stats, 0, 0);
+    if (rc) return rc;
+    g.preinit_done = true;
+    return 0;
+}
+
+void aerobulk_gpu_set_rdt(double v) { std::lock_guard<std::mutex> lk(g_mu); g.rdt = v; }
+void aerobulk_gpu_set_gdept(double v) { std::lock_guard<std::mutex> lk(g_mu); g.gdept = v; }
+void aerobulk_gpu_set_nb_iter(int v) { std::lock_guard<std::mutex> lk(g_mu); g.nb_iter = v; }
+int aerobulk_gpu_get_nb_iter(void) { return g.nb_iter; }
+int aerobulk_gpu_get_use_skin(void) { return g.l_use_skin_schemes ? 1 : 0; }
+const char *aerobulk_gpu_get_humidity_type(void) { return HUM_NAMES[g.ihum]; }
+
+int aerobulk_gpu_set_device(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.device_ready && device != g.device)
+        return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_set_device(%d): session already bound to device %d (call aerobulk_gpu_reset first)", device, g.device);
+    g.device = device;
+    return 0;
+}
+int aerobulk_gpu_get_device(void) { return g.device; }
+
+int aerobulk_gpu_set_stream(void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.user_stream = (cudaStream_t)stream;
+    g.use_user_stream = (stream != nullptr);
+    return 0;
+}
+
+void aerobulk_gpu_set_error_mode(int m) { g.error_mode = m ? 1 : 0; }
+void aerobulk_gpu_set_verbose(int on) { g.verbose = on ? 1 : 0; }
+const char *aerobulk_gpu_last_error(void) { return g.errmsg; }
+int aerobulk_gpu_last_error_code(void) { return g.errcode; }
+
+void aerobulk_gpu_reset(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.device_ready) {
+        cudaSetDevice(g.device);
+        cudaDeviceSynchronize();
+        free_coare_state();
+        free_ecmwf_state();
+        for (int k = 0; k < 8; ++k) { if (g.d_in[k]) cudaFree(g.d_in[k]); g.d_in[k] = nullptr; }
+        for (int k = 0; k < 6; ++k) { if (g.d_out[k]) cudaFree(g.d_out[k]); g.d_out[k] = nullptr; }
+        g.cap = 0;
+        if (g.h_bad) *g.h_bad = ~0ull;
+        if (g.d_bad) cudaMemset(g.d_bad, 0xFF, sizeof(unsigned long long));
+    }
+    g.nb_iter = 5;
+    g.nitend = 1;
+    g.l_use_skin_schemes = false;
+    g.ihum = 0;
+    g.rdt = 3600.;
+    g.gdept = 1.;
+    g.preinit_done = false;
+    g.bad_pending = false;
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+}
+
+static double *state_ptr(int which, long long *n)
+{
+    if (g.n_coare) {
+        *n = g.n_coare;
+        return (which >= 0 && which < 4) ? g.c_state[which] : nullptr;
+    }
+    if (g.n_ecmwf) {
+        *n = g.n_ecmwf;
+        return which == 0 ? g.e_dT_wl : nullptr;
+    }
+    *n = 0;
+    return nullptr;
+}
+
+long aerobulk_gpu_get_state(int which, double *host_out, long n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    long long have = 0;
+    double *p = state_ptr(which, &have);
+    if (!host_out || n != have || have == 0) return 0;
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(compute_stream());
+    if (!p) {
+        if (g.n_ecmwf && which == 1) {   // Hz_wl of the ECMWF scheme is the constant rd0 = 3 m
+            for (long i = 0; i < n; ++i) host_out[i] = 3.;
+            return n;
+        }
+        return 0;
+    }
+    if (cudaMemcpy(host_out, p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+}
+
+long aerobulk_gpu_set_state(int which, const double *host_in, long n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    long long have = 0;
+    double *p = state_ptr(which, &have);
+    if (!host_in || !p || n != have) return 0;
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(compute_stream());
+    if (cudaMemcpy(p, host_in, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+    return n;
+}
+
+long aerobulk_gpu_launch_count(void) { return g.launches; }
+void aerobulk_gpu_reset_launch_count(void) { g.launches = 0; }
+
+double aerobulk_gpu_measure_fp64_peak(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_device()) return -1.;
+    g.launches += 5;
+    return abk::measure_fp64_peak(compute_stream());
+}
+
+// SURVEY.md 8d / BASELINE.md 3: fx + nb_iter*it FP64-pipe instruction equivalents per point
+double aerobulk_gpu_work_per_point(const char *calgo, int skin, int nb_iter)
+{
+    const int a = calgo ? algo_id(calgo) : 0;
+    double it = 0., fx = 0.;
+    switch (a) {
+    case abd::NCAR: it = 595.; fx = 1947.; break;
+    case abd::ANDREAS: it = 2028.; fx = 1801.; break;
+    case abd::COARE3P0: if (skin) { it = 4756.; fx = 4721.; } else { it = 1790.; fx = 4360.; } break;
+    case abd::COARE3P6: if (skin) { it = 4733.; fx = 4698.; } else { it = 1767.; fx = 4337.; } break;
+    case abd::ECMWF: if (skin) { it = 5006.; fx = 5389.; } else { it = 1378.; fx = 5028.; } break;
+    default: return 0.;
+    }
+    return fx + nb_iter * it;
+}
+
+double aerobulk_gpu_bytes_per_point(const char *calgo, int skin)
+{
+    const int a = calgo ? algo_id(calgo) : 0;
+    if (!a) return 0.;
+    if (!skin || a == abd::NCAR || a == abd::ANDREAS) return 88.;
+    return a == abd::ECMWF ? 128. : 176.;
+}
+
+const char *aerobulk_gpu_version(void) { return "aerobulk-b200 0.1 (sm_100a, FP64)"; }
+
+}  // extern "C"

@@ -1,0 +1,916 @@
+// ab_device.cuh -- FP64 __device__ physics of the aerobulk_model hot path for sm_100a.
+//
+// Everything a grid point needs, register-resident: marine-boundary-layer
+// thermodynamics (reference src/mod_phymbl.f90), the Monin-Obukhov stability
+// functions and first guess (src/mod_common_coare.f90, src/mod_blk_*.f90), the
+// cool-skin / warm-layer schemes (src/mod_skin_coare.f90, src/mod_skin_ecmwf.f90)
+// and the five iterative solvers.  Written for the GPU, not transliterated:
+//   * only the selected side of every `zstab*A + (1-zstab)*B` blend is evaluated
+//     (same value: the unused side is finite by construction in the reference);
+//   * loop invariants are hoisted (e_sat(T) out of the barometric loop,
+//     alpha_sw(SST) and the Saunders constants out of the cool-skin loop, the
+//     warm-layer "mess-o-constants" out of the bulk iteration, log(zu) & co. to
+//     the host);
+//   * `x**y` uses sqrt/cbrt/exp10 or exp(y*log x) instead of the ~90-instruction
+//     pow(): a few ulp away from glibc, far inside the 1e-10 parity tolerance;
+//   * FMA contraction is on.
+// The reference's quirks (truncated literals 1.7320508/.3333/0.6667, grav=9.8 vs
+// 9.80665 in rcst_cs, rt0 in e_sat, MOD(nb_iter,jit) commit rule, ECMWF warm layer
+// stepping every iteration ...) are kept: they are part of the numbers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace abd {
+
+#define ABD __device__ __forceinline__
+
+// ---------------------------------------------------------------------------
+// constants, reference src/mod_const.f90:38-120 (derived ones folded in FP64
+// operation by operation, as gfortran does for PARAMETERs)
+// ---------------------------------------------------------------------------
+constexpr double GRAV = 9.8;
+constexpr double RPI = 3.141592653589793;
+constexpr double ROCE_ALB0 = 0.066;
+constexpr double EMISS_W = 0.98;
+constexpr double STEFAN = 5.67E-8;
+constexpr double RT0 = 273.15;
+constexpr double RCP0_W = 4190.;
+constexpr double RHO0_W = 1025.;
+constexpr double RNU0_W = 1.e-6;
+constexpr double RK0_W = 0.6;
+constexpr double RCP_DRY = 1005.0;
+constexpr double RCP_VAP = 1860.0;
+constexpr double R_DRY = 287.05;
+constexpr double R_VAP = 461.495;
+constexpr double R_GAS = 8.314510;
+constexpr double RMM_DRYAIR = 28.9647e-3;
+constexpr double RMM_WATER = 18.0153e-3;
+constexpr double RLEVAP = 2.46e+6;
+constexpr double VKARMN = 0.4;
+constexpr double VKARMN2 = 0.4 * 0.4;
+constexpr double RDCT_QSAT_SALT = 0.98;
+constexpr double Z0_SEA_MAX = 0.0025;
+constexpr double CX_MIN = 0.1E-3;
+constexpr double REF_TAU_MAX = 10.;
+constexpr double RPOISS_DRY = R_DRY / RCP_DRY;
+constexpr double RGAMMA_DRY = GRAV / RCP_DRY;
+constexpr double REPS0 = R_DRY / R_VAP;
+constexpr double RCTV0 = R_VAP / R_DRY - 1.;
+constexpr double RCST_CS = -16. * 9.80665 * RHO0_W * RCP0_W * RNU0_W * RNU0_W * RNU0_W / (RK0_W * RK0_W);
+constexpr double SQ_RADRW = 0x1.184c0ffddaa3cp-5;    // SQRT(1.2/1025.)           mod_const.f90:112
+constexpr double RCP0W_POW15 = 0x1.08dce4ef23084p+18; // 4190.**1.5               mod_skin_coare.f90:156
+constexpr double FLA_ECMWF = 0x1.1d9fee00723a0p+1;   // MAX(0.3**(-2./3.),1.)     mod_skin_ecmwf.f90:183-185
+constexpr double SR3 = 0x1.bb67ae8584caap+0;         // SQRT(3.)                  mod_blk_andreas.f90:325
+constexpr double SR5 = 0x1.1e3779b97f4a8p+1;         // SQRT(5.)                  mod_blk_andreas.f90:381
+constexpr double ZBM_A = 5. / 6.5;                   // b_m                       mod_blk_andreas.f90:322
+constexpr double ZBBM_A = 0x1.56bfea66ef78dp-1;      // ABS((1-b_m)/b_m)**(1/3)   mod_blk_andreas.f90:345
+
+enum Algo { COARE3P0 = 1, COARE3P6 = 2, NCAR = 3, ECMWF = 4, ANDREAS = 5 };
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+// SIGN(MIN(ABS(x),lim),x) and SIGN(MAX(ABS(x),lo),x)
+ABD double clip_abs(double x, double lim) { return copysign(fmin(fabs(x), lim), x); }
+ABD double floor_abs(double x, double lo) { return copysign(fmax(fabs(x), lo), x); }
+// x**y for x >= 0 (0**y = 0 for y > 0 through log(0) = -inf)
+ABD double powr(double x, double y) { return exp(y * log(x)); }
+// zstab = 0.5 + SIGN(0.5, x) is 1 unless the sign bit of x is set
+ABD bool nonneg(double x) { return !signbit(x); }
+
+// ---------------------------------------------------------------------------
+// thermodynamics, reference src/mod_phymbl.f90
+// ---------------------------------------------------------------------------
+ABD double virt_temp(double T, double q) { return T * (1. + RCTV0 * q); }           // :247-269
+
+// Goff (1957) saturation vapour pressure [Pa], :777-800 (rt0, not the triple point)
+ABD double e_sat(double T)
+{
+    const double zta = fmax(T, 180.);
+    const double ztmp = RT0 / zta;
+    const double r = zta / RT0;
+    const double a = 10.79574 * (1. - ztmp) - 5.028 * log10(r)
+                     + (1.50475 * 1.e-4) * (1. - exp10(-8.2969 * (r - 1.)))
+                     + (0.42873 * 1.e-3) * (exp10(4.76955 * (1. - ztmp)) - 1.) + 0.78614;
+    return 100. * exp10(a);
+}
+ABD double q_sat_from_e(double es, double p) { return REPS0 * es / (p - (1. - REPS0) * es); }  // :903
+ABD double q_sat(double T, double p) { return q_sat_from_e(e_sat(T), p); }                   // :881-904
+
+// Theta_from_z_P0_T_q, :283-318 + :163-187 + :343-365; e_sat(T) is loop-invariant
+ABD double theta_from_z_P0_T_q(double z, double slp, double T, double q)
+{
+    const double es = e_sat(T);
+    double pa = slp;
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const double f = q / q_sat_from_e(es, pa);
+        const double xm = (1. - f) * RMM_DRYAIR + f * RMM_WATER;
+        pa = slp * exp(-GRAV * xm * z / (R_GAS * T));
+    }
+    return T * powr(slp / pa, RPOISS_DRY);
+}
+
+ABD double rho_air(double T, double q, double p) { return fmax(p / (R_DRY * T * (1. + RCTV0 * q)), 0.8); }  // :522-537
+ABD double visc_air(double T)                                                                              // :549-563
+{
+    const double tc = T - RT0, tc2 = tc * tc;
+    return 1.326e-5 * (1. + 6.542E-3 * tc + 8.301e-6 * tc2 - 4.84e-9 * tc2 * tc);
+}
+ABD double L_vap(double T) { return (2.501 - 0.00237 * (T - RT0)) * 1.e6; }                               // :579-592
+ABD double cp_air(double q) { return RCP_DRY + RCP_VAP * q; }                                             // :603-616
+ABD double alpha_sw(double T) { return 2.1e-5 * powr(fmax(T - RT0 + 3.2, 0.), 0.79); }                    // :1267-1280
+ABD double qlw_net(double rlw, double Ts) { const double t2 = Ts * Ts; return EMISS_W * (rlw - STEFAN * t2 * t2); }  // :1291-1314
+
+// 1/L, :666-693
+ABD double one_on_L(double tha, double qa, double us, double ts, double qs)
+{
+    const double zqa = 1. + RCTV0 * qa;
+    const double r = GRAV * VKARMN * (ts * zqa + RCTV0 * tha * qs) / fmax(us * us * tha * zqa, 1.E-9);
+    return clip_abs(r, 200.);
+}
+
+// bulk Richardson number, :712-747
+ABD double ri_bulk(double z, double sst, double tha, double ssq, double qa, double ub)
+{
+    const double sstv = virt_temp(sst, ssq);
+    const double dthv = virt_temp(tha, qa) - sstv;
+    const double tv = 0.5 * (sstv + virt_temp(tha - RGAMMA_DRY * z, qa));
+    return GRAV * dthv * z / (tv * ub * ub);
+}
+
+ABD double q_air_rh(double rh, double T, double p)  // :963-985
+{
+    const double ze = 0.01 * rh * e_sat(T);
+    return ze * REPS0 / fmax(p - (1. - REPS0) * ze, 1.);
+}
+ABD double q_air_dp(double dp, double p)            // :990-1000
+{
+    const double e = fmax(e_sat(dp), 0.);
+    return e * REPS0 / fmax(p - (1. - REPS0) * e, 1.);
+}
+
+struct Flux {
+    double tau, qsen, qlat, evap;
+};
+
+// BULK_FORMULA_SCLR, :1149-1203 (over water)
+ABD Flux bulk_formula(double zu, double Ts, double qs, double tha, double qa, double Cd, double Ch, double Ce,
+                      double wnd, double Ub, double slp)
+{
+    const double ta = tha - RGAMMA_DRY * zu;
+    double rho = rho_air(ta, qa, slp);
+    rho = rho_air(ta, qa, slp - rho * GRAV * zu);
+    const double Urho = Ub * fmax(rho, 1.);
+    Flux f;
+    f.tau = Urho * Cd * wnd;
+    f.evap = Urho * Ce * (qa - qs);
+    f.qsen = Urho * Ch * (tha - Ts) * cp_air(qa);
+    f.qlat = L_vap(Ts) * f.evap;
+    return f;
+}
+
+// UPDATE_QNSOL_TAU_SCLR, :1059-1103 -> non-solar flux, stress and latent flux
+ABD void update_qnsol_tau(double zu, double Ts, double qs, double tha, double qa, double us, double ts,
+                          double qst, double wnd, double Ub, double slp, double rlw,
+                          double &Qns, double &Tau, double &Qlat)
+{
+    const double dt = floor_abs(tha - Ts, 1.E-09);
+    const double dq = floor_abs(qa - qs, 1.E-12);
+    const double z0 = us / Ub;
+    const Flux f = bulk_formula(zu, Ts, qs, tha, qa, z0 * z0, z0 * ts / dt, z0 * qst / dq, wnd, Ub, slp);
+    Qns = f.qlat + f.qsen + qlw_net(rlw, Ts);
+    Tau = f.tau;
+    Qlat = f.qlat;
+}
+
+// Liu-Katsaros-Businger z0t / z0q, :1635-1701 (iflag 1: temperature, 2: humidity)
+ABD double z0tq_LKB(int iflag, double Rer, double z0)
+{
+    double r = 999.;  // ABS(-999.)
+    if (Rer > 0. && Rer < 1000.) {
+        double a, b;
+        if (iflag == 1) {
+            if (Rer <= 0.11) { a = 0.177; b = 0.; }
+            else if (Rer <= 0.825) { a = 1.376; b = 0.929; }
+            else if (Rer <= 3.0) { a = 1.026; b = -0.599; }
+            else if (Rer <= 10.0) { a = 1.625; b = -1.018; }
+            else if (Rer <= 30.0) { a = 4.661; b = -1.475; }
+            else if (Rer <= 100.) { a = 34.904; b = -2.067; }
+            else if (Rer <= 300.) { a = 1667.19; b = -2.907; }
+            else { a = 5.88e5; b = -3.935; }
+        } else {
+            if (Rer <= 0.11) { a = 0.292; b = 0.; }
+            else if (Rer <= 0.825) { a = 1.808; b = 0.826; }
+            else if (Rer <= 3.0) { a = 1.393; b = -0.528; }
+            else if (Rer <= 10.0) { a = 1.956; b = -0.870; }
+            else if (Rer <= 30.0) { a = 4.994; b = -1.297; }
+            else if (Rer <= 100.) { a = 30.709; b = -1.845; }
+            else if (Rer <= 300.) { a = 1448.68; b = -2.682; }
+            else { a = 2.98e5; b = -3.616; }
+        }
+        r = fabs(a * powr(Rer, b) * z0 / Rer);
+    }
+    return fmin(fmax(r, 1.E-9), 0.05);
+}
+
+// ---------------------------------------------------------------------------
+// stability functions
+// ---------------------------------------------------------------------------
+// Large & Yeager, src/mod_blk_ncar.f90:333-407
+ABD double psi_m_ncar(double z)
+{
+    if (nonneg(z)) return -5. * z;
+    const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
+    const double x = sqrt(x2);
+    return 2. * log((1. + x) * 0.5) + log((1. + x2) * 0.5) - 2. * atan(x) + RPI * 0.5;
+}
+ABD double psi_h_ncar(double z)
+{
+    if (nonneg(z)) return -5. * z;
+    const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
+    return 2. * log(0.5 * (1. + x2));
+}
+
+// COARE 3.x, src/mod_common_coare.f90:217-254, :305-344.  Note psi(+0) = -4.524e-3:
+// SIGN(0.5,+0.) selects the stable branch and the truncated literals do not cancel.
+ABD double psi_coare_convective(double phi_c)
+{
+    return 1.5 * log((1. + phi_c + phi_c * phi_c) / 3.) - 1.7320508 * atan((1. + 2. * phi_c) / 1.7320508) + 1.813799447;
+}
+ABD double psi_m_coare(double z)
+{
+    if (nonneg(z)) {
+        const double zc = fmin(50., 0.35 * z);
+        return -(1. + 1. * z + 0.6667 * (z - 14.28) / exp(zc) + 8.525);
+    }
+    const double phi_m = sqrt(sqrt(fabs(1. - 15. * z)));                       // **.25
+    const double psi_k = 2. * log((1. + phi_m) / 2.) + log((1. + phi_m * phi_m) / 2.) - 2. * atan(phi_m) + 0.5 * RPI;
+    const double psi_c = psi_coare_convective(powr(fabs(1. - 10.15 * z), .3333));
+    double f = z * z;
+    f = f / (1. + f);
+    return (1. - f) * psi_k + f * psi_c;
+}
+ABD double psi_h_coare(double z)
+{
+    if (nonneg(z)) {
+        const double zc = fmin(50., 0.35 * z);
+        const double a = fabs(1. + 2. * z / 3.);
+        return -(a * sqrt(a) + .6667 * (z - 14.28) / exp(zc) + 8.525);            // **1.5
+    }
+    const double phi_h = sqrt(fabs(1. - 15. * z));                             // **.5
+    const double psi_k = 2. * log((1. + phi_h) / 2.);
+    const double psi_c = psi_coare_convective(powr(fabs(1. - 34.15 * z), .3333));
+    double f = z * z;
+    f = f / (1. + f);
+    return (1. - f) * psi_k + f * psi_c;
+}
+
+// IFS, src/mod_blk_ecmwf.f90:441-564 (zeta capped to [-50, 5])
+ABD double psi_m_ecmwf(double zeta)
+{
+    const double zc = 5. / 0.35;
+    const double z = fmin(fmax(zeta, -50.), 5.);
+    if (nonneg(z)) return -(2. / 3. * (z - zc) * exp(-0.35 * z)) - z - 2. / 3. * zc;
+    const double x2 = sqrt(fabs(1. - 16. * z));
+    const double x = sqrt(x2);
+    const double t = 1. + x;
+    return log(0.125 * t * t * (1. + x2)) - 2. * atan(x) + 0.5 * RPI;
+}
+ABD double psi_h_ecmwf(double zeta)
+{
+    const double zc = 5. / 0.35;
+    const double z = fmin(fmax(zeta, -50.), 5.);
+    if (nonneg(z)) {
+        const double a = fabs(1. + 2. / 3. * z);
+        return -(2. / 3. * (z - zc) * exp(-0.35 * z)) - a * sqrt(a) - 2. / 3. * zc + 1.;
+    }
+    const double x2 = sqrt(fabs(1. - 16. * z));
+    return 2. * log(0.5 * (1. + x2));
+}
+
+// Andreas et al. 2015 (Paulson unstable / Grachev 2007 stable), src/mod_blk_andreas.f90:307-410
+ABD double psi_m_andreas(double zeta)
+{
+    const double z = fmin(zeta, 15.);
+    if (nonneg(z)) {
+        const double zam = 5.;
+        const double x = cbrt(fabs(1. + z));
+        return -(3. * zam / ZBM_A * (x - 1.))
+               + zam * ZBBM_A / (2. * ZBM_A)
+                     * (2. * log(fabs((x + ZBBM_A) / (1. + ZBBM_A)))
+                        - log(fabs((x * x - x * ZBBM_A + ZBBM_A * ZBBM_A) / (1. - ZBBM_A + ZBBM_A * ZBBM_A)))
+                        + 2. * SR3 * (atan((2. * x - ZBBM_A) / (SR3 * ZBBM_A)) - atan((2. - ZBBM_A) / (SR3 * ZBBM_A))));
+    }
+    const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
+    const double x = sqrt(x2);
+    return 2. * log(fabs((1. + x) * 0.5)) + log(fabs((1. + x2) * 0.5)) - 2. * atan(x) + RPI * 0.5;
+}
+ABD double psi_h_andreas(double zeta)
+{
+    const double z = fmin(zeta, 15.);
+    if (nonneg(z)) {
+        const double zah = 5., zbh = 5., zch = 3.;
+        const double zz = 2. * z + zch;
+        return -(0.5 * zbh * log(fabs(1. + zch * z + z * z)))
+               + (-zah / SR5 + 0.5 * zbh * zch / SR5)
+                     * (log(fabs((zz - SR5) / (zz + SR5))) - log(fabs((zch - SR5) / (zch + SR5))));
+    }
+    const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
+    return 2. * log(0.5 * (1. + x2));
+}
+
+// ---------------------------------------------------------------------------
+// launch-uniform quantities computed once on the host (glibc, like the oracle)
+// ---------------------------------------------------------------------------
+struct Uniform {
+    double zt, zu;
+    double log_zt, log_zu, log_ztu, log_zu10, log_10;   // LOG(zt) LOG(zu) LOG(zt/zu) LOG(zu/10) LOG(10)
+    double fg_c_a;                                     // 0.035*LOG(10/1e-4)/LOG(zu/1e-4)   mod_common_coare.f90:107
+    double fg_1_o_Ribcu;                               // -0.004*600*1.2**3/zu              :108,:140
+    double rdt, gdept;                                 // mod_const.f90:31-32
+    int nb_iter;
+    int isd;                                           // seconds since 00h UTC (12 in aerobulk_compute)
+};
+
+// ---------------------------------------------------------------------------
+// COARE first guess of u*, theta*, q*, z0 (also used by ECMWF),
+// src/mod_common_coare.f90:33-179
+// ---------------------------------------------------------------------------
+struct Guess {
+    double us, ts, qs, t_zu, q_zu, Ub, z0;
+};
+
+template <bool ZTEQ>
+ABD Guess first_guess_coare(const Uniform &u, double sst, double t_zt, double ssq, double q_zt, double wnd, double charn)
+{
+    Guess g;
+    g.t_zu = fmax(t_zt, 180.);
+    g.q_zu = fmax(q_zt, 1.e-6);
+
+    double dt = floor_abs(g.t_zu - sst, 1.E-09);
+    double dq = floor_abs(g.q_zu - ssq, 1.E-12);
+
+    const double nu_a = visc_air(g.t_zu);
+    const double Ub = sqrt(wnd * wnd + 0.5 * 0.5);
+    double us = u.fg_c_a * Ub;
+
+    double z0 = charn * us * us / GRAV + 0.11 * nu_a / us;
+    z0 = fmin(fmax(fabs(z0), 1.E-8), 1.);
+    const double log_z0 = log(z0);
+
+    const double sq = VKARMN / (u.log_zu - log_z0);
+    const double Cd = sq * sq;
+    const double r1_o_sqrt_Cd10 = (u.log_10 - log_z0) / VKARMN;
+
+    double z0t = 10. / exp(VKARMN / (0.00115 * r1_o_sqrt_Cd10));
+    z0t = fmin(fmax(fabs(z0t), 1.E-8), 1.);
+    const double log_z0t = log(z0t);
+
+    const double Rib = ri_bulk(u.zu, sst, g.t_zu, ssq, g.q_zu, Ub);
+
+    const double cc = VKARMN2 / (Cd * (u.log_zt - log_z0t));
+    const double cc_ri = cc * Rib;
+    const double zeta_u = nonneg(Rib) ? (cc_ri + 27. / 9. * Rib * Rib) : cc_ri / (1. + Rib * u.fg_1_o_Ribcu);
+
+    const double psi_h_u = psi_h_coare(zeta_u);
+    us = fmax(Ub * VKARMN / (u.log_zu - log_z0 - psi_m_coare(zeta_u)), 1.E-9);
+    const double tmp = VKARMN / (u.log_zu - log_z0t - psi_h_u);
+    double ts = dt * tmp;
+    double qs = dq * tmp;
+
+    if (!ZTEQ) {
+        const double zeta_t = u.zt * zeta_u / u.zu;
+        const double prf = u.log_ztu + psi_h_u - psi_h_coare(zeta_t);
+        g.t_zu = t_zt - ts / VKARMN * prf;
+        g.q_zu = q_zt - qs / VKARMN * prf;
+        g.q_zu = signbit(g.q_zu) ? 0. : g.q_zu;
+        dt = floor_abs(g.t_zu - sst, 1.E-09);
+        dq = floor_abs(g.q_zu - ssq, 1.E-12);
+        ts = dt * tmp;
+        qs = dq * tmp;
+    }
+    g.us = us;
+    g.ts = ts;
+    g.qs = qs;
+    g.Ub = Ub;
+    z0 = charn * us * us / GRAV + 0.11 * nu_a / us;
+    g.z0 = fmin(fmax(fabs(z0), 1.E-8), 1.);
+    return g;
+}
+
+// ---------------------------------------------------------------------------
+// cool skin (Fairall 1996 / Zeng-Beljaars 2005)
+// src/mod_phymbl.f90:2010-2046, src/mod_skin_coare.f90:48-93, src/mod_skin_ecmwf.f90:68-110
+// ---------------------------------------------------------------------------
+// COARE_FORM: 0.137 coefficient and the latent-heat term in delta; else 0.065, no Qlat.
+template <bool COARE_FORM>
+ABD double cool_skin_dT(double alpha, double Qsw, double Qnsol, double us, double Qlat)
+{
+    // invariants of the five delta_skin_layer evaluations
+    const double usw = fmax(us, 1.E-4) * SQ_RADRW;
+    const double usw2 = usw * usw;
+    const double c_lamb = alpha * RCST_CS / (usw2 * usw2);
+    const double nu_o_usw = RNU0_W / usw;
+    const double d_warm = fmin(6. * nu_o_usw, 0.007);
+    const double q_lat_term = COARE_FORM ? 0.026 * fmin(Qlat, 0.) * RCP0_W / RLEVAP / alpha : 0.;
+
+    auto delta = [&](double Qd) -> double {
+        const double zQd = COARE_FORM ? Qd + q_lat_term : Qd;
+        if (nonneg(zQd)) return d_warm;                                  // warming of the viscous layer
+        const double x = fmax(c_lamb * zQd, 0.);
+        const double x75 = sqrt(x) * sqrt(sqrt(x));                      // **0.75
+        return 6. * rcbrt(1. + x75) * nu_o_usw;                           // **(-1./3.)
+    };
+
+    double Qabs = Qnsol;
+    double d = delta(Qabs);
+#pragma unroll 1
+    for (int jc = 0; jc < 4; ++jc) {
+        const double fr = fmax((COARE_FORM ? 0.137 : 0.065) + 11. * d - 6.6E-5 / d * (1. - exp(-d / 8.E-4)), 0.01);
+        Qabs = Qnsol + fr * Qsw;
+        d = delta(Qabs);
+    }
+    return Qabs * d / RK0_W;
+}
+
+// ---------------------------------------------------------------------------
+// warm layer -- persistent per-point state kept in registers across the bulk
+// iteration and device-resident across time steps
+// ---------------------------------------------------------------------------
+struct WarmLayer {
+    double dT, Hz, Qac, Tac;   // dT_wl, Hz_wl, Qnt_ac, Tau_ac
+};
+
+// Per-point invariants of WL_COARE, src/mod_skin_coare.f90:146-156
+struct WlCoareCtx {
+    double cd1, cd2;
+    bool dawn;     // local solar hour in ]4, 6.5]
+};
+ABD double f_modulo(double a, double p)
+{
+    double r = fmod(a, p);
+    if (r != 0. && ((r < 0.) != (p < 0.))) r += p;
+    return r;
+}
+ABD WlCoareCtx wl_coare_ctx(double alpha, double lon, int isd)
+{
+    WlCoareCtx c;
+    double lag = -1. * f_modulo((360. - f_modulo(lon, 360.)) / 15., 24.);
+    lag = -1. * copysign(fmin(fabs(lag), fabs(f_modulo(lag, 24.))), lag + 12.);
+    const int ilag = (int)(lag * 3600.);
+    int isol = (isd + ilag) % 86400;
+    if (isol < 0) isol += 86400;
+    const double hr = (double)isol / 3600.;
+    c.dawn = (hr > 4.) && (hr <= 6.5);
+    const double Rich0 = 0.65;
+    c.cd1 = sqrt(2. * Rich0 * RCP0_W / (alpha * GRAV * RHO0_W));
+    c.cd2 = sqrt(2. * alpha * GRAV / (Rich0 * RHO0_W)) / RCP0W_POW15;
+    return c;
+}
+ABD double wl_coare_absorption(double H)   // solar absorption profile, :167-168 / :205-206
+{
+    return 1. - (0.28 * 0.014 * (1. - exp(-H / 0.014)) + 0.27 * 0.357 * (1. - exp(-H / 0.357))
+                 + 0.45 * 12.82 * (1 - exp(-H / 12.82))) / H;
+}
+// WL_COARE, src/mod_skin_coare.f90:97-250; `commit` is (iwait == 0)
+ABD void wl_coare(WarmLayer &w, const WlCoareCtx &c, double Qsw, double Qnsol, double Tau, double rdt,
+                  double gdept, bool commit)
+{
+    const double Hwl_max = 20.;
+    double dT = w.dT;
+    double H = fmax(fmin(w.Hz, Hwl_max), 0.1);
+    double qac = w.Qac;
+    double tac = w.Tac;
+    bool l_exit = c.dawn, destroy = c.dawn;
+    double Qabs = 0.;
+
+    if (!l_exit) {
+        Qabs = wl_coare_absorption(H) * Qsw + Qnsol;
+        if (fabs(dT) < 1.E-6 && Qabs <= 0.) l_exit = true;
+    }
+    if (!l_exit && (w.Qac + Qabs * rdt <= 0.)) {
+        l_exit = true;
+        destroy = true;
+    }
+    if (!l_exit) {
+        tac = w.Tac + fmax(.002, Tau) * rdt;
+#pragma unroll 1
+        for (int jl = 0; jl < 5; ++jl) {
+            Qabs = wl_coare_absorption(H) * Qsw + Qnsol;
+            qac = w.Qac + Qabs * rdt;
+            if (qac <= 0.) break;
+            H = fmax(fmin(Hwl_max, c.cd1 * tac / sqrt(qac)), 0.1);
+        }
+        if (qac <= 0.) {
+            destroy = true;
+        } else {
+            dT = c.cd2 * (qac * sqrt(qac)) / tac * fmax(qac / fabs(qac), 0.);   // **1.5
+            if (signbit(gdept - H)) dT = dT * (gdept / H);                       // flg = 0
+        }
+    }
+    if (destroy) {
+        dT = 0.;
+        H = Hwl_max;
+        qac = 0.;
+        tac = 0.;
+    }
+    if (commit) {
+        w.dT = dT;
+        w.Hz = H;
+        w.Qac = qac;
+        w.Tac = tac;
+    }
+}
+
+// Takaya et al. 2010 Eq.5, src/mod_skin_ecmwf.f90:233-253
+ABD double phi_takaya(double z)
+{
+    const double z2 = z * z;
+    if (nonneg(z)) return 1. + (5. * z + 4. * z2) / (1. + 3. * z + 0.25 * z2);
+    return 1. / sqrt(1. - 16. * (-fabs(z)));
+}
+// WL_ECMWF, src/mod_skin_ecmwf.f90:113-230 -- advances dT_wl by rdt at EVERY call
+ABD void wl_ecmwf(WarmLayer &w, double alpha, double Qsw, double Qnsol, double us, double rdt, double gdept)
+{
+    const double rNuwl0 = 0.5;
+    const double RhoCp_w = RHO0_W * RCP0_W;
+    const double H = w.Hz;
+    const double tcorr = signbit(gdept - H) ? gdept / H : 1.;
+    const double dT_b = fmax(w.dT / tcorr, 0.);
+
+    const double fr = 1. - 0.28 * exp(-71.5 * H) - 0.27 * exp(-2.8 * H) - 0.45 * exp(-0.07 * H);
+    const double Qabs = fr * Qsw + Qnsol;
+
+    const double usw = fmax(us, 1.E-4) * SQ_RADRW;
+    const double usw2 = usw * usw;
+    const bool warming = nonneg(Qabs);
+
+    const double cst1 = VKARMN * GRAV * alpha;
+    const double L2 = cst1 * Qabs / (RhoCp_w * usw2 * usw);
+    const double cst2 = cst1 / (5. * H * usw2);
+    const double cst0 = rdt * (rNuwl0 + 1.) / H;
+    const double A = cst0 * Qabs / (rNuwl0 * RhoCp_w);
+    const double cst3 = -cst0 * VKARMN * usw * FLA_ECMWF;
+
+    double dT_n = dT_b;
+#pragma unroll 1
+    for (int jc = 0; jc < 10; ++jc) {
+        dT_n = 0.5 * (dT_n + dT_b);
+        const double zeta = warming ? H * L2 : H * sqrt(dT_n * cst2);
+        const double B = cst3 / phi_takaya(zeta);
+        dT_n = fmax(dT_b + A + B * dT_n, 0.);
+    }
+    w.dT = dT_n * tcorr;
+}
+
+// ---------------------------------------------------------------------------
+// per-point problem and result
+// ---------------------------------------------------------------------------
+struct PointIn {
+    double sst, theta_zt, ssq, q_zt, wnd, slp;   // after aerobulk_compute steps 1-5
+    double Qsw, rlw, lon;                          // skin only
+};
+struct Coeffs {
+    double Cd, Ch, Ce, t_zu, q_zu, Ub, Ts, qs;
+};
+
+// ---------------------------------------------------------------------------
+// NCAR (Large & Yeager 2004/2008), src/mod_blk_ncar.f90:57-271
+// ---------------------------------------------------------------------------
+ABD double cd_n10_ncar(double w)
+{
+    double w6 = w * w * w;
+    w6 = w6 * w6;
+    const double r = nonneg(w - 33.) ? 1.e-3 * 2.34
+                                     : 1.e-3 * (2.7 / w + 0.142 + w / 13.09 - 3.14807E-10 * w6);
+    return fmax(r, CX_MIN);
+}
+
+template <bool ZTEQ>
+ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p)
+{
+    const double Ub = fmax(0.5, p.wnd);
+    const bool stable0 = nonneg(virt_temp(p.theta_zt, p.q_zt) - virt_temp(p.sst, p.ssq));
+    double CdN = cd_n10_ncar(Ub);
+    double sqrt_CdN = sqrt(CdN);
+    double Cd = CdN;
+    double Ce = fmax(1.e-3 * (34.6 * sqrt_CdN), CX_MIN);
+    double Ch = fmax(1.e-3 * sqrt_CdN * (stable0 ? 18. : 32.7), CX_MIN);
+    double sqrt_Cd = sqrt_CdN;
+    double t_zu = fmax(p.theta_zt, 180.);
+    double q_zu = fmax(p.q_zt, 1.e-6);
+
+#pragma unroll 1
+    for (int jit = 0; jit < u.nb_iter; ++jit) {
+        const double dt = t_zu - p.sst;
+        const double dq = q_zu - p.ssq;
+        const double us = sqrt_Cd * Ub;
+        const double ts = Ch / sqrt_Cd * dt;
+        const double qs = Ce / sqrt_Cd * dq;
+        const double r1oL = one_on_L(t_zu, q_zu, us, ts, qs);
+        const double zeta_u = clip_abs(u.zu * r1oL, 10.);
+        const double psi_h_u = psi_h_ncar(zeta_u);           // used twice in the reference (:196,:217)
+        if (!ZTEQ) {
+            const double zeta_t = clip_abs(u.zt * r1oL, 10.);
+            const double tmp = u.log_ztu + psi_h_u - psi_h_ncar(zeta_t);
+            t_zu = p.theta_zt - ts / VKARMN * tmp;
+            q_zu = fmax(0., p.q_zt - qs / VKARMN * tmp);
+        }
+        const double psi_m = psi_m_ncar(zeta_u);
+        // UN10_from_CD (mod_phymbl.f90:1532-1547) with z0_from_Cd(zu, Cd, psi) (:1335-1352); SQRT(Cd) is sqrt_Cd
+        const double z0 = u.zu * exp(-(VKARMN / sqrt_Cd + psi_m));
+        const double Un10 = fmax(0.25, sqrt_Cd * Ub / VKARMN * log(10. / z0));
+        CdN = cd_n10_ncar(Un10);
+        sqrt_CdN = sqrt(CdN);
+        double tmp = 1. + sqrt_CdN / VKARMN * (u.log_zu10 - psi_m);
+        Cd = fmax(CdN / (tmp * tmp), CX_MIN);
+        sqrt_Cd = sqrt(Cd);
+        tmp = (u.log_zu10 - psi_h_u) / VKARMN / sqrt_CdN;
+        const double tmp2 = sqrt_Cd / sqrt_CdN;
+        const double ChN = 1.e-3 * sqrt_CdN * (nonneg(zeta_u) ? 18. : 32.7);
+        const double CeN = 1.e-3 * (34.6 * sqrt_CdN);
+        Ch = fmax(ChN * tmp2 / (1. + ChN * tmp), CX_MIN);
+        Ce = fmax(CeN * tmp2 / (1. + CeN * tmp), CX_MIN);
+    }
+    Coeffs c;
+    c.Cd = Cd; c.Ch = Ch; c.Ce = Ce; c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = p.sst; c.qs = p.ssq;
+    return c;
+}
+
+// ---------------------------------------------------------------------------
+// COARE 3.0 (Fairall 2003) and 3.6 (Edson 2013)
+// src/mod_blk_coare3p0.f90:54-447, src/mod_blk_coare3p6.f90:123-441
+// ---------------------------------------------------------------------------
+ABD double charn_coare3p0(double w)
+{
+    if (!nonneg(w - 10.)) return 0.011;
+    if (nonneg(w - 18.)) return 0.018;
+    return 0.011 + (0.018 - 0.011) * (w - 10.) / (18. - 10.);
+}
+ABD double charn_coare3p6(double w) { return fmax(fmin(0.0017 * w - 0.005, 0.028), 0.); }
+
+template <bool V36, bool SKIN, bool ZTEQ>
+ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
+{
+    const double zi0 = 600., Beta0 = V36 ? 1.2 : 1.25, zeta_abs_max = 50.;
+
+    double Ts = p.sst, qs_ = p.ssq;
+    double alpha = 0.;
+    WlCoareCtx wc = {};
+    if (SKIN) {
+        Ts = Ts - 0.25;
+        qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+        alpha = alpha_sw(p.sst);
+        wc = wl_coare_ctx(alpha, p.lon, u.isd);
+    }
+
+    const Guess g = first_guess_coare<ZTEQ>(u, Ts, p.theta_zt, qs_, p.q_zt, p.wnd,
+                                            V36 ? charn_coare3p6(p.wnd) : charn_coare3p0(p.wnd));
+    double us = g.us, ts = g.ts, qst = g.qs, t_zu = g.t_zu, q_zu = g.q_zu, Ub = g.Ub;
+    double log_z0 = log(g.z0);
+    // COARE 3.6 uses the first-guess t_zu, 3.0 the potential temperature at zt
+    const double nu_a = V36 ? visc_air(t_zu) : visc_air(p.theta_zt);
+
+    double dt = floor_abs(t_zu - Ts, 1.E-09);
+    double dq = floor_abs(q_zu - qs_, 1.E-12);
+    double dT_cs = 0.;
+
+#pragma unroll 1
+    for (int jit = 1; jit <= u.nb_iter; ++jit) {
+        const double us2 = us * us;
+        const double r1oL = one_on_L(t_zu, q_zu, us, ts, qst);    // already clipped to +-200
+
+        const double cv = cbrt(fmax(-zi0 * r1oL / VKARMN, 0.));
+        const double gust2 = Beta0 * Beta0 * us2 * (cv * cv);       // **(2./3.)
+        Ub = fmax(sqrt(p.wnd * p.wnd + gust2), 0.2);
+
+        const double zeta_u = clip_abs(u.zu * r1oL, zeta_abs_max);
+
+        const double Un10 = us / VKARMN * (u.log_10 - log_z0);
+        double z0 = (V36 ? charn_coare3p6(Un10) : charn_coare3p0(Un10)) * us2 / GRAV + 0.11 * nu_a / us;
+        z0 = fmin(fmax(fabs(z0), 1.E-9), 1.);
+        log_z0 = log(z0);
+
+        const double rr = powr(nu_a / (z0 * us), V36 ? 0.72 : 0.6);
+        double z0t = V36 ? fmin(1.6E-4, 5.8E-5 * rr) : fmin(1.1E-4, 5.5E-5 * rr);
+        z0t = fmin(fmax(fabs(z0t), 1.E-9), 1.);
+        const double log_z0t = log(z0t);
+
+        const double psi_h_u = psi_h_coare(zeta_u);
+        double tmp1 = VKARMN / (u.log_zu - log_z0t - psi_h_u);
+        ts = dt * tmp1;
+        qst = dq * tmp1;
+        us = fmax(Ub * VKARMN / (u.log_zu - log_z0 - psi_m_coare(zeta_u)), 1.E-9);
+
+        if (!ZTEQ) {
+            const double zeta_t = clip_abs(u.zt * r1oL, zeta_abs_max);
+            tmp1 = u.log_zt - u.log_zu + psi_h_u - psi_h_coare(zeta_t);
+            t_zu = p.theta_zt - ts / VKARMN * tmp1;
+            q_zu = p.q_zt - qst / VKARMN * tmp1;
+        } else if (!V36) {
+            t_zu = p.theta_zt;   // zm_ztzu = 0 in COARE 3.0: t_zu <- t_zt, q_zu <- q_zt every iteration
+            q_zu = p.q_zt;
+        }
+
+        if (SKIN) {
+            double Qns, Tau, Qlat;
+            // cool skin
+            update_qnsol_tau(u.zu, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.slp, p.rlw, Qns, Tau, Qlat);
+            dT_cs = cool_skin_dT<true>(alpha, p.Qsw, Qns, us, Qlat);
+            Ts = p.sst + dT_cs;
+            Ts = Ts + wl.dT;
+            qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+            // warm layer; state committed whenever jit divides nb_iter
+            update_qnsol_tau(u.zu, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.slp, p.rlw, Qns, Tau, Qlat);
+            wl_coare(wl, wc, p.Qsw, Qns, Tau, u.rdt, u.gdept, (u.nb_iter % jit) == 0);
+            Ts = p.sst + wl.dT;
+            Ts = Ts + dT_cs;
+            qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+        }
+        if (SKIN || !ZTEQ || !V36) {
+            dt = floor_abs(t_zu - Ts, 1.E-09);
+            dq = floor_abs(q_zu - qs_, 1.E-12);
+        }
+    }
+    Coeffs c;
+    const double r = us / Ub;
+    c.Cd = fmax(r * r, CX_MIN);
+    c.Ch = fmax(r * ts / dt, CX_MIN);
+    c.Ce = fmax(r * qst / dq, CX_MIN);
+    c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = Ts; c.qs = qs_;
+    return c;
+}
+
+// ---------------------------------------------------------------------------
+// ECMWF (IFS Cy40/45), src/mod_blk_ecmwf.f90:63-383
+// ---------------------------------------------------------------------------
+template <bool SKIN, bool ZTEQ>
+ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
+{
+    const double charn0 = 0.018, zi0 = 1000., Beta0 = 1., alpha_M = 0.11, alpha_H = 0.40, alpha_Q = 0.62;
+
+    double Ts = p.sst, qs_ = p.ssq;
+    double alpha = 0.;
+    if (SKIN) {
+        Ts = Ts - 0.25;
+        qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+        alpha = alpha_sw(p.sst);
+    }
+
+    const Guess g = first_guess_coare<ZTEQ>(u, Ts, p.theta_zt, qs_, p.q_zt, p.wnd, charn0);
+    double us = g.us, ts = g.ts, qst = g.qs, t_zu = g.t_zu, q_zu = g.q_zu, Ub = g.Ub;
+    double z0 = g.z0;
+    double log_z0 = log(z0);
+    const double nu_a = visc_air(p.theta_zt);
+
+    double dt = floor_abs(t_zu - Ts, 1.E-09);
+    double dq = floor_abs(q_zu - qs_, 1.E-12);
+
+    double r1oL = one_on_L(t_zu, q_zu, us, ts, qst);
+    double z0t = fmin(fmax(fabs(1. / (0.1 * exp(VKARMN / (0.00115 / (VKARMN / (u.log_10 - log_z0)))))), 1.E-9), 1.);
+    double log_z0t = log(z0t);
+
+    double Fm = u.log_zu - log_z0 - psi_m_ecmwf(u.zu * r1oL) + psi_m_ecmwf(z0 * r1oL);
+    double psi_h_u = psi_h_ecmwf(u.zu * r1oL);
+    double Fh = u.log_zu - log_z0t - psi_h_u + psi_h_ecmwf(z0t * r1oL);
+    double log_z0q = 0., psi_h_z0q = 0., dT_cs = 0.;
+
+#pragma unroll 1
+    for (int jit = 1; jit <= u.nb_iter; ++jit) {
+        const double Rib = ri_bulk(u.zu, Ts, t_zu, qs_, q_zu, Ub);
+        r1oL = clip_abs(Rib * Fm * Fm / Fh / u.zu, 200.);
+
+        const double psi_m_u = psi_m_ecmwf(u.zu * r1oL);
+        psi_h_u = psi_h_ecmwf(u.zu * r1oL);
+        const double psi_h_t = ZTEQ ? 0. : psi_h_ecmwf(u.zt * r1oL);
+
+        Fm = u.log_zu - log_z0 - psi_m_u + psi_m_ecmwf(z0 * r1oL);
+
+        us = Ub * VKARMN / Fm;
+        const double us2 = us * us;
+        double tmp0 = nu_a / us;
+        z0 = fmin(fabs(alpha_M * tmp0 + charn0 * us2 / GRAV), 0.001);
+        z0t = fmin(fabs(alpha_H * tmp0), 0.001);
+        const double z0q = fmin(fabs(alpha_Q * tmp0), 0.001);
+        log_z0 = log(z0);
+        log_z0t = log(z0t);
+        log_z0q = log(z0q);
+
+        const double psi_m_z0 = psi_m_ecmwf(z0 * r1oL);
+        const double psi_h_z0t = psi_h_ecmwf(z0t * r1oL);
+        psi_h_z0q = psi_h_ecmwf(z0q * r1oL);
+
+        const double cv = cbrt(fmax(-zi0 * r1oL / VKARMN, 0.));
+        tmp0 = Beta0 * Beta0 * us2 * (cv * cv);
+        Ub = fmax(sqrt(p.wnd * p.wnd + tmp0), 0.2);
+
+        tmp0 = psi_h_u - psi_h_z0t;
+        double tmp1 = VKARMN / (u.log_zu - log_z0t - tmp0);
+        ts = dt * tmp1;
+        if (!ZTEQ) {
+            tmp1 = u.log_ztu + tmp0 - psi_h_t + psi_h_z0t;
+            t_zu = p.theta_zt - ts / VKARMN * tmp1;
+        } else {
+            t_zu = p.theta_zt;
+        }
+        tmp0 = psi_h_u - psi_h_z0q;
+        tmp1 = VKARMN / (u.log_zu - log_z0q - tmp0);
+        qst = dq * tmp1;
+        if (!ZTEQ) {
+            tmp1 = u.log_ztu + tmp0 - psi_h_t + psi_h_z0q;
+            q_zu = fmax(p.q_zt - qst / VKARMN * tmp1, 0.);
+        } else {
+            q_zu = fmax(p.q_zt, 0.);
+        }
+
+        Fm = u.log_zu - log_z0 - psi_m_u + psi_m_z0;
+        Fh = u.log_zu - log_z0t - psi_h_u + psi_h_z0t;
+
+        if (SKIN) {
+            double Qns, Tau, Qlat;
+            update_qnsol_tau(u.zu, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.slp, p.rlw, Qns, Tau, Qlat);
+            dT_cs = cool_skin_dT<false>(alpha, p.Qsw, Qns, us, 0.);
+            Ts = p.sst + dT_cs;
+            Ts = Ts + wl.dT;
+            qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+            update_qnsol_tau(u.zu, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.slp, p.rlw, Qns, Tau, Qlat);
+            wl_ecmwf(wl, alpha, p.Qsw, Qns, us, u.rdt, u.gdept);     // every iteration
+            Ts = p.sst + wl.dT;
+            Ts = Ts + dT_cs;
+            qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+        }
+        dt = floor_abs(t_zu - Ts, 1.E-09);
+        dq = floor_abs(q_zu - qs_, 1.E-12);
+    }
+    Coeffs c;
+    const double Fq = u.log_zu - log_z0q - psi_h_u + psi_h_z0q;
+    c.Cd = fmax(VKARMN2 / (Fm * Fm), CX_MIN);
+    c.Ch = fmax(VKARMN2 / (Fm * Fh), CX_MIN);
+    c.Ce = fmax(VKARMN2 / (Fm * Fq), CX_MIN);
+    c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = Ts; c.qs = qs_;
+    return c;
+}
+
+// ---------------------------------------------------------------------------
+// ANDREAS (Andreas et al. 2015), src/mod_blk_andreas.f90:66-304
+// ---------------------------------------------------------------------------
+template <bool ZTEQ>
+ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p)
+{
+    const double rRi_max = 0.15, rCs_min = 0.35E-3;
+    const double Ub = fmax(0.25, p.wnd);
+    double UN10 = Ub;
+    double t_zu = p.theta_zt, q_zu = p.q_zt;
+    const double sq0 = sqrt(1.1E-3);
+    double t_star = 1.1E-3 / sq0 * (t_zu - p.sst);
+    double q_star = 1.1E-3 / sq0 * (q_zu - p.ssq);
+    double RiB = ri_bulk(u.zu, p.sst, t_zu, p.ssq, q_zu, Ub);
+    double u_star = 0.;
+
+#pragma unroll 1
+    for (int jit = 1; jit <= u.nb_iter; ++jit) {
+        if (RiB < rRi_max) {
+            const double za = UN10 - 8.271;
+            u_star = 0.239 + 0.0433 * (za + sqrt(0.12 * za * za + 0.181));   // :275-293
+        } else {
+            u_star = sqrt(CX_MIN) * Ub;
+        }
+        const double zeta_u = u.zu * one_on_L(t_zu, q_zu, u_star, t_star, q_star);
+        const double r = u_star / Ub;
+        const double Cd = fmax(r * r, CX_MIN);
+        const double psi_m = psi_m_andreas(zeta_u);
+        const double z0 = fmin(u.zu * exp(-(VKARMN / sqrt(Cd) + psi_m)), Z0_SEA_MAX);
+
+        const double Rer = z0 * u_star / visc_air(t_zu);
+        const double z0t = z0tq_LKB(1, Rer, z0);
+        const double z0q = z0tq_LKB(2, Rer, z0);
+
+        const double psi_h_u = psi_h_andreas(zeta_u);
+        t_star = (t_zu - p.sst) * VKARMN / (u.log_zu - log(z0t) - psi_h_u);
+        q_star = (q_zu - p.ssq) * VKARMN / (u.log_zu - log(z0q) - psi_h_u);
+
+        if (!ZTEQ && jit > 1) {
+            const double zeta_t = zeta_u / u.zu * u.zt;
+            const double tmp = u.log_ztu + psi_h_u - psi_h_andreas(zeta_t);
+            t_zu = p.theta_zt - t_star / VKARMN * tmp;
+            q_zu = p.q_zt - q_star / VKARMN * tmp;
+            RiB = ri_bulk(u.zu, p.sst, t_zu, p.ssq, q_zu, Ub);
+        }
+        UN10 = fmax(0.1, Ub - u_star / VKARMN * (u.log_zu10 - psi_m));   // UN10_from_ustar, mod_phymbl.f90:1498-1510
+    }
+    Coeffs c;
+    const double r = u_star / Ub;
+    c.Cd = fmax(r * r, CX_MIN);
+    const double d1 = floor_abs(t_zu - p.sst, 1.E-6);
+    const double d2 = floor_abs(q_zu - p.ssq, 1.E-9);
+    c.Ch = fmax(r * t_star / d1, rCs_min);
+    c.Ce = fmax(r * q_star / d2, rCs_min);
+    c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = p.sst; c.qs = p.ssq;
+    return c;
+}
+
+#undef ABD
+}  // namespace abd

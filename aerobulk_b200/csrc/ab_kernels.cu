@@ -1,0 +1,321 @@
+// ab_kernels.cu -- hand-written FP64 CUDA kernels for sm_100a.
+//
+//   flux_kernel<ALGO,SKIN,ZTEQ>  one thread per grid point: humidity conversion, scalar
+//       wind, ssq, theta(zt), the nb_iter Monin-Obukhov iteration of one of the five bulk
+//       algorithms (with cool-skin / warm-layer when SKIN), bulk formula and wind-stress
+//       vector -- reference src/mod_aerobulk_compute.f90:22-213 fused into one launch.
+//       All iteration state lives in registers; global memory is touched once per field
+//       (6-8 coalesced 8-byte loads, 5-6 stores, 1-4 state words R+W).
+//   stats_kernel / stats_final   the field statistics AEROBULK_INIT needs
+//       (src/mod_aerobulk.f90:104-153): mask, per-field masked sum/min/max, raw min/max.
+//   dfma_peak_kernel             dependent-chain DFMA microbenchmark (FP64 roofline denominator).
+//
+// The path is FP64-pipe bound (no contraction -> no tensor cores): see DESIGN.md.
+#include "ab_kernels.cuh"
+
+#include <float.h>
+#include <stdint.h>
+
+namespace abk {
+
+using namespace abd;
+
+static constexpr int FLUX_BLOCK = 128;
+
+template <int ALGO, bool SKIN, bool ZTEQ>
+__global__ void __launch_bounds__(FLUX_BLOCK) flux_kernel(const FluxArgs a)
+{
+    const long long i = (long long)blockIdx.x * FLUX_BLOCK + threadIdx.x;
+    if (i >= a.n) return;
+
+    // ---- coalesced loads of the 6 (8) input fields
+    const double sst = __ldg(a.sst + i);
+    const double t_air = __ldg(a.t_zt + i);
+    const double hum = __ldg(a.hum_zt + i);
+    const double U = __ldg(a.U_zu + i);
+    const double V = __ldg(a.V_zu + i);
+    const double slp = __ldg(a.slp + i);
+
+    PointIn p;
+    p.sst = sst;
+    p.slp = slp;
+    // humidity -> specific humidity (mod_aerobulk_compute.f90:99-108); slp floored at 5e4 Pa by the caller
+    if (a.ihum == 0) p.q_zt = hum;
+    else if (a.ihum == 1) p.q_zt = q_air_dp(hum, fmax(slp, 50000.));
+    else p.q_zt = q_air_rh(hum, t_air, fmax(slp, 50000.));
+    // :111 -- no FMA contraction here: U*U+V*V must not depend on the order of the components
+    p.wnd = sqrt(__dadd_rn(__dmul_rn(U, U), __dmul_rn(V, V)));
+    p.ssq = RDCT_QSAT_SALT * q_sat(sst, slp);                      // :114
+    p.theta_zt = theta_from_z_P0_T_q(a.u.zt, slp, t_air, p.q_zt);  // :118
+    p.Qsw = 0.;
+    p.rlw = 0.;
+    p.lon = 0.;
+
+    WarmLayer wl = {0., 0., 0., 0.};
+    if (SKIN) {
+        p.Qsw = (1. - ROCE_ALB0) * __ldg(a.rad_sw + i);            // :135,:146,:161
+        p.rlw = __ldg(a.rad_lw + i);
+        if (a.lon) p.lon = __ldg(a.lon + i);
+        if (ALGO == ECMWF) {
+            wl.Hz = 3.;                                            // rd0, mod_skin_ecmwf.f90:57 (constant)
+            wl.dT = a.first_step ? 0. : a.dT_wl[i];
+        } else if (a.first_step) {
+            wl.Hz = 20.;                                           // Hwl_max, mod_blk_coare3p6.f90:84-87
+        } else {
+            wl.dT = a.dT_wl[i];
+            wl.Hz = a.Hz_wl[i];
+            wl.Qac = a.Qnt_ac[i];
+            wl.Tac = a.Tau_ac[i];
+        }
+    }
+
+    Coeffs c;
+    if (ALGO == NCAR) c = solve_ncar<ZTEQ>(a.u, p);
+    else if (ALGO == ANDREAS) c = solve_andreas<ZTEQ>(a.u, p);
+    else if (ALGO == ECMWF) c = solve_ecmwf<SKIN, ZTEQ>(a.u, p, wl);
+    else c = solve_coare<ALGO == COARE3P6, SKIN, ZTEQ>(a.u, p, wl);
+
+    if (SKIN) {
+        a.dT_wl[i] = wl.dT;
+        if (ALGO != ECMWF) {
+            a.Hz_wl[i] = wl.Hz;
+            a.Qnt_ac[i] = wl.Qac;
+            a.Tau_ac[i] = wl.Tac;
+        }
+    }
+
+    // ---- flux assembly (BULK_FORMULA, :184-185) and stress vector (:189-194)
+    const Flux f = bulk_formula(a.u.zu, c.Ts, c.qs, c.t_zu, c.q_zu, c.Cd, c.Ch, c.Ce, p.wnd, c.Ub, slp);
+    if (f.tau > REF_TAU_MAX) atomicMin(a.bad_index, (unsigned long long)(a.index_offset + i));
+
+    double tx = 0., ty = 0.;
+    if (p.wnd > 1.E-3) {
+        const double s = f.tau / p.wnd;
+        tx = s * U;
+        ty = s * V;
+    }
+    a.QL[i] = f.qlat;
+    a.QH[i] = f.qsen;
+    a.Tau_x[i] = tx;
+    a.Tau_y[i] = ty;
+    a.Evap[i] = f.evap;
+    if (a.T_s) a.T_s[i] = c.Ts;
+}
+
+template <int ALGO, bool SKIN, bool ZTEQ>
+static cudaError_t launch_one(const FluxArgs &a, cudaStream_t s)
+{
+    if (a.n <= 0) return cudaSuccess;
+    const long long blocks = (a.n + FLUX_BLOCK - 1) / FLUX_BLOCK;
+    flux_kernel<ALGO, SKIN, ZTEQ><<<(unsigned)blocks, FLUX_BLOCK, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int ALGO, bool SKIN>
+static cudaError_t launch_zt(bool zteq, const FluxArgs &a, cudaStream_t s)
+{
+    return zteq ? launch_one<ALGO, SKIN, true>(a, s) : launch_one<ALGO, SKIN, false>(a, s);
+}
+
+cudaError_t launch_flux(int algo, bool skin, bool zteq, const FluxArgs &a, cudaStream_t s)
+{
+    switch (algo) {
+    case COARE3P0: return skin ? launch_zt<COARE3P0, true>(zteq, a, s) : launch_zt<COARE3P0, false>(zteq, a, s);
+    case COARE3P6: return skin ? launch_zt<COARE3P6, true>(zteq, a, s) : launch_zt<COARE3P6, false>(zteq, a, s);
+    case ECMWF: return skin ? launch_zt<ECMWF, true>(zteq, a, s) : launch_zt<ECMWF, false>(zteq, a, s);
+    case NCAR: return launch_zt<NCAR, false>(zteq, a, s);
+    case ANDREAS: return launch_zt<ANDREAS, false>(zteq, a, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+int flux_block_size() { return FLUX_BLOCK; }
+
+template <int ALGO, bool SKIN>
+static cudaError_t attr_zt(bool zteq, cudaFuncAttributes *attr)
+{
+    return zteq ? cudaFuncGetAttributes(attr, flux_kernel<ALGO, SKIN, true>)
+                : cudaFuncGetAttributes(attr, flux_kernel<ALGO, SKIN, false>);
+}
+cudaError_t flux_kernel_attributes(int algo, bool skin, bool zteq, cudaFuncAttributes *attr)
+{
+    switch (algo) {
+    case COARE3P0: return skin ? attr_zt<COARE3P0, true>(zteq, attr) : attr_zt<COARE3P0, false>(zteq, attr);
+    case COARE3P6: return skin ? attr_zt<COARE3P6, true>(zteq, attr) : attr_zt<COARE3P6, false>(zteq, attr);
+    case ECMWF: return skin ? attr_zt<ECMWF, true>(zteq, attr) : attr_zt<ECMWF, false>(zteq, attr);
+    case NCAR: return attr_zt<NCAR, false>(zteq, attr);
+    case ANDREAS: return attr_zt<ANDREAS, false>(zteq, attr);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// AEROBULK_INIT statistics (src/mod_aerobulk.f90:104-153, src/mod_phymbl.f90:1851-2007)
+// ---------------------------------------------------------------------------
+static constexpr int STATS_BLOCK = 256;
+static constexpr int STATS_MAX_BLOCKS = 148 * 4;
+
+// sanity ranges, src/mod_const.f90:138-146
+__device__ __forceinline__ bool point_unmasked(double sst, double ta, double slp, double wnd, bool rad, double rlw)
+{
+    bool m = true;
+    if (sst < 270. || sst > 320.) m = false;
+    if (ta < 180. || ta > 330.) m = false;
+    if (slp < 80000. || slp > 110000.) m = false;
+    if (wnd > 50.) m = false;
+    if (rad) {
+        if (rlw < 0. || rlw > 1500.) m = false;   // prsw=rad_lw (mod_aerobulk.f90:248): rad_lw vs the SW range
+        if (rlw < 0. || rlw > 750.) m = false;
+    }
+    return m;
+}
+
+__device__ __forceinline__ double warp_reduce(double v, int op)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_down_sync(0xffffffffu, v, o);
+        v = (op == 0) ? v + w : (op == 1) ? fmin(v, w) : fmax(v, w);
+    }
+    return v;
+}
+
+__host__ __device__ inline int stat_op(int k)   // 0 sum, 1 min, 2 max
+{
+    if (k < 2) return 0;
+    const int r = (k - 2) % 5;
+    if (k >= 2 + 5 * NFIELDS) return 0;
+    return (r == 0) ? 0 : (r == 1 || r == 3) ? 1 : 2;
+}
+
+__global__ void __launch_bounds__(STATS_BLOCK) stats_kernel(const StatsArgs a)
+{
+    double acc[2 + 5 * NFIELDS];
+    acc[0] = 0.;
+    acc[1] = 0.;
+#pragma unroll
+    for (int f = 0; f < NFIELDS; ++f) {
+        acc[2 + 5 * f + 0] = 0.;
+        acc[2 + 5 * f + 1] = DBL_MAX;
+        acc[2 + 5 * f + 2] = -DBL_MAX;
+        acc[2 + 5 * f + 3] = DBL_MAX;
+        acc[2 + 5 * f + 4] = -DBL_MAX;
+    }
+    const bool rad = (a.rad_lw != nullptr);
+    const long long stride = (long long)gridDim.x * STATS_BLOCK;
+    for (long long i = (long long)blockIdx.x * STATS_BLOCK + threadIdx.x; i < a.n; i += stride) {
+        double v[NFIELDS];
+        v[0] = __ldg(a.sst + i);
+        v[1] = __ldg(a.t_zt + i);
+        v[2] = __ldg(a.slp + i);
+        v[3] = __ldg(a.U_zu + i);
+        v[4] = __ldg(a.V_zu + i);
+        v[5] = sqrt(__dadd_rn(__dmul_rn(v[3], v[3]), __dmul_rn(v[4], v[4])));
+        v[6] = __ldg(a.hum_zt + i);
+        v[7] = rad ? __ldg(a.rad_lw + i) : 0.;
+        v[8] = v[7];
+        const bool m = point_unmasked(v[0], v[1], v[2], v[5], rad, v[7]);
+        acc[0] += m ? 1. : 0.;
+        acc[1] += 1.;
+#pragma unroll
+        for (int f = 0; f < NFIELDS; ++f) {
+            if (m) {
+                acc[2 + 5 * f + 0] += v[f];
+                acc[2 + 5 * f + 1] = fmin(acc[2 + 5 * f + 1], v[f]);
+                acc[2 + 5 * f + 2] = fmax(acc[2 + 5 * f + 2], v[f]);
+            }
+            acc[2 + 5 * f + 3] = fmin(acc[2 + 5 * f + 3], v[f]);
+            acc[2 + 5 * f + 4] = fmax(acc[2 + 5 * f + 4], v[f]);
+        }
+    }
+    __shared__ double sm[STATS_BLOCK / 32][2 + 5 * NFIELDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 2 + 5 * NFIELDS; ++k) {
+        const double r = warp_reduce(acc[k], stat_op(k));
+        if (lane == 0) sm[warp][k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 + 5 * NFIELDS) {
+        const int k = threadIdx.x, op = stat_op(k);
+        double r = sm[0][k];
+        for (int w = 1; w < STATS_BLOCK / 32; ++w)
+            r = (op == 0) ? r + sm[w][k] : (op == 1) ? fmin(r, sm[w][k]) : fmax(r, sm[w][k]);
+        a.partials[(long long)blockIdx.x * NSTATS + k] = r;
+    }
+}
+
+// fixed-order final reduction -> results do not depend on scheduling
+__global__ void stats_final(const double *partials, int nblocks, double *out)
+{
+    const int k = threadIdx.x;
+    if (k >= NSTATS) return;
+    if (k >= 2 + 5 * NFIELDS) {
+        out[k] = 0.;
+        return;
+    }
+    const int op = stat_op(k);
+    double r = partials[k];
+    for (int b = 1; b < nblocks; ++b) {
+        const double w = partials[(long long)b * NSTATS + k];
+        r = (op == 0) ? r + w : (op == 1) ? fmin(r, w) : fmax(r, w);
+    }
+    out[k] = r;
+}
+
+int stats_max_blocks() { return STATS_MAX_BLOCKS; }
+
+cudaError_t launch_stats(const StatsArgs &a, int nblocks, cudaStream_t s)
+{
+    stats_kernel<<<nblocks, STATS_BLOCK, 0, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    stats_final<<<1, NSTATS, 0, s>>>(a.partials, nblocks, a.out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// FP64 peak: 8 independent dependent-DFMA chains per thread
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3., x4 = x0 + 4., x5 = x0 + 5., x6 = x0 + 6., x7 = x0 + 7.;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+double measure_fp64_peak(cudaStream_t s)
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1.;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1.;
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    double *out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * (size_t)blocks * threads) != cudaSuccess) return -1.;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, s);
+        dfma_peak_kernel<<<blocks, threads, 0, s>>>(out, iters, 0.999999, 1.e-9);
+        cudaEventRecord(e1, s);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double n = (double)blocks * threads * (double)iters * 64.;
+        if (rep > 0 && ms > 0.f) best = fmax(best, n / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}
+
+}  // namespace abk

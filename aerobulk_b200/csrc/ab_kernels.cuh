@@ -1,0 +1,50 @@
+// ab_kernels.cuh -- host-visible launch interface of the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "ab_device.cuh"
+
+namespace abk {
+
+// One fused launch = reference aerobulk_compute (src/mod_aerobulk_compute.f90:22-213)
+// steps 1-9 for `n` consecutive grid points.
+struct FluxArgs {
+    // inputs (device)
+    const double *sst, *t_zt, *hum_zt, *U_zu, *V_zu, *slp;
+    const double *rad_sw, *rad_lw;   // skin only
+    const double *lon;               // optional longitudes [deg E]; NULL -> 0 (mod_aerobulk_compute.f90:126)
+    // outputs (device); T_s may be NULL
+    double *QL, *QH, *Tau_x, *Tau_y, *Evap, *T_s;
+    // persistent warm-layer state (device); COARE: 4 arrays, ECMWF: dT_wl only
+    double *dT_wl, *Hz_wl, *Qnt_ac, *Tau_ac;
+    long long n;
+    abd::Uniform u;
+    int ihum;          // 0 'sh', 1 'dp', 2 'rh'   (mod_aerobulk_compute.f90:99-108)
+    int first_step;    // kt == nit000: state starts from its *_INIT values, not from memory
+    // first linear index whose wind stress exceeds 10 N/m^2 (mod_phymbl.f90:1250-1253), else ~0ull
+    unsigned long long *bad_index;
+    long long index_offset;   // global index of point 0 (chunked / sharded launches)
+};
+
+// number of doubles in the statistics vector (see include/aerobulk_gpu.h)
+constexpr int NSTATS = 64;
+constexpr int NFIELDS = 9;
+
+struct StatsArgs {
+    const double *sst, *t_zt, *hum_zt, *U_zu, *V_zu, *slp, *rad_lw;   // rad_lw may be NULL
+    long long n;
+    double *partials;   // [gridDim.x][NSTATS]
+    double *out;        // [NSTATS]
+};
+
+cudaError_t launch_flux(int algo, bool skin, bool zt_eq_zu, const FluxArgs &a, cudaStream_t s);
+// block size / register info for reports
+int flux_block_size();
+cudaError_t launch_stats(const StatsArgs &a, int nblocks, cudaStream_t s);
+int stats_max_blocks();
+// DFMA-chain microbenchmark: returns FP64 FMA instructions per second, <0 on error
+double measure_fp64_peak(cudaStream_t s);
+cudaError_t flux_kernel_attributes(int algo, bool skin, bool zt_eq_zu, cudaFuncAttributes *attr);
+
+}  // namespace abk

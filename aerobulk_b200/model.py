@@ -1,0 +1,225 @@
+"""ctypes mirror of the reference's AEROBULK_MODEL interface (src/mod_aerobulk.f90:176-230)
+on top of the C ABI of libaerobulk_gpu.so.  Same argument names, meaning and optional
+arguments; Fortran STOPs become :class:`AerobulkError`."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libaerobulk_gpu.so")
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_lib = None
+NSTATS = 64
+
+
+class AerobulkError(RuntimeError):
+    """The reference would have STOPped here (ctl_stop / STOP); `code` is an AEROBULK_GPU_ERR_* value."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[aerobulk_gpu rc={code}] {message}")
+        self.code = code
+        self.message = message
+
+
+def lib():
+    """Load libaerobulk_gpu.so (built in-tree by `python -m aerobulk_b200.build`). No fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise ImportError(f"{_SO} is missing: build it with `python -m aerobulk_b200.build` "
+                          "(aerobulk_b200 has no CPU or PyTorch fallback)")
+    L = C.CDLL(_SO)
+    model_args = ([C.c_int, C.c_int, C.c_char_p, C.c_double, C.c_double, C.c_int, C.c_int] + [C.c_void_p] * 11 +
+                  [_ip, _ip, C.c_void_p, C.c_void_p, C.c_void_p])
+    for name in ("aerobulk_gpu_model", "aerobulk_gpu_model_device"):
+        f = getattr(L, name)
+        f.restype = C.c_int
+        f.argtypes = model_args
+    L.aerobulk_gpu_synchronize.restype = C.c_int
+    L.aerobulk_gpu_init_local_stats.restype = C.c_int
+    L.aerobulk_gpu_init_local_stats.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 7 + [_dp]
+    L.aerobulk_gpu_stats_reduce_op.restype = C.c_int
+    L.aerobulk_gpu_stats_reduce_op.argtypes = [C.c_int]
+    L.aerobulk_gpu_init_from_stats.restype = C.c_int
+    L.aerobulk_gpu_init_from_stats.argtypes = [C.c_int, C.c_char_p, _ip, C.c_int, _dp]
+    L.aerobulk_gpu_set_rdt.argtypes = [C.c_double]
+    L.aerobulk_gpu_set_gdept.argtypes = [C.c_double]
+    L.aerobulk_gpu_set_nb_iter.argtypes = [C.c_int]
+    L.aerobulk_gpu_get_humidity_type.restype = C.c_char_p
+    L.aerobulk_gpu_set_device.argtypes = [C.c_int]
+    L.aerobulk_gpu_set_stream.argtypes = [C.c_void_p]
+    L.aerobulk_gpu_set_error_mode.argtypes = [C.c_int]
+    L.aerobulk_gpu_set_verbose.argtypes = [C.c_int]
+    L.aerobulk_gpu_last_error.restype = C.c_char_p
+    L.aerobulk_gpu_get_state.restype = C.c_long
+    L.aerobulk_gpu_get_state.argtypes = [C.c_int, _dp, C.c_long]
+    L.aerobulk_gpu_set_state.restype = C.c_long
+    L.aerobulk_gpu_set_state.argtypes = [C.c_int, _dp, C.c_long]
+    L.aerobulk_gpu_launch_count.restype = C.c_long
+    L.aerobulk_gpu_measure_fp64_peak.restype = C.c_double
+    L.aerobulk_gpu_work_per_point.restype = C.c_double
+    L.aerobulk_gpu_work_per_point.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    L.aerobulk_gpu_bytes_per_point.restype = C.c_double
+    L.aerobulk_gpu_bytes_per_point.argtypes = [C.c_char_p, C.c_int]
+    L.aerobulk_gpu_version.restype = C.c_char_p
+    L.aerobulk_cxx_skin.restype = None
+    L.aerobulk_cxx_no_skin.restype = None
+    # language bindings get return codes instead of the reference's fail-stop
+    L.aerobulk_gpu_set_error_mode(1)
+    L.aerobulk_gpu_set_verbose(0)
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise AerobulkError(rc, lib().aerobulk_gpu_last_error().decode(errors="replace"))
+
+
+def _f64(a, shape=None):
+    a = np.asarray(a, dtype=np.float64)
+    if not (a.flags.f_contiguous or a.flags.c_contiguous):
+        a = np.asfortranarray(a)
+    if shape is not None and a.shape != shape:
+        raise AerobulkError(101, f"AEROBULK_INIT => arrays do not agree in shape: {a.shape} vs {shape}")
+    return a
+
+
+def _shape2(shape):
+    if len(shape) == 1:
+        return shape[0], 1
+    if len(shape) == 2:
+        return shape[0], shape[1]
+    raise AerobulkError(101, "fields must be 1-D or 2-D (Ni,Nj)")
+
+
+def aerobulk_model(jt: int, Nt: int, calgo: str, zt: float, zu: float, sst, t_zt, hum_zt, U_zu, V_zu, slp,
+                   Niter: Optional[int] = None, l_use_skin: Optional[bool] = None, rad_sw=None, rad_lw=None,
+                   out: Optional[dict] = None) -> dict:
+    """AEROBULK_MODEL with HOST (numpy) arrays, Fortran order (Ni,Nj).
+
+    Returns {"QL","QH","Tau_x","Tau_y","Evap"[,"T_s"]}; T_s is present iff rad_sw and rad_lw
+    are given (mod_aerobulk.f90:246-253).  `out` may hold preallocated (e.g. pinned) arrays.
+    """
+    L = lib()
+    sst = _f64(sst)
+    shape = sst.shape
+    Ni, Nj = _shape2(shape)
+    ins = [sst] + [_f64(a, shape) for a in (t_zt, hum_zt, U_zu, V_zu, slp)]
+    rs = None if rad_sw is None else _f64(rad_sw, shape)
+    rl = None if rad_lw is None else _f64(rad_lw, shape)
+    order = "F" if sst.flags.f_contiguous else "C"
+    names = ["QL", "QH", "Tau_x", "Tau_y", "Evap"] + (["T_s"] if (rs is not None and rl is not None) else [])
+    res = {}
+    for k in names:
+        if out is not None and k in out:
+            res[k] = out[k]
+        else:
+            res[k] = np.empty(shape, dtype=np.float64, order=order)
+    ni = None if Niter is None else C.byref(C.c_int(int(Niter)))
+    ls = None if l_use_skin is None else C.byref(C.c_int(int(bool(l_use_skin))))
+    ptr = lambda a: None if a is None else a.ctypes.data
+    rc = L.aerobulk_gpu_model(int(jt), int(Nt), calgo.encode(), float(zt), float(zu), Ni, Nj,
+                              *[ptr(a) for a in ins], *[ptr(res[k]) for k in names[:5]],
+                              ni, ls, ptr(rs), ptr(rl), ptr(res.get("T_s")))
+    _check(rc)
+    return res
+
+
+def aerobulk_model_device(jt: int, Nt: int, calgo: str, zt: float, zu: float, sst, t_zt, hum_zt, U_zu, V_zu, slp,
+                          out: dict, Niter: Optional[int] = None, l_use_skin: Optional[bool] = None,
+                          rad_sw=None, rad_lw=None, shape=None) -> dict:
+    """AEROBULK_MODEL on DEVICE-resident torch.float64 CUDA tensors (no host<->device traffic).
+
+    `out` holds preallocated CUDA tensors QL, QH, Tau_x, Tau_y, Evap (and T_s with radiation).
+    Tensors are flat buffers in Fortran (column-major) point order; `shape=(Ni,Nj)` names the
+    grid (default (numel,1)).  The launch goes to the stream set by :func:`set_stream`
+    (default: the library's own).
+    """
+    L = lib()
+    tensors = [sst, t_zt, hum_zt, U_zu, V_zu, slp]
+    n = sst.numel()
+    for t in tensors + [x for x in (rad_sw, rad_lw) if x is not None] + list(out.values()):
+        if (not t.is_cuda) or str(t.dtype) != "torch.float64" or not t.is_contiguous() or t.numel() != n:
+            raise AerobulkError(101, "device API needs contiguous float64 CUDA tensors of one size")
+    Ni, Nj = (n, 1) if shape is None else (int(shape[0]), int(shape[1]))
+    if Ni * Nj != n:
+        raise AerobulkError(101, f"shape {shape} does not match {n} points")
+    ni = None if Niter is None else C.byref(C.c_int(int(Niter)))
+    ls = None if l_use_skin is None else C.byref(C.c_int(int(bool(l_use_skin))))
+    ptr = lambda t: None if t is None else t.data_ptr()
+    rc = L.aerobulk_gpu_model_device(int(jt), int(Nt), calgo.encode(), float(zt), float(zu), Ni, Nj,
+                                     *[ptr(t) for t in tensors],
+                                     *[ptr(out[k]) for k in ("QL", "QH", "Tau_x", "Tau_y", "Evap")],
+                                     ni, ls, ptr(rad_sw), ptr(rad_lw), ptr(out.get("T_s")))
+    _check(rc)
+    return out
+
+
+def init_local_stats(sst, t_zt, hum_zt, U_zu, V_zu, slp, rad_lw=None) -> np.ndarray:
+    """Row-block statistics of AEROBULK_INIT on flat DEVICE tensors (see include/aerobulk_gpu.h)."""
+    L = lib()
+    Ni, Nj = sst.numel(), 1
+    st = np.zeros(NSTATS, dtype=np.float64)
+    ptr = lambda t: None if t is None else t.data_ptr()
+    _check(L.aerobulk_gpu_init_local_stats(Ni, Nj, ptr(sst), ptr(t_zt), ptr(hum_zt), ptr(U_zu), ptr(V_zu), ptr(slp),
+                                           ptr(rad_lw), st.ctypes.data_as(_dp)))
+    return st
+
+
+def stats_reduce_ops() -> np.ndarray:
+    L = lib()
+    return np.array([L.aerobulk_gpu_stats_reduce_op(i) for i in range(NSTATS)], dtype=np.int64)
+
+
+def init_from_stats(Nt: int, calgo: str, l_use_skin: Optional[bool], have_rad: bool, stats: np.ndarray):
+    L = lib()
+    st = np.ascontiguousarray(stats, dtype=np.float64)
+    ls = None if l_use_skin is None else C.byref(C.c_int(int(bool(l_use_skin))))
+    _check(L.aerobulk_gpu_init_from_stats(int(Nt), calgo.encode(), ls, int(bool(have_rad)), st.ctypes.data_as(_dp)))
+
+
+def synchronize():
+    _check(lib().aerobulk_gpu_synchronize())
+
+
+def set_stream(cuda_stream_handle: Optional[int]):
+    lib().aerobulk_gpu_set_stream(C.c_void_p(cuda_stream_handle) if cuda_stream_handle else None)
+
+
+def set_device(device: int):
+    _check(lib().aerobulk_gpu_set_device(int(device)))
+
+
+def set_rdt(v: float): lib().aerobulk_gpu_set_rdt(float(v))
+def set_gdept(v: float): lib().aerobulk_gpu_set_gdept(float(v))
+def set_nb_iter(v: int): lib().aerobulk_gpu_set_nb_iter(int(v))
+def set_verbose(on: bool): lib().aerobulk_gpu_set_verbose(int(bool(on)))
+def nb_iter() -> int: return lib().aerobulk_gpu_get_nb_iter()
+def use_skin() -> bool: return bool(lib().aerobulk_gpu_get_use_skin())
+def humidity_type() -> str: return lib().aerobulk_gpu_get_humidity_type().decode()
+def last_error() -> str: return lib().aerobulk_gpu_last_error().decode(errors="replace")
+def reset(): lib().aerobulk_gpu_reset()
+def launch_count() -> int: return lib().aerobulk_gpu_launch_count()
+def reset_launch_count(): lib().aerobulk_gpu_reset_launch_count()
+def measure_fp64_peak() -> float: return lib().aerobulk_gpu_measure_fp64_peak()
+def work_per_point(calgo: str, skin: bool, nb: int) -> float: return lib().aerobulk_gpu_work_per_point(calgo.encode(), int(skin), int(nb))
+def bytes_per_point(calgo: str, skin: bool) -> float: return lib().aerobulk_gpu_bytes_per_point(calgo.encode(), int(skin))
+
+
+def get_state(which: int, n: int) -> Optional[np.ndarray]:
+    """Copy of the device-resident warm-layer state (0 dT_wl, 1 Hz_wl, 2 Qnt_ac, 3 Tau_ac)."""
+    out = np.empty(n, dtype=np.float64)
+    got = lib().aerobulk_gpu_get_state(int(which), out.ctypes.data_as(_dp), n)
+    return out if got == n else None
+
+
+def set_state(which: int, values) -> bool:
+    v = np.ascontiguousarray(values, dtype=np.float64).ravel()
+    return lib().aerobulk_gpu_set_state(int(which), v.ctypes.data_as(_dp), v.size) == v.size

@@ -1,0 +1,165 @@
+/*
+ * aerobulk_gpu.h -- C ABI of libaerobulk_gpu.so, the B200 (sm_100a) replacement
+ * for the `aerobulk_model` hot path of brodeau/aerobulk.
+ *
+ * The library is a LINK-TIME DROP-IN for the two symbols the reference's C++
+ * bridge binds (reference: src/aerobulk.cpp:5-19 declares them,
+ * src/mod_aerobulk_cxx.f90:29-33,66-69 defines them with BIND(C)):
+ *
+ *     aerobulk_cxx_skin      aerobulk_cxx_no_skin
+ *
+ * plus `aerobulk_gpu_*` entry points that the Fortran shim
+ * (aerobulk_b200/fortran/mod_aerobulk_gpu.f90, behind the unchanged
+ * AEROBULK_MODEL signature of src/mod_aerobulk.f90:176-230) binds through
+ * ISO_C_BINDING.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Arrays are FP64, (Ni,Nj) column-major (Fortran order), contiguous.
+ * Unless stated otherwise a call is blocking and returns 0 on success or an
+ * AEROBULK_GPU_ERR_* code.  Error behaviour mirrors the reference: by default
+ * (fail-stop mode) an error prints ' *** E R R O R :' + message on stdout and
+ * terminates the process like `ctl_stop`/STOP does (src/mod_const.f90:238-278);
+ * unlike Fortran STOP the exit status is 1.  aerobulk_gpu_set_error_mode(1)
+ * makes the calls return the code instead (used by language bindings).
+ *
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef AEROBULK_GPU_H
+#define AEROBULK_GPU_H
+
+#include <stdbool.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ------------------------------------------------------- */
+enum {
+    AEROBULK_GPU_OK = 0,
+    AEROBULK_GPU_ERR_JT = 1,          /* jt < 1                (mod_aerobulk.f90:244)            */
+    AEROBULK_GPU_ERR_SKIN_ALGO = 2,   /* skin asked for ncar/andreas (mod_aerobulk.f90:69-70)    */
+    AEROBULK_GPU_ERR_SKIN_NORAD = 3,  /* skin asked, no radiation    (mod_aerobulk.f90:72)       */
+    AEROBULK_GPU_ERR_ALL_MASKED = 4,  /* whole domain masked         (mod_aerobulk.f90:122)      */
+    AEROBULK_GPU_ERR_HUMIDITY = 5,    /* humidity type unidentified  (mod_phymbl.f90:1996-2003)  */
+    AEROBULK_GPU_ERR_UNITS = 6,       /* unit-consistency check      (mod_phymbl.f90:1946-1950)  */
+    AEROBULK_GPU_ERR_ALGO = 7,        /* unknown algorithm string    (mod_aerobulk_compute.f90:173-176) */
+    AEROBULK_GPU_ERR_TAU = 8,         /* wind stress > 10 N/m^2      (mod_phymbl.f90:1250-1253)  */
+    AEROBULK_GPU_ERR_STATE = 9,       /* warm-layer state (re)allocation (mod_blk_coare3p6.f90:82-83) */
+    AEROBULK_GPU_ERR_CUDA = 100,      /* CUDA runtime failure / no device                         */
+    AEROBULK_GPU_ERR_ARG = 101        /* NULL / inconsistent argument                             */
+};
+
+/* ---- the two symbols of the reference's C++ bridge ------------------------ */
+
+/* Replaces SUBROUTINE aerobulk_cxx_skin BIND(c), src/mod_aerobulk_cxx.f90:29-62
+ * (declared in src/aerobulk.cpp:7-11).  All scalars by pointer; `calgo` holds `*l`
+ * characters (+NUL); every array has `*m` elements and is treated as (m,1).
+ * l_skin is read as ONE byte (the reference reads a 4-byte LOGICAL through a
+ * `const bool*`, a latent ABI bug: SURVEY 8a quirk 7). */
+void aerobulk_cxx_skin(const int *jt, const int *Nt, const char *calgo, const double *zt, const double *zu,
+                       const double *sst, const double *t_zt, const double *hum_zt, const double *U_zu,
+                       const double *V_zu, const double *slp,
+                       double *QL, double *QH, double *Tau_x, double *Tau_y, double *Evap,
+                       const int *Niter, const bool *l_skin, const double *rad_sw, const double *rad_lw,
+                       double *T_s, const int *l, const int *m);
+
+/* Replaces SUBROUTINE aerobulk_cxx_no_skin BIND(c), src/mod_aerobulk_cxx.f90:66-95
+ * (declared in src/aerobulk.cpp:13-17). */
+void aerobulk_cxx_no_skin(const int *jt, const int *Nt, const char *calgo, const double *zt, const double *zu,
+                          const double *sst, const double *t_zt, const double *hum_zt, const double *U_zu,
+                          const double *V_zu, const double *slp,
+                          double *QL, double *QH, double *Tau_x, double *Tau_y, double *Evap,
+                          const int *Niter, const int *l, const int *m);
+
+/* ---- AEROBULK_MODEL for 2-D fields (what mod_aerobulk_gpu.f90 binds) --------- */
+
+/* Replaces SUBROUTINE AEROBULK_MODEL, src/mod_aerobulk.f90:176-269, HOST arrays.
+ * Optional Fortran arguments: `Niter`/`l_use_skin` NULL when absent; `rad_sw`,
+ * `rad_lw`, `T_s` NULL when absent (the skin path is taken iff rad_sw and rad_lw
+ * are both present, mod_aerobulk.f90:242-246).  calgo is NUL-terminated. */
+int aerobulk_gpu_model(int jt, int Nt, const char *calgo, double zt, double zu, int Ni, int Nj,
+                       const double *sst, const double *t_zt, const double *hum_zt,
+                       const double *U_zu, const double *V_zu, const double *slp,
+                       double *QL, double *QH, double *Tau_x, double *Tau_y, double *Evap,
+                       const int *Niter, const int *l_use_skin,
+                       const double *rad_sw, const double *rad_lw, double *T_s);
+
+/* Same contract, but every array pointer is a DEVICE pointer on the session's
+ * device and the work is enqueued on the session's stream (see
+ * aerobulk_gpu_set_stream).  At jt==1 the call synchronises (AEROBULK_INIT needs
+ * the field statistics on the host); for jt>1 it returns after the launch and
+ * the wind-stress check is deferred to aerobulk_gpu_synchronize(). */
+int aerobulk_gpu_model_device(int jt, int Nt, const char *calgo, double zt, double zu, int Ni, int Nj,
+                              const double *sst, const double *t_zt, const double *hum_zt,
+                              const double *U_zu, const double *V_zu, const double *slp,
+                              double *QL, double *QH, double *Tau_x, double *Tau_y, double *Evap,
+                              const int *Niter, const int *l_use_skin,
+                              const double *rad_sw, const double *rad_lw, double *T_s);
+
+/* Waits for the session stream and reports a deferred error (wind stress too strong). */
+int aerobulk_gpu_synchronize(void);
+
+/* ---- AEROBULK_INIT split for row-block sharded grids (one process per GPU) ---- */
+
+#define AEROBULK_GPU_NSTATS 64
+/* Field statistics of this rank's row block, DEVICE pointers (rad_lw may be NULL):
+ * stats[0] = number of unmasked points, stats[1] = number of points, then for each
+ * of the 9 checked fields f (sst,t_air,slp,u10,v10,wnd,hum,rad_lw-as-rad_sw,rad_lw;
+ * mod_aerobulk.f90:143-153) 5 doubles at 2+5f: masked sum, masked min, masked max,
+ * min, max.  Sums/counts combine by +, mins by min, maxes by max across ranks
+ * (see aerobulk_gpu_stats_reduce_op). */
+int aerobulk_gpu_init_local_stats(int Ni, int Nj, const double *sst, const double *t_zt, const double *hum_zt,
+                                  const double *U_zu, const double *V_zu, const double *slp,
+                                  const double *rad_lw, double *stats /* host, AEROBULK_GPU_NSTATS */);
+/* 0: sum, 1: min, 2: max -- how stats[i] combines across ranks */
+int aerobulk_gpu_stats_reduce_op(int i);
+/* Runs AEROBULK_INIT's decisions (skin flag, nitend, humidity type, unit checks,
+ * src/mod_aerobulk.f90:24-160) from globally reduced statistics.  After it, calls of
+ * aerobulk_gpu_model*(jt==1, ...) on this rank skip their own local AEROBULK_INIT. */
+int aerobulk_gpu_init_from_stats(int Nt, const char *calgo, const int *l_use_skin, int have_rad,
+                                 const double *stats);
+
+/* ---- module globals of src/mod_const.f90:22-33 that callers may overwrite ------ */
+void aerobulk_gpu_set_rdt(double rdt_seconds);   /* default 3600 */
+void aerobulk_gpu_set_gdept(double depth_m);     /* default 1    */
+void aerobulk_gpu_set_nb_iter(int nb_iter);      /* default 5    */
+int aerobulk_gpu_get_nb_iter(void);
+int aerobulk_gpu_get_use_skin(void);             /* sticky l_use_skin_schemes */
+const char *aerobulk_gpu_get_humidity_type(void); /* "sh" | "rh" | "dp" */
+
+/* ---- session plumbing ------------------------------------------------------ */
+int aerobulk_gpu_set_device(int device);         /* default: $LOCAL_RANK or 0; before first compute call */
+int aerobulk_gpu_get_device(void);
+int aerobulk_gpu_set_stream(void *cuda_stream);  /* run on a caller-owned cudaStream_t (NULL: library stream) */
+void aerobulk_gpu_set_error_mode(int return_codes); /* 0: fail-stop like the reference (default), 1: return codes */
+void aerobulk_gpu_set_verbose(int on);           /* 1 (default): print the AeroBulk_init / _bye banners */
+const char *aerobulk_gpu_last_error(void);
+int aerobulk_gpu_last_error_code(void);
+/* Drops every piece of session state (sticky globals, warm-layer arrays, buffers):
+ * the equivalent of restarting the reference process. */
+void aerobulk_gpu_reset(void);
+
+/* Persistent warm-layer state, device-resident between jt==1 and jt==Nt
+ * (src/mod_skin_coare.f90:31-36, src/mod_skin_ecmwf.f90:52-55).
+ * which: 0 dT_wl, 1 Hz_wl, 2 Qnt_ac, 3 Tau_ac.  Returns the number of points
+ * copied (0 when the state does not exist). */
+long aerobulk_gpu_get_state(int which, double *host_out, long n);
+long aerobulk_gpu_set_state(int which, const double *host_in, long n);
+
+/* ---- measurement helpers --------------------------------------------------- */
+/* Number of kernels this library has launched since load / reset of the counter. */
+long aerobulk_gpu_launch_count(void);
+void aerobulk_gpu_reset_launch_count(void);
+/* Dependent-chain DFMA microbenchmark on the session device: returns FP64 FMA
+ * instructions per second (all SMs), the denominator of the FP64 roofline. */
+double aerobulk_gpu_measure_fp64_peak(void);
+/* Algorithmic FP64-pipe work per point (fx + nb_iter*it) and
+ * algorithmic bytes per point for (algo, skin). */
+double aerobulk_gpu_work_per_point(const char *calgo, int skin, int nb_iter);
+double aerobulk_gpu_bytes_per_point(const char *calgo, int skin);
+const char *aerobulk_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AEROBULK_GPU_H */
