@@ -44,14 +44,16 @@ struct Session {
     bool device_ready = false;
     cudaStream_t own_stream = nullptr, user_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
     bool use_user_stream = false;
-    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {}, ev_all_in = nullptr;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {}, ev_bad = nullptr;
     int error_mode = 0;
     int verbose = 1;
     char errmsg[1024] = {0};
     int errcode = 0;
     bool preinit_done = false;
     // ---- warm-layer state (device)
-    long long n_coare = 0, n_ecmwf = 0;
+    // n_* is the LOGICAL size (0: not allocated in the reference's sense); the device memory is kept
+    // across sessions (cap_*) because cudaMalloc/cudaFree cost 5-600 ms per session otherwise
+    long long n_coare = 0, n_ecmwf = 0, cap_coare = 0, cap_ecmwf = 0;
     double *c_state[4] = {nullptr, nullptr, nullptr, nullptr};   // dT_wl, Hz_wl, Qnt_ac, Tau_ac
     double *e_dT_wl = nullptr;
     // ---- staging for host-array calls
@@ -124,7 +126,7 @@ int ensure_device()
         CUDA_TRY(cudaEventCreateWithFlags(&g.ev_in[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&g.ev_k[i], cudaEventDisableTiming));
     }
-    CUDA_TRY(cudaEventCreateWithFlags(&g.ev_all_in, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&g.ev_bad, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&g.d_partials, sizeof(double) * abk::NSTATS * abk::stats_max_blocks()));
     CUDA_TRY(cudaMalloc(&g.d_stats, sizeof(double) * abk::NSTATS));
     CUDA_TRY(cudaMalloc(&g.d_bad, sizeof(unsigned long long)));
@@ -135,19 +137,42 @@ int ensure_device()
     return 0;
 }
 
+// *_EXIT of the reference: the state stops existing; the device memory stays cached
+void release_coare_state() { g.n_coare = 0; }
+void release_ecmwf_state() { g.n_ecmwf = 0; }
 void free_coare_state()
 {
     for (int k = 0; k < 4; ++k) {
         if (g.c_state[k]) cudaFree(g.c_state[k]);
         g.c_state[k] = nullptr;
     }
-    g.n_coare = 0;
+    g.n_coare = g.cap_coare = 0;
 }
 void free_ecmwf_state()
 {
     if (g.e_dT_wl) cudaFree(g.e_dT_wl);
     g.e_dT_wl = nullptr;
-    g.n_ecmwf = 0;
+    g.n_ecmwf = g.cap_ecmwf = 0;
+}
+int alloc_coare_state(long long n)
+{
+    if (n > g.cap_coare) {
+        free_coare_state();
+        for (int k = 0; k < 4; ++k) CUDA_TRY(cudaMalloc(&g.c_state[k], sizeof(double) * (size_t)n));
+        g.cap_coare = n;
+    }
+    g.n_coare = n;
+    return 0;
+}
+int alloc_ecmwf_state(long long n)
+{
+    if (n > g.cap_ecmwf) {
+        free_ecmwf_state();
+        CUDA_TRY(cudaMalloc(&g.e_dT_wl, sizeof(double) * (size_t)n));
+        g.cap_ecmwf = n;
+    }
+    g.n_ecmwf = n;
+    return 0;
 }
 
 int ensure_staging(long long n)
@@ -357,9 +382,9 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     const long long n = (long long)Ni * (long long)Nj;
     cudaStream_t cs = compute_stream();
 
-    // a pending deferred error from earlier asynchronous launches surfaces first
-    if (g.bad_pending) {
-        CUDA_TRY(cudaStreamSynchronize(cs));
+    // a deferred wind-stress error of earlier asynchronous launches surfaces as soon as its flag
+    // copy has landed (no synchronisation here: device-resident calls stay asynchronous)
+    if (g.bad_pending && cudaEventQuery(g.ev_bad) == cudaSuccess) {
         rc = check_bad_flag(nullptr, nullptr);
         if (rc) return rc;
     }
@@ -368,7 +393,6 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     const double *in_d[8];
     double *out_h[6] = {QL, QH, Tau_x, Tau_y, Evap, lsrad ? T_s : nullptr};
     double *out_d[6];
-    const size_t bytes = sizeof(double) * (size_t)n;
 
     // chunk plan (row blocks of the flattened array, multiples of the block size)
     int nchunks = 1;
@@ -438,13 +462,13 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     if (use_skin && jt == 1) {
         if (ialgo == abd::ECMWF) {
             if (g.n_ecmwf) return fail(AEROBULK_GPU_ERR_STATE, " ECMWF_INIT => allocation of dT_wl & Hz_wl failed!");
-            if (n > 0) CUDA_TRY(cudaMalloc(&g.e_dT_wl, bytes));
-            g.n_ecmwf = n;
+            rc = alloc_ecmwf_state(n);
+            if (rc) return rc;
         } else {
             if (g.n_coare)
                 return fail(AEROBULK_GPU_ERR_STATE, " COARE_INIT => allocation of Tau_ac, Qnt_ac, dT_wl & Hz_wl failed!");
-            for (int k = 0; k < 4 && n > 0; ++k) CUDA_TRY(cudaMalloc(&g.c_state[k], bytes));
-            g.n_coare = n;
+            rc = alloc_coare_state(n);
+            if (rc) return rc;
         }
     }
     if (use_skin) {
@@ -495,6 +519,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         }
     }
     CUDA_TRY(cudaMemcpyAsync(g.h_bad, g.d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaEventRecord(g.ev_bad, cs));
     g.bad_pending = true;
     g.last_Ni = Ni;
     g.last_taux = out_d[2];
@@ -509,8 +534,8 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
 
     // kt == nitend -> *_EXIT frees the state (mod_blk_coare3p6.f90:411); jt == Nt -> AEROBULK_BYE (:267)
     if (use_skin && last) {
-        if (ialgo == abd::ECMWF) free_ecmwf_state();
-        else free_coare_state();
+        if (ialgo == abd::ECMWF) release_ecmwf_state();
+        else release_coare_state();
     }
     if (rc) return rc;
     if (jt == Nt && g.verbose) {

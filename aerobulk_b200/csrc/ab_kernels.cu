@@ -153,7 +153,7 @@ cudaError_t flux_kernel_attributes(int algo, bool skin, bool zteq, cudaFuncAttri
 // AEROBULK_INIT statistics (src/mod_aerobulk.f90:104-153, src/mod_phymbl.f90:1851-2007)
 // ---------------------------------------------------------------------------
 static constexpr int STATS_BLOCK = 256;
-static constexpr int STATS_MAX_BLOCKS = 148 * 4;
+static constexpr int STATS_MAX_BLOCKS = 148 * 2;
 
 // sanity ranges, src/mod_const.f90:138-146
 __device__ __forceinline__ bool point_unmasked(double sst, double ta, double slp, double wnd, bool rad, double rlw)
@@ -245,22 +245,23 @@ __global__ void __launch_bounds__(STATS_BLOCK) stats_kernel(const StatsArgs a)
     }
 }
 
-// fixed-order final reduction -> results do not depend on scheduling
-__global__ void stats_final(const double *partials, int nblocks, double *out)
+// fixed-order final reduction (one warp per statistic) -> results do not depend on scheduling
+__global__ void __launch_bounds__(256) stats_final(const double *partials, int nblocks, double *out)
 {
-    const int k = threadIdx.x;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (k >= NSTATS) return;
     if (k >= 2 + 5 * NFIELDS) {
-        out[k] = 0.;
+        if (lane == 0) out[k] = 0.;
         return;
     }
     const int op = stat_op(k);
-    double r = partials[k];
-    for (int b = 1; b < nblocks; ++b) {
+    double r = (op == 0) ? 0. : (op == 1) ? DBL_MAX : -DBL_MAX;
+    for (int b = lane; b < nblocks; b += 32) {
         const double w = partials[(long long)b * NSTATS + k];
         r = (op == 0) ? r + w : (op == 1) ? fmin(r, w) : fmax(r, w);
     }
-    out[k] = r;
+    r = warp_reduce(r, op);
+    if (lane == 0) out[k] = r;
 }
 
 int stats_max_blocks() { return STATS_MAX_BLOCKS; }
@@ -270,7 +271,7 @@ cudaError_t launch_stats(const StatsArgs &a, int nblocks, cudaStream_t s)
     stats_kernel<<<nblocks, STATS_BLOCK, 0, s>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    stats_final<<<1, NSTATS, 0, s>>>(a.partials, nblocks, a.out);
+    stats_final<<<NSTATS * 32 / 256, 256, 0, s>>>(a.partials, nblocks, a.out);
     return cudaGetLastError();
 }
 

@@ -190,7 +190,12 @@ def synchronize():
 
 
 def set_stream(cuda_stream_handle: Optional[int]):
-    lib().aerobulk_gpu_set_stream(C.c_void_p(cuda_stream_handle) if cuda_stream_handle else None)
+    """Run on a caller-owned CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``).
+    None: the library's own stream.  Handle 0 is torch's legacy default stream -> cudaStreamLegacy (0x1)."""
+    if cuda_stream_handle is None:
+        lib().aerobulk_gpu_set_stream(None)
+    else:
+        lib().aerobulk_gpu_set_stream(C.c_void_p(cuda_stream_handle if cuda_stream_handle != 0 else 1))
 
 
 def set_device(device: int):

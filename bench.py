@@ -179,7 +179,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.init_process_group("nccl", device_id=dev)
     abm.set_device(local_rank)
     ab.reset()
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: the library launches on it, torch.cuda.Event times it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ab.set_stream(stream.cuda_stream)
 
     n = NI * NJ

@@ -130,7 +130,9 @@ const char *aerobulk_gpu_get_humidity_type(void); /* "sh" | "rh" | "dp" */
 /* ---- session plumbing ------------------------------------------------------ */
 int aerobulk_gpu_set_device(int device);         /* default: $LOCAL_RANK or 0; before first compute call */
 int aerobulk_gpu_get_device(void);
-int aerobulk_gpu_set_stream(void *cuda_stream);  /* run on a caller-owned cudaStream_t (NULL: library stream) */
+/* Run on a caller-owned cudaStream_t.  NULL selects the library's own non-blocking stream; to use the
+ * legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1), cudaStreamPerThread is (cudaStream_t)0x2. */
+int aerobulk_gpu_set_stream(void *cuda_stream);
 void aerobulk_gpu_set_error_mode(int return_codes); /* 0: fail-stop like the reference (default), 1: return codes */
 void aerobulk_gpu_set_verbose(int on);           /* 1 (default): print the AeroBulk_init / _bye banners */
 const char *aerobulk_gpu_last_error(void);

@@ -1,0 +1,47 @@
+"""Kernel micro-benchmark: device-resident time per aerobulk_model call for every kernel variant.
+usage: python tools/kbench.py [Ni Nj] ; prints one line per (algo, skin, day/night)."""
+import os, sys, json
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import aerobulk_b200 as ab
+from aerobulk_b200 import synth
+
+NI = int(sys.argv[1]) if len(sys.argv) > 2 else 1440
+NJ = int(sys.argv[2]) if len(sys.argv) > 2 else 720
+n = NI * NJ
+IN = ("sst", "t_zt", "hum_zt", "U_zu", "V_zu", "slp")
+OUT = ("QL", "QH", "Tau_x", "Tau_y", "Evap", "T_s")
+f = synth.fields(NI, NJ)
+dev = {k: torch.from_numpy(np.ravel(v, order="F").copy()).cuda() for k, v in f.items()}
+rsw_day = torch.from_numpy(np.ravel(synth.rad_sw_hour(NI, NJ, 12), order="F").copy()).cuda()
+rsw_night = torch.zeros(n, dtype=torch.float64, device="cuda")
+out = {k: torch.empty(n, dtype=torch.float64, device="cuda") for k in OUT}
+st = torch.cuda.Stream()
+torch.cuda.set_stream(st)
+ab.set_stream(st.cuda_stream)
+peak = ab.measure_fp64_peak()
+print(f"DFMA peak {peak/1e12:.2f} T instr/s")
+res = []
+cases = [(a, False, None) for a in ("ncar", "andreas", "coare3p0", "coare3p6", "ecmwf")] + \
+        [(a, True, r) for a in ("coare3p0", "coare3p6", "ecmwf") for r in ("night", "day")]
+for algo, skin, rad in cases:
+    ab.reset(); ab.set_stream(st.cuda_stream)
+    kw = dict(Niter=5)
+    o = {k: out[k] for k in OUT[:5]}
+    if skin:
+        kw.update(l_use_skin=True, rad_sw=rsw_day if rad == "day" else rsw_night, rad_lw=dev["rad_lw"])
+        o = out
+    NT = 12
+    ts = []
+    for jt in range(1, NT + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        ab.aerobulk_model_device(jt, NT, algo, 2., 10., *[dev[k] for k in IN], out=o, shape=(NI, NJ), **kw)
+        e1.record(st)
+        torch.cuda.synchronize()
+        if 3 <= jt < NT:
+            ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    W = ab.work_per_point(algo, skin, 5)
+    print(f"{algo:9s} skin={int(skin)} {rad or '-':5s}: {ms:7.3f} ms  {n/ms/1e3:8.1f} Mpt/s  W-frac {W*n/(ms*1e-3)/peak:5.2f}")
