@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include "ab_math.cuh"
+
 namespace abd {
 
 #define ABD __device__ __forceinline__
@@ -75,8 +77,8 @@ enum Algo { COARE3P0 = 1, COARE3P6 = 2, NCAR = 3, ECMWF = 4, ANDREAS = 5 };
 // SIGN(MIN(ABS(x),lim),x) and SIGN(MAX(ABS(x),lo),x)
 ABD double clip_abs(double x, double lim) { return copysign(fmin(fabs(x), lim), x); }
 ABD double floor_abs(double x, double lo) { return copysign(fmax(fabs(x), lo), x); }
-// x**y for x >= 0 (0**y = 0 for y > 0 through log(0) = -inf)
-ABD double powr(double x, double y) { return exp(y * log(x)); }
+// x**y for x >= 0 (0**y = 0 for y > 0); own exp/log/atan with constant-bank tables, see ab_math.cuh
+ABD double powr(double x, double y) { return abm::dpowr(x, y); }
 // zstab = 0.5 + SIGN(0.5, x) is 1 unless the sign bit of x is set
 ABD bool nonneg(double x) { return !signbit(x); }
 
@@ -91,10 +93,10 @@ ABD double e_sat(double T)
     const double zta = fmax(T, 180.);
     const double ztmp = RT0 / zta;
     const double r = zta / RT0;
-    const double a = 10.79574 * (1. - ztmp) - 5.028 * log10(r)
-                     + (1.50475 * 1.e-4) * (1. - exp10(-8.2969 * (r - 1.)))
-                     + (0.42873 * 1.e-3) * (exp10(4.76955 * (1. - ztmp)) - 1.) + 0.78614;
-    return 100. * exp10(a);
+    const double a = 10.79574 * (1. - ztmp) - 5.028 * abm::dlog10(r)
+                     + (1.50475 * 1.e-4) * (1. - abm::dexp10(-8.2969 * (r - 1.)))
+                     + (0.42873 * 1.e-3) * (abm::dexp10(4.76955 * (1. - ztmp)) - 1.) + 0.78614;
+    return 100. * abm::dexp10(a);
 }
 ABD double q_sat_from_e(double es, double p) { return REPS0 * es / (p - (1. - REPS0) * es); }  // :903
 ABD double q_sat(double T, double p) { return q_sat_from_e(e_sat(T), p); }                   // :881-904
@@ -108,7 +110,7 @@ ABD double theta_from_z_P0_T_q(double z, double slp, double T, double q)
     for (int it = 0; it < 3; ++it) {
         const double f = q / q_sat_from_e(es, pa);
         const double xm = (1. - f) * RMM_DRYAIR + f * RMM_WATER;
-        pa = slp * exp(-GRAV * xm * z / (R_GAS * T));
+        pa = slp * abm::dexp(-GRAV * xm * z / (R_GAS * T));
     }
     return T * powr(slp / pa, RPOISS_DRY);
 }
@@ -225,29 +227,29 @@ ABD double psi_m_ncar(double z)
     if (nonneg(z)) return -5. * z;
     const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
     const double x = sqrt(x2);
-    return 2. * log((1. + x) * 0.5) + log((1. + x2) * 0.5) - 2. * atan(x) + RPI * 0.5;
+    return 2. * abm::dlog((1. + x) * 0.5) + abm::dlog((1. + x2) * 0.5) - 2. * abm::datan(x) + RPI * 0.5;
 }
 ABD double psi_h_ncar(double z)
 {
     if (nonneg(z)) return -5. * z;
     const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
-    return 2. * log(0.5 * (1. + x2));
+    return 2. * abm::dlog(0.5 * (1. + x2));
 }
 
 // COARE 3.x, src/mod_common_coare.f90:217-254, :305-344.  Note psi(+0) = -4.524e-3:
 // SIGN(0.5,+0.) selects the stable branch and the truncated literals do not cancel.
 ABD double psi_coare_convective(double phi_c)
 {
-    return 1.5 * log((1. + phi_c + phi_c * phi_c) / 3.) - 1.7320508 * atan((1. + 2. * phi_c) / 1.7320508) + 1.813799447;
+    return 1.5 * abm::dlog((1. + phi_c + phi_c * phi_c) / 3.) - 1.7320508 * abm::datan((1. + 2. * phi_c) / 1.7320508) + 1.813799447;
 }
 ABD double psi_m_coare(double z)
 {
     if (nonneg(z)) {
         const double zc = fmin(50., 0.35 * z);
-        return -(1. + 1. * z + 0.6667 * (z - 14.28) / exp(zc) + 8.525);
+        return -(1. + 1. * z + 0.6667 * (z - 14.28) / abm::dexp(zc) + 8.525);
     }
     const double phi_m = sqrt(sqrt(fabs(1. - 15. * z)));                       // **.25
-    const double psi_k = 2. * log((1. + phi_m) / 2.) + log((1. + phi_m * phi_m) / 2.) - 2. * atan(phi_m) + 0.5 * RPI;
+    const double psi_k = 2. * abm::dlog((1. + phi_m) / 2.) + abm::dlog((1. + phi_m * phi_m) / 2.) - 2. * abm::datan(phi_m) + 0.5 * RPI;
     const double psi_c = psi_coare_convective(powr(fabs(1. - 10.15 * z), .3333));
     double f = z * z;
     f = f / (1. + f);
@@ -258,10 +260,10 @@ ABD double psi_h_coare(double z)
     if (nonneg(z)) {
         const double zc = fmin(50., 0.35 * z);
         const double a = fabs(1. + 2. * z / 3.);
-        return -(a * sqrt(a) + .6667 * (z - 14.28) / exp(zc) + 8.525);            // **1.5
+        return -(a * sqrt(a) + .6667 * (z - 14.28) / abm::dexp(zc) + 8.525);            // **1.5
     }
     const double phi_h = sqrt(fabs(1. - 15. * z));                             // **.5
-    const double psi_k = 2. * log((1. + phi_h) / 2.);
+    const double psi_k = 2. * abm::dlog((1. + phi_h) / 2.);
     const double psi_c = psi_coare_convective(powr(fabs(1. - 34.15 * z), .3333));
     double f = z * z;
     f = f / (1. + f);
@@ -273,11 +275,11 @@ ABD double psi_m_ecmwf(double zeta)
 {
     const double zc = 5. / 0.35;
     const double z = fmin(fmax(zeta, -50.), 5.);
-    if (nonneg(z)) return -(2. / 3. * (z - zc) * exp(-0.35 * z)) - z - 2. / 3. * zc;
+    if (nonneg(z)) return -(2. / 3. * (z - zc) * abm::dexp(-0.35 * z)) - z - 2. / 3. * zc;
     const double x2 = sqrt(fabs(1. - 16. * z));
     const double x = sqrt(x2);
     const double t = 1. + x;
-    return log(0.125 * t * t * (1. + x2)) - 2. * atan(x) + 0.5 * RPI;
+    return abm::dlog(0.125 * t * t * (1. + x2)) - 2. * abm::datan(x) + 0.5 * RPI;
 }
 ABD double psi_h_ecmwf(double zeta)
 {
@@ -285,10 +287,10 @@ ABD double psi_h_ecmwf(double zeta)
     const double z = fmin(fmax(zeta, -50.), 5.);
     if (nonneg(z)) {
         const double a = fabs(1. + 2. / 3. * z);
-        return -(2. / 3. * (z - zc) * exp(-0.35 * z)) - a * sqrt(a) - 2. / 3. * zc + 1.;
+        return -(2. / 3. * (z - zc) * abm::dexp(-0.35 * z)) - a * sqrt(a) - 2. / 3. * zc + 1.;
     }
     const double x2 = sqrt(fabs(1. - 16. * z));
-    return 2. * log(0.5 * (1. + x2));
+    return 2. * abm::dlog(0.5 * (1. + x2));
 }
 
 // Andreas et al. 2015 (Paulson unstable / Grachev 2007 stable), src/mod_blk_andreas.f90:307-410
@@ -300,13 +302,13 @@ ABD double psi_m_andreas(double zeta)
         const double x = cbrt(fabs(1. + z));
         return -(3. * zam / ZBM_A * (x - 1.))
                + zam * ZBBM_A / (2. * ZBM_A)
-                     * (2. * log(fabs((x + ZBBM_A) / (1. + ZBBM_A)))
-                        - log(fabs((x * x - x * ZBBM_A + ZBBM_A * ZBBM_A) / (1. - ZBBM_A + ZBBM_A * ZBBM_A)))
-                        + 2. * SR3 * (atan((2. * x - ZBBM_A) / (SR3 * ZBBM_A)) - atan((2. - ZBBM_A) / (SR3 * ZBBM_A))));
+                     * (2. * abm::dlog(fabs((x + ZBBM_A) / (1. + ZBBM_A)))
+                        - abm::dlog(fabs((x * x - x * ZBBM_A + ZBBM_A * ZBBM_A) / (1. - ZBBM_A + ZBBM_A * ZBBM_A)))
+                        + 2. * SR3 * (abm::datan((2. * x - ZBBM_A) / (SR3 * ZBBM_A)) - abm::datan((2. - ZBBM_A) / (SR3 * ZBBM_A))));
     }
     const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
     const double x = sqrt(x2);
-    return 2. * log(fabs((1. + x) * 0.5)) + log(fabs((1. + x2) * 0.5)) - 2. * atan(x) + RPI * 0.5;
+    return 2. * abm::dlog(fabs((1. + x) * 0.5)) + abm::dlog(fabs((1. + x2) * 0.5)) - 2. * abm::datan(x) + RPI * 0.5;
 }
 ABD double psi_h_andreas(double zeta)
 {
@@ -314,12 +316,12 @@ ABD double psi_h_andreas(double zeta)
     if (nonneg(z)) {
         const double zah = 5., zbh = 5., zch = 3.;
         const double zz = 2. * z + zch;
-        return -(0.5 * zbh * log(fabs(1. + zch * z + z * z)))
+        return -(0.5 * zbh * abm::dlog(fabs(1. + zch * z + z * z)))
                + (-zah / SR5 + 0.5 * zbh * zch / SR5)
-                     * (log(fabs((zz - SR5) / (zz + SR5))) - log(fabs((zch - SR5) / (zch + SR5))));
+                     * (abm::dlog(fabs((zz - SR5) / (zz + SR5))) - abm::dlog(fabs((zch - SR5) / (zch + SR5))));
     }
     const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
-    return 2. * log(0.5 * (1. + x2));
+    return 2. * abm::dlog(0.5 * (1. + x2));
 }
 
 // ---------------------------------------------------------------------------
@@ -359,15 +361,15 @@ ABD Guess first_guess_coare(const Uniform &u, double sst, double t_zt, double ss
 
     double z0 = charn * us * us / GRAV + 0.11 * nu_a / us;
     z0 = fmin(fmax(fabs(z0), 1.E-8), 1.);
-    const double log_z0 = log(z0);
+    const double log_z0 = abm::dlog(z0);
 
     const double sq = VKARMN / (u.log_zu - log_z0);
     const double Cd = sq * sq;
     const double r1_o_sqrt_Cd10 = (u.log_10 - log_z0) / VKARMN;
 
-    double z0t = 10. / exp(VKARMN / (0.00115 * r1_o_sqrt_Cd10));
+    double z0t = 10. / abm::dexp(VKARMN / (0.00115 * r1_o_sqrt_Cd10));
     z0t = fmin(fmax(fabs(z0t), 1.E-8), 1.);
-    const double log_z0t = log(z0t);
+    const double log_z0t = abm::dlog(z0t);
 
     const double Rib = ri_bulk(u.zu, sst, g.t_zu, ssq, g.q_zu, Ub);
 
@@ -429,7 +431,7 @@ ABD double cool_skin_dT(double alpha, double Qsw, double Qnsol, double us, doubl
     double d = delta(Qabs);
 #pragma unroll 1
     for (int jc = 0; jc < 4; ++jc) {
-        const double fr = fmax((COARE_FORM ? 0.137 : 0.065) + 11. * d - 6.6E-5 / d * (1. - exp(-d / 8.E-4)), 0.01);
+        const double fr = fmax((COARE_FORM ? 0.137 : 0.065) + 11. * d - 6.6E-5 / d * (1. - abm::dexp(-d / 8.E-4)), 0.01);
         Qabs = Qnsol + fr * Qsw;
         d = delta(Qabs);
     }
@@ -472,8 +474,8 @@ ABD WlCoareCtx wl_coare_ctx(double alpha, double lon, int isd)
 }
 ABD double wl_coare_absorption(double H)   // solar absorption profile, :167-168 / :205-206
 {
-    return 1. - (0.28 * 0.014 * (1. - exp(-H / 0.014)) + 0.27 * 0.357 * (1. - exp(-H / 0.357))
-                 + 0.45 * 12.82 * (1 - exp(-H / 12.82))) / H;
+    return 1. - (0.28 * 0.014 * (1. - abm::dexp(-H / 0.014)) + 0.27 * 0.357 * (1. - abm::dexp(-H / 0.357))
+                 + 0.45 * 12.82 * (1 - abm::dexp(-H / 12.82))) / H;
 }
 // WL_COARE, src/mod_skin_coare.f90:97-250; `commit` is (iwait == 0)
 ABD void wl_coare(WarmLayer &w, const WlCoareCtx &c, double Qsw, double Qnsol, double Tau, double rdt,
@@ -541,7 +543,7 @@ ABD void wl_ecmwf(WarmLayer &w, double alpha, double Qsw, double Qnsol, double u
     const double tcorr = signbit(gdept - H) ? gdept / H : 1.;
     const double dT_b = fmax(w.dT / tcorr, 0.);
 
-    const double fr = 1. - 0.28 * exp(-71.5 * H) - 0.27 * exp(-2.8 * H) - 0.45 * exp(-0.07 * H);
+    const double fr = 1. - 0.28 * abm::dexp(-71.5 * H) - 0.27 * abm::dexp(-2.8 * H) - 0.45 * abm::dexp(-0.07 * H);
     const double Qabs = fr * Qsw + Qnsol;
 
     const double usw = fmax(us, 1.E-4) * SQ_RADRW;
@@ -621,8 +623,8 @@ ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p)
         }
         const double psi_m = psi_m_ncar(zeta_u);
         // UN10_from_CD (mod_phymbl.f90:1532-1547) with z0_from_Cd(zu, Cd, psi) (:1335-1352); SQRT(Cd) is sqrt_Cd
-        const double z0 = u.zu * exp(-(VKARMN / sqrt_Cd + psi_m));
-        const double Un10 = fmax(0.25, sqrt_Cd * Ub / VKARMN * log(10. / z0));
+        const double z0 = u.zu * abm::dexp(-(VKARMN / sqrt_Cd + psi_m));
+        const double Un10 = fmax(0.25, sqrt_Cd * Ub / VKARMN * abm::dlog(10. / z0));
         CdN = cd_n10_ncar(Un10);
         sqrt_CdN = sqrt(CdN);
         double tmp = 1. + sqrt_CdN / VKARMN * (u.log_zu10 - psi_m);
@@ -670,7 +672,7 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
     const Guess g = first_guess_coare<ZTEQ>(u, Ts, p.theta_zt, qs_, p.q_zt, p.wnd,
                                             V36 ? charn_coare3p6(p.wnd) : charn_coare3p0(p.wnd));
     double us = g.us, ts = g.ts, qst = g.qs, t_zu = g.t_zu, q_zu = g.q_zu, Ub = g.Ub;
-    double log_z0 = log(g.z0);
+    double log_z0 = abm::dlog(g.z0);
     // COARE 3.6 uses the first-guess t_zu, 3.0 the potential temperature at zt
     const double nu_a = V36 ? visc_air(t_zu) : visc_air(p.theta_zt);
 
@@ -692,12 +694,12 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
         const double Un10 = us / VKARMN * (u.log_10 - log_z0);
         double z0 = (V36 ? charn_coare3p6(Un10) : charn_coare3p0(Un10)) * us2 / GRAV + 0.11 * nu_a / us;
         z0 = fmin(fmax(fabs(z0), 1.E-9), 1.);
-        log_z0 = log(z0);
+        log_z0 = abm::dlog(z0);
 
         const double rr = powr(nu_a / (z0 * us), V36 ? 0.72 : 0.6);
         double z0t = V36 ? fmin(1.6E-4, 5.8E-5 * rr) : fmin(1.1E-4, 5.5E-5 * rr);
         z0t = fmin(fmax(fabs(z0t), 1.E-9), 1.);
-        const double log_z0t = log(z0t);
+        const double log_z0t = abm::dlog(z0t);
 
         const double psi_h_u = psi_h_coare(zeta_u);
         double tmp1 = VKARMN / (u.log_zu - log_z0t - psi_h_u);
@@ -763,15 +765,15 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
     const Guess g = first_guess_coare<ZTEQ>(u, Ts, p.theta_zt, qs_, p.q_zt, p.wnd, charn0);
     double us = g.us, ts = g.ts, qst = g.qs, t_zu = g.t_zu, q_zu = g.q_zu, Ub = g.Ub;
     double z0 = g.z0;
-    double log_z0 = log(z0);
+    double log_z0 = abm::dlog(z0);
     const double nu_a = visc_air(p.theta_zt);
 
     double dt = floor_abs(t_zu - Ts, 1.E-09);
     double dq = floor_abs(q_zu - qs_, 1.E-12);
 
     double r1oL = one_on_L(t_zu, q_zu, us, ts, qst);
-    double z0t = fmin(fmax(fabs(1. / (0.1 * exp(VKARMN / (0.00115 / (VKARMN / (u.log_10 - log_z0)))))), 1.E-9), 1.);
-    double log_z0t = log(z0t);
+    double z0t = fmin(fmax(fabs(1. / (0.1 * abm::dexp(VKARMN / (0.00115 / (VKARMN / (u.log_10 - log_z0)))))), 1.E-9), 1.);
+    double log_z0t = abm::dlog(z0t);
 
     double Fm = u.log_zu - log_z0 - psi_m_ecmwf(u.zu * r1oL) + psi_m_ecmwf(z0 * r1oL);
     double psi_h_u = psi_h_ecmwf(u.zu * r1oL);
@@ -795,9 +797,9 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
         z0 = fmin(fabs(alpha_M * tmp0 + charn0 * us2 / GRAV), 0.001);
         z0t = fmin(fabs(alpha_H * tmp0), 0.001);
         const double z0q = fmin(fabs(alpha_Q * tmp0), 0.001);
-        log_z0 = log(z0);
-        log_z0t = log(z0t);
-        log_z0q = log(z0q);
+        log_z0 = abm::dlog(z0);
+        log_z0t = abm::dlog(z0t);
+        log_z0q = abm::dlog(z0q);
 
         const double psi_m_z0 = psi_m_ecmwf(z0 * r1oL);
         const double psi_h_z0t = psi_h_ecmwf(z0t * r1oL);
@@ -882,15 +884,15 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p)
         const double r = u_star / Ub;
         const double Cd = fmax(r * r, CX_MIN);
         const double psi_m = psi_m_andreas(zeta_u);
-        const double z0 = fmin(u.zu * exp(-(VKARMN / sqrt(Cd) + psi_m)), Z0_SEA_MAX);
+        const double z0 = fmin(u.zu * abm::dexp(-(VKARMN / sqrt(Cd) + psi_m)), Z0_SEA_MAX);
 
         const double Rer = z0 * u_star / visc_air(t_zu);
         const double z0t = z0tq_LKB(1, Rer, z0);
         const double z0q = z0tq_LKB(2, Rer, z0);
 
         const double psi_h_u = psi_h_andreas(zeta_u);
-        t_star = (t_zu - p.sst) * VKARMN / (u.log_zu - log(z0t) - psi_h_u);
-        q_star = (q_zu - p.ssq) * VKARMN / (u.log_zu - log(z0q) - psi_h_u);
+        t_star = (t_zu - p.sst) * VKARMN / (u.log_zu - abm::dlog(z0t) - psi_h_u);
+        q_star = (q_zu - p.ssq) * VKARMN / (u.log_zu - abm::dlog(z0q) - psi_h_u);
 
         if (!ZTEQ && jit > 1) {
             const double zeta_t = zeta_u / u.zu * u.zt;
