@@ -42,27 +42,31 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "") -> str:
+    """Build the library.  `defines`/`tag` produce an experiment variant build/lib<tag>.so
+    (loaded with AEROBULK_GPU_LIB=<path>); the default build is the shipped one."""
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     objs = []
+    lib = LIB if not tag else os.path.join(OBJ, f"libaerobulk_gpu_{tag}.so")
+    extra = [f"-D{d}" for d in defines]
     for src in SOURCES:
         path = os.path.join(CSRC, src)
-        obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+        obj = os.path.join(OBJ, os.path.splitext(src)[0] + (f"_{tag}" if tag else "") + ".o")
         objs.append(obj)
         if force or _stale(obj, [path] + HEADERS):
-            cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + ARCH + NVCC_FLAGS + ["-c", path, "-o", obj]
+            cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + ARCH + NVCC_FLAGS + extra + ["-c", path, "-o", obj]
             if src.endswith(".cu") and verbose:
                 cmd += ["-Xptxas", "-v"]
             if verbose:
                 print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"]
+    if force or _stale(lib, objs):
+        cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + ARCH + ["-shared", "-o", lib] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -27,6 +27,13 @@
 namespace abd {
 
 #define ABD __device__ __forceinline__
+// heavy helpers can be kept out of line (one shared body instead of 2-5 inlined copies) to shrink the
+// instruction footprint: -DAB_NOINLINE=1
+#if defined(AB_NOINLINE) && AB_NOINLINE
+#define ABD_HEAVY static __device__ __noinline__
+#else
+#define ABD_HEAVY __device__ __forceinline__
+#endif
 
 // ---------------------------------------------------------------------------
 // constants, reference src/mod_const.f90:38-120 (derived ones folded in FP64
@@ -81,6 +88,17 @@ ABD double floor_abs(double x, double lo) { return copysign(fmax(fabs(x), lo), x
 ABD double powr(double x, double y) { return abm::dpowr(x, y); }
 // zstab = 0.5 + SIGN(0.5, x) is 1 unless the sign bit of x is set
 ABD bool nonneg(double x) { return !signbit(x); }
+// a / b for normal-range operands: MUFU.RCP64H seed, Newton, one residual correction (<= 1 ulp).
+// CUDA's IEEE division spends as many non-FP64 instructions on its special-case guard as FP64 ones
+// on the quotient; the physics never feeds it denormals, infinities or zero denominators.
+ABD double fdiv(double a, double b)
+{
+    const double r = abm::fast_rcp(b);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+constexpr double INV_VKARMN = 1. / VKARMN;
+constexpr double INV_GRAV = 1. / GRAV;
 
 // ---------------------------------------------------------------------------
 // thermodynamics, reference src/mod_phymbl.f90
@@ -88,17 +106,17 @@ ABD bool nonneg(double x) { return !signbit(x); }
 ABD double virt_temp(double T, double q) { return T * (1. + RCTV0 * q); }           // :247-269
 
 // Goff (1957) saturation vapour pressure [Pa], :777-800 (rt0, not the triple point)
-ABD double e_sat(double T)
+ABD_HEAVY double e_sat(double T)
 {
     const double zta = fmax(T, 180.);
-    const double ztmp = RT0 / zta;
-    const double r = zta / RT0;
+    const double ztmp = fdiv(RT0, zta);
+    const double r = zta * (1. / RT0);
     const double a = 10.79574 * (1. - ztmp) - 5.028 * abm::dlog10(r)
                      + (1.50475 * 1.e-4) * (1. - abm::dexp10(-8.2969 * (r - 1.)))
                      + (0.42873 * 1.e-3) * (abm::dexp10(4.76955 * (1. - ztmp)) - 1.) + 0.78614;
     return 100. * abm::dexp10(a);
 }
-ABD double q_sat_from_e(double es, double p) { return REPS0 * es / (p - (1. - REPS0) * es); }  // :903
+ABD double q_sat_from_e(double es, double p) { return fdiv(REPS0 * es, p - (1. - REPS0) * es); }  // :903
 ABD double q_sat(double T, double p) { return q_sat_from_e(e_sat(T), p); }                   // :881-904
 
 // Theta_from_z_P0_T_q, :283-318 + :163-187 + :343-365; e_sat(T) is loop-invariant
@@ -108,14 +126,14 @@ ABD double theta_from_z_P0_T_q(double z, double slp, double T, double q)
     double pa = slp;
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
-        const double f = q / q_sat_from_e(es, pa);
+        const double f = fdiv(q, q_sat_from_e(es, pa));
         const double xm = (1. - f) * RMM_DRYAIR + f * RMM_WATER;
-        pa = slp * abm::dexp(-GRAV * xm * z / (R_GAS * T));
+        pa = slp * abm::dexp(fdiv(-GRAV * xm * z, R_GAS * T));
     }
-    return T * powr(slp / pa, RPOISS_DRY);
+    return T * powr(fdiv(slp, pa), RPOISS_DRY);
 }
 
-ABD double rho_air(double T, double q, double p) { return fmax(p / (R_DRY * T * (1. + RCTV0 * q)), 0.8); }  // :522-537
+ABD double rho_air(double T, double q, double p) { return fmax(fdiv(p, R_DRY * T * (1. + RCTV0 * q)), 0.8); }  // :522-537
 ABD double visc_air(double T)                                                                              // :549-563
 {
     const double tc = T - RT0, tc2 = tc * tc;
@@ -130,7 +148,7 @@ ABD double qlw_net(double rlw, double Ts) { const double t2 = Ts * Ts; return EM
 ABD double one_on_L(double tha, double qa, double us, double ts, double qs)
 {
     const double zqa = 1. + RCTV0 * qa;
-    const double r = GRAV * VKARMN * (ts * zqa + RCTV0 * tha * qs) / fmax(us * us * tha * zqa, 1.E-9);
+    const double r = fdiv(GRAV * VKARMN * (ts * zqa + RCTV0 * tha * qs), fmax(us * us * tha * zqa, 1.E-9));
     return clip_abs(r, 200.);
 }
 
@@ -140,18 +158,18 @@ ABD double ri_bulk(double z, double sst, double tha, double ssq, double qa, doub
     const double sstv = virt_temp(sst, ssq);
     const double dthv = virt_temp(tha, qa) - sstv;
     const double tv = 0.5 * (sstv + virt_temp(tha - RGAMMA_DRY * z, qa));
-    return GRAV * dthv * z / (tv * ub * ub);
+    return fdiv(GRAV * dthv * z, tv * ub * ub);
 }
 
 ABD double q_air_rh(double rh, double T, double p)  // :963-985
 {
     const double ze = 0.01 * rh * e_sat(T);
-    return ze * REPS0 / fmax(p - (1. - REPS0) * ze, 1.);
+    return fdiv(ze * REPS0, fmax(p - (1. - REPS0) * ze, 1.));
 }
 ABD double q_air_dp(double dp, double p)            // :990-1000
 {
     const double e = fmax(e_sat(dp), 0.);
-    return e * REPS0 / fmax(p - (1. - REPS0) * e, 1.);
+    return fdiv(e * REPS0, fmax(p - (1. - REPS0) * e, 1.));
 }
 
 struct Flux {
@@ -175,14 +193,14 @@ ABD Flux bulk_formula(double zu, double Ts, double qs, double tha, double qa, do
 }
 
 // UPDATE_QNSOL_TAU_SCLR, :1059-1103 -> non-solar flux, stress and latent flux
-ABD void update_qnsol_tau(double zu, double Ts, double qs, double tha, double qa, double us, double ts,
+ABD_HEAVY void update_qnsol_tau(double zu, double Ts, double qs, double tha, double qa, double us, double ts,
                           double qst, double wnd, double Ub, double slp, double rlw,
                           double &Qns, double &Tau, double &Qlat)
 {
     const double dt = floor_abs(tha - Ts, 1.E-09);
     const double dq = floor_abs(qa - qs, 1.E-12);
-    const double z0 = us / Ub;
-    const Flux f = bulk_formula(zu, Ts, qs, tha, qa, z0 * z0, z0 * ts / dt, z0 * qst / dq, wnd, Ub, slp);
+    const double z0 = fdiv(us, Ub);
+    const Flux f = bulk_formula(zu, Ts, qs, tha, qa, z0 * z0, fdiv(z0 * ts, dt), fdiv(z0 * qst, dq), wnd, Ub, slp);
     Qns = f.qlat + f.qsen + qlw_net(rlw, Ts);
     Tau = f.tau;
     Qlat = f.qlat;
@@ -213,7 +231,7 @@ ABD double z0tq_LKB(int iflag, double Rer, double z0)
             else if (Rer <= 300.) { a = 1448.68; b = -2.682; }
             else { a = 2.98e5; b = -3.616; }
         }
-        r = fabs(a * powr(Rer, b) * z0 / Rer);
+        r = fabs(fdiv(a * powr(Rer, b) * z0, Rer));
     }
     return fmin(fmax(r, 1.E-9), 0.05);
 }
@@ -240,38 +258,38 @@ ABD double psi_h_ncar(double z)
 // SIGN(0.5,+0.) selects the stable branch and the truncated literals do not cancel.
 ABD double psi_coare_convective(double phi_c)
 {
-    return 1.5 * abm::dlog((1. + phi_c + phi_c * phi_c) / 3.) - 1.7320508 * abm::datan((1. + 2. * phi_c) / 1.7320508) + 1.813799447;
+    return 1.5 * abm::dlog((1. + phi_c + phi_c * phi_c) * (1. / 3.)) - 1.7320508 * abm::datan((1. + 2. * phi_c) * (1. / 1.7320508)) + 1.813799447;
 }
-ABD double psi_m_coare(double z)
+ABD_HEAVY double psi_m_coare(double z)
 {
     if (nonneg(z)) {
         const double zc = fmin(50., 0.35 * z);
-        return -(1. + 1. * z + 0.6667 * (z - 14.28) / abm::dexp(zc) + 8.525);
+        return -(1. + 1. * z + 0.6667 * (z - 14.28) * abm::dexp(-zc) + 8.525);
     }
     const double phi_m = sqrt(sqrt(fabs(1. - 15. * z)));                       // **.25
-    const double psi_k = 2. * abm::dlog((1. + phi_m) / 2.) + abm::dlog((1. + phi_m * phi_m) / 2.) - 2. * abm::datan(phi_m) + 0.5 * RPI;
+    const double psi_k = 2. * abm::dlog((1. + phi_m) * 0.5) + abm::dlog((1. + phi_m * phi_m) * 0.5) - 2. * abm::datan(phi_m) + 0.5 * RPI;
     const double psi_c = psi_coare_convective(powr(fabs(1. - 10.15 * z), .3333));
     double f = z * z;
-    f = f / (1. + f);
+    f = fdiv(f, 1. + f);
     return (1. - f) * psi_k + f * psi_c;
 }
-ABD double psi_h_coare(double z)
+ABD_HEAVY double psi_h_coare(double z)
 {
     if (nonneg(z)) {
         const double zc = fmin(50., 0.35 * z);
-        const double a = fabs(1. + 2. * z / 3.);
-        return -(a * sqrt(a) + .6667 * (z - 14.28) / abm::dexp(zc) + 8.525);            // **1.5
+        const double a = fabs(1. + 2. * z * (1. / 3.));
+        return -(a * sqrt(a) + .6667 * (z - 14.28) * abm::dexp(-zc) + 8.525);            // **1.5
     }
     const double phi_h = sqrt(fabs(1. - 15. * z));                             // **.5
-    const double psi_k = 2. * abm::dlog((1. + phi_h) / 2.);
+    const double psi_k = 2. * abm::dlog((1. + phi_h) * 0.5);
     const double psi_c = psi_coare_convective(powr(fabs(1. - 34.15 * z), .3333));
     double f = z * z;
-    f = f / (1. + f);
+    f = fdiv(f, 1. + f);
     return (1. - f) * psi_k + f * psi_c;
 }
 
 // IFS, src/mod_blk_ecmwf.f90:441-564 (zeta capped to [-50, 5])
-ABD double psi_m_ecmwf(double zeta)
+ABD_HEAVY double psi_m_ecmwf(double zeta)
 {
     const double zc = 5. / 0.35;
     const double z = fmin(fmax(zeta, -50.), 5.);
@@ -281,7 +299,7 @@ ABD double psi_m_ecmwf(double zeta)
     const double t = 1. + x;
     return abm::dlog(0.125 * t * t * (1. + x2)) - 2. * abm::datan(x) + 0.5 * RPI;
 }
-ABD double psi_h_ecmwf(double zeta)
+ABD_HEAVY double psi_h_ecmwf(double zeta)
 {
     const double zc = 5. / 0.35;
     const double z = fmin(fmax(zeta, -50.), 5.);
@@ -294,7 +312,7 @@ ABD double psi_h_ecmwf(double zeta)
 }
 
 // Andreas et al. 2015 (Paulson unstable / Grachev 2007 stable), src/mod_blk_andreas.f90:307-410
-ABD double psi_m_andreas(double zeta)
+ABD_HEAVY double psi_m_andreas(double zeta)
 {
     const double z = fmin(zeta, 15.);
     if (nonneg(z)) {
@@ -302,15 +320,15 @@ ABD double psi_m_andreas(double zeta)
         const double x = cbrt(fabs(1. + z));
         return -(3. * zam / ZBM_A * (x - 1.))
                + zam * ZBBM_A / (2. * ZBM_A)
-                     * (2. * abm::dlog(fabs((x + ZBBM_A) / (1. + ZBBM_A)))
-                        - abm::dlog(fabs((x * x - x * ZBBM_A + ZBBM_A * ZBBM_A) / (1. - ZBBM_A + ZBBM_A * ZBBM_A)))
-                        + 2. * SR3 * (abm::datan((2. * x - ZBBM_A) / (SR3 * ZBBM_A)) - abm::datan((2. - ZBBM_A) / (SR3 * ZBBM_A))));
+                     * (2. * abm::dlog(fabs((x + ZBBM_A) * (1. / (1. + ZBBM_A))))
+                        - abm::dlog(fabs((x * x - x * ZBBM_A + ZBBM_A * ZBBM_A) * (1. / (1. - ZBBM_A + ZBBM_A * ZBBM_A))))
+                        + 2. * SR3 * (abm::datan((2. * x - ZBBM_A) * (1. / (SR3 * ZBBM_A))) - abm::datan((2. - ZBBM_A) / (SR3 * ZBBM_A))));
     }
     const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
     const double x = sqrt(x2);
     return 2. * abm::dlog(fabs((1. + x) * 0.5)) + abm::dlog(fabs((1. + x2) * 0.5)) - 2. * abm::datan(x) + RPI * 0.5;
 }
-ABD double psi_h_andreas(double zeta)
+ABD_HEAVY double psi_h_andreas(double zeta)
 {
     const double z = fmin(zeta, 15.);
     if (nonneg(z)) {
@@ -318,7 +336,7 @@ ABD double psi_h_andreas(double zeta)
         const double zz = 2. * z + zch;
         return -(0.5 * zbh * abm::dlog(fabs(1. + zch * z + z * z)))
                + (-zah / SR5 + 0.5 * zbh * zch / SR5)
-                     * (abm::dlog(fabs((zz - SR5) / (zz + SR5))) - abm::dlog(fabs((zch - SR5) / (zch + SR5))));
+                     * (abm::dlog(fabs(fdiv(zz - SR5, zz + SR5))) - abm::dlog(fabs((zch - SR5) / (zch + SR5))));
     }
     const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
     return 2. * abm::dlog(0.5 * (1. + x2));
@@ -359,35 +377,35 @@ ABD Guess first_guess_coare(const Uniform &u, double sst, double t_zt, double ss
     const double Ub = sqrt(wnd * wnd + 0.5 * 0.5);
     double us = u.fg_c_a * Ub;
 
-    double z0 = charn * us * us / GRAV + 0.11 * nu_a / us;
+    double z0 = charn * us * us * INV_GRAV + fdiv(0.11 * nu_a, us);
     z0 = fmin(fmax(fabs(z0), 1.E-8), 1.);
     const double log_z0 = abm::dlog(z0);
 
-    const double sq = VKARMN / (u.log_zu - log_z0);
+    const double sq = fdiv(VKARMN, u.log_zu - log_z0);
     const double Cd = sq * sq;
-    const double r1_o_sqrt_Cd10 = (u.log_10 - log_z0) / VKARMN;
+    const double r1_o_sqrt_Cd10 = (u.log_10 - log_z0) * INV_VKARMN;
 
-    double z0t = 10. / abm::dexp(VKARMN / (0.00115 * r1_o_sqrt_Cd10));
+    double z0t = 10. * abm::dexp(-fdiv(VKARMN, 0.00115 * r1_o_sqrt_Cd10));
     z0t = fmin(fmax(fabs(z0t), 1.E-8), 1.);
     const double log_z0t = abm::dlog(z0t);
 
     const double Rib = ri_bulk(u.zu, sst, g.t_zu, ssq, g.q_zu, Ub);
 
-    const double cc = VKARMN2 / (Cd * (u.log_zt - log_z0t));
+    const double cc = fdiv(VKARMN2, Cd * (u.log_zt - log_z0t));
     const double cc_ri = cc * Rib;
-    const double zeta_u = nonneg(Rib) ? (cc_ri + 27. / 9. * Rib * Rib) : cc_ri / (1. + Rib * u.fg_1_o_Ribcu);
+    const double zeta_u = nonneg(Rib) ? (cc_ri + 27. / 9. * Rib * Rib) : fdiv(cc_ri, 1. + Rib * u.fg_1_o_Ribcu);
 
     const double psi_h_u = psi_h_coare(zeta_u);
-    us = fmax(Ub * VKARMN / (u.log_zu - log_z0 - psi_m_coare(zeta_u)), 1.E-9);
-    const double tmp = VKARMN / (u.log_zu - log_z0t - psi_h_u);
+    us = fmax(fdiv(Ub * VKARMN, u.log_zu - log_z0 - psi_m_coare(zeta_u)), 1.E-9);
+    const double tmp = fdiv(VKARMN, u.log_zu - log_z0t - psi_h_u);
     double ts = dt * tmp;
     double qs = dq * tmp;
 
     if (!ZTEQ) {
-        const double zeta_t = u.zt * zeta_u / u.zu;
+        const double zeta_t = fdiv(u.zt * zeta_u, u.zu);
         const double prf = u.log_ztu + psi_h_u - psi_h_coare(zeta_t);
-        g.t_zu = t_zt - ts / VKARMN * prf;
-        g.q_zu = q_zt - qs / VKARMN * prf;
+        g.t_zu = t_zt - ts * INV_VKARMN * prf;
+        g.q_zu = q_zt - qs * INV_VKARMN * prf;
         g.q_zu = signbit(g.q_zu) ? 0. : g.q_zu;
         dt = floor_abs(g.t_zu - sst, 1.E-09);
         dq = floor_abs(g.q_zu - ssq, 1.E-12);
@@ -398,7 +416,7 @@ ABD Guess first_guess_coare(const Uniform &u, double sst, double t_zt, double ss
     g.ts = ts;
     g.qs = qs;
     g.Ub = Ub;
-    z0 = charn * us * us / GRAV + 0.11 * nu_a / us;
+    z0 = charn * us * us * INV_GRAV + fdiv(0.11 * nu_a, us);
     g.z0 = fmin(fmax(fabs(z0), 1.E-8), 1.);
     return g;
 }
@@ -414,10 +432,10 @@ ABD double cool_skin_dT(double alpha, double Qsw, double Qnsol, double us, doubl
     // invariants of the five delta_skin_layer evaluations
     const double usw = fmax(us, 1.E-4) * SQ_RADRW;
     const double usw2 = usw * usw;
-    const double c_lamb = alpha * RCST_CS / (usw2 * usw2);
-    const double nu_o_usw = RNU0_W / usw;
+    const double c_lamb = fdiv(alpha * RCST_CS, usw2 * usw2);
+    const double nu_o_usw = fdiv(RNU0_W, usw);
     const double d_warm = fmin(6. * nu_o_usw, 0.007);
-    const double q_lat_term = COARE_FORM ? 0.026 * fmin(Qlat, 0.) * RCP0_W / RLEVAP / alpha : 0.;
+    const double q_lat_term = COARE_FORM ? fdiv(0.026 * fmin(Qlat, 0.) * RCP0_W * (1. / RLEVAP), alpha) : 0.;
 
     auto delta = [&](double Qd) -> double {
         const double zQd = COARE_FORM ? Qd + q_lat_term : Qd;
@@ -431,11 +449,11 @@ ABD double cool_skin_dT(double alpha, double Qsw, double Qnsol, double us, doubl
     double d = delta(Qabs);
 #pragma unroll 1
     for (int jc = 0; jc < 4; ++jc) {
-        const double fr = fmax((COARE_FORM ? 0.137 : 0.065) + 11. * d - 6.6E-5 / d * (1. - abm::dexp(-d / 8.E-4)), 0.01);
+        const double fr = fmax((COARE_FORM ? 0.137 : 0.065) + 11. * d - fdiv(6.6E-5, d) * (1. - abm::dexp(-d * (1. / 8.E-4))), 0.01);
         Qabs = Qnsol + fr * Qsw;
         d = delta(Qabs);
     }
-    return Qabs * d / RK0_W;
+    return Qabs * d * (1. / RK0_W);
 }
 
 // ---------------------------------------------------------------------------
@@ -474,8 +492,8 @@ ABD WlCoareCtx wl_coare_ctx(double alpha, double lon, int isd)
 }
 ABD double wl_coare_absorption(double H)   // solar absorption profile, :167-168 / :205-206
 {
-    return 1. - (0.28 * 0.014 * (1. - abm::dexp(-H / 0.014)) + 0.27 * 0.357 * (1. - abm::dexp(-H / 0.357))
-                 + 0.45 * 12.82 * (1 - abm::dexp(-H / 12.82))) / H;
+    return 1. - fdiv(0.28 * 0.014 * (1. - abm::dexp(-H * (1. / 0.014))) + 0.27 * 0.357 * (1. - abm::dexp(-H * (1. / 0.357)))
+                     + 0.45 * 12.82 * (1 - abm::dexp(-H * (1. / 12.82))), H);
 }
 // WL_COARE, src/mod_skin_coare.f90:97-250; `commit` is (iwait == 0)
 ABD void wl_coare(WarmLayer &w, const WlCoareCtx &c, double Qsw, double Qnsol, double Tau, double rdt,
@@ -504,13 +522,13 @@ ABD void wl_coare(WarmLayer &w, const WlCoareCtx &c, double Qsw, double Qnsol, d
             Qabs = wl_coare_absorption(H) * Qsw + Qnsol;
             qac = w.Qac + Qabs * rdt;
             if (qac <= 0.) break;
-            H = fmax(fmin(Hwl_max, c.cd1 * tac / sqrt(qac)), 0.1);
+            H = fmax(fmin(Hwl_max, c.cd1 * tac * rsqrt(qac)), 0.1);
         }
         if (qac <= 0.) {
             destroy = true;
         } else {
-            dT = c.cd2 * (qac * sqrt(qac)) / tac * fmax(qac / fabs(qac), 0.);   // **1.5
-            if (signbit(gdept - H)) dT = dT * (gdept / H);                       // flg = 0
+            dT = fdiv(c.cd2 * (qac * sqrt(qac)), tac);                       // qac > 0 here: MAX(qac/ABS(qac),0) = 1   // **1.5
+            if (signbit(gdept - H)) dT = dT * fdiv(gdept, H);                       // flg = 0
         }
     }
     if (destroy) {
@@ -531,8 +549,8 @@ ABD void wl_coare(WarmLayer &w, const WlCoareCtx &c, double Qsw, double Qnsol, d
 ABD double phi_takaya(double z)
 {
     const double z2 = z * z;
-    if (nonneg(z)) return 1. + (5. * z + 4. * z2) / (1. + 3. * z + 0.25 * z2);
-    return 1. / sqrt(1. - 16. * (-fabs(z)));
+    if (nonneg(z)) return 1. + fdiv(5. * z + 4. * z2, 1. + 3. * z + 0.25 * z2);
+    return rsqrt(1. - 16. * (-fabs(z)));
 }
 // WL_ECMWF, src/mod_skin_ecmwf.f90:113-230 -- advances dT_wl by rdt at EVERY call
 ABD void wl_ecmwf(WarmLayer &w, double alpha, double Qsw, double Qnsol, double us, double rdt, double gdept)
@@ -540,8 +558,8 @@ ABD void wl_ecmwf(WarmLayer &w, double alpha, double Qsw, double Qnsol, double u
     const double rNuwl0 = 0.5;
     const double RhoCp_w = RHO0_W * RCP0_W;
     const double H = w.Hz;
-    const double tcorr = signbit(gdept - H) ? gdept / H : 1.;
-    const double dT_b = fmax(w.dT / tcorr, 0.);
+    const double tcorr = signbit(gdept - H) ? fdiv(gdept, H) : 1.;
+    const double dT_b = fmax(fdiv(w.dT, tcorr), 0.);
 
     const double fr = 1. - 0.28 * abm::dexp(-71.5 * H) - 0.27 * abm::dexp(-2.8 * H) - 0.45 * abm::dexp(-0.07 * H);
     const double Qabs = fr * Qsw + Qnsol;
@@ -551,10 +569,10 @@ ABD void wl_ecmwf(WarmLayer &w, double alpha, double Qsw, double Qnsol, double u
     const bool warming = nonneg(Qabs);
 
     const double cst1 = VKARMN * GRAV * alpha;
-    const double L2 = cst1 * Qabs / (RhoCp_w * usw2 * usw);
-    const double cst2 = cst1 / (5. * H * usw2);
-    const double cst0 = rdt * (rNuwl0 + 1.) / H;
-    const double A = cst0 * Qabs / (rNuwl0 * RhoCp_w);
+    const double L2 = fdiv(cst1 * Qabs, RhoCp_w * usw2 * usw);
+    const double cst2 = fdiv(cst1, 5. * H * usw2);
+    const double cst0 = fdiv(rdt * (rNuwl0 + 1.), H);
+    const double A = cst0 * Qabs * (1. / (rNuwl0 * RhoCp_w));
     const double cst3 = -cst0 * VKARMN * usw * FLA_ECMWF;
 
     double dT_n = dT_b;
@@ -562,7 +580,7 @@ ABD void wl_ecmwf(WarmLayer &w, double alpha, double Qsw, double Qnsol, double u
     for (int jc = 0; jc < 10; ++jc) {
         dT_n = 0.5 * (dT_n + dT_b);
         const double zeta = warming ? H * L2 : H * sqrt(dT_n * cst2);
-        const double B = cst3 / phi_takaya(zeta);
+        const double B = fdiv(cst3, phi_takaya(zeta));
         dT_n = fmax(dT_b + A + B * dT_n, 0.);
     }
     w.dT = dT_n * tcorr;
@@ -587,7 +605,7 @@ ABD double cd_n10_ncar(double w)
     double w6 = w * w * w;
     w6 = w6 * w6;
     const double r = nonneg(w - 33.) ? 1.e-3 * 2.34
-                                     : 1.e-3 * (2.7 / w + 0.142 + w / 13.09 - 3.14807E-10 * w6);
+                                     : 1.e-3 * (fdiv(2.7, w) + 0.142 + w * (1. / 13.09) - 3.14807E-10 * w6);
     return fmax(r, CX_MIN);
 }
 
@@ -610,32 +628,34 @@ ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p)
         const double dt = t_zu - p.sst;
         const double dq = q_zu - p.ssq;
         const double us = sqrt_Cd * Ub;
-        const double ts = Ch / sqrt_Cd * dt;
-        const double qs = Ce / sqrt_Cd * dq;
+        const double r_sqrt_Cd = abm::fast_rcp(sqrt_Cd);
+        const double ts = Ch * r_sqrt_Cd * dt;
+        const double qs = Ce * r_sqrt_Cd * dq;
         const double r1oL = one_on_L(t_zu, q_zu, us, ts, qs);
         const double zeta_u = clip_abs(u.zu * r1oL, 10.);
         const double psi_h_u = psi_h_ncar(zeta_u);           // used twice in the reference (:196,:217)
         if (!ZTEQ) {
             const double zeta_t = clip_abs(u.zt * r1oL, 10.);
             const double tmp = u.log_ztu + psi_h_u - psi_h_ncar(zeta_t);
-            t_zu = p.theta_zt - ts / VKARMN * tmp;
-            q_zu = fmax(0., p.q_zt - qs / VKARMN * tmp);
+            t_zu = p.theta_zt - ts * INV_VKARMN * tmp;
+            q_zu = fmax(0., p.q_zt - qs * INV_VKARMN * tmp);
         }
         const double psi_m = psi_m_ncar(zeta_u);
         // UN10_from_CD (mod_phymbl.f90:1532-1547) with z0_from_Cd(zu, Cd, psi) (:1335-1352); SQRT(Cd) is sqrt_Cd
-        const double z0 = u.zu * abm::dexp(-(VKARMN / sqrt_Cd + psi_m));
-        const double Un10 = fmax(0.25, sqrt_Cd * Ub / VKARMN * abm::dlog(10. / z0));
+        const double z0 = u.zu * abm::dexp(-(VKARMN * r_sqrt_Cd + psi_m));
+        const double Un10 = fmax(0.25, sqrt_Cd * Ub * INV_VKARMN * abm::dlog(fdiv(10., z0)));
         CdN = cd_n10_ncar(Un10);
         sqrt_CdN = sqrt(CdN);
-        double tmp = 1. + sqrt_CdN / VKARMN * (u.log_zu10 - psi_m);
-        Cd = fmax(CdN / (tmp * tmp), CX_MIN);
+        double tmp = 1. + sqrt_CdN * INV_VKARMN * (u.log_zu10 - psi_m);
+        Cd = fmax(fdiv(CdN, tmp * tmp), CX_MIN);
         sqrt_Cd = sqrt(Cd);
-        tmp = (u.log_zu10 - psi_h_u) / VKARMN / sqrt_CdN;
-        const double tmp2 = sqrt_Cd / sqrt_CdN;
+        const double r_sqrt_CdN = abm::fast_rcp(sqrt_CdN);
+        tmp = (u.log_zu10 - psi_h_u) * INV_VKARMN * r_sqrt_CdN;
+        const double tmp2 = sqrt_Cd * r_sqrt_CdN;
         const double ChN = 1.e-3 * sqrt_CdN * (nonneg(zeta_u) ? 18. : 32.7);
         const double CeN = 1.e-3 * (34.6 * sqrt_CdN);
-        Ch = fmax(ChN * tmp2 / (1. + ChN * tmp), CX_MIN);
-        Ce = fmax(CeN * tmp2 / (1. + CeN * tmp), CX_MIN);
+        Ch = fmax(fdiv(ChN * tmp2, 1. + ChN * tmp), CX_MIN);
+        Ce = fmax(fdiv(CeN * tmp2, 1. + CeN * tmp), CX_MIN);
     }
     Coeffs c;
     c.Cd = Cd; c.Ch = Ch; c.Ce = Ce; c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = p.sst; c.qs = p.ssq;
@@ -650,7 +670,7 @@ ABD double charn_coare3p0(double w)
 {
     if (!nonneg(w - 10.)) return 0.011;
     if (nonneg(w - 18.)) return 0.018;
-    return 0.011 + (0.018 - 0.011) * (w - 10.) / (18. - 10.);
+    return 0.011 + (0.018 - 0.011) * (w - 10.) * (1. / (18. - 10.));
 }
 ABD double charn_coare3p6(double w) { return fmax(fmin(0.0017 * w - 0.005, 0.028), 0.); }
 
@@ -685,33 +705,34 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
         const double us2 = us * us;
         const double r1oL = one_on_L(t_zu, q_zu, us, ts, qst);    // already clipped to +-200
 
-        const double cv = cbrt(fmax(-zi0 * r1oL / VKARMN, 0.));
+        const double cv = cbrt(fmax(-zi0 * r1oL * INV_VKARMN, 0.));
         const double gust2 = Beta0 * Beta0 * us2 * (cv * cv);       // **(2./3.)
         Ub = fmax(sqrt(p.wnd * p.wnd + gust2), 0.2);
 
         const double zeta_u = clip_abs(u.zu * r1oL, zeta_abs_max);
 
-        const double Un10 = us / VKARMN * (u.log_10 - log_z0);
-        double z0 = (V36 ? charn_coare3p6(Un10) : charn_coare3p0(Un10)) * us2 / GRAV + 0.11 * nu_a / us;
+        const double Un10 = us * INV_VKARMN * (u.log_10 - log_z0);
+        const double r_us = abm::fast_rcp(us);
+        double z0 = (V36 ? charn_coare3p6(Un10) : charn_coare3p0(Un10)) * us2 * INV_GRAV + 0.11 * nu_a * r_us;
         z0 = fmin(fmax(fabs(z0), 1.E-9), 1.);
         log_z0 = abm::dlog(z0);
 
-        const double rr = powr(nu_a / (z0 * us), V36 ? 0.72 : 0.6);
+        const double rr = powr(fdiv(nu_a * r_us, z0), V36 ? 0.72 : 0.6);
         double z0t = V36 ? fmin(1.6E-4, 5.8E-5 * rr) : fmin(1.1E-4, 5.5E-5 * rr);
         z0t = fmin(fmax(fabs(z0t), 1.E-9), 1.);
         const double log_z0t = abm::dlog(z0t);
 
         const double psi_h_u = psi_h_coare(zeta_u);
-        double tmp1 = VKARMN / (u.log_zu - log_z0t - psi_h_u);
+        double tmp1 = fdiv(VKARMN, u.log_zu - log_z0t - psi_h_u);
         ts = dt * tmp1;
         qst = dq * tmp1;
-        us = fmax(Ub * VKARMN / (u.log_zu - log_z0 - psi_m_coare(zeta_u)), 1.E-9);
+        us = fmax(fdiv(Ub * VKARMN, u.log_zu - log_z0 - psi_m_coare(zeta_u)), 1.E-9);
 
         if (!ZTEQ) {
             const double zeta_t = clip_abs(u.zt * r1oL, zeta_abs_max);
             tmp1 = u.log_zt - u.log_zu + psi_h_u - psi_h_coare(zeta_t);
-            t_zu = p.theta_zt - ts / VKARMN * tmp1;
-            q_zu = p.q_zt - qst / VKARMN * tmp1;
+            t_zu = p.theta_zt - ts * INV_VKARMN * tmp1;
+            q_zu = p.q_zt - qst * INV_VKARMN * tmp1;
         } else if (!V36) {
             t_zu = p.theta_zt;   // zm_ztzu = 0 in COARE 3.0: t_zu <- t_zt, q_zu <- q_zt every iteration
             q_zu = p.q_zt;
@@ -738,10 +759,10 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
         }
     }
     Coeffs c;
-    const double r = us / Ub;
+    const double r = fdiv(us, Ub);
     c.Cd = fmax(r * r, CX_MIN);
-    c.Ch = fmax(r * ts / dt, CX_MIN);
-    c.Ce = fmax(r * qst / dq, CX_MIN);
+    c.Ch = fmax(fdiv(r * ts, dt), CX_MIN);
+    c.Ce = fmax(fdiv(r * qst, dq), CX_MIN);
     c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = Ts; c.qs = qs_;
     return c;
 }
@@ -772,7 +793,7 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
     double dq = floor_abs(q_zu - qs_, 1.E-12);
 
     double r1oL = one_on_L(t_zu, q_zu, us, ts, qst);
-    double z0t = fmin(fmax(fabs(1. / (0.1 * abm::dexp(VKARMN / (0.00115 / (VKARMN / (u.log_10 - log_z0)))))), 1.E-9), 1.);
+    double z0t = fmin(fmax(fabs(10. * abm::dexp(-fdiv(VKARMN, fdiv(0.00115, fdiv(VKARMN, u.log_10 - log_z0))))), 1.E-9), 1.);
     double log_z0t = abm::dlog(z0t);
 
     double Fm = u.log_zu - log_z0 - psi_m_ecmwf(u.zu * r1oL) + psi_m_ecmwf(z0 * r1oL);
@@ -783,7 +804,7 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
 #pragma unroll 1
     for (int jit = 1; jit <= u.nb_iter; ++jit) {
         const double Rib = ri_bulk(u.zu, Ts, t_zu, qs_, q_zu, Ub);
-        r1oL = clip_abs(Rib * Fm * Fm / Fh / u.zu, 200.);
+        r1oL = clip_abs(fdiv(Rib * Fm * Fm, Fh * u.zu), 200.);
 
         const double psi_m_u = psi_m_ecmwf(u.zu * r1oL);
         psi_h_u = psi_h_ecmwf(u.zu * r1oL);
@@ -791,10 +812,10 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
 
         Fm = u.log_zu - log_z0 - psi_m_u + psi_m_ecmwf(z0 * r1oL);
 
-        us = Ub * VKARMN / Fm;
+        us = fdiv(Ub * VKARMN, Fm);
         const double us2 = us * us;
-        double tmp0 = nu_a / us;
-        z0 = fmin(fabs(alpha_M * tmp0 + charn0 * us2 / GRAV), 0.001);
+        double tmp0 = fdiv(nu_a, us);
+        z0 = fmin(fabs(alpha_M * tmp0 + charn0 * us2 * INV_GRAV), 0.001);
         z0t = fmin(fabs(alpha_H * tmp0), 0.001);
         const double z0q = fmin(fabs(alpha_Q * tmp0), 0.001);
         log_z0 = abm::dlog(z0);
@@ -805,25 +826,25 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
         const double psi_h_z0t = psi_h_ecmwf(z0t * r1oL);
         psi_h_z0q = psi_h_ecmwf(z0q * r1oL);
 
-        const double cv = cbrt(fmax(-zi0 * r1oL / VKARMN, 0.));
+        const double cv = cbrt(fmax(-zi0 * r1oL * INV_VKARMN, 0.));
         tmp0 = Beta0 * Beta0 * us2 * (cv * cv);
         Ub = fmax(sqrt(p.wnd * p.wnd + tmp0), 0.2);
 
         tmp0 = psi_h_u - psi_h_z0t;
-        double tmp1 = VKARMN / (u.log_zu - log_z0t - tmp0);
+        double tmp1 = fdiv(VKARMN, u.log_zu - log_z0t - tmp0);
         ts = dt * tmp1;
         if (!ZTEQ) {
             tmp1 = u.log_ztu + tmp0 - psi_h_t + psi_h_z0t;
-            t_zu = p.theta_zt - ts / VKARMN * tmp1;
+            t_zu = p.theta_zt - ts * INV_VKARMN * tmp1;
         } else {
             t_zu = p.theta_zt;
         }
         tmp0 = psi_h_u - psi_h_z0q;
-        tmp1 = VKARMN / (u.log_zu - log_z0q - tmp0);
+        tmp1 = fdiv(VKARMN, u.log_zu - log_z0q - tmp0);
         qst = dq * tmp1;
         if (!ZTEQ) {
             tmp1 = u.log_ztu + tmp0 - psi_h_t + psi_h_z0q;
-            q_zu = fmax(p.q_zt - qst / VKARMN * tmp1, 0.);
+            q_zu = fmax(p.q_zt - qst * INV_VKARMN * tmp1, 0.);
         } else {
             q_zu = fmax(p.q_zt, 0.);
         }
@@ -849,9 +870,10 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
     }
     Coeffs c;
     const double Fq = u.log_zu - log_z0q - psi_h_u + psi_h_z0q;
-    c.Cd = fmax(VKARMN2 / (Fm * Fm), CX_MIN);
-    c.Ch = fmax(VKARMN2 / (Fm * Fh), CX_MIN);
-    c.Ce = fmax(VKARMN2 / (Fm * Fq), CX_MIN);
+    const double k2_o_Fm = fdiv(VKARMN2, Fm);
+    c.Cd = fmax(fdiv(k2_o_Fm, Fm), CX_MIN);
+    c.Ch = fmax(fdiv(k2_o_Fm, Fh), CX_MIN);
+    c.Ce = fmax(fdiv(k2_o_Fm, Fq), CX_MIN);
     c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = Ts; c.qs = qs_;
     return c;
 }
@@ -864,6 +886,7 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p)
 {
     const double rRi_max = 0.15, rCs_min = 0.35E-3;
     const double Ub = fmax(0.25, p.wnd);
+    const double r_Ub = abm::fast_rcp(Ub);
     double UN10 = Ub;
     double t_zu = p.theta_zt, q_zu = p.q_zt;
     const double sq0 = sqrt(1.1E-3);
@@ -881,35 +904,35 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p)
             u_star = sqrt(CX_MIN) * Ub;
         }
         const double zeta_u = u.zu * one_on_L(t_zu, q_zu, u_star, t_star, q_star);
-        const double r = u_star / Ub;
+        const double r = u_star * r_Ub;
         const double Cd = fmax(r * r, CX_MIN);
         const double psi_m = psi_m_andreas(zeta_u);
-        const double z0 = fmin(u.zu * abm::dexp(-(VKARMN / sqrt(Cd) + psi_m)), Z0_SEA_MAX);
+        const double z0 = fmin(u.zu * abm::dexp(-(VKARMN * rsqrt(Cd) + psi_m)), Z0_SEA_MAX);
 
-        const double Rer = z0 * u_star / visc_air(t_zu);
+        const double Rer = fdiv(z0 * u_star, visc_air(t_zu));
         const double z0t = z0tq_LKB(1, Rer, z0);
         const double z0q = z0tq_LKB(2, Rer, z0);
 
         const double psi_h_u = psi_h_andreas(zeta_u);
-        t_star = (t_zu - p.sst) * VKARMN / (u.log_zu - abm::dlog(z0t) - psi_h_u);
-        q_star = (q_zu - p.ssq) * VKARMN / (u.log_zu - abm::dlog(z0q) - psi_h_u);
+        t_star = fdiv((t_zu - p.sst) * VKARMN, u.log_zu - abm::dlog(z0t) - psi_h_u);
+        q_star = fdiv((q_zu - p.ssq) * VKARMN, u.log_zu - abm::dlog(z0q) - psi_h_u);
 
         if (!ZTEQ && jit > 1) {
-            const double zeta_t = zeta_u / u.zu * u.zt;
+            const double zeta_t = fdiv(zeta_u, u.zu) * u.zt;
             const double tmp = u.log_ztu + psi_h_u - psi_h_andreas(zeta_t);
-            t_zu = p.theta_zt - t_star / VKARMN * tmp;
-            q_zu = p.q_zt - q_star / VKARMN * tmp;
+            t_zu = p.theta_zt - t_star * INV_VKARMN * tmp;
+            q_zu = p.q_zt - q_star * INV_VKARMN * tmp;
             RiB = ri_bulk(u.zu, p.sst, t_zu, p.ssq, q_zu, Ub);
         }
-        UN10 = fmax(0.1, Ub - u_star / VKARMN * (u.log_zu10 - psi_m));   // UN10_from_ustar, mod_phymbl.f90:1498-1510
+        UN10 = fmax(0.1, Ub - u_star * INV_VKARMN * (u.log_zu10 - psi_m));   // UN10_from_ustar, mod_phymbl.f90:1498-1510
     }
     Coeffs c;
-    const double r = u_star / Ub;
+    const double r = u_star * r_Ub;
     c.Cd = fmax(r * r, CX_MIN);
     const double d1 = floor_abs(t_zu - p.sst, 1.E-6);
     const double d2 = floor_abs(q_zu - p.ssq, 1.E-9);
-    c.Ch = fmax(r * t_star / d1, rCs_min);
-    c.Ce = fmax(r * q_star / d2, rCs_min);
+    c.Ch = fmax(fdiv(r * t_star, d1), rCs_min);
+    c.Ce = fmax(fdiv(r * q_star, d2), rCs_min);
     c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = p.sst; c.qs = p.ssq;
     return c;
 }

@@ -20,10 +20,16 @@ namespace abk {
 
 using namespace abd;
 
-static constexpr int FLUX_BLOCK = 128;
+#ifndef AB_FLUX_BLOCK
+#define AB_FLUX_BLOCK 256
+#endif
+#ifndef AB_MIN_BLOCKS
+#define AB_MIN_BLOCKS 3   // 256 x 3 = 24 warps/SM, <= 85 registers: measured best (tools/build_variants.py, round 1)
+#endif
+static constexpr int FLUX_BLOCK = AB_FLUX_BLOCK;
 
 template <int ALGO, bool SKIN, bool ZTEQ>
-__global__ void __launch_bounds__(FLUX_BLOCK) flux_kernel(const FluxArgs a)
+__global__ void __launch_bounds__(FLUX_BLOCK, AB_MIN_BLOCKS) flux_kernel(const FluxArgs a)
 {
     const long long i = (long long)blockIdx.x * FLUX_BLOCK + threadIdx.x;
     if (i >= a.n) return;

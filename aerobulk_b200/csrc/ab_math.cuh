@@ -53,22 +53,26 @@ ABM_FN double rcp_seed(double y)
 
 namespace abm {
 
-// 1/y for normal y: seed + two Newton steps (2^-23 -> 2^-46 -> rounding), no special cases
+// 1/y for normal y: seed r0 (rel. error e <= 2^-23), then r1 = r0(1+e) and r2 = r1(1+e^2): the second
+// step reuses e*e instead of a fresh residual (one dependent FMA less; ~1.5 ulp, corrected by callers
+// that need a quotient, see abd::fdiv)
 ABM_FN double fast_rcp(double y)
 {
-    double r = rcp_seed(y);
-    double e = fma(-y, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-y, r, 1.0);
-    return fma(r, e, r);
+    const double r0 = rcp_seed(y);
+    const double e = fma(-y, r0, 1.0);
+    const double r1 = fma(r0, e, r0);
+    return fma(r1, e * e, r1);
 }
 
-// p(r) ~ exp(r) on |r| <= ln2/2, then * 2^k through the exponent field
+// p(r) ~ exp(r) on |r| <= ln2/2 (Estrin: depth 5 instead of 11 dependent FMAs), then * 2^k through
+// the exponent field
 ABM_FN double exp_core(double r, int k)
 {
-    double p = EXP_C[11];
-#pragma unroll
-    for (int i = 10; i >= 0; --i) p = fma(p, r, EXP_C[i]);
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = fma(EXP_C[1], r, EXP_C[0]), a1 = fma(EXP_C[3], r, EXP_C[2]), a2 = fma(EXP_C[5], r, EXP_C[4]);
+    const double a3 = fma(EXP_C[7], r, EXP_C[6]), a4 = fma(EXP_C[9], r, EXP_C[8]), a5 = fma(EXP_C[11], r, EXP_C[10]);
+    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+    const double p = fma(b2, r8, fma(b1, r4, b0));
     return make_double(hi_word(p) + (k << 20), lo_word(p));
 }
 
@@ -108,9 +112,9 @@ ABM_FN double dlog(double x)
     const double f = make_double(hx, lo_word(x)) - 1.0;
     const double s = f * fast_rcp(2.0 + f);
     const double z = s * s;
-    double p = LOG_C[6];
-#pragma unroll
-    for (int j = 5; j >= 0; --j) p = fma(p, z, LOG_C[j]);
+    const double z2 = z * z;
+    const double a0 = fma(LOG_C[1], z, LOG_C[0]), a1 = fma(LOG_C[3], z, LOG_C[2]), a2 = fma(LOG_C[5], z, LOG_C[4]);
+    const double p = fma(fma(LOG_C[6], z2, a2), z2 * z2, fma(a1, z2, a0));
     const double R = z * p;
     const double hfsq = 0.5 * f * f;
     const double dk = (double)k;
@@ -131,9 +135,10 @@ ABM_FN double datan(double x)
     }
     const double t = num * fast_rcp(den);
     const double z = t * t;
-    double q = ATAN_C[10];
-#pragma unroll
-    for (int j = 9; j >= 0; --j) q = fma(q, z, ATAN_C[j]);
+    const double z2 = z * z, z4 = z2 * z2;
+    const double a0 = fma(ATAN_C[1], z, ATAN_C[0]), a1 = fma(ATAN_C[3], z, ATAN_C[2]), a2 = fma(ATAN_C[5], z, ATAN_C[4]);
+    const double a3 = fma(ATAN_C[7], z, ATAN_C[6]), a4 = fma(ATAN_C[9], z, ATAN_C[8]);
+    const double q = fma(fma(ATAN_C[10], z2, a4), z4 * z4, fma(fma(a3, z2, a2), z4, fma(a1, z2, a0)));
     const double a = fma(t * z, q, t);          // atan(t)
     return copysign(bhi + (a + blo), x);
 }

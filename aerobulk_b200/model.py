@@ -10,7 +10,8 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libaerobulk_gpu.so")
+# AEROBULK_GPU_LIB selects an experiment build (see aerobulk_b200/build.py); default: the in-tree library
+_SO = os.environ.get("AEROBULK_GPU_LIB") or os.path.join(_HERE, "libaerobulk_gpu.so")
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 _lib = None
