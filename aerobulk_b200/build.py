@@ -70,4 +70,4 @@ def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "")
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

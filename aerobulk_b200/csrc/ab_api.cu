@@ -59,6 +59,10 @@ struct Session {
     // ---- staging for host-array calls
     long long cap = 0;
     double *d_in[8] = {}, *d_out[6] = {};
+    // ---- stability-sort permutation (one uint16 per point, see classify_kernel)
+    unsigned short *d_perm = nullptr;
+    long long cap_perm = 0;
+    int sort_points = 1;   // 0 never, 1 auto (where it measured faster), 2 always
     // ---- statistics + deferred wind-stress flag
     double *d_partials = nullptr, *d_stats = nullptr;
     unsigned long long *d_bad = nullptr, *h_bad = nullptr;   // h_bad: pinned
@@ -331,6 +335,7 @@ abd::Uniform make_uniform(double zt, double zu)
     u.gdept = g.gdept;
     u.nb_iter = g.nb_iter;
     u.isd = 12;   // aerobulk_compute passes isecday_utc=12 (seconds), mod_aerobulk_compute.f90:136,146
+    u.dawn = abd::wl_coare_dawn(0., u.isd) ? 1 : 0;   // longitude fixed to 0, mod_aerobulk_compute.f90:126
     return u;
 }
 
@@ -477,6 +482,22 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
             return fail(AEROBULK_GPU_ERR_STATE, "warm-layer state missing or of another size at jt=%d (no jt==1 call for this session?)", jt);
     }
 
+    // Stability sort (classify_kernel).  Measured on B200 (tools/kbench.py, round 1): a gain for ANDREAS
+    // and the COARE / ECMWF kernels without skin schemes, a loss for NCAR (too little work per point)
+    // and for the skin kernels (instruction-cache bound: homogeneous blocks run different code regions)
+    const bool do_sort = g.sort_points == 2 || (g.sort_points == 1 && !use_skin && ialgo != abd::NCAR);
+    if (do_sort) {
+        // every chunk is padded to whole sort windows
+        const long long need = n + (long long)(nchunks + 1) * abk::sort_window();
+        if (need > g.cap_perm) {
+            if (g.d_perm) cudaFree(g.d_perm);
+            g.d_perm = nullptr;
+            g.cap_perm = 0;
+            CUDA_TRY(cudaMalloc(&g.d_perm, sizeof(unsigned short) * (size_t)need));
+            g.cap_perm = need;
+        }
+    }
+
     abk::FluxArgs a;
     memset(&a, 0, sizeof(a));
     a.u = make_uniform(zt, zu);
@@ -507,6 +528,13 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         a.n = len;
         a.index_offset = s0;
         if (!device_ptrs) CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_in[c], 0));
+        a.perm = nullptr;
+        if (do_sort) {
+            unsigned short *perm = g.d_perm + s0 + (long long)c * abk::sort_window();
+            CUDA_TRY(abk::launch_classify(a, perm, cs));
+            g.launches += 1;
+            a.perm = perm;
+        }
         CUDA_TRY(abk::launch_flux(ialgo, use_skin, zteq, a, cs));
         g.launches += 1;
         if (!device_ptrs) {
@@ -687,6 +715,7 @@ int aerobulk_gpu_set_stream(void *stream)
 
 void aerobulk_gpu_set_error_mode(int m) { g.error_mode = m ? 1 : 0; }
 void aerobulk_gpu_set_verbose(int on) { g.verbose = on ? 1 : 0; }
+void aerobulk_gpu_set_sort(int mode) { g.sort_points = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 const char *aerobulk_gpu_last_error(void) { return g.errmsg; }
 int aerobulk_gpu_last_error_code(void) { return g.errcode; }
 
@@ -701,6 +730,9 @@ void aerobulk_gpu_reset(void)
         for (int k = 0; k < 8; ++k) { if (g.d_in[k]) cudaFree(g.d_in[k]); g.d_in[k] = nullptr; }
         for (int k = 0; k < 6; ++k) { if (g.d_out[k]) cudaFree(g.d_out[k]); g.d_out[k] = nullptr; }
         g.cap = 0;
+        if (g.d_perm) cudaFree(g.d_perm);
+        g.d_perm = nullptr;
+        g.cap_perm = 0;
         if (g.h_bad) *g.h_bad = ~0ull;
         if (g.d_bad) cudaMemset(g.d_bad, 0xFF, sizeof(unsigned long long));
     }

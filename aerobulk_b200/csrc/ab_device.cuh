@@ -97,6 +97,15 @@ ABD double fdiv(double a, double b)
     const double q = a * r;
     return fma(fma(-b, q, a), r, q);
 }
+// natural logs of literals of the reference (glibc values), for roughness lengths handled in log space
+constexpr double LOG_1EM9 = -0x1.4b927f32bffb8p+4;   // LOG(1.E-9)
+constexpr double LOG_1EM8 = -18.420680743952367;     // LOG(1.E-8)
+constexpr double LOG_0P05 = -0x1.7f7427b73e391p+1;   // LOG(0.05)
+constexpr double LOG_1P6EM4 = -0x1.17b0d6ae41bdfp+3, LOG_5P8EM5 = -0x1.3829836acdc7ap+3;   // COARE 3.6 z0t
+constexpr double LOG_1P1EM4 = -0x1.23ae53cc2dc88p+3, LOG_5P5EM5 = -0x1.39dc96cb28027p+3;   // COARE 3.0 z0t
+constexpr double LOG_0P40 = -0x1.d5240f0e0e077p-1, LOG_0P62 = -0x1.e982378d782aap-2;       // ECMWF alpha_H, alpha_Q
+constexpr double LOG_1EM3 = -0x1.ba18a998fffa0p+2;   // LOG(0.001)
+constexpr double LOG_Z0_SEA_MAX = -0x1.7f7427b73e391p+2;   // LOG(0.0025)
 constexpr double INV_VKARMN = 1. / VKARMN;
 constexpr double INV_GRAV = 1. / GRAV;
 
@@ -206,53 +215,64 @@ ABD_HEAVY void update_qnsol_tau(double zu, double Ts, double qs, double tha, dou
     Qlat = f.qlat;
 }
 
-// Liu-Katsaros-Businger z0t / z0q, :1635-1701 (iflag 1: temperature, 2: humidity)
-ABD double z0tq_LKB(int iflag, double Rer, double z0)
+// Liu-Katsaros-Businger z0t / z0q, :1635-1701 (iflag 1: temperature, 2: humidity), in log space:
+// LOG(z0t) = LOG(XA) + (XB - 1) LOG(Rer) + LOG(z0), clipped to [LOG(1e-9), LOG(0.05)]; Rer outside
+// ]0,1000[ gives the reference's ABS(-999.) -> 0.05.  (One log of Rer instead of two pow and two log.)
+ABD double log_z0tq_LKB(int iflag, double Rer, double log_Rer, double log_z0)
 {
-    double r = 999.;  // ABS(-999.)
-    if (Rer > 0. && Rer < 1000.) {
-        double a, b;
-        if (iflag == 1) {
-            if (Rer <= 0.11) { a = 0.177; b = 0.; }
-            else if (Rer <= 0.825) { a = 1.376; b = 0.929; }
-            else if (Rer <= 3.0) { a = 1.026; b = -0.599; }
-            else if (Rer <= 10.0) { a = 1.625; b = -1.018; }
-            else if (Rer <= 30.0) { a = 4.661; b = -1.475; }
-            else if (Rer <= 100.) { a = 34.904; b = -2.067; }
-            else if (Rer <= 300.) { a = 1667.19; b = -2.907; }
-            else { a = 5.88e5; b = -3.935; }
-        } else {
-            if (Rer <= 0.11) { a = 0.292; b = 0.; }
-            else if (Rer <= 0.825) { a = 1.808; b = 0.826; }
-            else if (Rer <= 3.0) { a = 1.393; b = -0.528; }
-            else if (Rer <= 10.0) { a = 1.956; b = -0.870; }
-            else if (Rer <= 30.0) { a = 4.994; b = -1.297; }
-            else if (Rer <= 100.) { a = 30.709; b = -1.845; }
-            else if (Rer <= 300.) { a = 1448.68; b = -2.682; }
-            else { a = 2.98e5; b = -3.616; }
-        }
-        r = fabs(fdiv(a * powr(Rer, b) * z0, Rer));
+    if (!(Rer > 0. && Rer < 1000.)) return LOG_0P05;
+    double la, b;
+    if (iflag == 1) {
+        if (Rer <= 0.11) { la = -0x1.bb4a804765594p+0; b = 0.; }
+        else if (Rer <= 0.825) { la = 0x1.46d750d6da9dbp-2; b = 0.929; }
+        else if (Rer <= 3.0) { la = 0x1.a48a553637bd3p-6; b = -0.599; }
+        else if (Rer <= 10.0) { la = 0x1.f128f5faf06edp-2; b = -1.018; }
+        else if (Rer <= 30.0) { la = 0x1.8a0afa79b6d2dp+0; b = -1.475; }
+        else if (Rer <= 100.) { la = 0x1.c6bba4d3499efp+1; b = -2.067; }
+        else if (Rer <= 300.) { la = 0x1.dacf2c5c04d22p+2; b = -2.907; }
+        else { la = 0x1.a91a7a7897e05p+3; b = -3.935; }
+    } else {
+        if (Rer <= 0.11) { la = -0x1.3b22e9abd04f9p+0; b = 0.; }
+        else if (Rer <= 0.825) { la = 0x1.2f37a01050599p-1; b = 0.826; }
+        else if (Rer <= 3.0) { la = 0x1.536a2b94647bcp-2; b = -0.528; }
+        else if (Rer <= 10.0) { la = 0x1.57806929d28c9p-1; b = -0.870; }
+        else if (Rer <= 30.0) { la = 0x1.9bb56ebf3d3b9p+0; b = -1.297; }
+        else if (Rer <= 100.) { la = 0x1.b657d7f0668f0p+1; b = -1.845; }
+        else if (Rer <= 300.) { la = 0x1.d1d1701b4f5c8p+2; b = -2.682; }
+        else { la = 0x1.935aebcc59706p+3; b = -3.616; }
     }
-    return fmin(fmax(r, 1.E-9), 0.05);
+    return fmin(fmax(la + (b - 1.) * log_Rer + log_z0, LOG_1EM9), LOG_0P05);
 }
 
 // ---------------------------------------------------------------------------
-// stability functions
+// stability functions.  Every algorithm evaluates psi_m and psi_h at several heights of the same
+// sign of 1/L per iteration; the grouped evaluators below take ONE branch on the stability class and
+// compute all of them inside it: independent dependency chains the scheduler can interleave
+// ("wait" was the top stall with one branch per psi), shared sub-expressions computed once
+// (exp(-0.35 zeta), sqrt(|1-15 zeta|), zeta^2/(1+zeta^2): bit-identical), fewer branches.
 // ---------------------------------------------------------------------------
+struct PsiMH {
+    double m, h;
+};
+
 // Large & Yeager, src/mod_blk_ncar.f90:333-407
-ABD double psi_m_ncar(double z)
+ABD PsiMH psi_mh_ncar_unstable(double z)
 {
-    if (nonneg(z)) return -5. * z;
     const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
     const double x = sqrt(x2);
-    return 2. * abm::dlog((1. + x) * 0.5) + abm::dlog((1. + x2) * 0.5) - 2. * abm::datan(x) + RPI * 0.5;
+    const double l2 = abm::dlog((1. + x2) * 0.5);
+    PsiMH r;
+    r.m = 2. * abm::dlog((1. + x) * 0.5) + l2 - 2. * abm::datan(x) + RPI * 0.5;
+    r.h = 2. * l2;
+    return r;
 }
-ABD double psi_h_ncar(double z)
+ABD double psi_h_ncar_unstable(double z)
 {
-    if (nonneg(z)) return -5. * z;
     const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
     return 2. * abm::dlog(0.5 * (1. + x2));
 }
+ABD double psi_m_ncar(double z) { return nonneg(z) ? -5. * z : psi_mh_ncar_unstable(z).m; }
+ABD double psi_h_ncar(double z) { return nonneg(z) ? -5. * z : psi_h_ncar_unstable(z); }
 
 // COARE 3.x, src/mod_common_coare.f90:217-254, :305-344.  Note psi(+0) = -4.524e-3:
 // SIGN(0.5,+0.) selects the stable branch and the truncated literals do not cancel.
@@ -260,85 +280,130 @@ ABD double psi_coare_convective(double phi_c)
 {
     return 1.5 * abm::dlog((1. + phi_c + phi_c * phi_c) * (1. / 3.)) - 1.7320508 * abm::datan((1. + 2. * phi_c) * (1. / 1.7320508)) + 1.813799447;
 }
-ABD_HEAVY double psi_m_coare(double z)
+ABD PsiMH psi_mh_coare_stable(double z)
 {
-    if (nonneg(z)) {
-        const double zc = fmin(50., 0.35 * z);
-        return -(1. + 1. * z + 0.6667 * (z - 14.28) * abm::dexp(-zc) + 8.525);
-    }
-    const double phi_m = sqrt(sqrt(fabs(1. - 15. * z)));                       // **.25
-    const double psi_k = 2. * abm::dlog((1. + phi_m) * 0.5) + abm::dlog((1. + phi_m * phi_m) * 0.5) - 2. * abm::datan(phi_m) + 0.5 * RPI;
-    const double psi_c = psi_coare_convective(powr(fabs(1. - 10.15 * z), .3333));
-    double f = z * z;
-    f = fdiv(f, 1. + f);
-    return (1. - f) * psi_k + f * psi_c;
+    const double e = abm::dexp(-fmin(50., 0.35 * z));
+    const double a = fabs(1. + 2. * z * (1. / 3.));
+    PsiMH r;
+    r.m = -(1. + 1. * z + 0.6667 * (z - 14.28) * e + 8.525);
+    r.h = -(a * sqrt(a) + .6667 * (z - 14.28) * e + 8.525);                      // **1.5
+    return r;
 }
-ABD_HEAVY double psi_h_coare(double z)
+ABD double psi_h_coare_stable(double z)
 {
-    if (nonneg(z)) {
-        const double zc = fmin(50., 0.35 * z);
-        const double a = fabs(1. + 2. * z * (1. / 3.));
-        return -(a * sqrt(a) + .6667 * (z - 14.28) * abm::dexp(-zc) + 8.525);            // **1.5
-    }
-    const double phi_h = sqrt(fabs(1. - 15. * z));                             // **.5
-    const double psi_k = 2. * abm::dlog((1. + phi_h) * 0.5);
-    const double psi_c = psi_coare_convective(powr(fabs(1. - 34.15 * z), .3333));
+    const double e = abm::dexp(-fmin(50., 0.35 * z));
+    const double a = fabs(1. + 2. * z * (1. / 3.));
+    return -(a * sqrt(a) + .6667 * (z - 14.28) * e + 8.525);
+}
+ABD PsiMH psi_mh_coare_unstable(double z)
+{
+    const double phi_h = sqrt(fabs(1. - 15. * z));                               // **.5
+    const double phi_m = sqrt(phi_h);                                            // **.25
     double f = z * z;
     f = fdiv(f, 1. + f);
-    return (1. - f) * psi_k + f * psi_c;
+    const double km = 2. * abm::dlog((1. + phi_m) * 0.5) + abm::dlog((1. + phi_m * phi_m) * 0.5) - 2. * abm::datan(phi_m) + 0.5 * RPI;
+    const double kh = 2. * abm::dlog((1. + phi_h) * 0.5);
+    const double cm = psi_coare_convective(powr(fabs(1. - 10.15 * z), .3333));
+    const double ch = psi_coare_convective(powr(fabs(1. - 34.15 * z), .3333));
+    PsiMH r;
+    r.m = (1. - f) * km + f * cm;
+    r.h = (1. - f) * kh + f * ch;
+    return r;
+}
+ABD double psi_h_coare_unstable(double z)
+{
+    const double phi_h = sqrt(fabs(1. - 15. * z));
+    double f = z * z;
+    f = fdiv(f, 1. + f);
+    const double kh = 2. * abm::dlog((1. + phi_h) * 0.5);
+    const double ch = psi_coare_convective(powr(fabs(1. - 34.15 * z), .3333));
+    return (1. - f) * kh + f * ch;
+}
+// psi_m(zeta_u), psi_h(zeta_u), psi_h(zeta_t); zeta_t has the sign of zeta_u
+template <bool ZTEQ>
+ABD void psi3_coare(double zeta_u, double zeta_t, double &m_u, double &h_u, double &h_t)
+{
+    h_t = 0.;
+    if (nonneg(zeta_u)) {
+        const PsiMH r = psi_mh_coare_stable(zeta_u);
+        m_u = r.m;
+        h_u = r.h;
+        if (!ZTEQ) h_t = psi_h_coare_stable(zeta_t);
+    } else {
+        const PsiMH r = psi_mh_coare_unstable(zeta_u);
+        m_u = r.m;
+        h_u = r.h;
+        if (!ZTEQ) h_t = psi_h_coare_unstable(zeta_t);
+    }
 }
 
-// IFS, src/mod_blk_ecmwf.f90:441-564 (zeta capped to [-50, 5])
-ABD_HEAVY double psi_m_ecmwf(double zeta)
+// IFS, src/mod_blk_ecmwf.f90:441-564 (zeta capped to [-50, 5]; the cap keeps the sign)
+ABD double cap_zeta(double zeta) { return fmin(fmax(zeta, -50.), 5.); }
+ABD PsiMH psi_mh_ecmwf_stable(double zeta)
 {
     const double zc = 5. / 0.35;
-    const double z = fmin(fmax(zeta, -50.), 5.);
-    if (nonneg(z)) return -(2. / 3. * (z - zc) * abm::dexp(-0.35 * z)) - z - 2. / 3. * zc;
+    const double z = cap_zeta(zeta);
+    const double t = 2. / 3. * (z - zc) * abm::dexp(-0.35 * z);
+    const double a = fabs(1. + 2. / 3. * z);
+    PsiMH r;
+    r.m = -t - z - 2. / 3. * zc;
+    r.h = -t - a * sqrt(a) - 2. / 3. * zc + 1.;
+    return r;
+}
+ABD PsiMH psi_mh_ecmwf_unstable(double zeta)
+{
+    const double z = cap_zeta(zeta);
     const double x2 = sqrt(fabs(1. - 16. * z));
     const double x = sqrt(x2);
     const double t = 1. + x;
-    return abm::dlog(0.125 * t * t * (1. + x2)) - 2. * abm::datan(x) + 0.5 * RPI;
+    PsiMH r;
+    r.m = abm::dlog(0.125 * t * t * (1. + x2)) - 2. * abm::datan(x) + 0.5 * RPI;
+    r.h = 2. * abm::dlog(0.5 * (1. + x2));
+    return r;
 }
-ABD_HEAVY double psi_h_ecmwf(double zeta)
+ABD double psi_m_ecmwf_stable(double zeta) { return psi_mh_ecmwf_stable(zeta).m; }
+ABD double psi_h_ecmwf_stable(double zeta) { return psi_mh_ecmwf_stable(zeta).h; }
+ABD double psi_m_ecmwf_unstable(double zeta) { return psi_mh_ecmwf_unstable(zeta).m; }
+ABD double psi_h_ecmwf_unstable(double zeta)
 {
-    const double zc = 5. / 0.35;
-    const double z = fmin(fmax(zeta, -50.), 5.);
-    if (nonneg(z)) {
-        const double a = fabs(1. + 2. / 3. * z);
-        return -(2. / 3. * (z - zc) * abm::dexp(-0.35 * z)) - a * sqrt(a) - 2. / 3. * zc + 1.;
-    }
-    const double x2 = sqrt(fabs(1. - 16. * z));
+    const double x2 = sqrt(fabs(1. - 16. * cap_zeta(zeta)));
     return 2. * abm::dlog(0.5 * (1. + x2));
 }
 
 // Andreas et al. 2015 (Paulson unstable / Grachev 2007 stable), src/mod_blk_andreas.f90:307-410
-ABD_HEAVY double psi_m_andreas(double zeta)
+ABD double psi_m_andreas_stable(double zeta)
 {
     const double z = fmin(zeta, 15.);
-    if (nonneg(z)) {
-        const double zam = 5.;
-        const double x = cbrt(fabs(1. + z));
-        return -(3. * zam / ZBM_A * (x - 1.))
-               + zam * ZBBM_A / (2. * ZBM_A)
-                     * (2. * abm::dlog(fabs((x + ZBBM_A) * (1. / (1. + ZBBM_A))))
-                        - abm::dlog(fabs((x * x - x * ZBBM_A + ZBBM_A * ZBBM_A) * (1. / (1. - ZBBM_A + ZBBM_A * ZBBM_A))))
-                        + 2. * SR3 * (abm::datan((2. * x - ZBBM_A) * (1. / (SR3 * ZBBM_A))) - abm::datan((2. - ZBBM_A) / (SR3 * ZBBM_A))));
-    }
+    const double zam = 5.;
+    const double x = cbrt(fabs(1. + z));
+    return -(3. * zam / ZBM_A * (x - 1.))
+           + zam * ZBBM_A / (2. * ZBM_A)
+                 * (2. * abm::dlog(fabs((x + ZBBM_A) * (1. / (1. + ZBBM_A))))
+                    - abm::dlog(fabs((x * x - x * ZBBM_A + ZBBM_A * ZBBM_A) * (1. / (1. - ZBBM_A + ZBBM_A * ZBBM_A))))
+                    + 2. * SR3 * (abm::datan((2. * x - ZBBM_A) * (1. / (SR3 * ZBBM_A))) - abm::datan((2. - ZBBM_A) / (SR3 * ZBBM_A))));
+}
+ABD double psi_h_andreas_stable(double zeta)
+{
+    const double z = fmin(zeta, 15.);
+    const double zah = 5., zbh = 5., zch = 3.;
+    const double zz = 2. * z + zch;
+    return -(0.5 * zbh * abm::dlog(fabs(1. + zch * z + z * z)))
+           + (-zah / SR5 + 0.5 * zbh * zch / SR5)
+                 * (abm::dlog(fabs(fdiv(zz - SR5, zz + SR5))) - abm::dlog(fabs((zch - SR5) / (zch + SR5))));
+}
+ABD PsiMH psi_mh_andreas_unstable(double zeta)
+{
+    const double z = fmin(zeta, 15.);
     const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
     const double x = sqrt(x2);
-    return 2. * abm::dlog(fabs((1. + x) * 0.5)) + abm::dlog(fabs((1. + x2) * 0.5)) - 2. * abm::datan(x) + RPI * 0.5;
+    PsiMH r;
+    r.m = 2. * abm::dlog(fabs((1. + x) * 0.5)) + abm::dlog(fabs((1. + x2) * 0.5)) - 2. * abm::datan(x) + RPI * 0.5;
+    r.h = 2. * abm::dlog(0.5 * (1. + x2));
+    return r;
 }
-ABD_HEAVY double psi_h_andreas(double zeta)
+ABD double psi_h_andreas_unstable(double zeta)
 {
-    const double z = fmin(zeta, 15.);
-    if (nonneg(z)) {
-        const double zah = 5., zbh = 5., zch = 3.;
-        const double zz = 2. * z + zch;
-        return -(0.5 * zbh * abm::dlog(fabs(1. + zch * z + z * z)))
-               + (-zah / SR5 + 0.5 * zbh * zch / SR5)
-                     * (abm::dlog(fabs(fdiv(zz - SR5, zz + SR5))) - abm::dlog(fabs((zch - SR5) / (zch + SR5))));
-    }
-    const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
+    const double x2 = fmax(sqrt(fabs(1. - 16. * fmin(zeta, 15.))), 1.);
     return 2. * abm::dlog(0.5 * (1. + x2));
 }
 
@@ -353,6 +418,7 @@ struct Uniform {
     double rdt, gdept;                                 // mod_const.f90:31-32
     int nb_iter;
     int isd;                                           // seconds since 00h UTC (12 in aerobulk_compute)
+    int dawn;                                          // WL_COARE dawn reset for longitude 0 (host-computed)
 };
 
 // ---------------------------------------------------------------------------
@@ -385,9 +451,8 @@ ABD Guess first_guess_coare(const Uniform &u, double sst, double t_zt, double ss
     const double Cd = sq * sq;
     const double r1_o_sqrt_Cd10 = (u.log_10 - log_z0) * INV_VKARMN;
 
-    double z0t = 10. * abm::dexp(-fdiv(VKARMN, 0.00115 * r1_o_sqrt_Cd10));
-    z0t = fmin(fmax(fabs(z0t), 1.E-8), 1.);
-    const double log_z0t = abm::dlog(z0t);
+    // z0t = 10 / EXP(k / (0.00115 r)) clipped to [1e-8, 1], only needed as LOG(z0t)
+    const double log_z0t = fmin(fmax(u.log_10 - fdiv(VKARMN, 0.00115 * r1_o_sqrt_Cd10), LOG_1EM8), 0.);
 
     const double Rib = ri_bulk(u.zu, sst, g.t_zu, ssq, g.q_zu, Ub);
 
@@ -395,15 +460,16 @@ ABD Guess first_guess_coare(const Uniform &u, double sst, double t_zt, double ss
     const double cc_ri = cc * Rib;
     const double zeta_u = nonneg(Rib) ? (cc_ri + 27. / 9. * Rib * Rib) : fdiv(cc_ri, 1. + Rib * u.fg_1_o_Ribcu);
 
-    const double psi_h_u = psi_h_coare(zeta_u);
-    us = fmax(fdiv(Ub * VKARMN, u.log_zu - log_z0 - psi_m_coare(zeta_u)), 1.E-9);
+    const double zeta_t = ZTEQ ? zeta_u : fdiv(u.zt * zeta_u, u.zu);
+    double psi_m_u, psi_h_u, psi_h_t;
+    psi3_coare<ZTEQ>(zeta_u, zeta_t, psi_m_u, psi_h_u, psi_h_t);
+    us = fmax(fdiv(Ub * VKARMN, u.log_zu - log_z0 - psi_m_u), 1.E-9);
     const double tmp = fdiv(VKARMN, u.log_zu - log_z0t - psi_h_u);
     double ts = dt * tmp;
     double qs = dq * tmp;
 
     if (!ZTEQ) {
-        const double zeta_t = fdiv(u.zt * zeta_u, u.zu);
-        const double prf = u.log_ztu + psi_h_u - psi_h_coare(zeta_t);
+        const double prf = u.log_ztu + psi_h_u - psi_h_t;
         g.t_zu = t_zt - ts * INV_VKARMN * prf;
         g.q_zu = q_zt - qs * INV_VKARMN * prf;
         g.q_zu = signbit(g.q_zu) ? 0. : g.q_zu;
@@ -445,12 +511,15 @@ ABD double cool_skin_dT(double alpha, double Qsw, double Qnsol, double us, doubl
         return 6. * rcbrt(1. + x75) * nu_o_usw;                           // **(-1./3.)
     };
 
-    double Qabs = Qnsol;
-    double d = delta(Qabs);
+    // delta(Qnsol), then 4 x { solar absorption fr(delta) -> Qabs -> delta(Qabs) }: one rolled loop so that
+    // the delta code exists once (instruction-cache footprint)
+    double Qabs = Qnsol, d = 0.;
 #pragma unroll 1
-    for (int jc = 0; jc < 4; ++jc) {
-        const double fr = fmax((COARE_FORM ? 0.137 : 0.065) + 11. * d - fdiv(6.6E-5, d) * (1. - abm::dexp(-d * (1. / 8.E-4))), 0.01);
-        Qabs = Qnsol + fr * Qsw;
+    for (int jc = 0; jc < 5; ++jc) {
+        if (jc > 0) {
+            const double fr = fmax((COARE_FORM ? 0.137 : 0.065) + 11. * d - fdiv(6.6E-5, d) * (1. - abm::dexp(-d * (1. / 8.E-4))), 0.01);
+            Qabs = Qnsol + fr * Qsw;
+        }
         d = delta(Qabs);
     }
     return Qabs * d * (1. / RK0_W);
@@ -469,22 +538,26 @@ struct WlCoareCtx {
     double cd1, cd2;
     bool dawn;     // local solar hour in ]4, 6.5]
 };
-ABD double f_modulo(double a, double p)
+// local solar time from longitude and UTC seconds, src/mod_skin_coare.f90:146-150,159
+__host__ __device__ inline bool wl_coare_dawn(double lon, int isd)
 {
-    double r = fmod(a, p);
-    if (r != 0. && ((r < 0.) != (p < 0.))) r += p;
-    return r;
-}
-ABD WlCoareCtx wl_coare_ctx(double alpha, double lon, int isd)
-{
-    WlCoareCtx c;
-    double lag = -1. * f_modulo((360. - f_modulo(lon, 360.)) / 15., 24.);
-    lag = -1. * copysign(fmin(fabs(lag), fabs(f_modulo(lag, 24.))), lag + 12.);
+    auto f_mod = [](double a, double p) {
+        double r = fmod(a, p);
+        if (r != 0. && ((r < 0.) != (p < 0.))) r += p;
+        return r;
+    };
+    double lag = -1. * f_mod((360. - f_mod(lon, 360.)) / 15., 24.);
+    lag = -1. * copysign(fmin(fabs(lag), fabs(f_mod(lag, 24.))), lag + 12.);
     const int ilag = (int)(lag * 3600.);
     int isol = (isd + ilag) % 86400;
     if (isol < 0) isol += 86400;
     const double hr = (double)isol / 3600.;
-    c.dawn = (hr > 4.) && (hr <= 6.5);
+    return (hr > 4.) && (hr <= 6.5);
+}
+ABD WlCoareCtx wl_coare_ctx(double alpha, bool dawn)
+{
+    WlCoareCtx c;
+    c.dawn = dawn;
     const double Rich0 = 0.65;
     c.cd1 = sqrt(2. * Rich0 * RCP0_W / (alpha * GRAV * RHO0_W));
     c.cd2 = sqrt(2. * alpha * GRAV / (Rich0 * RHO0_W)) / RCP0W_POW15;
@@ -592,6 +665,7 @@ ABD void wl_ecmwf(WarmLayer &w, double alpha, double Qsw, double Qnsol, double u
 struct PointIn {
     double sst, theta_zt, ssq, q_zt, wnd, slp;   // after aerobulk_compute steps 1-5
     double Qsw, rlw, lon;                          // skin only
+    bool has_lon;                                  // per-point longitude given (else Uniform::dawn)
 };
 struct Coeffs {
     double Cd, Ch, Ce, t_zu, q_zu, Ub, Ts, qs;
@@ -633,17 +707,26 @@ ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p)
         const double qs = Ce * r_sqrt_Cd * dq;
         const double r1oL = one_on_L(t_zu, q_zu, us, ts, qs);
         const double zeta_u = clip_abs(u.zu * r1oL, 10.);
-        const double psi_h_u = psi_h_ncar(zeta_u);           // used twice in the reference (:196,:217)
+        const double zeta_t = clip_abs(u.zt * r1oL, 10.);
+        // psi_h(zeta_u) is used twice in the reference (:196,:217); one stability branch for all three
+        double psi_m, psi_h_u, psi_h_t = 0.;
+        if (nonneg(zeta_u)) {
+            psi_m = psi_h_u = -5. * zeta_u;
+            if (!ZTEQ) psi_h_t = -5. * zeta_t;
+        } else {
+            const PsiMH r = psi_mh_ncar_unstable(zeta_u);
+            psi_m = r.m;
+            psi_h_u = r.h;
+            if (!ZTEQ) psi_h_t = psi_h_ncar_unstable(zeta_t);
+        }
         if (!ZTEQ) {
-            const double zeta_t = clip_abs(u.zt * r1oL, 10.);
-            const double tmp = u.log_ztu + psi_h_u - psi_h_ncar(zeta_t);
+            const double tmp = u.log_ztu + psi_h_u - psi_h_t;
             t_zu = p.theta_zt - ts * INV_VKARMN * tmp;
             q_zu = fmax(0., p.q_zt - qs * INV_VKARMN * tmp);
         }
-        const double psi_m = psi_m_ncar(zeta_u);
         // UN10_from_CD (mod_phymbl.f90:1532-1547) with z0_from_Cd(zu, Cd, psi) (:1335-1352); SQRT(Cd) is sqrt_Cd
-        const double z0 = u.zu * abm::dexp(-(VKARMN * r_sqrt_Cd + psi_m));
-        const double Un10 = fmax(0.25, sqrt_Cd * Ub * INV_VKARMN * abm::dlog(fdiv(10., z0)));
+        // z0 = zu EXP(-(k/SQRT(Cd) + psi_m)) only enters as LOG(10/z0) = k/SQRT(Cd) + psi_m - LOG(zu/10)
+        const double Un10 = fmax(0.25, sqrt_Cd * Ub * INV_VKARMN * (VKARMN * r_sqrt_Cd + psi_m - u.log_zu10));
         CdN = cd_n10_ncar(Un10);
         sqrt_CdN = sqrt(CdN);
         double tmp = 1. + sqrt_CdN * INV_VKARMN * (u.log_zu10 - psi_m);
@@ -686,7 +769,7 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
         Ts = Ts - 0.25;
         qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
         alpha = alpha_sw(p.sst);
-        wc = wl_coare_ctx(alpha, p.lon, u.isd);
+        wc = wl_coare_ctx(alpha, p.has_lon ? wl_coare_dawn(p.lon, u.isd) : (u.dawn != 0));
     }
 
     const Guess g = first_guess_coare<ZTEQ>(u, Ts, p.theta_zt, qs_, p.q_zt, p.wnd,
@@ -717,20 +800,22 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
         z0 = fmin(fmax(fabs(z0), 1.E-9), 1.);
         log_z0 = abm::dlog(z0);
 
-        const double rr = powr(fdiv(nu_a * r_us, z0), V36 ? 0.72 : 0.6);
-        double z0t = V36 ? fmin(1.6E-4, 5.8E-5 * rr) : fmin(1.1E-4, 5.5E-5 * rr);
-        z0t = fmin(fmax(fabs(z0t), 1.E-9), 1.);
-        const double log_z0t = abm::dlog(z0t);
+        // z0t = MIN(1.6e-4, 5.8e-5 (nu/(z0 u*))**0.72) [3.6] / MIN(1.1e-4, 5.5e-5 (..)**0.6) [3.0], floored at
+        // 1e-9, is only needed as LOG(z0t): monotonic, so MIN / MAX act on the logarithms (no pow)
+        const double log_rr = abm::dlog(nu_a * r_us) - log_z0;
+        const double log_z0t = V36 ? fmax(fmin(LOG_1P6EM4, LOG_5P8EM5 + 0.72 * log_rr), LOG_1EM9)
+                                   : fmax(fmin(LOG_1P1EM4, LOG_5P5EM5 + 0.6 * log_rr), LOG_1EM9);
 
-        const double psi_h_u = psi_h_coare(zeta_u);
+        const double zeta_t = clip_abs(u.zt * r1oL, zeta_abs_max);
+        double psi_m_u, psi_h_u, psi_h_t;
+        psi3_coare<ZTEQ>(zeta_u, zeta_t, psi_m_u, psi_h_u, psi_h_t);
         double tmp1 = fdiv(VKARMN, u.log_zu - log_z0t - psi_h_u);
         ts = dt * tmp1;
         qst = dq * tmp1;
-        us = fmax(fdiv(Ub * VKARMN, u.log_zu - log_z0 - psi_m_coare(zeta_u)), 1.E-9);
+        us = fmax(fdiv(Ub * VKARMN, u.log_zu - log_z0 - psi_m_u), 1.E-9);
 
         if (!ZTEQ) {
-            const double zeta_t = clip_abs(u.zt * r1oL, zeta_abs_max);
-            tmp1 = u.log_zt - u.log_zu + psi_h_u - psi_h_coare(zeta_t);
+            tmp1 = u.log_zt - u.log_zu + psi_h_u - psi_h_t;
             t_zu = p.theta_zt - ts * INV_VKARMN * tmp1;
             q_zu = p.q_zt - qst * INV_VKARMN * tmp1;
         } else if (!V36) {
@@ -739,19 +824,23 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
         }
 
         if (SKIN) {
-            double Qns, Tau, Qlat;
-            // cool skin
-            update_qnsol_tau(u.zu, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.slp, p.rlw, Qns, Tau, Qlat);
-            dT_cs = cool_skin_dT<true>(alpha, p.Qsw, Qns, us, Qlat);
-            Ts = p.sst + dT_cs;
-            Ts = Ts + wl.dT;
-            qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
-            // warm layer; state committed whenever jit divides nb_iter
-            update_qnsol_tau(u.zu, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.slp, p.rlw, Qns, Tau, Qlat);
-            wl_coare(wl, wc, p.Qsw, Qns, Tau, u.rdt, u.gdept, (u.nb_iter % jit) == 0);
-            Ts = p.sst + wl.dT;
-            Ts = Ts + dT_cs;
-            qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+            // pass 0: cool skin, pass 1: warm layer (state committed whenever jit divides nb_iter, SURVEY 8a
+            // quirk 1); rolled so that UPDATE_QNSOL_TAU and q_sat exist once in the loop body
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                double Qns, Tau, Qlat;
+                update_qnsol_tau(u.zu, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.slp, p.rlw, Qns, Tau, Qlat);
+                if (pass == 0) {
+                    dT_cs = cool_skin_dT<true>(alpha, p.Qsw, Qns, us, Qlat);
+                    Ts = p.sst + dT_cs;
+                    Ts = Ts + wl.dT;
+                } else {
+                    wl_coare(wl, wc, p.Qsw, Qns, Tau, u.rdt, u.gdept, (u.nb_iter % jit) == 0);
+                    Ts = p.sst + wl.dT;
+                    Ts = Ts + dT_cs;
+                }
+                qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+            }
         }
         if (SKIN || !ZTEQ || !V36) {
             dt = floor_abs(t_zu - Ts, 1.E-09);
@@ -793,12 +882,22 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
     double dq = floor_abs(q_zu - qs_, 1.E-12);
 
     double r1oL = one_on_L(t_zu, q_zu, us, ts, qst);
-    double z0t = fmin(fmax(fabs(10. * abm::dexp(-fdiv(VKARMN, fdiv(0.00115, fdiv(VKARMN, u.log_10 - log_z0))))), 1.E-9), 1.);
-    double log_z0t = abm::dlog(z0t);
+    const double x0 = fdiv(VKARMN, fdiv(0.00115, fdiv(VKARMN, u.log_10 - log_z0)));
+    double z0t = fmin(fmax(10. * abm::dexp(-x0), 1.E-9), 1.);
+    double log_z0t = fmin(fmax(u.log_10 - x0, LOG_1EM9), 0.);
 
-    double Fm = u.log_zu - log_z0 - psi_m_ecmwf(u.zu * r1oL) + psi_m_ecmwf(z0 * r1oL);
-    double psi_h_u = psi_h_ecmwf(u.zu * r1oL);
-    double Fh = u.log_zu - log_z0t - psi_h_u + psi_h_ecmwf(z0t * r1oL);
+    double Fm, Fh, psi_h_u;
+    if (nonneg(r1oL)) {
+        const PsiMH pu = psi_mh_ecmwf_stable(u.zu * r1oL);
+        psi_h_u = pu.h;
+        Fm = u.log_zu - log_z0 - pu.m + psi_m_ecmwf_stable(z0 * r1oL);
+        Fh = u.log_zu - log_z0t - psi_h_u + psi_h_ecmwf_stable(z0t * r1oL);
+    } else {
+        const PsiMH pu = psi_mh_ecmwf_unstable(u.zu * r1oL);
+        psi_h_u = pu.h;
+        Fm = u.log_zu - log_z0 - pu.m + psi_m_ecmwf_unstable(z0 * r1oL);
+        Fh = u.log_zu - log_z0t - psi_h_u + psi_h_ecmwf_unstable(z0t * r1oL);
+    }
     double log_z0q = 0., psi_h_z0q = 0., dT_cs = 0.;
 
 #pragma unroll 1
@@ -806,11 +905,24 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
         const double Rib = ri_bulk(u.zu, Ts, t_zu, qs_, q_zu, Ub);
         r1oL = clip_abs(fdiv(Rib * Fm * Fm, Fh * u.zu), 200.);
 
-        const double psi_m_u = psi_m_ecmwf(u.zu * r1oL);
-        psi_h_u = psi_h_ecmwf(u.zu * r1oL);
-        const double psi_h_t = ZTEQ ? 0. : psi_h_ecmwf(u.zt * r1oL);
+        // one stability branch for the four psi of this half-step (all arguments share the sign of 1/L)
+        const bool stable = nonneg(r1oL);
+        double psi_m_u, psi_h_t = 0., psi_m_z0old;
+        if (stable) {
+            const PsiMH pu = psi_mh_ecmwf_stable(u.zu * r1oL);
+            psi_m_u = pu.m;
+            psi_h_u = pu.h;
+            if (!ZTEQ) psi_h_t = psi_h_ecmwf_stable(u.zt * r1oL);
+            psi_m_z0old = psi_m_ecmwf_stable(z0 * r1oL);
+        } else {
+            const PsiMH pu = psi_mh_ecmwf_unstable(u.zu * r1oL);
+            psi_m_u = pu.m;
+            psi_h_u = pu.h;
+            if (!ZTEQ) psi_h_t = psi_h_ecmwf_unstable(u.zt * r1oL);
+            psi_m_z0old = psi_m_ecmwf_unstable(z0 * r1oL);
+        }
 
-        Fm = u.log_zu - log_z0 - psi_m_u + psi_m_ecmwf(z0 * r1oL);
+        Fm = u.log_zu - log_z0 - psi_m_u + psi_m_z0old;
 
         us = fdiv(Ub * VKARMN, Fm);
         const double us2 = us * us;
@@ -819,12 +931,20 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
         z0t = fmin(fabs(alpha_H * tmp0), 0.001);
         const double z0q = fmin(fabs(alpha_Q * tmp0), 0.001);
         log_z0 = abm::dlog(z0);
-        log_z0t = abm::dlog(z0t);
-        log_z0q = abm::dlog(z0q);
+        const double log_t0 = abm::dlog(fabs(tmp0));          // LOG(alpha nu/u*) = LOG(alpha) + LOG(nu/u*)
+        log_z0t = fmin(LOG_0P40 + log_t0, LOG_1EM3);
+        log_z0q = fmin(LOG_0P62 + log_t0, LOG_1EM3);
 
-        const double psi_m_z0 = psi_m_ecmwf(z0 * r1oL);
-        const double psi_h_z0t = psi_h_ecmwf(z0t * r1oL);
-        psi_h_z0q = psi_h_ecmwf(z0q * r1oL);
+        double psi_m_z0, psi_h_z0t;
+        if (stable) {
+            psi_m_z0 = psi_m_ecmwf_stable(z0 * r1oL);
+            psi_h_z0t = psi_h_ecmwf_stable(z0t * r1oL);
+            psi_h_z0q = psi_h_ecmwf_stable(z0q * r1oL);
+        } else {
+            psi_m_z0 = psi_m_ecmwf_unstable(z0 * r1oL);
+            psi_h_z0t = psi_h_ecmwf_unstable(z0t * r1oL);
+            psi_h_z0q = psi_h_ecmwf_unstable(z0q * r1oL);
+        }
 
         const double cv = cbrt(fmax(-zi0 * r1oL * INV_VKARMN, 0.));
         tmp0 = Beta0 * Beta0 * us2 * (cv * cv);
@@ -853,17 +973,22 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
         Fh = u.log_zu - log_z0t - psi_h_u + psi_h_z0t;
 
         if (SKIN) {
-            double Qns, Tau, Qlat;
-            update_qnsol_tau(u.zu, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.slp, p.rlw, Qns, Tau, Qlat);
-            dT_cs = cool_skin_dT<false>(alpha, p.Qsw, Qns, us, 0.);
-            Ts = p.sst + dT_cs;
-            Ts = Ts + wl.dT;
-            qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
-            update_qnsol_tau(u.zu, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.slp, p.rlw, Qns, Tau, Qlat);
-            wl_ecmwf(wl, alpha, p.Qsw, Qns, us, u.rdt, u.gdept);     // every iteration
-            Ts = p.sst + wl.dT;
-            Ts = Ts + dT_cs;
-            qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+            // pass 0: cool skin, pass 1: warm layer -- advanced at every iteration
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                double Qns, Tau, Qlat;
+                update_qnsol_tau(u.zu, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.slp, p.rlw, Qns, Tau, Qlat);
+                if (pass == 0) {
+                    dT_cs = cool_skin_dT<false>(alpha, p.Qsw, Qns, us, 0.);
+                    Ts = p.sst + dT_cs;
+                    Ts = Ts + wl.dT;
+                } else {
+                    wl_ecmwf(wl, alpha, p.Qsw, Qns, us, u.rdt, u.gdept);
+                    Ts = p.sst + wl.dT;
+                    Ts = Ts + dT_cs;
+                }
+                qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+            }
         }
         dt = floor_abs(t_zu - Ts, 1.E-09);
         dq = floor_abs(q_zu - qs_, 1.E-12);
@@ -906,20 +1031,33 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p)
         const double zeta_u = u.zu * one_on_L(t_zu, q_zu, u_star, t_star, q_star);
         const double r = u_star * r_Ub;
         const double Cd = fmax(r * r, CX_MIN);
-        const double psi_m = psi_m_andreas(zeta_u);
-        const double z0 = fmin(u.zu * abm::dexp(-(VKARMN * rsqrt(Cd) + psi_m)), Z0_SEA_MAX);
+        const double zeta_t = fdiv(zeta_u, u.zu) * u.zt;
+        const bool adjust = !ZTEQ && jit > 1;
+        double psi_m, psi_h_u, psi_h_t = 0.;
+        if (nonneg(fmin(zeta_u, 15.))) {
+            psi_m = psi_m_andreas_stable(zeta_u);
+            psi_h_u = psi_h_andreas_stable(zeta_u);
+            if (adjust) psi_h_t = psi_h_andreas_stable(zeta_t);
+        } else {
+            const PsiMH r = psi_mh_andreas_unstable(zeta_u);
+            psi_m = r.m;
+            psi_h_u = r.h;
+            if (adjust) psi_h_t = psi_h_andreas_unstable(zeta_t);
+        }
+        // z0 = MIN(zu EXP(-(k/SQRT(Cd) + psi_m)), z0_sea_max), kept together with its logarithm
+        const double log_z0 = fmin(u.log_zu - (VKARMN * rsqrt(Cd) + psi_m), LOG_Z0_SEA_MAX);
+        const double z0 = abm::dexp(log_z0);
 
         const double Rer = fdiv(z0 * u_star, visc_air(t_zu));
-        const double z0t = z0tq_LKB(1, Rer, z0);
-        const double z0q = z0tq_LKB(2, Rer, z0);
+        const double log_Rer = abm::dlog(fmax(Rer, 1.E-300));
+        const double log_z0t = log_z0tq_LKB(1, Rer, log_Rer, log_z0);
+        const double log_z0q = log_z0tq_LKB(2, Rer, log_Rer, log_z0);
 
-        const double psi_h_u = psi_h_andreas(zeta_u);
-        t_star = fdiv((t_zu - p.sst) * VKARMN, u.log_zu - abm::dlog(z0t) - psi_h_u);
-        q_star = fdiv((q_zu - p.ssq) * VKARMN, u.log_zu - abm::dlog(z0q) - psi_h_u);
+        t_star = fdiv((t_zu - p.sst) * VKARMN, u.log_zu - log_z0t - psi_h_u);
+        q_star = fdiv((q_zu - p.ssq) * VKARMN, u.log_zu - log_z0q - psi_h_u);
 
-        if (!ZTEQ && jit > 1) {
-            const double zeta_t = fdiv(zeta_u, u.zu) * u.zt;
-            const double tmp = u.log_ztu + psi_h_u - psi_h_andreas(zeta_t);
+        if (adjust) {
+            const double tmp = u.log_ztu + psi_h_u - psi_h_t;
             t_zu = p.theta_zt - t_star * INV_VKARMN * tmp;
             q_zu = p.q_zt - q_star * INV_VKARMN * tmp;
             RiB = ri_bulk(u.zu, p.sst, t_zu, p.ssq, q_zu, Ub);

@@ -28,10 +28,83 @@ using namespace abd;
 #endif
 static constexpr int FLUX_BLOCK = AB_FLUX_BLOCK;
 
+// Cheap proxy of the sign of the air-sea virtual potential temperature difference, i.e. of the
+// stability class every psi_m/psi_h evaluation branches on.  Only used to GROUP points (performance);
+// the physics below never sees it.
+__device__ __forceinline__ bool stable_proxy(const FluxArgs &a, long long i)
+{
+    const double sst = __ldg(a.sst + i), ta = __ldg(a.t_zt + i) + RGAMMA_DRY * a.u.zt;
+    if (a.ihum != 0) return ta >= sst;
+    const double q = __ldg(a.hum_zt + i), p = __ldg(a.slp + i);
+    const double tc = sst - 273.15;
+    const double es = 611.2 * abm::dexp(17.67 * tc * abm::fast_rcp(tc + 243.5));     // Magnus
+    const double qs = 0.98 * 0.622 * es * abm::fast_rcp(p - 0.378 * es);
+    return ta * (1. + 0.608 * q) >= sst * (1. + 0.608 * qs);
+}
+
+// ---------------------------------------------------------------------------
+// classify_kernel: stability sort inside windows of SORT_WIN consecutive points.
+// The iteration branches on the stability class in every psi function (and the two sides differ a
+// lot in cost); where stability is not spatially coherent a warp would execute both sides (23/32
+// active lanes in the round-1 profile).  One block per window writes perm[] such that slots
+// [0,n_stable) of the window hold its stable points and the rest the unstable ones; flux_kernel
+// then runs 256 consecutive SLOTS per block, so all but one block per window are homogeneous --
+// and a homogeneous block retires as a whole (sorting inside a block left its fast warps idle
+// behind the slow ones and was slower).  Accesses stay inside the window's 16 KB of each field.
+// ---------------------------------------------------------------------------
+static constexpr int SORT_WIN = 2048;
+static constexpr int SORT_BLOCK = 256;
+static constexpr int SORT_ITEMS = SORT_WIN / SORT_BLOCK;
+
+__global__ void __launch_bounds__(SORT_BLOCK) classify_kernel(const FluxArgs a, unsigned short *perm)
+{
+    __shared__ unsigned short s_c0[SORT_ITEMS * SORT_BLOCK / 32], s_c1[SORT_ITEMS * SORT_BLOCK / 32];
+    const long long base = (long long)blockIdx.x * SORT_WIN;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int NW = SORT_BLOCK / 32;
+    int cls[SORT_ITEMS];
+    unsigned m0[SORT_ITEMS], m1[SORT_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        const long long i = base + k * SORT_BLOCK + tid;
+        cls[k] = 2;
+        if (i < a.n) cls[k] = stable_proxy(a, i) ? 0 : 1;
+        m0[k] = __ballot_sync(0xffffffffu, cls[k] == 0);
+        m1[k] = __ballot_sync(0xffffffffu, cls[k] == 1);
+        if (lane == 0) {
+            s_c0[k * NW + w] = (unsigned short)__popc(m0[k]);
+            s_c1[k * NW + w] = (unsigned short)__popc(m1[k]);
+        }
+    }
+    __syncthreads();
+    int tot0 = 0, tot1 = 0;
+    for (int g = 0; g < SORT_ITEMS * NW; ++g) {
+        tot0 += s_c0[g];
+        tot1 += s_c1[g];
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    int off0 = 0, off1 = 0, g = 0;
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        // counts of the groups (k', w') that precede (k, w)
+        for (; g < k * NW + w; ++g) {
+            off0 += s_c0[g];
+            off1 += s_c1[g];
+        }
+        const int item = k * SORT_BLOCK + tid;
+        int slot;
+        if (cls[k] == 0) slot = off0 + __popc(m0[k] & lt);
+        else if (cls[k] == 1) slot = tot0 + off1 + __popc(m1[k] & lt);
+        else slot = tot0 + tot1 + (item - (off0 + off1 + __popc((m0[k] | m1[k]) & lt)));
+        perm[base + slot] = (unsigned short)item;
+    }
+}
+
 template <int ALGO, bool SKIN, bool ZTEQ>
 __global__ void __launch_bounds__(FLUX_BLOCK, AB_MIN_BLOCKS) flux_kernel(const FluxArgs a)
 {
-    const long long i = (long long)blockIdx.x * FLUX_BLOCK + threadIdx.x;
+    long long i = (long long)blockIdx.x * FLUX_BLOCK + threadIdx.x;
+    if (a.perm) i = (i / SORT_WIN) * SORT_WIN + a.perm[i];   // slot -> point (perm is padded to whole windows)
     if (i >= a.n) return;
 
     // ---- coalesced loads of the 6 (8) input fields
@@ -56,12 +129,16 @@ __global__ void __launch_bounds__(FLUX_BLOCK, AB_MIN_BLOCKS) flux_kernel(const F
     p.Qsw = 0.;
     p.rlw = 0.;
     p.lon = 0.;
+    p.has_lon = false;
 
     WarmLayer wl = {0., 0., 0., 0.};
     if (SKIN) {
         p.Qsw = (1. - ROCE_ALB0) * __ldg(a.rad_sw + i);            // :135,:146,:161
         p.rlw = __ldg(a.rad_lw + i);
-        if (a.lon) p.lon = __ldg(a.lon + i);
+        if (a.lon) {
+            p.lon = __ldg(a.lon + i);
+            p.has_lon = true;
+        }
         if (ALGO == ECMWF) {
             wl.Hz = 3.;                                            // rd0, mod_skin_ecmwf.f90:57 (constant)
             wl.dT = a.first_step ? 0. : a.dT_wl[i];
@@ -112,7 +189,8 @@ template <int ALGO, bool SKIN, bool ZTEQ>
 static cudaError_t launch_one(const FluxArgs &a, cudaStream_t s)
 {
     if (a.n <= 0) return cudaSuccess;
-    const long long blocks = (a.n + FLUX_BLOCK - 1) / FLUX_BLOCK;
+    const long long span = a.perm ? (a.n + SORT_WIN - 1) / SORT_WIN * SORT_WIN : a.n;   // whole windows of slots
+    const long long blocks = (span + FLUX_BLOCK - 1) / FLUX_BLOCK;
     flux_kernel<ALGO, SKIN, ZTEQ><<<(unsigned)blocks, FLUX_BLOCK, 0, s>>>(a);
     return cudaGetLastError();
 }
@@ -136,6 +214,16 @@ cudaError_t launch_flux(int algo, bool skin, bool zteq, const FluxArgs &a, cudaS
 }
 
 int flux_block_size() { return FLUX_BLOCK; }
+
+int sort_window() { return SORT_WIN; }
+
+cudaError_t launch_classify(const FluxArgs &a, unsigned short *perm, cudaStream_t s)
+{
+    if (a.n <= 0) return cudaSuccess;
+    const long long nwin = (a.n + SORT_WIN - 1) / SORT_WIN;
+    classify_kernel<<<(unsigned)nwin, SORT_BLOCK, 0, s>>>(a, perm);
+    return cudaGetLastError();
+}
 
 template <int ALGO, bool SKIN>
 static cudaError_t attr_zt(bool zteq, cudaFuncAttributes *attr)

@@ -25,6 +25,9 @@ struct FluxArgs {
     // first linear index whose wind stress exceeds 10 N/m^2 (mod_phymbl.f90:1250-1253), else ~0ull
     unsigned long long *bad_index;
     long long index_offset;   // global index of point 0 (chunked / sharded launches)
+    // optional stability sort (classify_kernel): slot -> point inside windows of sort_window() points,
+    // padded to a whole number of windows; NULL: identity
+    const unsigned short *perm;
 };
 
 // number of doubles in the statistics vector (see include/aerobulk_gpu.h)
@@ -41,6 +44,9 @@ struct StatsArgs {
 cudaError_t launch_flux(int algo, bool skin, bool zt_eq_zu, const FluxArgs &a, cudaStream_t s);
 // block size / register info for reports
 int flux_block_size();
+int sort_window();
+// fills perm[] (ceil(n / sort_window()) * sort_window() entries) for the launch described by `a`
+cudaError_t launch_classify(const FluxArgs &a, unsigned short *perm, cudaStream_t s);
 cudaError_t launch_stats(const StatsArgs &a, int nblocks, cudaStream_t s);
 int stats_max_blocks();
 // DFMA-chain microbenchmark: returns FP64 FMA instructions per second, <0 on error

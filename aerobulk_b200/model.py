@@ -207,6 +207,7 @@ def set_rdt(v: float): lib().aerobulk_gpu_set_rdt(float(v))
 def set_gdept(v: float): lib().aerobulk_gpu_set_gdept(float(v))
 def set_nb_iter(v: int): lib().aerobulk_gpu_set_nb_iter(int(v))
 def set_verbose(on: bool): lib().aerobulk_gpu_set_verbose(int(bool(on)))
+def set_sort(mode: int): lib().aerobulk_gpu_set_sort(int(mode))
 def nb_iter() -> int: return lib().aerobulk_gpu_get_nb_iter()
 def use_skin() -> bool: return bool(lib().aerobulk_gpu_get_use_skin())
 def humidity_type() -> str: return lib().aerobulk_gpu_get_humidity_type().decode()

@@ -134,6 +134,9 @@ int aerobulk_gpu_get_device(void);
  * legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1), cudaStreamPerThread is (cudaStream_t)0x2. */
 int aerobulk_gpu_set_stream(void *cuda_stream);
 void aerobulk_gpu_set_error_mode(int return_codes); /* 0: fail-stop like the reference (default), 1: return codes */
+/* Grouping of points of equal stability class into the same thread blocks (performance only; results
+ * are bit-identical either way): 0 never, 1 (default) where it measured faster, 2 always. */
+void aerobulk_gpu_set_sort(int mode);
 void aerobulk_gpu_set_verbose(int on);           /* 1 (default): print the AeroBulk_init / _bye banners */
 const char *aerobulk_gpu_last_error(void);
 int aerobulk_gpu_last_error_code(void);

@@ -3,10 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from aerobulk_b200 import build as B
 VARIANTS = {
-    "mb4": ["AB_MIN_BLOCKS=4"],      # <= 128 regs
-    "mb5": ["AB_MIN_BLOCKS=5"],      # <= 102 regs
-    "mb8": ["AB_MIN_BLOCKS=8"],      # <= 64 regs
-    "b256mb3": ["AB_FLUX_BLOCK=256", "AB_MIN_BLOCKS=3"],
+    "nosort": ["AB_SORT=0"],
+    "mb4": ["AB_FLUX_BLOCK=256", "AB_MIN_BLOCKS=2"],   # <= 128 regs
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)

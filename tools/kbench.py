@@ -20,12 +20,17 @@ out = {k: torch.empty(n, dtype=torch.float64, device="cuda") for k in OUT}
 st = torch.cuda.Stream()
 torch.cuda.set_stream(st)
 ab.set_stream(st.cuda_stream)
+from aerobulk_b200 import model as abm
+abm.set_sort(int(os.environ.get('KBENCH_SORT', '1')))
 peak = ab.measure_fp64_peak()
 print(f"lib {os.environ.get('AEROBULK_GPU_LIB','default')}  DFMA peak {peak/1e12:.2f} T instr/s")
 res = []
 cases = [(a, False, None) for a in ("ncar", "andreas", "coare3p0", "coare3p6", "ecmwf")] + \
         [(a, True, r) for a in ("coare3p0", "coare3p6", "ecmwf") for r in ("night", "day")]
-if os.environ.get("KBENCH_QUICK"):
+if os.environ.get("KBENCH_ONE"):
+    a_, s_, r_ = os.environ["KBENCH_ONE"].split(",")
+    cases = [(a_, s_ == "1", r_ if r_ != "-" else None)]
+elif os.environ.get("KBENCH_QUICK"):
     cases = [("ncar", False, None), ("andreas", False, None), ("coare3p6", False, None), ("coare3p6", True, "night"), ("coare3p6", True, "day"), ("ecmwf", True, "day")]
 for algo, skin, rad in cases:
     ab.reset(); ab.set_stream(st.cuda_stream)
