@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <cstring>
 #define ABM_FN static inline
+#define ABM_BIG static inline
 #define ABM_TABLE static const
 namespace abm {
 static inline int hi_word(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
@@ -36,6 +37,13 @@ static inline double rcp_seed(double y) { return (double)(float)(1.0 / y); }   /
 #else
 #include <cuda_runtime.h>
 #define ABM_FN __device__ __forceinline__
+// -DABM_NOINLINE=1 keeps exp/log/atan out of line (one body per kernel): smaller instruction footprint
+// at the price of call overhead and less interleaving
+#if defined(ABM_NOINLINE) && ABM_NOINLINE
+#define ABM_BIG static __device__ __noinline__
+#else
+#define ABM_BIG __device__ __forceinline__
+#endif
 namespace abm {
 ABM_FN int hi_word(double x) { return __double2hiint(x); }
 ABM_FN int lo_word(double x) { return __double2loint(x); }
@@ -76,7 +84,7 @@ ABM_FN double exp_core(double r, int k)
     return make_double(hi_word(p) + (k << 20), lo_word(p));
 }
 
-ABM_FN double dexp(double x)
+ABM_BIG double dexp(double x)
 {
     const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to nearest integer
     const double t = fma(x, MATH_K[K_L2E], MAGIC);
@@ -88,7 +96,7 @@ ABM_FN double dexp(double x)
     return (x < -700.) ? 0. : v;
 }
 
-ABM_FN double dexp10(double x)
+ABM_BIG double dexp10(double x)
 {
     const double MAGIC = 6755399441055744.0;
     const double t = fma(x, MATH_K[K_L2T], MAGIC);
@@ -101,7 +109,7 @@ ABM_FN double dexp10(double x)
 }
 
 // log(x) = k ln2 + log(m), m in [sqrt(2)/2, sqrt(2)); log(m) = 2 atanh(s), s = (m-1)/(m+1)
-ABM_FN double dlog(double x)
+ABM_BIG double dlog(double x)
 {
     int hx = hi_word(x);
     int k = (hx >> 20) - 1023;
@@ -124,7 +132,7 @@ ABM_FN double dlog(double x)
 ABM_FN double dlog10(double x) { return dlog(x) * MATH_K[K_LOG10E]; }
 
 // atan: |x| <= tan(pi/8): poly; <= tan(3pi/8): pi/4 + atan((x-1)/(x+1)); else pi/2 - atan(1/x)
-ABM_FN double datan(double x)
+ABM_BIG double datan(double x)
 {
     const double ax = fabs(x);
     double num = ax, den = 1.0, bhi = 0., blo = 0.;

@@ -3,8 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from aerobulk_b200 import build as B
 VARIANTS = {
-    "nosort": ["AB_SORT=0"],
-    "mb4": ["AB_FLUX_BLOCK=256", "AB_MIN_BLOCKS=2"],   # <= 128 regs
+    "mathcall": ["ABM_NOINLINE=1"],
+    "mathcall_heavy": ["ABM_NOINLINE=1", "AB_NOINLINE=1"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
