@@ -408,7 +408,7 @@ ABD double psi_h_andreas_unstable(double zeta)
 }
 
 // ---------------------------------------------------------------------------
-// launch-uniform quantities computed once on the host (glibc, like the oracle)
+// launch-uniform quantities computed once on the host (glibc libm, as the reference build uses)
 // ---------------------------------------------------------------------------
 struct Uniform {
     double zt, zu;

@@ -1,0 +1,115 @@
+"""CPU-side checks of the drop-in boundary (no compute without a GPU):
+the C-ABI library loads, exports every symbol include/aerobulk_gpu.h declares, its pure-host entry
+points behave, compute entry points fail loudly without a device, and the C++ API links."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HDR = os.path.join(ROOT, "include", "aerobulk_gpu.h")
+
+
+@pytest.fixture(scope="module")
+def ab():
+    from aerobulk_b200 import build
+    build.build()
+    import aerobulk_b200 as ab
+    ab.lib()
+    return ab
+
+
+def _declared_symbols():
+    txt = open(HDR).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(aerobulk_(?:gpu_\w+|cxx_skin|cxx_no_skin))\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(ab):
+    L = ab.lib()
+    syms = _declared_symbols()
+    assert "aerobulk_cxx_skin" in syms and "aerobulk_cxx_no_skin" in syms and len(syms) >= 25
+    for s in syms:
+        assert hasattr(L, s), f"{s} is declared in include/aerobulk_gpu.h but not exported"
+
+
+def test_no_unexpected_exports(ab):
+    """Only the declared C ABI and the aerobulk:: C++ API are exported (-fvisibility=hidden)."""
+    from aerobulk_b200.model import _SO
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _SO], text=True)
+    names = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    declared = set(_declared_symbols())
+    for n in names:
+        assert n in declared or n.startswith("_ZN8aerobulk"), n
+
+
+def test_pure_host_entry_points(ab):
+    L = ab.lib()
+    assert ab.work_per_point("ncar", False, 5) == 1947 + 5 * 595
+    assert ab.work_per_point("coare3p6", True, 5) == 4698 + 5 * 4733
+    assert ab.bytes_per_point("ncar", False) == 88 and ab.bytes_per_point("coare3p0", True) == 176
+    assert ab.bytes_per_point("ecmwf", True) == 128 and ab.bytes_per_point("andreas", True) == 88
+    ab.reset()
+    assert ab.nb_iter() == 5 and not ab.use_skin() and ab.humidity_type() == "sh"
+    ab.set_nb_iter(7)
+    assert ab.nb_iter() == 7
+    ab.reset()
+    assert ab.nb_iter() == 5
+    ops = [L.aerobulk_gpu_stats_reduce_op(i) for i in range(64)]
+    assert ops[:2] == [0, 0] and ops[2:7] == [0, 1, 2, 1, 2] and ops[47:] == [0] * 17
+
+
+@pytest.mark.skipif("torch" in sys.modules and __import__("torch").cuda.is_available(), reason="needs a box WITHOUT a GPU")
+def test_compute_fails_loudly_without_device(ab):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    x = np.full(4, 290.0)
+    with pytest.raises(ab.AerobulkError) as e:
+        ab.aerobulk_model(1, 1, "ncar", 2.0, 10.0, x, x, x * 0 + 0.01, x * 0 + 5, x * 0, x * 0 + 101000.0)
+    assert e.value.code == 100 and "no CPU fallback" in e.value.message
+    # argument errors are detected before any device work
+    with pytest.raises(ab.AerobulkError) as e:
+        ab.aerobulk_model(0, 1, "ncar", 2.0, 10.0, x, x, x, x, x, x)
+    assert e.value.code == 1
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under aerobulk_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "aerobulk_b200")
+    for base, _, files in os.walk(pkg):
+        if os.path.basename(base) == "build":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", ".f90")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                assert "oracle" not in txt.lower(), (base, f)
+
+
+def test_cpp_api_links_and_reports(ab, tmp_path):
+    """The C++ API (include/aerobulk.hpp) compiles and links against libaerobulk_gpu.so like the
+    reference's `make cpp` target (Makefile:120-122) links -laerobulk_cxx -laerobulk."""
+    from aerobulk_b200.model import _SO
+    exe = str(tmp_path / "example_call_aerobulk_cxx.x")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "example_call_aerobulk.cpp"),
+                           "-o", exe, "-L", os.path.dirname(_SO), "-laerobulk_gpu",
+                           "-Wl,-rpath," + os.path.dirname(_SO)])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except ImportError:
+        has_gpu = False
+    if has_gpu:
+        assert r.returncode == 0 and r.stdout.count("RESULT") == 5, r.stdout + r.stderr
+    else:
+        # fail-stop like the reference's ctl_stop: message on stdout, process ends (exit status 1)
+        assert r.returncode == 1 and "E R R O R" in r.stdout and "no CUDA device" in r.stdout, r.stdout + r.stderr

@@ -177,3 +177,87 @@ def test_full_size_properties_4320x2160(ab, algo, skin):
     r = ab.aerobulk_model(1, 1, algo, 2.0, 10.0, *_ins(rot), **kw)
     assert np.array_equal(r["QL"], big["QL"]) and np.array_equal(r["QH"], big["QH"]) and np.array_equal(r["Evap"], big["Evap"])
     assert np.array_equal(r["Tau_x"], -big["Tau_y"]) and np.array_equal(r["Tau_y"], big["Tau_x"])
+
+
+def test_cpp_example_matches_oracle(ab, tmp_path):
+    """tests/cpp/example_call_aerobulk.cpp (the reference's C++ example, same inputs: U=(4,9), 8 iterations)
+    built against include/aerobulk.hpp + libaerobulk_gpu.so, compared with the CPU oracle."""
+    import os, subprocess
+    from aerobulk_b200.model import _SO
+    from oracle.oracle import OracleSession
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "example_call_aerobulk_cxx.x")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-O1", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "example_call_aerobulk.cpp"), "-o", exe,
+                           "-L", os.path.dirname(_SO), "-laerobulk_gpu", "-Wl,-rpath," + os.path.dirname(_SO)])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = {l.split()[1]: np.array(l.split()[2:], dtype=float) for l in r.stdout.splitlines() if l.startswith("RESULT")}
+    assert set(rows) == {"coare3p0", "coare3p6", "ecmwf", "ncar", "andreas"}
+    rt0 = 273.15
+    arr = lambda *v: np.array(v, dtype=np.float64)
+    ins = [arr(22 + rt0, 22 + rt0), arr(20 + rt0, 25 + rt0), arr(.012, .012), arr(4., 4.), arr(9., 9.), arr(101000., 101000.)]
+    for algo, got in rows.items():
+        kw = dict(Niter=8)
+        if algo in ("coare3p0", "coare3p6", "ecmwf"):
+            kw.update(l_use_skin=True, rad_sw=arr(0., 0.), rad_lw=arr(350., 350.))
+        ref = OracleSession().model(1, 1, algo, 2.0, 10.0, *ins, **kw)
+        want = np.concatenate([ref["QH"], ref["QL"], ref["Evap"], ref["Tau_x"], ref["Tau_y"], ref.get("T_s", ins[0])])
+        scale = np.repeat([10.0, 10.0, 1e-5, 1e-2, 1e-2, 1.0], 2)
+        assert (np.abs(got - want) / (np.abs(want) + scale)).max() <= 1e-10, algo
+
+
+def test_sharded_init_on_device(ab):
+    """aerobulk_gpu_init_local_stats on two row blocks + init_from_stats == one-shot AEROBULK_INIT."""
+    import torch
+    from aerobulk_b200 import model as abm
+    Ni, Nj = 96, 64
+    keys = IN_KEYS
+    full = synth.fields(Ni, Nj, humidity="rh")
+    ops = abm.stats_reduce_ops()
+    parts = []
+    for j0, j1 in ((0, 20), (20, 64)):
+        b = synth.fields(Ni, Nj, j0=j0, j1=j1, humidity="rh")
+        dev = {k: torch.from_numpy(np.ravel(v, order="F").copy()).cuda() for k, v in b.items()}
+        parts.append(abm.init_local_stats(*[dev[k] for k in keys], rad_lw=dev["rad_lw"]))
+    g = np.where(ops == 0, parts[0] + parts[1], np.where(ops == 1, np.minimum(parts[0], parts[1]), np.maximum(parts[0], parts[1])))
+    dev = {k: torch.from_numpy(np.ravel(v, order="F").copy()).cuda() for k, v in full.items()}
+    one = abm.init_local_stats(*[dev[k] for k in keys], rad_lw=dev["rad_lw"])
+    assert g[0] == one[0] == Ni * Nj and g[1] == one[1]
+    for k in range(9):
+        bse = 2 + 5 * k
+        assert g[bse] == pytest.approx(one[bse], rel=1e-13)
+        assert np.array_equal(g[bse + 1:bse + 5], one[bse + 1:bse + 5])
+        assert one[bse + 3] == np.ravel([full["sst"], full["t_zt"], full["slp"], full["U_zu"], full["V_zu"],
+                                         np.hypot(full["U_zu"], full["V_zu"]), full["hum_zt"], full["rad_lw"], full["rad_lw"]][k]).min() \
+            or k == 5
+    ab.reset()
+    abm.init_from_stats(2, "ecmwf", True, True, g)
+    assert ab.humidity_type() == "rh" and ab.use_skin()
+    # the following jt==1 call skips its local AEROBULK_INIT and computes with the global decisions
+    b = synth.fields(Ni, Nj, j0=0, j1=20, humidity="rh")
+    o = ab.aerobulk_model(1, 2, "ecmwf", 2.0, 10.0, *[b[k] for k in keys], l_use_skin=True, rad_sw=b["rad_sw"], rad_lw=b["rad_lw"])
+    ab.reset()
+    ref = ab.aerobulk_model(1, 2, "ecmwf", 2.0, 10.0, *[full[k] for k in keys], l_use_skin=True, rad_sw=full["rad_sw"], rad_lw=full["rad_lw"])
+    for k in o:
+        assert np.array_equal(o[k], ref[k][:, 0:20]), k
+    ab.reset()
+
+
+def test_deferred_wind_stress_error_on_device_api(ab):
+    """Device-resident calls are asynchronous for jt>1: tau > 10 N/m2 surfaces at synchronize()."""
+    import torch
+    Ni, Nj = 64, 16
+    f = synth.fields(Ni, Nj)
+    dev = {k: torch.from_numpy(np.ravel(v, order="F").copy()).cuda() for k, v in f.items()}
+    out = {k: torch.empty(Ni * Nj, dtype=torch.float64, device="cuda") for k in ("QL", "QH", "Tau_x", "Tau_y", "Evap")}
+    ab.reset()
+    ins = [dev[k] for k in IN_KEYS]
+    ab.aerobulk_model_device(1, 3, "coare3p6", 2.0, 10.0, *ins, out=out, shape=(Ni, Nj))
+    storm = dev["U_zu"] * 0 + 48.0
+    ins2 = [dev["sst"], dev["t_zt"], dev["hum_zt"], storm, dev["V_zu"] * 0, dev["slp"]]
+    ab.aerobulk_model_device(2, 3, "coare3p6", 2.0, 10.0, *ins2, out=out, shape=(Ni, Nj))
+    with pytest.raises(ab.AerobulkError) as e:
+        ab.synchronize()
+    assert e.value.code == 8
+    ab.reset()
