@@ -185,31 +185,46 @@ struct Flux {
     double tau, qsen, qlat, evap;
 };
 
-// BULK_FORMULA_SCLR, :1149-1203 (over water)
-ABD Flux bulk_formula(double zu, double Ts, double qs, double tha, double qa, double Cd, double Ch, double Ce,
-                      double wnd, double Ub, double slp)
+// Air column at zu, the part of BULK_FORMULA_SCLR (:1149-1203) that only depends on (theta_zu, q_zu, slp):
+// density by the 2-pass estimate of :1182-1186 (MAX(rho,1) as used in zUrho) and cp of moist air.
+// Computed once per iteration and shared by the two UPDATE_QNSOL_TAU calls and the final flux assembly.
+struct AirZu {
+    double rho1, cp;
+};
+ABD AirZu air_at_zu(double zu, double tha, double qa, double slp)
 {
     const double ta = tha - RGAMMA_DRY * zu;
-    double rho = rho_air(ta, qa, slp);
-    rho = rho_air(ta, qa, slp - rho * GRAV * zu);
-    const double Urho = Ub * fmax(rho, 1.);
+    const double r = abm::fast_rcp(R_DRY * ta * (1. + RCTV0 * qa));     // rho_air = MAX(p / (R T (1 + rctv0 q)), 0.8)
+    double rho = fmax(slp * r, 0.8);
+    rho = fmax((slp - rho * GRAV * zu) * r, 0.8);
+    AirZu a;
+    a.rho1 = fmax(rho, 1.);
+    a.cp = cp_air(qa);
+    return a;
+}
+
+// BULK_FORMULA_SCLR, :1149-1203 (over water)
+ABD Flux bulk_formula(const AirZu &air, double Ts, double qs, double tha, double qa, double Cd, double Ch, double Ce,
+                      double wnd, double Ub)
+{
+    const double Urho = Ub * air.rho1;
     Flux f;
     f.tau = Urho * Cd * wnd;
     f.evap = Urho * Ce * (qa - qs);
-    f.qsen = Urho * Ch * (tha - Ts) * cp_air(qa);
+    f.qsen = Urho * Ch * (tha - Ts) * air.cp;
     f.qlat = L_vap(Ts) * f.evap;
     return f;
 }
 
 // UPDATE_QNSOL_TAU_SCLR, :1059-1103 -> non-solar flux, stress and latent flux
-ABD_HEAVY void update_qnsol_tau(double zu, double Ts, double qs, double tha, double qa, double us, double ts,
-                          double qst, double wnd, double Ub, double slp, double rlw,
-                          double &Qns, double &Tau, double &Qlat)
+ABD_HEAVY void update_qnsol_tau(const AirZu &air, double Ts, double qs, double tha, double qa, double us, double ts,
+                                double qst, double wnd, double Ub, double rlw,
+                                double &Qns, double &Tau, double &Qlat)
 {
     const double dt = floor_abs(tha - Ts, 1.E-09);
     const double dq = floor_abs(qa - qs, 1.E-12);
     const double z0 = fdiv(us, Ub);
-    const Flux f = bulk_formula(zu, Ts, qs, tha, qa, z0 * z0, fdiv(z0 * ts, dt), fdiv(z0 * qst, dq), wnd, Ub, slp);
+    const Flux f = bulk_formula(air, Ts, qs, tha, qa, z0 * z0, fdiv(z0 * ts, dt), fdiv(z0 * qst, dq), wnd, Ub);
     Qns = f.qlat + f.qsen + qlw_net(rlw, Ts);
     Tau = f.tau;
     Qlat = f.qlat;
@@ -565,7 +580,11 @@ ABD WlCoareCtx wl_coare_ctx(double alpha, bool dawn)
 }
 ABD double wl_coare_absorption(double H)   // solar absorption profile, :167-168 / :205-206
 {
-    return 1. - fdiv(0.28 * 0.014 * (1. - abm::dexp(-H * (1. / 0.014))) + 0.27 * 0.357 * (1. - abm::dexp(-H * (1. / 0.357)))
+    // 1 - EXP(-x) is exactly 1 in FP64 once EXP(-x) < 2**-54, i.e. x > 37.43: the two short-wave bands
+    // are only evaluated for shallow layers (H <= 0.53 m, H <= 13.4 m) -- bit-identical, fewer exps
+    const double e1 = (H > 0.53) ? 0. : abm::dexp(-H * (1. / 0.014));
+    const double e2 = (H > 13.4) ? 0. : abm::dexp(-H * (1. / 0.357));
+    return 1. - fdiv(0.28 * 0.014 * (1. - e1) + 0.27 * 0.357 * (1. - e2)
                      + 0.45 * 12.82 * (1 - abm::dexp(-H * (1. / 12.82))), H);
 }
 // WL_COARE, src/mod_skin_coare.f90:97-250; `commit` is (iwait == 0)
@@ -592,7 +611,7 @@ ABD void wl_coare(WarmLayer &w, const WlCoareCtx &c, double Qsw, double Qnsol, d
         tac = w.Tac + fmax(.002, Tau) * rdt;
 #pragma unroll 1
         for (int jl = 0; jl < 5; ++jl) {
-            Qabs = wl_coare_absorption(H) * Qsw + Qnsol;
+            if (jl > 0) Qabs = wl_coare_absorption(H) * Qsw + Qnsol;   // jl == 0: H unchanged since the test above
             qac = w.Qac + Qabs * rdt;
             if (qac <= 0.) break;
             H = fmax(fmin(Hwl_max, c.cd1 * tac * rsqrt(qac)), 0.1);
@@ -626,16 +645,27 @@ ABD double phi_takaya(double z)
     return rsqrt(1. - 16. * (-fabs(z)));
 }
 // WL_ECMWF, src/mod_skin_ecmwf.f90:113-230 -- advances dT_wl by rdt at EVERY call
-ABD void wl_ecmwf(WarmLayer &w, double alpha, double Qsw, double Qnsol, double us, double rdt, double gdept)
+// quantities of WL_ECMWF that only depend on the (constant) layer depth: hoisted out of the bulk iteration
+struct WlEcmwfCtx {
+    double fr, tcorr, r_tcorr;
+};
+ABD WlEcmwfCtx wl_ecmwf_ctx(double H, double gdept)
+{
+    WlEcmwfCtx c;
+    c.tcorr = signbit(gdept - H) ? gdept / H : 1.;
+    c.r_tcorr = 1. / c.tcorr;
+    c.fr = 1. - 0.28 * abm::dexp(-71.5 * H) - 0.27 * abm::dexp(-2.8 * H) - 0.45 * abm::dexp(-0.07 * H);   // Eq. 8.157
+    return c;
+}
+ABD void wl_ecmwf(WarmLayer &w, const WlEcmwfCtx &c, double alpha, double Qsw, double Qnsol, double us, double rdt)
 {
     const double rNuwl0 = 0.5;
     const double RhoCp_w = RHO0_W * RCP0_W;
     const double H = w.Hz;
-    const double tcorr = signbit(gdept - H) ? fdiv(gdept, H) : 1.;
-    const double dT_b = fmax(fdiv(w.dT, tcorr), 0.);
+    const double tcorr = c.tcorr;
+    const double dT_b = fmax(w.dT * c.r_tcorr, 0.);
 
-    const double fr = 1. - 0.28 * abm::dexp(-71.5 * H) - 0.27 * abm::dexp(-2.8 * H) - 0.45 * abm::dexp(-0.07 * H);
-    const double Qabs = fr * Qsw + Qnsol;
+    const double Qabs = c.fr * Qsw + Qnsol;
 
     const double usw = fmax(us, 1.E-4) * SQ_RADRW;
     const double usw2 = usw * usw;
@@ -826,10 +856,11 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
         if (SKIN) {
             // pass 0: cool skin, pass 1: warm layer (state committed whenever jit divides nb_iter, SURVEY 8a
             // quirk 1); rolled so that UPDATE_QNSOL_TAU and q_sat exist once in the loop body
+            const AirZu air = air_at_zu(u.zu, t_zu, q_zu, p.slp);
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 double Qns, Tau, Qlat;
-                update_qnsol_tau(u.zu, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.slp, p.rlw, Qns, Tau, Qlat);
+                update_qnsol_tau(air, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.rlw, Qns, Tau, Qlat);
                 if (pass == 0) {
                     dT_cs = cool_skin_dT<true>(alpha, p.Qsw, Qns, us, Qlat);
                     Ts = p.sst + dT_cs;
@@ -866,10 +897,12 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
 
     double Ts = p.sst, qs_ = p.ssq;
     double alpha = 0.;
+    WlEcmwfCtx wec = {};
     if (SKIN) {
         Ts = Ts - 0.25;
         qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
         alpha = alpha_sw(p.sst);
+        wec = wl_ecmwf_ctx(wl.Hz, u.gdept);
     }
 
     const Guess g = first_guess_coare<ZTEQ>(u, Ts, p.theta_zt, qs_, p.q_zt, p.wnd, charn0);
@@ -974,16 +1007,17 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
 
         if (SKIN) {
             // pass 0: cool skin, pass 1: warm layer -- advanced at every iteration
+            const AirZu air = air_at_zu(u.zu, t_zu, q_zu, p.slp);
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 double Qns, Tau, Qlat;
-                update_qnsol_tau(u.zu, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.slp, p.rlw, Qns, Tau, Qlat);
+                update_qnsol_tau(air, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.rlw, Qns, Tau, Qlat);
                 if (pass == 0) {
                     dT_cs = cool_skin_dT<false>(alpha, p.Qsw, Qns, us, 0.);
                     Ts = p.sst + dT_cs;
                     Ts = Ts + wl.dT;
                 } else {
-                    wl_ecmwf(wl, alpha, p.Qsw, Qns, us, u.rdt, u.gdept);
+                    wl_ecmwf(wl, wec, alpha, p.Qsw, Qns, us, u.rdt);
                     Ts = p.sst + wl.dT;
                     Ts = Ts + dT_cs;
                 }

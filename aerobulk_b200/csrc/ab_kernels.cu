@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(FLUX_BLOCK, AB_MIN_BLOCKS) flux_kernel(const F
     }
 
     // ---- flux assembly (BULK_FORMULA, :184-185) and stress vector (:189-194)
-    const Flux f = bulk_formula(a.u.zu, c.Ts, c.qs, c.t_zu, c.q_zu, c.Cd, c.Ch, c.Ce, p.wnd, c.Ub, slp);
+    const Flux f = bulk_formula(air_at_zu(a.u.zu, c.t_zu, c.q_zu, slp), c.Ts, c.qs, c.t_zu, c.q_zu, c.Cd, c.Ch, c.Ce, p.wnd, c.Ub);
     if (f.tau > REF_TAU_MAX) atomicMin(a.bad_index, (unsigned long long)(a.index_offset + i));
 
     double tx = 0., ty = 0.;
