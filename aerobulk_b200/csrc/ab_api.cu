@@ -59,6 +59,9 @@ struct Session {
     // ---- staging for host-array calls
     long long cap = 0;
     double *d_in[8] = {}, *d_out[6] = {};
+    // ---- staging of aerobulk_gpu_turb host-array calls (one slab, grow-only)
+    double *d_turb = nullptr;
+    long long cap_turb = 0;
     // ---- stability-sort permutation (one uint16 per point, see classify_kernel)
     unsigned short *d_perm = nullptr;
     long long cap_perm = 0;
@@ -583,6 +586,121 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------
+// TURB_* 
+// ---------------------------------------------------------------------------
+int turb_impl(const char *calgo, int kt, double zt, double zu, int Ni, int Nj, double *T_s, const double *t_zt,
+              double *q_s, const double *q_zt, const double *U_zu, int l_use_cs, int l_use_wl, double *Cd, double *Ch,
+              double *Ce, double *t_zu, double *q_zu, double *Ubzu, const double *Qsw, const double *rad_lw,
+              const double *slp, int isecday_utc, const double *plong, const aerobulk_gpu_turb_optional *opt,
+              int on_device)
+{
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!calgo || !T_s || !t_zt || !q_s || !q_zt || !U_zu || !Cd || !Ch || !Ce || !t_zu || !q_zu || !Ubzu)
+        return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_turb: NULL mandatory argument");
+    const int ialgo = algo_id(calgo);
+    if (!ialgo) return fail(AEROBULK_GPU_ERR_ALGO, "aerobulk_gpu_turb: bulk algorithm %s is unknown!!!", calgo);
+    const bool skin_algo = (ialgo == abd::COARE3P0 || ialgo == abd::COARE3P6 || ialgo == abd::ECMWF);
+    if (!skin_algo && (l_use_cs || l_use_wl))
+        return fail(AEROBULK_GPU_ERR_SKIN_ALGO, "aerobulk_gpu_turb: TURB_%s has no cool-skin / warm-layer option", calgo);
+    const bool cs = l_use_cs != 0, wl = l_use_wl != 0;
+    // mod_blk_coare3p6.f90:263-269, mod_blk_ecmwf.f90:202-206
+    if (cs && !(Qsw && rad_lw && slp))
+        return fail(AEROBULK_GPU_ERR_SKIN_NORAD, "[turb_%s] => you need to provide Qsw, rad_lw & slp to use cool-skin param!", calgo);
+    if (wl && !(Qsw && rad_lw && slp && (ialgo == abd::ECMWF || plong)))
+        return fail(AEROBULK_GPU_ERR_SKIN_NORAD,
+                    "[turb_%s] => you need to provide Qsw, rad_lw, slp, isecday_utc & plong to use warm-layer param!", calgo);
+    int rc = ensure_device();
+    if (rc) return rc;
+    const long long n = (long long)Ni * Nj;
+    cudaStream_t cs_ = compute_stream();
+
+    // kt == nit000 -> *_INIT ; state shared with the aerobulk_model path, like the module arrays of the reference
+    if (wl && kt == 1) {
+        if (ialgo == abd::ECMWF) {
+            if (g.n_ecmwf) return fail(AEROBULK_GPU_ERR_STATE, " ECMWF_INIT => allocation of dT_wl & Hz_wl failed!");
+            rc = alloc_ecmwf_state(n);
+        } else {
+            if (g.n_coare) return fail(AEROBULK_GPU_ERR_STATE, " COARE_INIT => allocation of Tau_ac, Qnt_ac, dT_wl & Hz_wl failed!");
+            rc = alloc_coare_state(n);
+        }
+        if (rc) return rc;
+    }
+    if (wl) {
+        const long long have = (ialgo == abd::ECMWF) ? g.n_ecmwf : g.n_coare;
+        if (have != n || n == 0) return fail(AEROBULK_GPU_ERR_STATE, "warm-layer state missing or of another size at kt=%d", kt);
+    }
+
+    abk::TurbArgs a;
+    memset(&a, 0, sizeof(a));
+    a.u = make_uniform(zt, zu);
+    a.u.isd = isecday_utc;
+    a.u.dawn = abd::wl_coare_dawn(0., isecday_utc) ? 1 : 0;
+    a.n = n;
+    a.first_step = (kt == 1);
+    double *optp[10] = {nullptr};
+    if (opt) {
+        optp[0] = opt->CdN; optp[1] = opt->ChN; optp[2] = opt->CeN; optp[3] = opt->xz0; optp[4] = opt->xu_star;
+        optp[5] = opt->xL; optp[6] = opt->xUN10; optp[7] = opt->pdT_cs; optp[8] = opt->pdT_wl; optp[9] = opt->pHz_wl;
+    }
+    // host arrays: 5 in/out + 4 skin inputs + 6 outputs + 10 optionals staged in one slab
+    const double *hin[9] = {T_s, q_s, t_zt, q_zt, U_zu, Qsw, rad_lw, slp, plong};
+    double *hout[18] = {T_s, q_s, Cd, Ch, Ce, t_zu, q_zu, Ubzu, optp[0], optp[1], optp[2], optp[3], optp[4],
+                        optp[5], optp[6], optp[7], optp[8], optp[9]};
+    double *din[9], *dout[18];
+    if (on_device) {
+        for (int k = 0; k < 9; ++k) din[k] = const_cast<double *>(hin[k]);
+        for (int k = 0; k < 18; ++k) dout[k] = hout[k];
+    } else {
+        const long long need = n * 25;
+        if (need > g.cap_turb) {
+            if (g.d_turb) cudaFree(g.d_turb);
+            g.d_turb = nullptr;
+            g.cap_turb = 0;
+            if (need > 0) CUDA_TRY(cudaMalloc(&g.d_turb, sizeof(double) * (size_t)need));
+            g.cap_turb = need;
+        }
+        for (int k = 0; k < 9; ++k) {
+            din[k] = hin[k] ? g.d_turb + (long long)k * n : nullptr;
+            if (hin[k] && n > 0)
+                CUDA_TRY(cudaMemcpyAsync(din[k], hin[k], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs_));
+        }
+        dout[0] = din[0];
+        dout[1] = din[1];
+        for (int k = 2; k < 18; ++k) dout[k] = hout[k] ? g.d_turb + (long long)(7 + k) * n : nullptr;
+    }
+    a.T_s = dout[0]; a.q_s = dout[1];
+    a.t_zt = din[2]; a.q_zt = din[3]; a.U_zu = din[4];
+    a.Qsw = din[5]; a.rad_lw = din[6]; a.slp = din[7]; a.lon = din[8];
+    a.Cd = dout[2]; a.Ch = dout[3]; a.Ce = dout[4]; a.t_zu = dout[5]; a.q_zu = dout[6]; a.Ubzu = dout[7];
+    for (int k = 0; k < 10; ++k) a.opt[k] = dout[8 + k];
+    if (wl) {
+        if (ialgo == abd::ECMWF) {
+            a.dT_wl = g.e_dT_wl;
+        } else {
+            a.dT_wl = g.c_state[0]; a.Hz_wl = g.c_state[1]; a.Qnt_ac = g.c_state[2]; a.Tau_ac = g.c_state[3];
+        }
+    }
+    CUDA_TRY(abk::launch_turb(ialgo, cs, wl, fabs(zu - zt) < 0.01, a, cs_));
+    g.launches += 1;
+    if (!on_device) {
+        const bool skin = cs || wl;
+        for (int k = skin ? 0 : 2; k < 18; ++k)
+            if (hout[k] && n > 0)
+                CUDA_TRY(cudaMemcpyAsync(hout[k], dout[k], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, cs_));
+        CUDA_TRY(cudaStreamSynchronize(cs_));
+    }
+    // kt == nitend -> *_EXIT
+    if (wl && kt == g.nitend) {
+        if (on_device) CUDA_TRY(cudaStreamSynchronize(cs_));
+        if (ialgo == abd::ECMWF) release_ecmwf_state();
+        else release_coare_state();
+    }
+    return 0;
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -646,6 +764,19 @@ void aerobulk_cxx_no_skin(const int *jt, const int *Nt, const char *calgo, const
     model_impl(false, *jt, *Nt, algo, *zt, *zu, *m, 1, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y, Evap,
                Niter, nullptr, nullptr, nullptr, nullptr);
 }
+
+int aerobulk_gpu_turb(const char *calgo, int kt, double zt, double zu, int Ni, int Nj, double *T_s, const double *t_zt,
+                      double *q_s, const double *q_zt, const double *U_zu, int l_use_cs, int l_use_wl, double *Cd,
+                      double *Ch, double *Ce, double *t_zu, double *q_zu, double *Ubzu, const double *Qsw,
+                      const double *rad_lw, const double *slp, int isecday_utc, const double *plong,
+                      const aerobulk_gpu_turb_optional *opt, int on_device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return turb_impl(calgo, kt, zt, zu, Ni, Nj, T_s, t_zt, q_s, q_zt, U_zu, l_use_cs, l_use_wl, Cd, Ch, Ce, t_zu, q_zu,
+                     Ubzu, Qsw, rad_lw, slp, isecday_utc, plong, opt, on_device);
+}
+
+void aerobulk_gpu_set_nitend(int nitend) { std::lock_guard<std::mutex> lk(g_mu); g.nitend = nitend; }
 
 int aerobulk_gpu_synchronize(void)
 {
@@ -741,6 +872,9 @@ void aerobulk_gpu_reset(void)
         if (g.d_perm) cudaFree(g.d_perm);
         g.d_perm = nullptr;
         g.cap_perm = 0;
+        if (g.d_turb) cudaFree(g.d_turb);
+        g.d_turb = nullptr;
+        g.cap_turb = 0;
         if (g.h_bad) *g.h_bad = ~0ull;
         if (g.d_bad) cudaMemset(g.d_bad, 0xFF, sizeof(unsigned long long));
     }

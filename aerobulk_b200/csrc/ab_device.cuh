@@ -700,6 +700,11 @@ struct PointIn {
 struct Coeffs {
     double Cd, Ch, Ce, t_zu, q_zu, Ub, Ts, qs;
 };
+// optional outputs of the TURB_* routines (CdN, ChN, CeN, xz0, xu_star, xL, xUN10, pdT_cs); dead code in
+// the aerobulk_model kernels, which do not read them
+struct Diag {
+    double CdN, ChN, CeN, z0, us, L, UN10, dT_cs;
+};
 
 // ---------------------------------------------------------------------------
 // NCAR (Large & Yeager 2004/2008), src/mod_blk_ncar.f90:57-271
@@ -714,7 +719,7 @@ ABD double cd_n10_ncar(double w)
 }
 
 template <bool ZTEQ>
-ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p)
+ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p, Diag &dg)
 {
     const double Ub = fmax(0.5, p.wnd);
     const bool stable0 = nonneg(virt_temp(p.theta_zt, p.q_zt) - virt_temp(p.sst, p.ssq));
@@ -726,16 +731,17 @@ ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p)
     double sqrt_Cd = sqrt_CdN;
     double t_zu = fmax(p.theta_zt, 180.);
     double q_zu = fmax(p.q_zt, 1.e-6);
+    double us = 0., r1oL = 0., Un10 = 0., ChN = 0., CeN = 0.;
 
 #pragma unroll 1
     for (int jit = 0; jit < u.nb_iter; ++jit) {
         const double dt = t_zu - p.sst;
         const double dq = q_zu - p.ssq;
-        const double us = sqrt_Cd * Ub;
+        us = sqrt_Cd * Ub;
         const double r_sqrt_Cd = abm::fast_rcp(sqrt_Cd);
         const double ts = Ch * r_sqrt_Cd * dt;
         const double qs = Ce * r_sqrt_Cd * dq;
-        const double r1oL = one_on_L(t_zu, q_zu, us, ts, qs);
+        r1oL = one_on_L(t_zu, q_zu, us, ts, qs);
         const double zeta_u = clip_abs(u.zu * r1oL, 10.);
         const double zeta_t = clip_abs(u.zt * r1oL, 10.);
         // psi_h(zeta_u) is used twice in the reference (:196,:217); one stability branch for all three
@@ -756,7 +762,7 @@ ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p)
         }
         // UN10_from_CD (mod_phymbl.f90:1532-1547) with z0_from_Cd(zu, Cd, psi) (:1335-1352); SQRT(Cd) is sqrt_Cd
         // z0 = zu EXP(-(k/SQRT(Cd) + psi_m)) only enters as LOG(10/z0) = k/SQRT(Cd) + psi_m - LOG(zu/10)
-        const double Un10 = fmax(0.25, sqrt_Cd * Ub * INV_VKARMN * (VKARMN * r_sqrt_Cd + psi_m - u.log_zu10));
+        Un10 = fmax(0.25, sqrt_Cd * Ub * INV_VKARMN * (VKARMN * r_sqrt_Cd + psi_m - u.log_zu10));
         CdN = cd_n10_ncar(Un10);
         sqrt_CdN = sqrt(CdN);
         double tmp = 1. + sqrt_CdN * INV_VKARMN * (u.log_zu10 - psi_m);
@@ -765,13 +771,17 @@ ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p)
         const double r_sqrt_CdN = abm::fast_rcp(sqrt_CdN);
         tmp = (u.log_zu10 - psi_h_u) * INV_VKARMN * r_sqrt_CdN;
         const double tmp2 = sqrt_Cd * r_sqrt_CdN;
-        const double ChN = 1.e-3 * sqrt_CdN * (nonneg(zeta_u) ? 18. : 32.7);
-        const double CeN = 1.e-3 * (34.6 * sqrt_CdN);
+        ChN = 1.e-3 * sqrt_CdN * (nonneg(zeta_u) ? 18. : 32.7);
+        CeN = 1.e-3 * (34.6 * sqrt_CdN);
         Ch = fmax(fdiv(ChN * tmp2, 1. + ChN * tmp), CX_MIN);
         Ce = fmax(fdiv(CeN * tmp2, 1. + CeN * tmp), CX_MIN);
     }
     Coeffs c;
     c.Cd = Cd; c.Ch = Ch; c.Ce = Ce; c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = p.sst; c.qs = p.ssq;
+    // optional outputs, src/mod_blk_ncar.f90:229-235
+    dg.CdN = CdN; dg.ChN = ChN; dg.CeN = CeN; dg.UN10 = Un10; dg.L = 1. / r1oL; dg.us = us;
+    dg.z0 = fmin(u.zu * abm::dexp(-VKARMN * rsqrt(CdN)), Z0_SEA_MAX);
+    dg.dT_cs = 0.;
     return c;
 }
 
@@ -787,19 +797,21 @@ ABD double charn_coare3p0(double w)
 }
 ABD double charn_coare3p6(double w) { return fmax(fmin(0.0017 * w - 0.005, 0.028), 0.); }
 
-template <bool V36, bool SKIN, bool ZTEQ>
-ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
+// CS / WL: l_use_cs / l_use_wl of the reference (aerobulk_model switches both on together)
+template <bool V36, bool CS, bool WL, bool ZTEQ>
+ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &dg)
 {
+    constexpr bool SKIN = CS || WL;
     const double zi0 = 600., Beta0 = V36 ? 1.2 : 1.25, zeta_abs_max = 50.;
 
     double Ts = p.sst, qs_ = p.ssq;
     double alpha = 0.;
     WlCoareCtx wc = {};
     if (SKIN) {
-        Ts = Ts - 0.25;
+        if (CS) Ts = Ts - 0.25;
         qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
         alpha = alpha_sw(p.sst);
-        wc = wl_coare_ctx(alpha, p.has_lon ? wl_coare_dawn(p.lon, u.isd) : (u.dawn != 0));
+        if (WL) wc = wl_coare_ctx(alpha, p.has_lon ? wl_coare_dawn(p.lon, u.isd) : (u.dawn != 0));
     }
 
     const Guess g = first_guess_coare<ZTEQ>(u, Ts, p.theta_zt, qs_, p.q_zt, p.wnd,
@@ -811,12 +823,12 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
 
     double dt = floor_abs(t_zu - Ts, 1.E-09);
     double dq = floor_abs(q_zu - qs_, 1.E-12);
-    double dT_cs = 0.;
+    double dT_cs = 0., r1oL = 0., z0 = g.z0, log_z0t = 0.;
 
 #pragma unroll 1
     for (int jit = 1; jit <= u.nb_iter; ++jit) {
         const double us2 = us * us;
-        const double r1oL = one_on_L(t_zu, q_zu, us, ts, qst);    // already clipped to +-200
+        r1oL = one_on_L(t_zu, q_zu, us, ts, qst);    // already clipped to +-200
 
         const double cv = cbrt(fmax(-zi0 * r1oL * INV_VKARMN, 0.));
         const double gust2 = Beta0 * Beta0 * us2 * (cv * cv);       // **(2./3.)
@@ -826,15 +838,15 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
 
         const double Un10 = us * INV_VKARMN * (u.log_10 - log_z0);
         const double r_us = abm::fast_rcp(us);
-        double z0 = (V36 ? charn_coare3p6(Un10) : charn_coare3p0(Un10)) * us2 * INV_GRAV + 0.11 * nu_a * r_us;
+        z0 = (V36 ? charn_coare3p6(Un10) : charn_coare3p0(Un10)) * us2 * INV_GRAV + 0.11 * nu_a * r_us;
         z0 = fmin(fmax(fabs(z0), 1.E-9), 1.);
         log_z0 = abm::dlog(z0);
 
         // z0t = MIN(1.6e-4, 5.8e-5 (nu/(z0 u*))**0.72) [3.6] / MIN(1.1e-4, 5.5e-5 (..)**0.6) [3.0], floored at
         // 1e-9, is only needed as LOG(z0t): monotonic, so MIN / MAX act on the logarithms (no pow)
         const double log_rr = abm::dlog(nu_a * r_us) - log_z0;
-        const double log_z0t = V36 ? fmax(fmin(LOG_1P6EM4, LOG_5P8EM5 + 0.72 * log_rr), LOG_1EM9)
-                                   : fmax(fmin(LOG_1P1EM4, LOG_5P5EM5 + 0.6 * log_rr), LOG_1EM9);
+        log_z0t = V36 ? fmax(fmin(LOG_1P6EM4, LOG_5P8EM5 + 0.72 * log_rr), LOG_1EM9)
+                      : fmax(fmin(LOG_1P1EM4, LOG_5P5EM5 + 0.6 * log_rr), LOG_1EM9);
 
         const double zeta_t = clip_abs(u.zt * r1oL, zeta_abs_max);
         double psi_m_u, psi_h_u, psi_h_t;
@@ -858,17 +870,17 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
             // quirk 1); rolled so that UPDATE_QNSOL_TAU and q_sat exist once in the loop body
             const AirZu air = air_at_zu(u.zu, t_zu, q_zu, p.slp);
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
+            for (int pass = CS ? 0 : 1; pass < (WL ? 2 : 1); ++pass) {
                 double Qns, Tau, Qlat;
                 update_qnsol_tau(air, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.rlw, Qns, Tau, Qlat);
-                if (pass == 0) {
+                if (CS && pass == 0) {
                     dT_cs = cool_skin_dT<true>(alpha, p.Qsw, Qns, us, Qlat);
                     Ts = p.sst + dT_cs;
-                    Ts = Ts + wl.dT;
+                    if (WL) Ts = Ts + wl.dT;
                 } else {
                     wl_coare(wl, wc, p.Qsw, Qns, Tau, u.rdt, u.gdept, (u.nb_iter % jit) == 0);
                     Ts = p.sst + wl.dT;
-                    Ts = Ts + dT_cs;
+                    if (CS) Ts = Ts + dT_cs;
                 }
                 qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
             }
@@ -884,25 +896,32 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl)
     c.Ch = fmax(fdiv(r * ts, dt), CX_MIN);
     c.Ce = fmax(fdiv(r * qst, dq), CX_MIN);
     c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = Ts; c.qs = qs_;
+    // optional outputs, src/mod_blk_coare3p6.f90:391-401
+    const double t0 = 1. / (u.log_zu - log_z0);
+    dg.CdN = fmax(VKARMN2 * t0 * t0, CX_MIN);
+    dg.ChN = dg.CeN = fmax(VKARMN2 * t0 / (u.log_zu - log_z0t), CX_MIN);
+    dg.z0 = z0; dg.us = us; dg.L = 1. / r1oL; dg.UN10 = us * INV_VKARMN * (u.log_10 - log_z0);
+    dg.dT_cs = dT_cs;
     return c;
 }
 
 // ---------------------------------------------------------------------------
 // ECMWF (IFS Cy40/45), src/mod_blk_ecmwf.f90:63-383
 // ---------------------------------------------------------------------------
-template <bool SKIN, bool ZTEQ>
-ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
+template <bool CS, bool WL, bool ZTEQ>
+ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &dg)
 {
+    constexpr bool SKIN = CS || WL;
     const double charn0 = 0.018, zi0 = 1000., Beta0 = 1., alpha_M = 0.11, alpha_H = 0.40, alpha_Q = 0.62;
 
     double Ts = p.sst, qs_ = p.ssq;
     double alpha = 0.;
     WlEcmwfCtx wec = {};
     if (SKIN) {
-        Ts = Ts - 0.25;
+        if (CS) Ts = Ts - 0.25;
         qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
         alpha = alpha_sw(p.sst);
-        wec = wl_ecmwf_ctx(wl.Hz, u.gdept);
+        if (WL) wec = wl_ecmwf_ctx(wl.Hz, u.gdept);
     }
 
     const Guess g = first_guess_coare<ZTEQ>(u, Ts, p.theta_zt, qs_, p.q_zt, p.wnd, charn0);
@@ -1009,17 +1028,17 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
             // pass 0: cool skin, pass 1: warm layer -- advanced at every iteration
             const AirZu air = air_at_zu(u.zu, t_zu, q_zu, p.slp);
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
+            for (int pass = CS ? 0 : 1; pass < (WL ? 2 : 1); ++pass) {
                 double Qns, Tau, Qlat;
                 update_qnsol_tau(air, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.rlw, Qns, Tau, Qlat);
-                if (pass == 0) {
+                if (CS && pass == 0) {
                     dT_cs = cool_skin_dT<false>(alpha, p.Qsw, Qns, us, 0.);
                     Ts = p.sst + dT_cs;
-                    Ts = Ts + wl.dT;
+                    if (WL) Ts = Ts + wl.dT;
                 } else {
                     wl_ecmwf(wl, wec, alpha, p.Qsw, Qns, us, u.rdt);
                     Ts = p.sst + wl.dT;
-                    Ts = Ts + dT_cs;
+                    if (CS) Ts = Ts + dT_cs;
                 }
                 qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
             }
@@ -1034,6 +1053,12 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
     c.Ch = fmax(fdiv(k2_o_Fm, Fh), CX_MIN);
     c.Ce = fmax(fdiv(k2_o_Fm, Fq), CX_MIN);
     c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = Ts; c.qs = qs_;
+    // optional outputs, src/mod_blk_ecmwf.f90:361-371
+    const double t0 = 1. / (u.log_zu - log_z0);
+    dg.CdN = fmax(VKARMN2 * t0 * t0, CX_MIN);
+    dg.ChN = dg.CeN = fmax(VKARMN2 * t0 / (u.log_zu - log_z0t), CX_MIN);
+    dg.z0 = z0; dg.us = us; dg.L = 1. / r1oL; dg.UN10 = us * INV_VKARMN * (u.log_10 - log_z0);
+    dg.dT_cs = dT_cs;
     return c;
 }
 
@@ -1041,7 +1066,7 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl)
 // ANDREAS (Andreas et al. 2015), src/mod_blk_andreas.f90:66-304
 // ---------------------------------------------------------------------------
 template <bool ZTEQ>
-ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p)
+ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p, Diag &dg)
 {
     const double rRi_max = 0.15, rCs_min = 0.35E-3;
     const double Ub = fmax(0.25, p.wnd);
@@ -1052,7 +1077,7 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p)
     double t_star = 1.1E-3 / sq0 * (t_zu - p.sst);
     double q_star = 1.1E-3 / sq0 * (q_zu - p.ssq);
     double RiB = ri_bulk(u.zu, p.sst, t_zu, p.ssq, q_zu, Ub);
-    double u_star = 0.;
+    double u_star = 0., zeta_u = 0., z0 = 0., psi_m = 0.;
 
 #pragma unroll 1
     for (int jit = 1; jit <= u.nb_iter; ++jit) {
@@ -1062,12 +1087,12 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p)
         } else {
             u_star = sqrt(CX_MIN) * Ub;
         }
-        const double zeta_u = u.zu * one_on_L(t_zu, q_zu, u_star, t_star, q_star);
+        zeta_u = u.zu * one_on_L(t_zu, q_zu, u_star, t_star, q_star);
         const double r = u_star * r_Ub;
         const double Cd = fmax(r * r, CX_MIN);
         const double zeta_t = fdiv(zeta_u, u.zu) * u.zt;
         const bool adjust = !ZTEQ && jit > 1;
-        double psi_m, psi_h_u, psi_h_t = 0.;
+        double psi_h_u, psi_h_t = 0.;
         if (nonneg(fmin(zeta_u, 15.))) {
             psi_m = psi_m_andreas_stable(zeta_u);
             psi_h_u = psi_h_andreas_stable(zeta_u);
@@ -1080,7 +1105,7 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p)
         }
         // z0 = MIN(zu EXP(-(k/SQRT(Cd) + psi_m)), z0_sea_max), kept together with its logarithm
         const double log_z0 = fmin(u.log_zu - (VKARMN * rsqrt(Cd) + psi_m), LOG_Z0_SEA_MAX);
-        const double z0 = abm::dexp(log_z0);
+        z0 = abm::dexp(log_z0);
 
         const double Rer = fdiv(z0 * u_star, visc_air(t_zu));
         const double log_Rer = abm::dlog(fmax(Rer, 1.E-300));
@@ -1106,6 +1131,17 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p)
     c.Ch = fmax(fdiv(r * t_star, d1), rCs_min);
     c.Ce = fmax(fdiv(r * q_star, d2), rCs_min);
     c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = p.sst; c.qs = p.ssq;
+    // optional outputs, src/mod_blk_andreas.f90:256-267
+    const double log_z0 = abm::dlog(z0);
+    const double t0 = 1. / (u.log_zu - log_z0);
+    dg.CdN = fmax(VKARMN2 * t0 * t0, CX_MIN);
+    const double Rer = z0 * u_star / visc_air(t_zu);
+    const double log_Rer = abm::dlog(fmax(Rer, 1.E-300));
+    dg.ChN = VKARMN2 * t0 / (u.log_zu - log_z0tq_LKB(1, Rer, log_Rer, log_z0));
+    dg.CeN = VKARMN2 * t0 / (u.log_zu - log_z0tq_LKB(2, Rer, log_Rer, log_z0));
+    dg.z0 = z0; dg.us = u_star; dg.L = u.zu / zeta_u;
+    dg.UN10 = Ub - u_star * INV_VKARMN * (u.log_zu10 - psi_m);
+    dg.dT_cs = 0.;
     return c;
 }
 

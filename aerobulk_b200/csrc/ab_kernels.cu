@@ -153,10 +153,11 @@ __global__ void __launch_bounds__(FLUX_BLOCK, AB_MIN_BLOCKS) flux_kernel(const F
     }
 
     Coeffs c;
-    if (ALGO == NCAR) c = solve_ncar<ZTEQ>(a.u, p);
-    else if (ALGO == ANDREAS) c = solve_andreas<ZTEQ>(a.u, p);
-    else if (ALGO == ECMWF) c = solve_ecmwf<SKIN, ZTEQ>(a.u, p, wl);
-    else c = solve_coare<ALGO == COARE3P6, SKIN, ZTEQ>(a.u, p, wl);
+    Diag dg;   // optional TURB_* outputs: unused here, eliminated by the compiler
+    if (ALGO == NCAR) c = solve_ncar<ZTEQ>(a.u, p, dg);
+    else if (ALGO == ANDREAS) c = solve_andreas<ZTEQ>(a.u, p, dg);
+    else if (ALGO == ECMWF) c = solve_ecmwf<SKIN, SKIN, ZTEQ>(a.u, p, wl, dg);
+    else c = solve_coare<ALGO == COARE3P6, SKIN, SKIN, ZTEQ>(a.u, p, wl, dg);
 
     if (SKIN) {
         a.dT_wl[i] = wl.dT;
@@ -209,6 +210,111 @@ cudaError_t launch_flux(int algo, bool skin, bool zteq, const FluxArgs &a, cudaS
     case ECMWF: return skin ? launch_zt<ECMWF, true>(zteq, a, s) : launch_zt<ECMWF, false>(zteq, a, s);
     case NCAR: return launch_zt<NCAR, false>(zteq, a, s);
     case ANDREAS: return launch_zt<ANDREAS, false>(zteq, a, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+
+// ---------------------------------------------------------------------------
+// turb_kernel<ALGO,CS,WL,ZTEQ>: the direct TURB_* entry on the same solvers
+// ---------------------------------------------------------------------------
+template <int ALGO, bool CS, bool WL, bool ZTEQ>
+__global__ void __launch_bounds__(FLUX_BLOCK, AB_MIN_BLOCKS) turb_kernel(const TurbArgs a)
+{
+    const long long i = (long long)blockIdx.x * FLUX_BLOCK + threadIdx.x;
+    if (i >= a.n) return;
+    constexpr bool SKIN = CS || WL;
+    PointIn p;
+    p.sst = a.T_s[i];
+    p.ssq = a.q_s[i];
+    p.theta_zt = __ldg(a.t_zt + i);
+    p.q_zt = __ldg(a.q_zt + i);
+    p.wnd = __ldg(a.U_zu + i);
+    p.slp = 0.;
+    p.Qsw = 0.;
+    p.rlw = 0.;
+    p.lon = 0.;
+    p.has_lon = false;
+    WarmLayer wl = {0., 0., 0., 0.};
+    if (SKIN) {
+        p.Qsw = __ldg(a.Qsw + i);
+        p.rlw = __ldg(a.rad_lw + i);
+        p.slp = __ldg(a.slp + i);
+        if (a.lon) {
+            p.lon = __ldg(a.lon + i);
+            p.has_lon = true;
+        }
+    }
+    if (WL) {
+        if (ALGO == ECMWF) {
+            wl.Hz = 3.;
+            wl.dT = a.first_step ? 0. : a.dT_wl[i];
+        } else if (a.first_step) {
+            wl.Hz = 20.;
+        } else {
+            wl.dT = a.dT_wl[i];
+            wl.Hz = a.Hz_wl[i];
+            wl.Qac = a.Qnt_ac[i];
+            wl.Tac = a.Tau_ac[i];
+        }
+    }
+    Coeffs c;
+    Diag dg;
+    if (ALGO == NCAR) c = solve_ncar<ZTEQ>(a.u, p, dg);
+    else if (ALGO == ANDREAS) c = solve_andreas<ZTEQ>(a.u, p, dg);
+    else if (ALGO == ECMWF) c = solve_ecmwf<CS, WL, ZTEQ>(a.u, p, wl, dg);
+    else c = solve_coare<ALGO == COARE3P6, CS, WL, ZTEQ>(a.u, p, wl, dg);
+    if (WL) {
+        a.dT_wl[i] = wl.dT;
+        if (ALGO != ECMWF) {
+            a.Hz_wl[i] = wl.Hz;
+            a.Qnt_ac[i] = wl.Qac;
+            a.Tau_ac[i] = wl.Tac;
+        }
+    }
+    if (SKIN) {
+        a.T_s[i] = c.Ts;
+        a.q_s[i] = c.qs;
+    }
+    a.Cd[i] = c.Cd; a.Ch[i] = c.Ch; a.Ce[i] = c.Ce;
+    a.t_zu[i] = c.t_zu; a.q_zu[i] = c.q_zu; a.Ubzu[i] = c.Ub;
+    if (a.opt[0]) a.opt[0][i] = dg.CdN;
+    if (a.opt[1]) a.opt[1][i] = dg.ChN;
+    if (a.opt[2]) a.opt[2][i] = dg.CeN;
+    if (a.opt[3]) a.opt[3][i] = dg.z0;
+    if (a.opt[4]) a.opt[4][i] = dg.us;
+    if (a.opt[5]) a.opt[5][i] = dg.L;
+    if (a.opt[6]) a.opt[6][i] = dg.UN10;
+    if (CS && a.opt[7]) a.opt[7][i] = dg.dT_cs;
+    if (WL && a.opt[8]) a.opt[8][i] = wl.dT;
+    if (WL && a.opt[9]) a.opt[9][i] = wl.Hz;
+}
+
+template <int ALGO, bool CS, bool WL>
+static cudaError_t turb_zt(bool zteq, const TurbArgs &a, cudaStream_t s)
+{
+    if (a.n <= 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((a.n + FLUX_BLOCK - 1) / FLUX_BLOCK);
+    if (zteq) turb_kernel<ALGO, CS, WL, true><<<blocks, FLUX_BLOCK, 0, s>>>(a);
+    else turb_kernel<ALGO, CS, WL, false><<<blocks, FLUX_BLOCK, 0, s>>>(a);
+    return cudaGetLastError();
+}
+template <int ALGO>
+static cudaError_t turb_skin(bool cs, bool wl, bool zteq, const TurbArgs &a, cudaStream_t s)
+{
+    if (cs && wl) return turb_zt<ALGO, true, true>(zteq, a, s);
+    if (cs) return turb_zt<ALGO, true, false>(zteq, a, s);
+    if (wl) return turb_zt<ALGO, false, true>(zteq, a, s);
+    return turb_zt<ALGO, false, false>(zteq, a, s);
+}
+cudaError_t launch_turb(int algo, bool cs, bool wl, bool zteq, const TurbArgs &a, cudaStream_t s)
+{
+    switch (algo) {
+    case COARE3P0: return turb_skin<COARE3P0>(cs, wl, zteq, a, s);
+    case COARE3P6: return turb_skin<COARE3P6>(cs, wl, zteq, a, s);
+    case ECMWF: return turb_skin<ECMWF>(cs, wl, zteq, a, s);
+    case NCAR: return turb_zt<NCAR, false, false>(zteq, a, s);
+    case ANDREAS: return turb_zt<ANDREAS, false, false>(zteq, a, s);
     default: return cudaErrorInvalidValue;
     }
 }

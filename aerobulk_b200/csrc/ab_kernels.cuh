@@ -30,6 +30,22 @@ struct FluxArgs {
     const unsigned short *perm;
 };
 
+// One launch = one TURB_* call of the reference (interfaces
+// src/mod_blk_coare3p6.f90:123-127, mod_blk_coare3p0.f90:54-59, mod_blk_ecmwf.f90:63-68, mod_blk_ncar.f90:57-59,
+// mod_blk_andreas.f90:66-68): inputs are already potential temperature, specific humidity and scalar wind.
+struct TurbArgs {
+    double *T_s, *q_s;                        // in: bulk SST and its ssq; out: skin values when cs/wl are used
+    const double *t_zt, *q_zt, *U_zu;
+    const double *Qsw, *rad_lw, *slp, *lon;   // skin only; Qsw is the NET solar flux; lon may be NULL (-> 0)
+    double *Cd, *Ch, *Ce, *t_zu, *q_zu, *Ubzu;
+    double *opt[10];                          // CdN ChN CeN xz0 xu_star xL xUN10 pdT_cs pdT_wl pHz_wl (NULL: not wanted)
+    double *dT_wl, *Hz_wl, *Qnt_ac, *Tau_ac;  // persistent warm-layer state
+    long long n;
+    abd::Uniform u;
+    int first_step;
+};
+cudaError_t launch_turb(int algo, bool cs, bool wl, bool zt_eq_zu, const TurbArgs &a, cudaStream_t s);
+
 // number of doubles in the statistics vector (see include/aerobulk_gpu.h)
 constexpr int NSTATS = 64;
 constexpr int NFIELDS = 9;

@@ -16,10 +16,18 @@ MODULE mod_aerobulk_gpu
    PRIVATE
 
    PUBLIC :: aerobulk_gpu_model, aerobulk_gpu_synchronize,                       &
+      &      aerobulk_gpu_turb, aerobulk_gpu_turb_optional, aerobulk_gpu_set_nitend, &
       &      aerobulk_gpu_set_rdt, aerobulk_gpu_set_gdept, aerobulk_gpu_set_nb_iter, &
       &      aerobulk_gpu_get_nb_iter, aerobulk_gpu_get_use_skin,                 &
       &      aerobulk_gpu_set_device, aerobulk_gpu_set_verbose, aerobulk_gpu_reset,  &
       &      aerobulk_gpu_get_state, aerobulk_gpu_set_state
+
+   !! optional outputs of the TURB_* routines (struct aerobulk_gpu_turb_optional); C_NULL_PTR = not wanted
+   TYPE, BIND(C) :: aerobulk_gpu_turb_optional
+      TYPE(c_ptr) :: CdN = C_NULL_PTR, ChN = C_NULL_PTR, CeN = C_NULL_PTR
+      TYPE(c_ptr) :: xz0 = C_NULL_PTR, xu_star = C_NULL_PTR, xL = C_NULL_PTR, xUN10 = C_NULL_PTR
+      TYPE(c_ptr) :: pdT_cs = C_NULL_PTR, pdT_wl = C_NULL_PTR, pHz_wl = C_NULL_PTR
+   END TYPE aerobulk_gpu_turb_optional
 
    INTERFACE
 
@@ -42,6 +50,32 @@ MODULE mod_aerobulk_gpu
          TYPE(c_ptr),            VALUE                     :: rad_sw, rad_lw, T_s    !: double*, NULL if absent
          INTEGER(c_int)                                    :: ierr
       END FUNCTION aerobulk_gpu_model
+
+      !! Direct TURB_COARE3P0 / TURB_COARE3P6 / TURB_ECMWF / TURB_NCAR / TURB_ANDREAS (selected by calgo);
+      !! pt_zt: POTENTIAL temperature, pQsw: NET solar flux, pT_s/pq_s in-out; popt: C_LOC of a
+      !! TYPE(aerobulk_gpu_turb_optional) or C_NULL_PTR; on_device = 0 for host arrays.
+      FUNCTION aerobulk_gpu_turb( calgo, kt, zt, zu, Ni, Nj, pT_s, pt_zt, pq_s, pq_zt, pU_zu, l_use_cs, l_use_wl, &
+         &                        pCd, pCh, pCe, pt_zu, pq_zu, pUbzu, pQsw, prad_lw, pslp, isecday_utc, plong,    &
+         &                        popt, on_device ) BIND(C, NAME='aerobulk_gpu_turb') RESULT(ierr)
+         IMPORT :: c_int, c_double, c_char, c_ptr
+         CHARACTER(KIND=c_char), DIMENSION(*), INTENT(in) :: calgo
+         INTEGER(c_int), VALUE :: kt
+         REAL(c_double), VALUE :: zt, zu
+         INTEGER(c_int), VALUE :: Ni, Nj
+         TYPE(c_ptr),    VALUE :: pT_s, pt_zt, pq_s, pq_zt, pU_zu
+         INTEGER(c_int), VALUE :: l_use_cs, l_use_wl
+         TYPE(c_ptr),    VALUE :: pCd, pCh, pCe, pt_zu, pq_zu, pUbzu
+         TYPE(c_ptr),    VALUE :: pQsw, prad_lw, pslp
+         INTEGER(c_int), VALUE :: isecday_utc
+         TYPE(c_ptr),    VALUE :: plong, popt
+         INTEGER(c_int), VALUE :: on_device
+         INTEGER(c_int)        :: ierr
+      END FUNCTION aerobulk_gpu_turb
+
+      SUBROUTINE aerobulk_gpu_set_nitend( knitend ) BIND(C, NAME='aerobulk_gpu_set_nitend')
+         IMPORT :: c_int
+         INTEGER(c_int), VALUE :: knitend
+      END SUBROUTINE aerobulk_gpu_set_nitend
 
       FUNCTION aerobulk_gpu_synchronize() BIND(C, NAME='aerobulk_gpu_synchronize') RESULT(ierr)
          IMPORT :: c_int

@@ -69,6 +69,11 @@ def lib():
     L.aerobulk_gpu_bytes_per_point.restype = C.c_double
     L.aerobulk_gpu_bytes_per_point.argtypes = [C.c_char_p, C.c_int]
     L.aerobulk_gpu_version.restype = C.c_char_p
+    L.aerobulk_gpu_turb.restype = C.c_int
+    L.aerobulk_gpu_turb.argtypes = ([C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int] + [C.c_void_p] * 5 +
+                                    [C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_void_p] * 3 + [C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_int])
+    L.aerobulk_gpu_set_nitend.argtypes = [C.c_int]
     L.aerobulk_cxx_skin.restype = None
     L.aerobulk_cxx_no_skin.restype = None
     # language bindings get return codes instead of the reference's fail-stop
@@ -230,3 +235,35 @@ def get_state(which: int, n: int) -> Optional[np.ndarray]:
 def set_state(which: int, values) -> bool:
     v = np.ascontiguousarray(values, dtype=np.float64).ravel()
     return lib().aerobulk_gpu_set_state(int(which), v.ctypes.data_as(_dp), v.size) == v.size
+
+
+TURB_OPTIONAL = ("CdN", "ChN", "CeN", "xz0", "xu_star", "xL", "xUN10", "pdT_cs", "pdT_wl", "pHz_wl")
+
+
+def set_nitend(v: int): lib().aerobulk_gpu_set_nitend(int(v))
+
+
+def turb(calgo: str, kt: int, zt: float, zu: float, T_s, t_zt, q_s, q_zt, U_zu, l_use_cs: bool = False,
+         l_use_wl: bool = False, Qsw=None, rad_lw=None, slp=None, isecday_utc: int = 0, plong=None, want=()) -> dict:
+    """Direct TURB_* call on HOST (numpy) arrays, mirroring e.g. TURB_COARE3P6 (src/mod_blk_coare3p6.f90:123-127).
+    Returns {"T_s","q_s","Cd","Ch","Ce","t_zu","q_zu","Ubzu"} plus the optional outputs named in `want`."""
+    L = lib()
+    Ts = np.array(T_s, dtype=np.float64, order="F", copy=True)
+    shape = Ts.shape
+    Ni, Nj = _shape2(shape)
+    qs = np.array(q_s, dtype=np.float64, order="F", copy=True)
+    ins = [_f64(a, shape) for a in (t_zt, q_zt, U_zu)]
+    opt_in = [None if a is None else _f64(a, shape) for a in (Qsw, rad_lw, slp, plong)]
+    outs = {k: np.empty(shape, dtype=np.float64, order="F") for k in ("Cd", "Ch", "Ce", "t_zu", "q_zu", "Ubzu")}
+    optv = {k: np.zeros(shape, dtype=np.float64, order="F") for k in want}
+    ptr = lambda a: None if a is None else a.ctypes.data
+    arr = (C.c_void_p * 10)(*[ptr(optv.get(k)) for k in TURB_OPTIONAL])
+    rc = L.aerobulk_gpu_turb(calgo.encode(), int(kt), float(zt), float(zu), Ni, Nj, ptr(Ts), ptr(ins[0]), ptr(qs),
+                             ptr(ins[1]), ptr(ins[2]), int(bool(l_use_cs)), int(bool(l_use_wl)),
+                             *[ptr(outs[k]) for k in ("Cd", "Ch", "Ce", "t_zu", "q_zu", "Ubzu")],
+                             ptr(opt_in[0]), ptr(opt_in[1]), ptr(opt_in[2]), int(isecday_utc), ptr(opt_in[3]),
+                             C.cast(arr, C.c_void_p), 0)
+    _check(rc)
+    outs.update(optv)
+    outs["T_s"], outs["q_s"] = Ts, qs
+    return outs

@@ -294,10 +294,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     bytes_pt = ab.bytes_per_point(ALGO, SKIN)
     work_pt = ab.work_per_point(ALGO, SKIN, NB_ITER)
     fp64_peak = ab.measure_fp64_peak() if rank == 0 else 0.0
-    traffic = None
+    traffic, fp64_inst = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj["flux_kernel<COARE3P6,skin,zt!=zu>@1440x720"]["traffic"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["flux_kernel<COARE3P6,skin,zt!=zu>@1440x720"]
+        traffic = tj["traffic"]
+        fp64_inst = tj.get("fp64_thread_inst_per_launch")
     except Exception:
         pass
     achieved_gbs = bytes_pt * n / (kern_ms * 1e-3) / 1e9
@@ -330,8 +331,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "roofline_fp64": {"bound": "fp64", "achieved": achieved_fp64 / 1e12, "peak": fp64_peak / 1e12,
                           "unit": "T FP64-pipe instr/s", "frac": (achieved_fp64 / fp64_peak) if fp64_peak > 0 else None,
                           "work_per_point": work_pt,
+                          "executed_frac": (fp64_inst / (kern_ms * 1e-3) / fp64_peak) if (fp64_inst and fp64_peak > 0) else None,
                           "note": "achieved = algorithmic FP64-pipe instruction equivalents of the REFERENCE arithmetic "
-                                  "(SURVEY 8d: fx + nb_iter*it) x points / kernel time; peak = DFMA chain measured live"},
+                                  "(SURVEY 8d: fx + nb_iter*it) x points / kernel time; peak = DFMA chain measured live; "
+                                  "frac > 1 because the kernel needs ~2.7x fewer FP64 instructions than that arithmetic "
+                                  "(own exp/log/atan, no pow, fast division: DESIGN.md 3.1); executed_frac = FP64-pipe "
+                                  "instructions actually executed per launch (ncu, profiles/traffic.json) / time / peak"},
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1)

@@ -96,6 +96,33 @@ int aerobulk_gpu_model_device(int jt, int Nt, const char *calgo, double zt, doub
                               const int *Niter, const int *l_use_skin,
                               const double *rad_sw, const double *rad_lw, double *T_s);
 
+/* ---- direct TURB_* entry (what GCMs such as NEMO's sbcblk and the reference's test programs call) ------ */
+
+/* Optional outputs of the TURB_* routines; any member may be NULL. */
+typedef struct aerobulk_gpu_turb_optional {
+    double *CdN, *ChN, *CeN;   /* neutral-stability transfer coefficients                      */
+    double *xz0, *xu_star, *xL, *xUN10; /* roughness length [m], u* [m/s], Obukhov length [m], UN10 [m/s] */
+    double *pdT_cs, *pdT_wl, *pHz_wl;   /* cool-skin / warm-layer increments [K], warm-layer depth [m]      */
+} aerobulk_gpu_turb_optional;
+
+/* Replaces TURB_COARE3P0 / TURB_COARE3P6 / TURB_ECMWF / TURB_NCAR / TURB_ANDREAS
+ * (src/mod_blk_coare3p0.f90:54-59, mod_blk_coare3p6.f90:123-127, mod_blk_ecmwf.f90:63-68,
+ * mod_blk_ncar.f90:57-59, mod_blk_andreas.f90:66-68), selected by calgo.
+ * t_zt is the POTENTIAL air temperature, q_zt specific humidity, U_zu the scalar wind, Qsw the NET solar flux.
+ * T_s / q_s: bulk SST and its saturation humidity in; skin values out when l_use_cs or l_use_wl.
+ * Qsw, rad_lw, slp are needed with l_use_cs or l_use_wl, plong with l_use_wl (COARE) -- NULL otherwise.
+ * kt is the time step (1: warm-layer state created; == nitend, see aerobulk_gpu_set_nitend: released);
+ * the number of iterations is the nb_iter global (aerobulk_gpu_set_nb_iter).
+ * on_device: 0 host arrays (blocking), 1 device pointers (asynchronous on the session stream). */
+int aerobulk_gpu_turb(const char *calgo, int kt, double zt, double zu, int Ni, int Nj,
+                      double *T_s, const double *t_zt, double *q_s, const double *q_zt, const double *U_zu,
+                      int l_use_cs, int l_use_wl,
+                      double *Cd, double *Ch, double *Ce, double *t_zu, double *q_zu, double *Ubzu,
+                      const double *Qsw, const double *rad_lw, const double *slp,
+                      int isecday_utc, const double *plong,
+                      const aerobulk_gpu_turb_optional *opt, int on_device);
+void aerobulk_gpu_set_nitend(int nitend);        /* mod_const.f90:22 (set by AEROBULK_INIT in the model path) */
+
 /* Waits for the session stream and reports a deferred error (wind stress too strong). */
 int aerobulk_gpu_synchronize(void);
 

@@ -1615,6 +1615,113 @@ int abo_model(abo_session *s, int jt, int Nt, const char *calgo, double zt, doub
     return rc;
 }
 
+
+/* ------------------------------------------------------------------ */
+/* Direct TURB_* call on arrays: what GCMs (NEMO sbcblk) and the reference's own   */
+/* test programs call -- real isecday_utc / plong, l_use_cs and l_use_wl independent, optional outputs.   */
+/* Interfaces: mod_blk_coare3p6.f90:123-127, mod_blk_coare3p0.f90:54-59, mod_blk_ecmwf.f90:63-68,          */
+/* mod_blk_ncar.f90:57-59, mod_blk_andreas.f90:66-68.  nitend is the mod_const global (abo_set_nitend).    */
+/* opt[10] = CdN ChN CeN xz0 xu_star xL xUN10 pdT_cs pdT_wl pHz_wl, each NULL when not wanted.              */
+/* ------------------------------------------------------------------ */
+void abo_set_nitend(abo_session *s, int nitend) { s->nitend = nitend; }
+
+int abo_turb(abo_session *s, const char *calgo, int kt, double zt, double zu, long n,
+             double *T_s, const double *t_zt, double *q_s, const double *q_zt, const double *U_zu,
+             int l_use_cs, int l_use_wl,
+             double *Cd, double *Ch, double *Ce, double *t_zu, double *q_zu, double *Ubzu,
+             const double *Qsw, const double *rad_lw, const double *slp, int isecday_utc, const double *plong,
+             double *const *opt)
+{
+    init_consts();
+    s->errmsg[0] = 0;
+    int ialgo = algo_id(calgo);
+    if (!ialgo) { snprintf(s->errmsg, sizeof(s->errmsg), "unknown algorithm %s", calgo); return ABO_ERR_ALGO; }
+    int skin_algo = (ialgo == ABO_COARE3P0 || ialgo == ABO_COARE3P6 || ialgo == ABO_ECMWF);
+    if (!skin_algo) { l_use_cs = 0; l_use_wl = 0; }
+    if ((l_use_cs || l_use_wl) && !(Qsw && rad_lw && slp)) {
+        snprintf(s->errmsg, sizeof(s->errmsg), "you need to provide Qsw, rad_lw & slp to use cool-skin / warm-layer param!");
+        return ABO_ERR_SKIN_NORAD;
+    }
+    if (l_use_wl && ialgo != ABO_ECMWF && !plong) {
+        snprintf(s->errmsg, sizeof(s->errmsg), "you need to provide Qsw, rad_lw, slp, isecday_utc & plong to use warm-layer param!");
+        return ABO_ERR_SKIN_NORAD;
+    }
+    if (kt == 1 && l_use_wl) {   /* *_INIT */
+        if (ialgo == ABO_ECMWF) {
+            if (s->n_ecmwf) { snprintf(s->errmsg, sizeof(s->errmsg), "ECMWF_INIT => allocation failed"); return ABO_ERR_STATE; }
+            s->n_ecmwf = n;
+            s->e_dT_wl = (double *)malloc((size_t)n * sizeof(double));
+            s->e_Hz_wl = (double *)malloc((size_t)n * sizeof(double));
+            for (long i = 0; i < n; i++) { s->e_dT_wl[i] = 0.; s->e_Hz_wl[i] = 3.; }
+        } else {
+            if (s->n_coare) { snprintf(s->errmsg, sizeof(s->errmsg), "COARE_INIT => allocation failed"); return ABO_ERR_STATE; }
+            s->n_coare = n;
+            s->c_dT_wl = (double *)malloc((size_t)n * sizeof(double));
+            s->c_Hz_wl = (double *)malloc((size_t)n * sizeof(double));
+            s->c_Qnt_ac = (double *)malloc((size_t)n * sizeof(double));
+            s->c_Tau_ac = (double *)malloc((size_t)n * sizeof(double));
+            for (long i = 0; i < n; i++) { s->c_Tau_ac[i] = 0.; s->c_Qnt_ac[i] = 0.; s->c_dT_wl[i] = 0.; s->c_Hz_wl[i] = 20.; }
+        }
+    }
+    if (l_use_wl) {
+        long have = (ialgo == ABO_ECMWF) ? s->n_ecmwf : s->n_coare;
+        if (have != n) { snprintf(s->errmsg, sizeof(s->errmsg), "warm-layer state missing (kt=%d)", kt); return ABO_ERR_STATE; }
+    }
+    const int nb_iter = s->nb_iter;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(s->nthreads) schedule(static)
+#endif
+    for (long i = 0; i < n; i++) {
+        turb_io o;
+        memset(&o, 0, sizeof(o));
+        o.T_s = T_s[i];
+        o.q_s = q_s[i];
+        skin_in sk;
+        memset(&sk, 0, sizeof(sk));
+        sk.l_use_cs = l_use_cs;
+        sk.l_use_wl = l_use_wl;
+        sk.rdt = s->rdt;
+        sk.gdept = s->gdept;
+        if (l_use_cs || l_use_wl) {
+            sk.Qsw = Qsw[i];
+            sk.rad_lw = rad_lw[i];
+            sk.slp = slp[i];
+            sk.isd = isecday_utc;
+            sk.plong = plong ? plong[i] : 0.;
+        }
+        if (l_use_wl) {
+            if (ialgo == ABO_ECMWF) { sk.st.dT_wl = &s->e_dT_wl[i]; sk.st.Hz_wl = &s->e_Hz_wl[i]; }
+            else { sk.st.dT_wl = &s->c_dT_wl[i]; sk.st.Hz_wl = &s->c_Hz_wl[i]; sk.st.Qnt_ac = &s->c_Qnt_ac[i]; sk.st.Tau_ac = &s->c_Tau_ac[i]; }
+        }
+        switch (ialgo) {
+        case ABO_COARE3P0: turb_coare3p0(nb_iter, zt, zu, t_zt[i], q_zt[i], U_zu[i], &sk, &o); break;
+        case ABO_COARE3P6: turb_coare3p6(nb_iter, zt, zu, t_zt[i], q_zt[i], U_zu[i], &sk, &o); break;
+        case ABO_NCAR: turb_ncar(nb_iter, zt, zu, o.T_s, t_zt[i], o.q_s, q_zt[i], U_zu[i], &o); break;
+        case ABO_ECMWF: turb_ecmwf(nb_iter, zt, zu, t_zt[i], q_zt[i], U_zu[i], &sk, &o); break;
+        default: turb_andreas(nb_iter, zt, zu, o.T_s, t_zt[i], o.q_s, q_zt[i], U_zu[i], &o); break;
+        }
+        T_s[i] = o.T_s; q_s[i] = o.q_s;
+        Cd[i] = o.Cd; Ch[i] = o.Ch; Ce[i] = o.Ce; t_zu[i] = o.t_zu; q_zu[i] = o.q_zu; Ubzu[i] = o.Ubzu;
+        if (opt) {
+            if (opt[0]) opt[0][i] = o.CdN;
+            if (opt[1]) opt[1][i] = o.ChN;
+            if (opt[2]) opt[2][i] = o.CeN;
+            if (opt[3]) opt[3][i] = o.z0;
+            if (opt[4]) opt[4][i] = o.us;
+            if (opt[5]) opt[5][i] = o.L;
+            if (opt[6]) opt[6][i] = o.UN10;
+            if (opt[7] && l_use_cs) opt[7][i] = o.dT_cs;
+            if (opt[8] && l_use_wl) opt[8][i] = *sk.st.dT_wl;
+            if (opt[9] && l_use_wl) opt[9][i] = *sk.st.Hz_wl;
+        }
+    }
+    if (l_use_wl && kt == s->nitend) {   /* *_EXIT */
+        if (ialgo == ABO_ECMWF) free_ecmwf_state(s);
+        else free_coare_state(s);
+    }
+    return ABO_OK;
+}
+
 /* ------------------------------------------------------------------ */
 /* building blocks for unit tests                                      */
 /* ------------------------------------------------------------------ */

@@ -107,6 +107,16 @@ double abo_u_star_andreas(double un10);
 void abo_turb_noskin(int algo, int nb_iter, double zt, double zu, double sst, double tha_zt,
                      double ssq, double q_zt, double U_zu, double *out13);
 
+/* Direct TURB_* call on arrays (see .c): t_zt is POTENTIAL temperature, q_zt specific humidity, U_zu the scalar
+ * wind, Qsw the NET solar flux; T_s/q_s are in/out; opt[10] = CdN ChN CeN xz0 xu_star xL xUN10 pdT_cs pdT_wl pHz_wl. */
+void abo_set_nitend(abo_session *s, int nitend);
+int abo_turb(abo_session *s, const char *calgo, int kt, double zt, double zu, long n,
+             double *T_s, const double *t_zt, double *q_s, const double *q_zt, const double *U_zu,
+             int l_use_cs, int l_use_wl,
+             double *Cd, double *Ch, double *Ce, double *t_zu, double *q_zu, double *Ubzu,
+             const double *Qsw, const double *rad_lw, const double *slp, int isecday_utc, const double *plong,
+             double *const *opt);
+
 /* test-only: reproduce the pre-drift COARE 3.0 viscosity line (see .c) */
 void abo_debug_coare3p0_visc_at_tzu(int on);
 

@@ -73,6 +73,10 @@ def lib():
         L.abo_psi_h.restype = C.c_double
         L.abo_psi_h.argtypes = [C.c_int, C.c_double]
         L.abo_turb_noskin.argtypes = [C.c_int, C.c_int] + [C.c_double] * 7 + [_dp]
+        L.abo_set_nitend.argtypes = [C.c_void_p, C.c_int]
+        L.abo_turb.restype = C.c_int
+        L.abo_turb.argtypes = ([C.c_void_p, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_long] + [_dp] * 5 +
+                               [C.c_int, C.c_int] + [_dp] * 6 + [_dp] * 3 + [C.c_int, _dp, C.POINTER(_dp)])
         _lib = L
     return _lib
 
@@ -139,6 +143,31 @@ class OracleSession:
             raise OracleError(rc, self._L.abo_errmsg(self._s).decode())
         if Ts is not None:
             outs["T_s"] = Ts
+        return outs
+
+    def set_nitend(self, v): self._L.abo_set_nitend(self._s, int(v))
+
+    TURB_OPT = ("CdN", "ChN", "CeN", "xz0", "xu_star", "xL", "xUN10", "pdT_cs", "pdT_wl", "pHz_wl")
+
+    def turb(self, calgo, kt, zt, zu, T_s, t_zt, q_s, q_zt, U_zu, l_use_cs=False, l_use_wl=False,
+             Qsw=None, rad_lw=None, slp=None, isecday_utc=0, plong=None, want=()):
+        """Direct TURB_* call; returns dict with T_s, q_s (updated copies), Cd..Ubzu and the wanted optionals."""
+        f = lambda a: None if a is None else np.ascontiguousarray(np.ravel(a, order="F"), dtype=np.float64)
+        Ts, qs = f(T_s).copy(), f(q_s).copy()
+        n = Ts.size
+        ins = [f(t_zt), f(q_zt), f(U_zu)]
+        outs = {k: np.zeros(n) for k in ("Cd", "Ch", "Ce", "t_zu", "q_zu", "Ubzu")}
+        optv = {k: np.zeros(n) for k in want}
+        arr = (_dp * 10)(*[_ptr(optv[k]) if k in optv else None for k in self.TURB_OPT])
+        rs, rl, sp, pl = f(Qsw), f(rad_lw), f(slp), f(plong)
+        rc = self._L.abo_turb(self._s, calgo.encode(), int(kt), float(zt), float(zu), n, _ptr(Ts), _ptr(ins[0]), _ptr(qs),
+                              _ptr(ins[1]), _ptr(ins[2]), int(bool(l_use_cs)), int(bool(l_use_wl)),
+                              *[_ptr(outs[k]) for k in ("Cd", "Ch", "Ce", "t_zu", "q_zu", "Ubzu")],
+                              _ptr(rs), _ptr(rl), _ptr(sp), int(isecday_utc), _ptr(pl), arr)
+        if rc != 0:
+            raise OracleError(rc, self._L.abo_errmsg(self._s).decode())
+        outs.update(optv)
+        outs["T_s"], outs["q_s"] = Ts, qs
         return outs
 
     def state(self, which: int, n: int):
