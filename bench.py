@@ -111,7 +111,13 @@ def cpu_baseline(threads: int, target_seconds: float = 12.0) -> dict:
     rate = NI * probe_nj * NT / t
     nj = int(min(NJ, max(probe_nj, round(rate * target_seconds / (NI * NT)))))
     t = run(nj)
+    # the reference itself is serial: one thread on a 16-row sample, for the record
+    threads_all, threads = threads, 1
+    run(2)
+    t1 = run(16)
+    threads = threads_all
     return {"value": NI * nj * NT / t, "unit": "grid points/s", "cores": threads, "kind": "port",
+            "serial_value": NI * 16 * NT / t1, "serial_sample": f"{NI}x16 rows x {NT} steps, 1 thread, {t1:.1f} s",
             "sample": f"{NI}x{nj} rows (centre of the 1440x720 grid) x {NT} steps, {t:.1f} s, "
                       f"oracle/aerobulk_oracle.c gcc -O2 -ffp-contract=off, OpenMP row blocks"}
 
