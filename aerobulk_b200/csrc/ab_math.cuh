@@ -24,6 +24,8 @@
 #define ABM_FN static inline
 #define ABM_BIG static inline
 #define ABM_TABLE static const
+#define ABM_GTABLE static const
+#define ABM_LDG(p) (*(p))
 namespace abm {
 static inline int hi_word(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
 static inline int lo_word(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b & 0xffffffff); }
@@ -37,6 +39,7 @@ static inline double rcp_seed(double y) { return (double)(float)(1.0 / y); }   /
 #else
 #include <cuda_runtime.h>
 #define ABM_FN __device__ __forceinline__
+#define ABM_LDG(p) __ldg(p)
 // -DABM_NOINLINE=1 keeps exp/log/atan out of line (one body per kernel): smaller instruction footprint
 // at the price of call overhead and less interleaving
 #if defined(ABM_NOINLINE) && ABM_NOINLINE
@@ -84,7 +87,7 @@ ABM_FN double exp_core(double r, int k)
     return make_double(hi_word(p) + (k << 20), lo_word(p));
 }
 
-ABM_BIG double dexp(double x)
+ABM_BIG double dexp_poly(double x)
 {
     const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to nearest integer
     const double t = fma(x, MATH_K[K_L2E], MAGIC);
@@ -96,7 +99,7 @@ ABM_BIG double dexp(double x)
     return (x < -700.) ? 0. : v;
 }
 
-ABM_BIG double dexp10(double x)
+ABM_BIG double dexp10_poly(double x)
 {
     const double MAGIC = 6755399441055744.0;
     const double t = fma(x, MATH_K[K_L2T], MAGIC);
@@ -109,7 +112,7 @@ ABM_BIG double dexp10(double x)
 }
 
 // log(x) = k ln2 + log(m), m in [sqrt(2)/2, sqrt(2)); log(m) = 2 atanh(s), s = (m-1)/(m+1)
-ABM_BIG double dlog(double x)
+ABM_BIG double dlog_poly(double x)
 {
     int hx = hi_word(x);
     int k = (hx >> 20) - 1023;
@@ -128,6 +131,75 @@ ABM_BIG double dlog(double x)
     const double dk = (double)k;
     return dk * MATH_K[K_LN2_HI] - ((hfsq - fma(s, hfsq + R, dk * MATH_K[K_LN2_LO])) - f);
 }
+
+// ---------------------------------------------------------------------------
+// Table-driven exp / log (default): a 64-entry table of 2^(j/64) and a 256-entry table of
+// {1/c_j, -log(1/c_j)} (read with __ldg, L1-resident, 4.5 KB) shrink the polynomials to degree 3 / 4:
+// 10 FP64 instructions per exp instead of 18, 13 per log instead of 23 (no reciprocal).
+// ---------------------------------------------------------------------------
+// exp(r) for |r| <= ln2/128 times 2^(k/64), k = 64 m + j
+ABM_FN double expt_core(double r, int k)
+{
+    const double T = ABM_LDG(&EXP_T[k & 63]);
+    const double r2 = r * r;
+    double q = fma(EXPT_C[3], r, EXPT_C[2]);
+    q = fma(q, r, EXPT_C[1]);
+    q = fma(q, r, EXPT_C[0]);
+    const double v = fma(T, fma(r2, q, r), T);
+    return make_double(hi_word(v) + ((k >> 6) << 20), lo_word(v));
+}
+ABM_BIG double dexp_table(double x)
+{
+    const double MAGIC = 6755399441055744.0;
+    const double t = fma(x, MATH_K[K_L2E64], MAGIC);
+    const int k = lo_word(t);
+    const double kf = t - MAGIC;
+    double r = fma(kf, -MATH_K[K_LN2_64_HI], x);
+    r = fma(kf, -MATH_K[K_LN2_64_LO], r);
+    const double v = expt_core(r, k);
+    return (x < -700.) ? 0. : v;
+}
+ABM_BIG double dexp10_table(double x)
+{
+    const double MAGIC = 6755399441055744.0;
+    const double t = fma(x, MATH_K[K_L2T64], MAGIC);
+    const int k = lo_word(t);
+    const double kf = t - MAGIC;
+    double r = fma(kf, -MATH_K[K_LG2_64_HI], x);
+    r = fma(kf, -MATH_K[K_LG2_64_LO], r);
+    const double v = expt_core(r * MATH_K[K_LN10], k);
+    return (x < -304.) ? 0. : v;
+}
+// log(x) = e ln2 + lc_j + log1p(m rc_j - 1), m in [0.708, 1.416) (so that x ~ 1 has e = 0 and the exact
+// entry c = 1), j = interval of m's hi word
+ABM_BIG double dlog_table(double x)
+{
+    const int hx = hi_word(x);
+    const int e = (hx - 0x3fe6a800) >> 20;
+    const int u = hx - (e << 20);
+    const int j = (u - 0x3fe6a800) >> 12;
+    const double m = make_double(u, lo_word(x));
+    const double rc = ABM_LDG(&LOG_T[2 * j]), lc = ABM_LDG(&LOG_T[2 * j + 1]);
+    const double r = fma(m, rc, -1.0);
+    const double r2 = r * r;
+    double q = fma(LOGT_C[4], r, LOGT_C[3]);
+    q = fma(q, r, LOGT_C[2]);
+    q = fma(q, r, LOGT_C[1]);
+    q = fma(q, r, LOGT_C[0]);
+    const double lp = fma(r2, q, r);
+    const double de = (double)e;
+    return fma(de, MATH_K[K_LN2_HI], lc) + fma(de, MATH_K[K_LN2_LO], lp);
+}
+
+#if defined(ABM_POLY_MATH) && ABM_POLY_MATH
+ABM_FN double dexp(double x) { return dexp_poly(x); }
+ABM_FN double dexp10(double x) { return dexp10_poly(x); }
+ABM_FN double dlog(double x) { return dlog_poly(x); }
+#else
+ABM_FN double dexp(double x) { return dexp_table(x); }
+ABM_FN double dexp10(double x) { return dexp10_table(x); }
+ABM_FN double dlog(double x) { return dlog_table(x); }
+#endif
 
 ABM_FN double dlog10(double x) { return dlog(x) * MATH_K[K_LOG10E]; }
 

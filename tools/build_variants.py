@@ -3,8 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from aerobulk_b200 import build as B
 VARIANTS = {
-    "mathcall": ["ABM_NOINLINE=1"],
-    "mathcall_heavy": ["ABM_NOINLINE=1", "AB_NOINLINE=1"],
+    "polymath": ["ABM_POLY_MATH=1"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
