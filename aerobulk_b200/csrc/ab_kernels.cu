@@ -59,6 +59,7 @@ static constexpr int SORT_ITEMS = SORT_WIN / SORT_BLOCK;
 __global__ void __launch_bounds__(SORT_BLOCK) classify_kernel(const FluxArgs a, unsigned short *perm)
 {
     __shared__ unsigned short s_c0[SORT_ITEMS * SORT_BLOCK / 32], s_c1[SORT_ITEMS * SORT_BLOCK / 32];
+    abm::load_tables();
     const long long base = (long long)blockIdx.x * SORT_WIN;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     constexpr int NW = SORT_BLOCK / 32;
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) classify_kernel(const FluxArgs a, 
 template <int ALGO, bool SKIN, bool ZTEQ>
 __global__ void __launch_bounds__(FLUX_BLOCK, AB_MIN_BLOCKS) flux_kernel(const FluxArgs a)
 {
+    abm::load_tables();
     long long i = (long long)blockIdx.x * FLUX_BLOCK + threadIdx.x;
     if (a.perm) i = (i / SORT_WIN) * SORT_WIN + a.perm[i];   // slot -> point (perm is padded to whole windows)
     if (i >= a.n) return;
@@ -221,6 +223,7 @@ cudaError_t launch_flux(int algo, bool skin, bool zteq, const FluxArgs &a, cudaS
 template <int ALGO, bool CS, bool WL, bool ZTEQ>
 __global__ void __launch_bounds__(FLUX_BLOCK, AB_MIN_BLOCKS) turb_kernel(const TurbArgs a)
 {
+    abm::load_tables();
     const long long i = (long long)blockIdx.x * FLUX_BLOCK + threadIdx.x;
     if (i >= a.n) return;
     constexpr bool SKIN = CS || WL;

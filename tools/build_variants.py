@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from aerobulk_b200 import build as B
 VARIANTS = {
-    "polymath": ["ABM_POLY_MATH=1"],
+    "smemtab": ["ABM_SMEM_TABLES=1"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
