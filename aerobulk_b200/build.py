@@ -3,7 +3,7 @@
     python -m aerobulk_b200.build [--force]
 
 The shared library lands next to this file (git-ignored, shipped to the GPU box by
-gpurun).  No JIT cache, no torch extension machinery: three translation units,
+gpurun).  No JIT cache, no torch extension machinery: four translation units,
 one link step.
 """
 from __future__ import annotations
@@ -23,7 +23,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 # -fmad=true (default): FMA contraction is part of the documented GPU arithmetic
 
-SOURCES = ["ab_kernels.cu", "ab_api.cu", "aerobulk.cpp"]
+SOURCES = ["ab_kernels.cu", "ab_series.cu", "ab_api.cu", "aerobulk.cpp"]
 HEADERS = [os.path.join(CSRC, h) for h in ("ab_device.cuh", "ab_kernels.cuh", "ab_math.cuh", "ab_math_tables.cuh")] + [
     os.path.join(ROOT, "include", h) for h in ("aerobulk_gpu.h", "aerobulk.hpp")]
 
@@ -50,6 +50,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "")
     objs = []
     lib = LIB if not tag else os.path.join(OBJ, f"libaerobulk_gpu_{tag}.so")
     extra = [f"-D{d}" for d in defines]
+    jobs = []
     for src in SOURCES:
         path = os.path.join(CSRC, src)
         obj = os.path.join(OBJ, os.path.splitext(src)[0] + (f"_{tag}" if tag else "") + ".o")
@@ -60,7 +61,10 @@ def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "")
                 cmd += ["-Xptxas", "-v"]
             if verbose:
                 print(" ".join(cmd), flush=True)
-            subprocess.check_call(cmd)
+            jobs.append((cmd, subprocess.Popen(cmd)))   # the translation units compile side by side
+    for cmd, job in jobs:
+        if job.wait() != 0:
+            raise subprocess.CalledProcessError(job.returncode, cmd)
     if force or _stale(lib, objs):
         cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + ARCH + ["-shared", "-o", lib] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"]
         if verbose:

@@ -22,7 +22,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <fstream>
 #include <mutex>
+#include <string>
+#include <vector>
 
 #include "ab_kernels.cuh"
 
@@ -701,6 +704,267 @@ int turb_impl(const char *calgo, int kt, double zt, double zu, int Ni, int Nj, d
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// station time series: one launch for the whole series
+// ---------------------------------------------------------------------------
+int series_impl(const char *calgo, int Nt, long long S, double zt, double zu, const int *isd, const double *lon,
+                const double *sst, const double *t_zt, const double *hum_zt, int hum_kind, const double *wind,
+                const double *slp, const double *rad_sw, const double *rad_lw, int l_use_skin,
+                const aerobulk_gpu_series_out *out, int on_device)
+{
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!calgo || !isd || !lon || !sst || !t_zt || !hum_zt || !wind || !slp || !rad_sw || !rad_lw || !out)
+        return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_series: NULL mandatory argument");
+    if (Nt < 0 || S < 0 || hum_kind < 0 || hum_kind > 2)
+        return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_series: bad Nt=%d, S=%lld or hum_kind=%d", Nt, S, hum_kind);
+    const int ialgo = algo_id(calgo);
+    if (!ialgo) return fail(AEROBULK_GPU_ERR_ALGO, "aerobulk_gpu_series: bulk algorithm %s is unknown!!!", calgo);
+    const bool skin = l_use_skin && (ialgo == abd::COARE3P0 || ialgo == abd::COARE3P6 || ialgo == abd::ECMWF);
+    int rc = ensure_device();
+    if (rc) return rc;
+    const long long n = (long long)Nt * S;
+    if (n == 0) return 0;
+    cudaStream_t cs_ = compute_stream();
+    rc = check_bad_flag(nullptr, nullptr);   // a deferred error of earlier aerobulk_gpu_model_device calls
+    if (rc) return rc;
+
+    double *const hout[abk::NSERIES_OUT] = {
+        out->rho_zu, out->QL, out->QH, out->Qlw, out->QNS, out->Qsw, out->dT_cs, out->dT_wl, out->TAU, out->dT,
+        out->Hz_wl, out->Qnt_ac, out->Tau_ac, out->Cd, out->Ce, out->Ch, out->theta_zu, out->q_zu, out->t_zu,
+        out->RiB, out->z0, out->u_star, out->L, out->UN10, out->Ts, out->Evap, out->q_zt, out->theta_zt};
+    const double *hin[7] = {sst, t_zt, hum_zt, wind, slp, rad_sw, rad_lw};
+
+    abk::SeriesArgs a;
+    memset(&a, 0, sizeof(a));
+    a.S = S;
+    a.Nt = Nt;
+    a.hum_kind = hum_kind;
+    a.u = make_uniform(zt, zu);
+    a.bad_index = g.d_bad;
+
+    // one slab: [isd as doubles' worth of ints | lon | 7 inputs | wanted outputs]
+    int nout = 0;
+    for (int k = 0; k < abk::NSERIES_OUT; ++k) nout += hout[k] ? 1 : 0;
+    const long long isd_words = ((long long)Nt * (long long)sizeof(int) + 7) / 8;
+    const long long need = isd_words + (on_device ? 0 : S + (7 + nout) * n);
+    if (need > g.cap_turb) {
+        if (g.d_turb) cudaFree(g.d_turb);
+        g.d_turb = nullptr;
+        g.cap_turb = 0;
+        CUDA_TRY(cudaMalloc(&g.d_turb, sizeof(double) * (size_t)need));
+        g.cap_turb = need;
+    }
+    int *d_isd = reinterpret_cast<int *>(g.d_turb);
+    CUDA_TRY(cudaMemcpyAsync(d_isd, isd, sizeof(int) * (size_t)Nt, cudaMemcpyHostToDevice, cs_));
+    a.isd = d_isd;
+    double *dout[abk::NSERIES_OUT];
+    if (on_device) {
+        a.lon = lon;
+        a.sst = sst; a.t_zt = t_zt; a.hum_zt = hum_zt; a.wnd = wind; a.slp = slp; a.rad_sw = rad_sw; a.rad_lw = rad_lw;
+        for (int k = 0; k < abk::NSERIES_OUT; ++k) dout[k] = hout[k];
+    } else {
+        double *p = g.d_turb + isd_words;
+        CUDA_TRY(cudaMemcpyAsync(p, lon, sizeof(double) * (size_t)S, cudaMemcpyHostToDevice, cs_));
+        a.lon = p;
+        p += S;
+        const double *din[7];
+        for (int k = 0; k < 7; ++k) {
+            CUDA_TRY(cudaMemcpyAsync(p, hin[k], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs_));
+            din[k] = p;
+            p += n;
+        }
+        a.sst = din[0]; a.t_zt = din[1]; a.hum_zt = din[2]; a.wnd = din[3]; a.slp = din[4]; a.rad_sw = din[5]; a.rad_lw = din[6];
+        for (int k = 0; k < abk::NSERIES_OUT; ++k) {
+            dout[k] = hout[k] ? p : nullptr;
+            if (hout[k]) p += n;
+        }
+    }
+    for (int k = 0; k < abk::NSERIES_OUT; ++k) a.out[k] = dout[k];
+    CUDA_TRY(abk::launch_series(ialgo, skin, fabs(zu - zt) < 0.01, a, cs_));
+    g.launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(g.h_bad, g.d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs_));
+    if (!on_device)
+        for (int k = 0; k < abk::NSERIES_OUT; ++k)
+            if (hout[k])
+                CUDA_TRY(cudaMemcpyAsync(hout[k], dout[k], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, cs_));
+    CUDA_TRY(cudaStreamSynchronize(cs_));
+    const unsigned long long bad = *g.h_bad;
+    if (bad != ~0ull) {
+        *g.h_bad = ~0ull;
+        cudaMemset(g.d_bad, 0xFF, sizeof(unsigned long long));
+        return fail(AEROBULK_GPU_ERR_TAU,
+                    "BULK_FORMULA_VCTR()@mod_phymbl: wind stress too strong!\n  => at record %lld, station %lld",
+                    (long long)(bad / (unsigned long long)S) + 1, (long long)(bad % (unsigned long long)S) + 1);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// one station, CSV in / CSV out: src/tests/test_aerobulk_buoy_series_oce.f90 with text files for NetCDF
+// ---------------------------------------------------------------------------
+std::vector<std::string> split_csv(const std::string &line)
+{
+    std::vector<std::string> out;
+    std::string cur;
+    for (char ch : line) {
+        if (ch == ',') {
+            out.push_back(cur);
+            cur.clear();
+        } else if (ch != '\r' && ch != '\n' && ch != '"') {
+            cur.push_back(ch);
+        }
+    }
+    out.push_back(cur);
+    for (auto &f : out) {
+        size_t b = f.find_first_not_of(" \t"), e = f.find_last_not_of(" \t");
+        f = (b == std::string::npos) ? std::string() : f.substr(b, e - b + 1);
+    }
+    return out;
+}
+
+// "YYYY?MM?DD?hh?mm[?ss]" with any non-digit separators -> hh*3600 + mm*60 (the program drops the seconds, :373)
+bool parse_isecday(const std::string &t, int *isd)
+{
+    int f[6] = {0, 0, 0, 0, 0, 0}, nf = 0;
+    size_t i = 0;
+    while (i < t.size() && nf < 6) {
+        if (t[i] >= '0' && t[i] <= '9') {
+            long v = 0;
+            while (i < t.size() && t[i] >= '0' && t[i] <= '9') v = v * 10 + (t[i++] - '0');
+            f[nf++] = (int)v;
+        } else {
+            ++i;
+        }
+    }
+    if (nf < 5 || f[3] > 23 || f[4] > 59) return false;
+    *isd = f[3] * 3600 + f[4] * 60;
+    return true;
+}
+
+// TO_KELVIN_3D, src/mod_phymbl.f90:1826-1847
+int to_kelvin(std::vector<double> &v, const char *name)
+{
+    double sum = 0.;
+    for (double x : v) sum += x;
+    const double zm = sum / (double)v.size();
+    if (zm < 50. && zm > -80.) {
+        for (double &x : v) x = x + 273.15;
+        return 0;
+    }
+    if (zm > 200. && zm < 320.) return 0;
+    return fail(AEROBULK_GPU_ERR_UNITS, " *** PROBLEM: cannot figure out unit of variable %s !!!", name);
+}
+
+int series_csv_impl(const char *path_in, const char *path_out, const char *calgo, double zt, double zu, int l_use_skin)
+{
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!path_in || !path_out || !calgo) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_series_csv: NULL argument");
+    if (!algo_id(calgo)) return fail(AEROBULK_GPU_ERR_ALGO, "aerobulk_gpu_series_csv: bulk algorithm %s is unknown!!!", calgo);
+    std::ifstream in(path_in);
+    if (!in) return fail(AEROBULK_GPU_ERR_IO, "aerobulk_gpu_series_csv: cannot open %s", path_in);
+    std::string line;
+    do {
+        if (!std::getline(in, line)) return fail(AEROBULK_GPU_ERR_IO, "aerobulk_gpu_series_csv: %s is empty", path_in);
+    } while (line.empty() || line[0] == '#');
+    std::vector<std::string> names = split_csv(line);
+    auto col = [&](const char *nm) {
+        for (size_t k = 0; k < names.size(); ++k) {
+            std::string low = names[k];
+            for (char &c : low) c = (char)tolower((unsigned char)c);
+            if (low == nm) return (int)k;
+        }
+        return -1;
+    };
+    // the reference's default variable names, src/mod_const.f90:208-220
+    const int c_time = col("time"), c_lon = col("lon"), c_sst = col("sst"), c_ta = col("t_air"), c_q = col("q_air"),
+              c_rh = col("rh_air"), c_dp = col("dp_air"), c_w = col("wndspd"), c_u = col("u10"), c_v = col("v10"),
+              c_p = col("msl"), c_sw = col("ssrd"), c_lw = col("strd");
+    if (c_time < 0 || c_sst < 0 || c_ta < 0 || c_p < 0 || c_sw < 0 || c_lw < 0)
+        return fail(AEROBULK_GPU_ERR_IO, "aerobulk_gpu_series_csv: %s needs the columns time, sst, t_air, msl, ssrd, strd", path_in);
+    const int hum_kind = (c_q >= 0) ? 0 : (c_rh >= 0) ? 2 : (c_dp >= 0) ? 1 : -1;
+    if (hum_kind < 0) return fail(AEROBULK_GPU_ERR_IO, "aerobulk_gpu_series_csv: %s needs one of q_air, rh_air, dp_air", path_in);
+    const int c_hum = hum_kind == 0 ? c_q : hum_kind == 2 ? c_rh : c_dp;
+    if (c_w < 0 && (c_u < 0 || c_v < 0))
+        return fail(AEROBULK_GPU_ERR_IO, "aerobulk_gpu_series_csv: %s needs wndspd, or u10 and v10", path_in);
+
+    std::vector<std::string> stamp;
+    std::vector<int> isd;
+    std::vector<double> sst, ta, hum, wnd, slp, rsw, rlw;
+    double lon = 0.;
+    long lineno = 1;
+    while (std::getline(in, line)) {
+        ++lineno;
+        if (line.empty() || line[0] == '#' || line.find_first_not_of(" \t\r") == std::string::npos) continue;
+        std::vector<std::string> f = split_csv(line);
+        if (f.size() < names.size())
+            return fail(AEROBULK_GPU_ERR_IO, "aerobulk_gpu_series_csv: %s line %ld has %zu fields, header has %zu", path_in,
+                        lineno, f.size(), names.size());
+        int sd = 0;
+        if (!parse_isecday(f[c_time], &sd))
+            return fail(AEROBULK_GPU_ERR_IO, "aerobulk_gpu_series_csv: %s line %ld: cannot read the time '%s'", path_in, lineno,
+                        f[c_time].c_str());
+        bool ok = true;
+        auto num = [&](int c) {
+            char *end = nullptr;
+            const double v = strtod(f[c].c_str(), &end);
+            if (end == f[c].c_str()) ok = false;
+            return v;
+        };
+        stamp.push_back(f[c_time]);
+        isd.push_back(sd);
+        sst.push_back(num(c_sst));
+        ta.push_back(num(c_ta));
+        hum.push_back(num(c_hum));
+        if (c_w >= 0) {
+            wnd.push_back(num(c_w));
+        } else {
+            const double u = num(c_u), v = num(c_v);
+            wnd.push_back(sqrt(u * u + v * v));   // :206 (no FMA on the host build: -ffp-contract is off for .cu host code)
+        }
+        slp.push_back(num(c_p));
+        rsw.push_back(num(c_sw));
+        rlw.push_back(num(c_lw));
+        if (stamp.size() == 1 && c_lon >= 0) lon = num(c_lon);
+        if (!ok) return fail(AEROBULK_GPU_ERR_IO, "aerobulk_gpu_series_csv: %s line %ld: not a number", path_in, lineno);
+    }
+    const int Nt = (int)stamp.size();
+    if (Nt == 0) return fail(AEROBULK_GPU_ERR_IO, "aerobulk_gpu_series_csv: %s holds no record", path_in);
+    int rc = to_kelvin(ta, "t_air");   // :212
+    if (rc) return rc;
+    rc = to_kelvin(sst, "sst");        // :299
+    if (rc) return rc;
+
+    std::vector<std::vector<double>> o(abk::NSERIES_OUT, std::vector<double>((size_t)Nt));
+    aerobulk_gpu_series_out out = {o[0].data(), o[1].data(), o[2].data(), o[3].data(), o[4].data(), o[5].data(), o[6].data(),
+                                   o[7].data(), o[8].data(), o[9].data(), o[10].data(), o[11].data(), o[12].data(),
+                                   o[13].data(), o[14].data(), o[15].data(), o[16].data(), o[17].data(), o[18].data(),
+                                   o[19].data(), o[20].data(), o[21].data(), o[22].data(), o[23].data(), o[24].data(),
+                                   o[25].data(), o[26].data(), o[27].data()};
+    rc = series_impl(calgo, Nt, 1, zt, zu, isd.data(), &lon, sst.data(), ta.data(), hum.data(), hum_kind, wnd.data(),
+                     slp.data(), rsw.data(), rlw.data(), l_use_skin, &out, 0);
+    if (rc) return rc;
+
+    FILE *fo = fopen(path_out, "w");
+    if (!fo) return fail(AEROBULK_GPU_ERR_IO, "aerobulk_gpu_series_csv: cannot write %s", path_out);
+    // names of src/tests/test_aerobulk_buoy_series_oce.f90:539-577, then the extras
+    static const char *onames[abk::NSERIES_OUT] = {"rho_a", "Qlat", "Qsen", "Qlw", "QNS", "Qsw", "dTcs", "dTwl", "Tau", "dT",
+                                                    "H_wl", "Qnt_ac", "Tau_ac", "Cd", "Ce", "Ch", "theta_zu", "q_zu",
+                                                    "t_zu", "RiB", "z0", "u_star", "L", "UN10", "Ts", "Evap", "q_zt",
+                                                    "theta_zt"};
+    fprintf(fo, "time,isecday_utc,Wind");
+    for (int k = 0; k < abk::NSERIES_OUT; ++k) fprintf(fo, ",%s", onames[k]);
+    fprintf(fo, "\n");
+    for (int jt = 0; jt < Nt; ++jt) {
+        fprintf(fo, "%s,%d,%.17g", stamp[jt].c_str(), isd[jt], wnd[jt]);
+        for (int k = 0; k < abk::NSERIES_OUT; ++k) fprintf(fo, ",%.17g", o[k][jt]);
+        fprintf(fo, "\n");
+    }
+    if (fclose(fo) != 0) return fail(AEROBULK_GPU_ERR_IO, "aerobulk_gpu_series_csv: error writing %s", path_out);
+    return 0;
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -774,6 +1038,23 @@ int aerobulk_gpu_turb(const char *calgo, int kt, double zt, double zu, int Ni, i
     std::lock_guard<std::mutex> lk(g_mu);
     return turb_impl(calgo, kt, zt, zu, Ni, Nj, T_s, t_zt, q_s, q_zt, U_zu, l_use_cs, l_use_wl, Cd, Ch, Ce, t_zu, q_zu,
                      Ubzu, Qsw, rad_lw, slp, isecday_utc, plong, opt, on_device);
+}
+
+int aerobulk_gpu_series(const char *calgo, int Nt, long long S, double zt, double zu, const int *isecday_utc,
+                        const double *lon, const double *sst, const double *t_zt, const double *hum_zt, int hum_kind,
+                        const double *wind, const double *slp, const double *rad_sw, const double *rad_lw,
+                        int l_use_skin, const aerobulk_gpu_series_out *out, int on_device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return series_impl(calgo, Nt, S, zt, zu, isecday_utc, lon, sst, t_zt, hum_zt, hum_kind, wind, slp, rad_sw, rad_lw,
+                       l_use_skin, out, on_device);
+}
+
+int aerobulk_gpu_series_csv(const char *path_in, const char *path_out, const char *calgo, double zt, double zu,
+                            int l_use_skin)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return series_csv_impl(path_in, path_out, calgo, zt, zu, l_use_skin);
 }
 
 void aerobulk_gpu_set_nitend(int nitend) { std::lock_guard<std::mutex> lk(g_mu); g.nitend = nitend; }

@@ -150,6 +150,16 @@ ABD double visc_air(double T)                                                   
 }
 ABD double L_vap(double T) { return (2.501 - 0.00237 * (T - RT0)) * 1.e6; }                               // :579-592
 ABD double cp_air(double q) { return RCP_DRY + RCP_VAP * q; }                                             // :603-616
+// moist adiabatic lapse rate [K/m], :627-649
+ABD double gamma_moist(double T, double q)
+{
+    const double ta = fmax(T, 180.);
+    const double qa = fmax(q, 1.E-6);
+    const double wa = fdiv(qa, 1. - qa);
+    const double iRT = abm::fast_rcp(R_DRY * ta);
+    const double Lv = L_vap(T);
+    return fdiv(GRAV * (1. + Lv * wa * iRT), RCP_DRY + fdiv(Lv * Lv * wa * REPS0 * iRT, ta));
+}
 ABD double alpha_sw(double T) { return 2.1e-5 * powr(fmax(T - RT0 + 3.2, 0.), 0.79); }                    // :1267-1280
 ABD double qlw_net(double rlw, double Ts) { const double t2 = Ts * Ts; return EMISS_W * (rlw - STEFAN * t2 * t2); }  // :1291-1314
 
@@ -190,6 +200,7 @@ struct Flux {
 // Computed once per iteration and shared by the two UPDATE_QNSOL_TAU calls and the final flux assembly.
 struct AirZu {
     double rho1, cp;
+    double rho;      // before the MAX(.,1): the prhoa output of BULK_FORMULA (dead in the flux kernels)
 };
 ABD AirZu air_at_zu(double zu, double tha, double qa, double slp)
 {
@@ -198,6 +209,7 @@ ABD AirZu air_at_zu(double zu, double tha, double qa, double slp)
     double rho = fmax(slp * r, 0.8);
     rho = fmax((slp - rho * GRAV * zu) * r, 0.8);
     AirZu a;
+    a.rho = rho;
     a.rho1 = fmax(rho, 1.);
     a.cp = cp_air(qa);
     return a;

@@ -46,6 +46,25 @@ struct TurbArgs {
 };
 cudaError_t launch_turb(int algo, bool cs, bool wl, bool zt_eq_zu, const TurbArgs &a, cudaStream_t s);
 
+// Station time series: the time loop of src/tests/test_aerobulk_buoy_series_oce.f90:364-537 for S
+// independent stations in ONE launch -- one thread per station walks its Nt records with the warm-layer state in
+// registers.  Records are [Nt][S] (station index fastest: coalesced).
+constexpr int NSERIES_OUT = 28;
+struct SeriesArgs {
+    const int *isd;                  // [Nt] UTC seconds since midnight of each record
+    const double *lon;               // [S]
+    const double *sst, *t_zt, *hum_zt, *wnd, *slp, *rad_sw, *rad_lw;   // [Nt][S]
+    // rho_zu QL QH Qlw QNS Qsw dT_cs dT_wl TAU dT Hz_wl Qnt_ac Tau_ac Cd Ce Ch theta_zu q_zu t_zu RiB z0 u_star L UN10
+    // Ts Evap q_zt theta_zt  (NULL: not wanted)
+    double *out[NSERIES_OUT];
+    long long S;
+    int Nt;
+    int hum_kind;                    // 0 specific humidity, 1 dew-point [K], 2 relative humidity [%]
+    abd::Uniform u;                  // isd / dawn are per record here and ignored
+    unsigned long long *bad_index;   // first record*S + station whose stress exceeds 10 N/m^2, else ~0ull
+};
+cudaError_t launch_series(int algo, bool skin, bool zt_eq_zu, const SeriesArgs &a, cudaStream_t s);
+
 // number of doubles in the statistics vector (see include/aerobulk_gpu.h)
 constexpr int NSTATS = 64;
 constexpr int NFIELDS = 9;

@@ -74,6 +74,11 @@ def lib():
                                     [C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_void_p] * 3 + [C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_int])
     L.aerobulk_gpu_set_nitend.argtypes = [C.c_int]
+    L.aerobulk_gpu_series.restype = C.c_int
+    L.aerobulk_gpu_series.argtypes = ([C.c_char_p, C.c_int, C.c_longlong, C.c_double, C.c_double] + [C.c_void_p] * 5 +
+                                      [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int])
+    L.aerobulk_gpu_series_csv.restype = C.c_int
+    L.aerobulk_gpu_series_csv.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_int]
     L.aerobulk_cxx_skin.restype = None
     L.aerobulk_cxx_no_skin.restype = None
     # language bindings get return codes instead of the reference's fail-stop
@@ -267,3 +272,65 @@ def turb(calgo: str, kt: int, zt: float, zu: float, T_s, t_zt, q_s, q_zt, U_zu, 
     outs.update(optv)
     outs["T_s"], outs["q_s"] = Ts, qs
     return outs
+
+
+# ---------------------------------------------------------------------------
+# station time series
+# ---------------------------------------------------------------------------
+SERIES_OUT = ("rho_zu", "QL", "QH", "Qlw", "QNS", "Qsw", "dT_cs", "dT_wl", "TAU", "dT", "Hz_wl", "Qnt_ac", "Tau_ac",
+              "Cd", "Ce", "Ch", "theta_zu", "q_zu", "t_zu", "RiB", "z0", "u_star", "L", "UN10", "Ts", "Evap", "q_zt",
+              "theta_zt")
+HUM_KINDS = {"q": 0, "sh": 0, "dp": 1, "rh": 2}
+
+
+def series(calgo: str, zt: float, zu: float, isecday_utc, lon, sst, t_zt, hum_zt, wind, slp, rad_sw, rad_lw,
+           hum_kind="q", l_use_skin: bool = True, want=SERIES_OUT) -> dict:
+    """The time loop of src/tests/test_aerobulk_buoy_series_oce.f90:364-537 for S stations in one launch.
+    Inputs are (Nt, S) C-ordered numpy arrays (station index fastest), `isecday_utc` (Nt,) ints, `lon` (S,).
+    Returns the series named in `want`, each (Nt, S)."""
+    L = lib()
+    isd = np.ascontiguousarray(isecday_utc, dtype=np.int32)
+    Nt = isd.shape[0]
+    lon = np.ascontiguousarray(lon, dtype=np.float64).reshape(-1)
+    S = lon.shape[0]
+    ins = []
+    for a in (sst, t_zt, hum_zt, wind, slp, rad_sw, rad_lw):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.size != Nt * S:
+            raise ValueError(f"series input of {a.size} values, expected Nt*S = {Nt}*{S}")
+        ins.append(a)
+    outs = {k: np.zeros((Nt, S), dtype=np.float64) for k in want}
+    ptr = lambda a: None if a is None else a.ctypes.data
+    arr = (C.c_void_p * len(SERIES_OUT))(*[ptr(outs.get(k)) for k in SERIES_OUT])
+    hk = HUM_KINDS[hum_kind] if isinstance(hum_kind, str) else int(hum_kind)
+    rc = L.aerobulk_gpu_series(calgo.encode(), Nt, S, float(zt), float(zu), ptr(isd), ptr(lon),
+                               *[ptr(a) for a in ins[:3]], hk, *[ptr(a) for a in ins[3:]],
+                               int(bool(l_use_skin)), C.cast(arr, C.c_void_p), 0)
+    _check(rc)
+    return outs
+
+
+def series_device(calgo: str, zt: float, zu: float, isecday_utc, lon, sst, t_zt, hum_zt, wind, slp, rad_sw, rad_lw,
+                  out: dict, hum_kind="q", l_use_skin: bool = True) -> dict:
+    """:func:`series` on DEVICE-resident torch.float64 CUDA tensors ((Nt, S) contiguous; `lon` (S,)); `out` maps
+    names of SERIES_OUT to preallocated (Nt, S) CUDA tensors.  `isecday_utc` stays a host int array.  Blocking."""
+    L = lib()
+    isd = np.ascontiguousarray(isecday_utc, dtype=np.int32)
+    Nt, S = isd.shape[0], lon.numel()
+    ins = [sst, t_zt, hum_zt, wind, slp, rad_sw, rad_lw]
+    for t in ins + list(out.values()):
+        if (not t.is_cuda) or str(t.dtype) != "torch.float64" or not t.is_contiguous() or t.numel() != Nt * S:
+            raise AerobulkError(101, "series_device needs contiguous float64 CUDA tensors of Nt*S values")
+    arr = (C.c_void_p * len(SERIES_OUT))(*[out[k].data_ptr() if k in out else None for k in SERIES_OUT])
+    hk = HUM_KINDS[hum_kind] if isinstance(hum_kind, str) else int(hum_kind)
+    rc = L.aerobulk_gpu_series(calgo.encode(), Nt, S, float(zt), float(zu), isd.ctypes.data, lon.data_ptr(),
+                               *[t.data_ptr() for t in ins[:3]], hk, *[t.data_ptr() for t in ins[3:]],
+                               int(bool(l_use_skin)), C.cast(arr, C.c_void_p), 1)
+    _check(rc)
+    return out
+
+
+def series_csv(path_in: str, path_out: str, calgo: str, zt: float, zu: float, l_use_skin: bool = True) -> None:
+    """One station, CSV in / CSV out (see include/aerobulk_gpu.h: aerobulk_gpu_series_csv)."""
+    _check(lib().aerobulk_gpu_series_csv(os.fsencode(path_in), os.fsencode(path_out), calgo.encode(), float(zt),
+                                         float(zu), int(bool(l_use_skin))))

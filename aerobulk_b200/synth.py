@@ -86,3 +86,46 @@ PARITY_SCALE = {"QL": 10.0, "QH": 10.0, "Tau_x": 1e-2, "Tau_y": 1e-2, "Evap": 1e
 def parity_errors(got: dict, ref: dict) -> dict:
     """Per-field array of scaled errors."""
     return {k: np.abs(got[k] - ref[k]) / (np.abs(ref[k]) + PARITY_SCALE[k]) for k in ref if k in got}
+
+
+def station_series(Nt: int, S: int, seed: int = SEED, humidity: str = "q", dt_s: int = 3600, start_s: int = 0) -> dict:
+    """Synthetic forcing of S stations over Nt records spaced dt_s seconds, arrays (Nt, S).
+
+    Longitudes cover [-180, 180); short-wave follows the LOCAL solar hour so that the COARE warm layer builds
+    by day and its dawn reset (src/mod_skin_coare.f90:159-163) fires; wind, air-sea temperature difference and
+    humidity wander slowly (weather) plus per-record noise.  Wind is either an exact calm (1 record in 512) or
+    at least 0.5 m/s: between the two the ECMWF iteration is ill-conditioned (a 1e-15 relative input perturbation moves
+    the ORACLE's fluxes by up to 1e-9 at 0.1 m/s), which would test the conditioning rather than the implementation.  humidity: 'q' [kg/kg], 'rh' [%], 'dp' [K]."""
+    jt = np.arange(Nt, dtype=np.uint64)
+    st = np.arange(S, dtype=np.uint64)
+    idx = jt[:, None] * np.uint64(S) + st[None, :]
+    u = lambda name, k=0: _u01(seed + 7919 * (k + 1), _F[name], idx)
+    us = lambda name, k=0: _u01(seed + 104729 * (k + 1), _F[name], st)[None, :]      # per station
+    lon = -180.0 + 360.0 * (np.arange(S) + 0.5) / S
+    secs = start_s + dt_s * np.arange(Nt, dtype=np.int64)
+    isd = ((secs % 86400) // 60 * 60).astype(np.int32)
+    hour_loc = ((secs[:, None] / 3600.0 + lon[None, :] / 15.0) % 24.0)
+    day = secs[:, None] / 86400.0
+    sst = 273.15 + 8.0 + 20.0 * us("sst") + 0.3 * np.sin(2 * np.pi * day / 9.0 + 6.28 * us("sst", 1))
+    dT = -3.0 + 4.5 * us("dT") + 2.5 * np.sin(2 * np.pi * day / 3.7 + 6.28 * us("dT", 1)) + 0.6 * (u("dT") - 0.5)
+    t_zt = sst + dT
+    slp = 101325.0 + 1200.0 * np.sin(2 * np.pi * day / 5.3 + 6.28 * us("slp")) + 200.0 * (u("slp") - 0.5)
+    frac = np.clip(0.62 + 0.3 * us("hum") + 0.08 * np.sin(2 * np.pi * day / 2.9 + 6.28 * us("hum", 1)) + 0.04 * (u("hum") - 0.5), 0.3, 0.97)
+    tc = t_zt - 273.15
+    esat = 611.2 * np.exp(17.67 * tc / (tc + 243.5))
+    if humidity in ("q", "sh"):
+        hum = frac * 0.622 * esat / slp
+    elif humidity == "rh":
+        hum = 100.0 * frac
+    elif humidity == "dp":
+        ln = np.log(frac * esat / 611.2)
+        hum = 273.15 + 243.5 * ln / (17.67 - ln)
+    else:
+        raise ValueError(humidity)
+    wind = np.clip(1.0 + 10.0 * us("wspd") + 4.0 * np.sin(2 * np.pi * day / 2.3 + 6.28 * us("wspd", 1)) + 1.5 * (u("wspd") - 0.5), 0.5, 24.0)
+    wind = np.where(u("calm") < 1.0 / 512.0, 0.0, wind)
+    rad_lw = 330.0 + 80.0 * us("rlw") + 20.0 * (u("rlw") - 0.5)
+    rad_sw = np.maximum(0.0, 950.0 * np.sin(np.pi * (hour_loc - 6.0) / 12.0)) * (0.35 + 0.65 * u("rsw"))
+    c = lambda a: np.array(np.broadcast_to(a, (Nt, S)), dtype=np.float64, order="C")
+    return dict(isecday_utc=isd, lon=lon, sst=c(sst), t_zt=c(t_zt), hum_zt=c(hum), wind=c(wind), slp=c(slp),
+                rad_sw=c(rad_sw), rad_lw=c(rad_lw))

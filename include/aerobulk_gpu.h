@@ -46,7 +46,8 @@ enum {
     AEROBULK_GPU_ERR_TAU = 8,         /* wind stress > 10 N/m^2      (mod_phymbl.f90:1250-1253)  */
     AEROBULK_GPU_ERR_STATE = 9,       /* warm-layer state (re)allocation (mod_blk_coare3p6.f90:82-83) */
     AEROBULK_GPU_ERR_CUDA = 100,      /* CUDA runtime failure / no device                         */
-    AEROBULK_GPU_ERR_ARG = 101        /* NULL / inconsistent argument                             */
+    AEROBULK_GPU_ERR_ARG = 101,       /* NULL / inconsistent argument                             */
+    AEROBULK_GPU_ERR_IO = 102         /* series CSV: file cannot be opened / parsed               */
 };
 
 /* ---- the two symbols of the reference's C++ bridge ------------------------ */
@@ -122,6 +123,43 @@ int aerobulk_gpu_turb(const char *calgo, int kt, double zt, double zu, int Ni, i
                       int isecday_utc, const double *plong,
                       const aerobulk_gpu_turb_optional *opt, int on_device);
 void aerobulk_gpu_set_nitend(int nitend);        /* mod_const.f90:22 (set by AEROBULK_INIT in the model path) */
+
+/* ---- station time series (the reference's buoy-series workflow, without NetCDF) ------------------------ */
+
+/* Output series of aerobulk_gpu_series, each [Nt][S] (station index fastest); any member may be NULL.
+ * The first 16 are the variables src/tests/test_aerobulk_buoy_series_oce.f90:539-577 writes (Wind is an input). */
+typedef struct aerobulk_gpu_series_out {
+    double *rho_zu, *QL, *QH, *Qlw, *QNS, *Qsw, *dT_cs, *dT_wl, *TAU, *dT, *Hz_wl, *Qnt_ac, *Tau_ac, *Cd, *Ce, *Ch;
+    double *theta_zu, *q_zu, *t_zu, *RiB, *z0, *u_star, *L, *UN10, *Ts, *Evap, *q_zt, *theta_zt;
+} aerobulk_gpu_series_out;
+#define AEROBULK_GPU_SERIES_NOUT 28
+
+/* Runs the time loop of src/tests/test_aerobulk_buoy_series_oce.f90:364-537 for S independent stations in one
+ * launch (one thread per station; warm-layer state in registers, created at record 1 and dropped after record Nt).
+ * Inputs are [Nt][S]: sst [K], t_zt ABSOLUTE air temperature [K], hum_zt (hum_kind 0: specific humidity [kg/kg],
+ * 1: dew-point [K], 2: relative humidity [%], capped at 99.999 as :227), wind scalar wind speed [m/s], slp [Pa],
+ * rad_sw / rad_lw DOWNWELLING fluxes [W/m^2]; isecday_utc[Nt] (host memory, always) = hh*3600+mm*60 of each record
+ * (:373), lon[S] station longitudes [deg E].  l_use_skin: cool-skin AND warm-layer on (as the program runs COARE
+ * and ECMWF, :456-479); ignored for ncar / andreas.  The step between records is the rdt global
+ * (aerobulk_gpu_set_rdt), the iteration count nb_iter (the program uses 20, :86).  'coare3p0' runs TURB_COARE3P0
+ * (the program's slip of running 3.6 for that choice, :456, is not reproduced).
+ * on_device: 0 host arrays, 1 device pointers (isecday_utc stays on the host); blocking either way. */
+int aerobulk_gpu_series(const char *calgo, int Nt, long long S, double zt, double zu,
+                        const int *isecday_utc, const double *lon,
+                        const double *sst, const double *t_zt, const double *hum_zt, int hum_kind,
+                        const double *wind, const double *slp, const double *rad_sw, const double *rad_lw,
+                        int l_use_skin, const aerobulk_gpu_series_out *out, int on_device);
+
+/* One station from / to CSV files: the whole program above (options -f/-r/-w, prompts for algorithm, zu, zt)
+ * with CSV in place of NetCDF.  Input: one header line then one record per line; columns by the reference's
+ * default names (src/mod_const.f90:208-220): time, lon, sst, t_air, one of q_air | rh_air | dp_air,
+ * wndspd or u10 + v10, msl, ssrd, strd.  `time` is "YYYY-MM-DD hh:mm[:ss]" (also with 'T' or '/' '-' as in the
+ * program's own date stamp); `lon` is read from the first record.  sst and t_air may be in deg C or K
+ * (TO_KELVIN_3D rule of src/mod_phymbl.f90:1826-1847: series mean in ]-80,50[ -> deg C).
+ * Output: time + the 16 series of the program + the inputs-derived extras, one line per record.
+ * Returns 0, or an error code (AEROBULK_GPU_ERR_IO for file / format problems). */
+int aerobulk_gpu_series_csv(const char *path_in, const char *path_out, const char *calgo, double zt, double zu,
+                            int l_use_skin);
 
 /* Waits for the session stream and reports a deferred error (wind stress too strong). */
 int aerobulk_gpu_synchronize(void);

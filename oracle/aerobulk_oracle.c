@@ -177,6 +177,17 @@ static double L_vap(double psst) { return (2.501 - 0.00237 * (psst - rt0)) * 1.e
 /* cp_air_sclr, mod_phymbl.f90:603-616 */
 static double cp_air(double pqa) { return rCp_dry + rCp_vap * pqa; }
 
+/* gamma_moist_sclr, mod_phymbl.f90:627-649 */
+static double gamma_moist(double pTa, double pqa)
+{
+    double zta = MAX(pTa, 180.);
+    double zqa = MAX(pqa, 1.E-6);
+    double zwa = zqa / (1. - zqa);
+    double ziRT = 1. / (R_dry * zta);
+    double zLvap = L_vap(pTa);
+    return grav * (1. + zLvap * zwa * ziRT) / (rCp_dry + zLvap * zLvap * zwa * reps0 * ziRT / zta);
+}
+
 /* One_on_L_sclr, mod_phymbl.f90:666-693 */
 static double One_on_L(double pThta, double pqa, double pus, double pts, double pqs)
 {
@@ -1722,6 +1733,90 @@ int abo_turb(abo_session *s, const char *calgo, int kt, double zt, double zu, lo
     return ABO_OK;
 }
 
+/*
+ * Station time series: the workflow of src/tests/test_aerobulk_buoy_series_oce.f90:364-537 (time loop) for S
+ * independent stations.  Records are [Nt][S] (station index fastest).  Per record jt (1-based), per station:
+ *   q_zt from dew-point / RH (:220-236; RH capped at 99.999 %), theta_zt = t_zt + gamma_moist*zt (:399),
+ *   ssq = 0.98 q_sat(SST,SLP) (:413), Qsw = (1-albedo) rad_sw (:447), TURB_<algo>(kt=jt, l_use_cs = l_use_wl = l_skin)
+ *   (:450-491; the program runs COARE 3.6 for the 'coare3p0' choice, SURVEY 8a quirk 8 -- a test-program slip that is
+ *   NOT reproduced: 'coare3p0' runs TURB_COARE3P0), dT = Ts - SST (:493), t_zu by 4 lapse-rate passes (:499-503),
+ *   RiB (:506), BULK_FORMULA (:509-512), Qlw, QNS (:515-518).
+ * out[28] (NULL = skip), each [Nt][S]: rho_zu QL QH Qlw QNS Qsw dT_cs dT_wl TAU dT Hz_wl Qnt_ac Tau_ac Cd Ce Ch
+ *   theta_zu q_zu t_zu RiB z0 u_star L UN10 Ts Evap q_zt theta_zt.
+ * hum_kind: 0 specific humidity, 1 dew-point [K], 2 relative humidity [%].
+ * The warm-layer state lives from record 1 to record Nt and is released on return (also after an error).
+ */
+int abo_series(abo_session *s, const char *calgo, int Nt, long S, double zt, double zu,
+               const int *isecday_utc, const double *lon,
+               const double *sst, const double *t_zt, const double *hum_zt, int hum_kind, const double *wnd,
+               const double *slp, const double *rad_sw, const double *rad_lw, int l_skin, double *const *out)
+{
+    init_consts();
+    int ialgo = algo_id(calgo);
+    if (!ialgo) { snprintf(s->errmsg, sizeof(s->errmsg), "unknown algorithm %s", calgo); return ABO_ERR_ALGO; }
+    int skin_algo = (ialgo == ABO_COARE3P0 || ialgo == ABO_COARE3P6 || ialgo == ABO_ECMWF);
+    int lsk = (l_skin && skin_algo) ? 1 : 0;
+    if (S <= 0 || Nt <= 0) return ABO_OK;
+    const int nitend_saved = s->nitend;
+    s->nitend = -1;   /* the state is released after the last record, below (its values are still reported) */
+    double *w[17];
+    for (int k = 0; k < 17; k++) w[k] = (double *)malloc((size_t)S * sizeof(double));
+    double *Ts = w[0], *qs = w[1], *tha = w[2], *qa = w[3], *Qsw = w[4], *Cd = w[5], *Ch = w[6], *Ce = w[7],
+           *thu = w[8], *qu = w[9], *Ub = w[10], *z0 = w[11], *us = w[12], *xL = w[13], *un10 = w[14],
+           *dTcs = w[15], *dTwl = w[16];
+    double *Hwl = (double *)malloc((size_t)S * sizeof(double));
+    int rc = ABO_OK;
+    for (int jt = 1; jt <= Nt && rc == ABO_OK; jt++) {
+        const long o = (long)(jt - 1) * S;
+        for (long i = 0; i < S; i++) {
+            const double T = t_zt[o + i], P = slp[o + i];
+            double q;
+            if (hum_kind == 2) q = q_air_rh(MIN(99.999, hum_zt[o + i]), T, P);
+            else if (hum_kind == 1) q = q_air_dp(hum_zt[o + i], P);
+            else q = hum_zt[o + i];
+            qa[i] = q;
+            tha[i] = T + gamma_moist(T, q) * zt;
+            qs[i] = rdct_qsat_salt * q_sat(sst[o + i], P);
+            Ts[i] = sst[o + i];
+            Qsw[i] = (1. - roce_alb0) * rad_sw[o + i];
+            dTcs[i] = 0.; dTwl[i] = 0.; Hwl[i] = 0.;
+        }
+        double *opt[10] = {NULL, NULL, NULL, z0, us, xL, un10, dTcs, dTwl, Hwl};
+        rc = abo_turb(s, calgo, jt, zt, zu, S, Ts, tha, qs, qa, wnd + o, lsk, lsk, Cd, Ch, Ce, thu, qu, Ub,
+                      Qsw, rad_lw + o, slp + o, isecday_utc[jt - 1], lon, opt);
+        if (rc != ABO_OK) break;
+        for (long i = 0; i < S; i++) {
+            double tz = thu[i];
+            for (int jq = 0; jq < 4; jq++) tz = thu[i] - gamma_moist(tz, qu[i]) * zu;
+            const double rib = Ri_bulk(zu, Ts[i], thu[i], qs[i], qu[i], Ub[i]);
+            double tau, qh, ql, ev, rho;
+            bulk_formula(zu, Ts[i], qs[i], thu[i], qu[i], Cd[i], Ch[i], Ce[i], wnd[o + i], Ub[i], slp[o + i],
+                         &tau, &qh, &ql, &ev, &rho);
+            if (tau > 10.) {   /* BULK_FORMULA_VCTR, mod_phymbl.f90:1250-1253 */
+                snprintf(s->errmsg, sizeof(s->errmsg), "wind stress too strong (record %d, station %ld)", jt, i);
+                rc = ABO_ERR_TAU;
+            }
+            const double qlw = qlw_net(rad_lw[o + i], Ts[i]);
+            const double v[28] = {rho, ql, qh, qlw, qh + ql + qlw, Qsw[i], dTcs[i], dTwl[i], tau, Ts[i] - sst[o + i],
+                                  Hwl[i],
+                                  (lsk && ialgo != ABO_ECMWF && s->c_Qnt_ac) ? s->c_Qnt_ac[i] : 0.,
+                                  (lsk && ialgo != ABO_ECMWF && s->c_Tau_ac) ? s->c_Tau_ac[i] : 0.,
+                                  Cd[i], Ce[i], Ch[i], thu[i], qu[i], tz, rib, z0[i], us[i], xL[i], un10[i], Ts[i], ev,
+                                  qa[i], tha[i]};
+            for (int k = 0; k < 28; k++)
+                if (out[k]) out[k][o + i] = v[k];
+        }
+    }
+    if (lsk) {
+        if (ialgo == ABO_ECMWF) free_ecmwf_state(s);
+        else free_coare_state(s);
+    }
+    s->nitend = nitend_saved;
+    for (int k = 0; k < 17; k++) free(w[k]);
+    free(Hwl);
+    return rc;
+}
+
 /* ------------------------------------------------------------------ */
 /* building blocks for unit tests                                      */
 /* ------------------------------------------------------------------ */
@@ -1732,6 +1827,7 @@ double abo_rho_air(double T, double q, double p) { init_consts(); return rho_air
 double abo_visc_air(double T) { init_consts(); return visc_air(T); }
 double abo_L_vap(double T) { init_consts(); return L_vap(T); }
 double abo_cp_air(double q) { init_consts(); return cp_air(q); }
+double abo_gamma_moist(double T, double q) { init_consts(); return gamma_moist(T, q); }
 double abo_alpha_sw(double T) { init_consts(); return alpha_sw(T); }
 double abo_qlw_net(double rlw, double Ts) { init_consts(); return qlw_net(rlw, Ts); }
 double abo_one_on_L(double tha, double qa, double us, double ts, double qs) { init_consts(); return One_on_L(tha, qa, us, ts, qs); }

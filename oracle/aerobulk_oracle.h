@@ -84,6 +84,7 @@ double abo_rho_air(double T, double q, double p);
 double abo_visc_air(double T);
 double abo_L_vap(double T);
 double abo_cp_air(double q);
+double abo_gamma_moist(double T, double q);
 double abo_alpha_sw(double T);
 double abo_qlw_net(double rlw, double Ts);
 double abo_one_on_L(double tha, double qa, double us, double ts, double qs);
@@ -116,6 +117,14 @@ int abo_turb(abo_session *s, const char *calgo, int kt, double zt, double zu, lo
              double *Cd, double *Ch, double *Ce, double *t_zu, double *q_zu, double *Ubzu,
              const double *Qsw, const double *rad_lw, const double *slp, int isecday_utc, const double *plong,
              double *const *opt);
+
+/* Station time series (src/tests/test_aerobulk_buoy_series_oce.f90:364-537) for S stations, records [Nt][S];
+ * out[28]: rho_zu QL QH Qlw QNS Qsw dT_cs dT_wl TAU dT Hz_wl Qnt_ac Tau_ac Cd Ce Ch theta_zu q_zu t_zu RiB z0 u_star L
+ * UN10 Ts Evap q_zt theta_zt (NULL = skip).  hum_kind 0 q, 1 dew-point [K], 2 RH [%]. */
+int abo_series(abo_session *s, const char *calgo, int Nt, long S, double zt, double zu,
+               const int *isecday_utc, const double *lon,
+               const double *sst, const double *t_zt, const double *hum_zt, int hum_kind, const double *wnd,
+               const double *slp, const double *rad_sw, const double *rad_lw, int l_skin, double *const *out);
 
 /* test-only: reproduce the pre-drift COARE 3.0 viscosity line (see .c) */
 void abo_debug_coare3p0_visc_at_tzu(int on);

@@ -77,6 +77,11 @@ def lib():
         L.abo_turb.restype = C.c_int
         L.abo_turb.argtypes = ([C.c_void_p, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_long] + [_dp] * 5 +
                                [C.c_int, C.c_int] + [_dp] * 6 + [_dp] * 3 + [C.c_int, _dp, C.POINTER(_dp)])
+        L.abo_series.restype = C.c_int
+        L.abo_series.argtypes = ([C.c_void_p, C.c_char_p, C.c_int, C.c_long, C.c_double, C.c_double, C.POINTER(C.c_int), _dp] +
+                                 [_dp] * 3 + [C.c_int] + [_dp] * 4 + [C.c_int, C.POINTER(_dp)])
+        L.abo_gamma_moist.restype = C.c_double
+        L.abo_gamma_moist.argtypes = [C.c_double, C.c_double]
         _lib = L
     return _lib
 
@@ -168,6 +173,28 @@ class OracleSession:
             raise OracleError(rc, self._L.abo_errmsg(self._s).decode())
         outs.update(optv)
         outs["T_s"], outs["q_s"] = Ts, qs
+        return outs
+
+    SERIES_OUT = ("rho_zu", "QL", "QH", "Qlw", "QNS", "Qsw", "dT_cs", "dT_wl", "TAU", "dT", "Hz_wl", "Qnt_ac", "Tau_ac",
+                  "Cd", "Ce", "Ch", "theta_zu", "q_zu", "t_zu", "RiB", "z0", "u_star", "L", "UN10", "Ts", "Evap", "q_zt",
+                  "theta_zt")
+
+    def series(self, calgo, zt, zu, isecday_utc, lon, sst, t_zt, hum_zt, wind, slp, rad_sw, rad_lw,
+               hum_kind=0, l_use_skin=True):
+        """Buoy-series time loop (abo_series); inputs (Nt,S) C-ordered; returns all 28 series."""
+        isd = np.ascontiguousarray(isecday_utc, dtype=np.int32)
+        Nt = isd.shape[0]
+        lon = np.ascontiguousarray(lon, dtype=np.float64).reshape(-1)
+        S = lon.shape[0]
+        ins = [np.ascontiguousarray(a, dtype=np.float64) for a in (sst, t_zt, hum_zt, wind, slp, rad_sw, rad_lw)]
+        outs = {k: np.zeros((Nt, S)) for k in self.SERIES_OUT}
+        arr = (_dp * 28)(*[_ptr(outs[k]) for k in self.SERIES_OUT])
+        rc = self._L.abo_series(self._s, calgo.encode(), Nt, S, float(zt), float(zu),
+                                isd.ctypes.data_as(C.POINTER(C.c_int)), _ptr(lon), _ptr(ins[0]), _ptr(ins[1]), _ptr(ins[2]),
+                                int(hum_kind), _ptr(ins[3]), _ptr(ins[4]), _ptr(ins[5]), _ptr(ins[6]),
+                                int(bool(l_use_skin)), arr)
+        if rc != 0:
+            raise OracleError(rc, self._L.abo_errmsg(self._s).decode())
         return outs
 
     def state(self, which: int, n: int):

@@ -4,6 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from aerobulk_b200 import build as B
 VARIANTS = {
     "smemtab": ["ABM_SMEM_TABLES=1"],
+    "ser64x1": ["AB_SERIES_MIN_BLOCKS=1"],
+    "ser64x8": ["AB_SERIES_MIN_BLOCKS=8"],
+    "ser128x6": ["AB_SERIES_BLOCK=128", "AB_SERIES_MIN_BLOCKS=6"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
