@@ -95,7 +95,7 @@ def station_series(Nt: int, S: int, seed: int = SEED, humidity: str = "q", dt_s:
     by day and its dawn reset (src/mod_skin_coare.f90:159-163) fires; wind, air-sea temperature difference and
     humidity wander slowly (weather) plus per-record noise.  Wind is either an exact calm (1 record in 512) or
     at least 0.5 m/s: between the two the ECMWF iteration is ill-conditioned (a 1e-15 relative input perturbation moves
-    the ORACLE's fluxes by up to 1e-9 at 0.1 m/s), which would test the conditioning rather than the implementation.  humidity: 'q' [kg/kg], 'rh' [%], 'dp' [K]."""
+    the fluxes of the CPU restatement by up to 1e-9 at 0.1 m/s), which would test the conditioning rather than the implementation.  humidity: 'q' [kg/kg], 'rh' [%], 'dp' [K]."""
     jt = np.arange(Nt, dtype=np.uint64)
     st = np.arange(S, dtype=np.uint64)
     idx = jt[:, None] * np.uint64(S) + st[None, :]
