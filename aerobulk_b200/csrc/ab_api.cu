@@ -69,6 +69,7 @@ struct Session {
     unsigned short *d_perm = nullptr;
     long long cap_perm = 0;
     int sort_points = 1;   // 0 never, 1 auto (where it measured faster), 2 always
+    int ice_form_per_point = 0;   // 0: LG15 form drag from the LAST point's ice fraction (reference), 1: per point
     // ---- statistics + deferred wind-stress flag
     double *d_partials = nullptr, *d_stats = nullptr;
     unsigned long long *d_bad = nullptr, *h_bad = nullptr;   // h_bad: pinned
@@ -139,10 +140,11 @@ int ensure_device()
     CUDA_TRY(cudaEventCreateWithFlags(&g.ev_bad, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&g.d_partials, sizeof(double) * abk::NSTATS * abk::stats_max_blocks()));
     CUDA_TRY(cudaMalloc(&g.d_stats, sizeof(double) * abk::NSTATS));
-    CUDA_TRY(cudaMalloc(&g.d_bad, sizeof(unsigned long long)));
-    CUDA_TRY(cudaHostAlloc(&g.h_bad, sizeof(unsigned long long), cudaHostAllocDefault));
-    *g.h_bad = ~0ull;
-    CUDA_TRY(cudaMemset(g.d_bad, 0xFF, sizeof(unsigned long long)));
+    // word 0: wind stress > 10 N/m^2; word 1 (sea-ice calls only): rough_leng_tq fail-stop
+    CUDA_TRY(cudaMalloc(&g.d_bad, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaHostAlloc(&g.h_bad, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    g.h_bad[0] = g.h_bad[1] = ~0ull;
+    CUDA_TRY(cudaMemset(g.d_bad, 0xFF, 2 * sizeof(unsigned long long)));
     g.device_ready = true;
     return 0;
 }
@@ -965,6 +967,227 @@ int series_csv_impl(const char *path_in, const char *path_out, const char *calgo
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// sea ice
+// ---------------------------------------------------------------------------
+int ice_algo_id(const char *c)
+{
+    if (!strcmp(c, "nemo")) return abd::ICE_NEMO;
+    if (!strcmp(c, "easy")) return abd::ICE_EASY;
+    if (!strcmp(c, "an05")) return abd::ICE_AN05;
+    if (!strcmp(c, "lu12")) return abd::ICE_LU12;
+    if (!strcmp(c, "lg15") || !strcmp(c, "lg15_io")) return abd::ICE_LG15;
+    return 0;
+}
+
+abd::IceUniform make_ice_uniform(double zt, double zu, const double *cxn)
+{
+    abd::IceUniform u;
+    memset(&u, 0, sizeof(u));
+    u.zt = zt;
+    u.zu = zu;
+    u.log_zu = log(zu);
+    u.log_ztu = log(zt / zu);
+    u.log_zu10 = log(zu / 10.);
+    if (cxn) {
+        u.cxn[0] = cxn[0]; u.cxn[1] = cxn[1]; u.cxn[2] = cxn[2];
+        u.sqrt_cdn = sqrt(cxn[0]);
+    }
+    const double r = 1. / log(zu / abd::RZ0_I_S_0);                 // Cd_from_z0, mod_phymbl.f90:1396-1414
+    u.cdn_s = abd::VKARMN2 * r * r;
+    u.chn_s = abd::VKARMN2 / (log(zu / abd::RZ0_I_S_0) * log(zu / (abd::RALPHA_0 * abd::RZ0_I_S_0)));   // LG15 Eq.11-12
+    const double t = 1. / abd::RZ0_I_F_0;
+    u.lg15_log_ratio = log(10. * t) / log(zu * t);                 // mod_cdn_form_ice.f90:322
+    u.an05_us_c = 0.035 * log(10. / 8.0E-4) / log(zu / 8.0E-4);    // mod_blk_ice_an05.f90:151
+    u.nb_iter = g.nb_iter;
+    return u;
+}
+
+// copies both flag words back, synchronises, reports
+int finish_ice_call(cudaStream_t cs_, const char *what)
+{
+    CUDA_TRY(cudaMemcpyAsync(g.h_bad, g.d_bad, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs_));
+    CUDA_TRY(cudaStreamSynchronize(cs_));
+    const unsigned long long bad_tau = g.h_bad[0], bad_rough = g.h_bad[1];
+    if (bad_tau != ~0ull || bad_rough != ~0ull) {
+        g.h_bad[0] = g.h_bad[1] = ~0ull;
+        cudaMemset(g.d_bad, 0xFF, 2 * sizeof(unsigned long long));
+        if (bad_rough != ~0ull)
+            return fail(AEROBULK_GPU_ERR_ICE_ROUGH,
+                        " rough_leng_tq@mod_blk_ice_an05.f90 => something wrong with zsmoot, ztrans, zrough!\n  (%s, point %lld)",
+                        what, (long long)bad_rough + 1);
+        return fail(AEROBULK_GPU_ERR_TAU, "BULK_FORMULA_VCTR()@mod_phymbl: wind stress too strong!\n  (%s, point %lld)", what,
+                    (long long)bad_tau + 1);
+    }
+    return 0;
+}
+
+int ensure_turb_slab(long long need)
+{
+    if (need > g.cap_turb) {
+        if (g.d_turb) cudaFree(g.d_turb);
+        g.d_turb = nullptr;
+        g.cap_turb = 0;
+        if (need > 0) CUDA_TRY(cudaMalloc(&g.d_turb, sizeof(double) * (size_t)need));
+        g.cap_turb = need;
+    }
+    return 0;
+}
+
+int turb_ice_impl(const char *calgo, double zt, double zu, int Ni, int Nj, const double *Ts_i, const double *t_zt,
+                  const double *qs_i, const double *q_zt, const double *U_zu, const double *frice, const double *cxn,
+                  double *Cd, double *Ch, double *Ce, double *t_zu, double *q_zu, double *Ubzu,
+                  const aerobulk_gpu_turb_ice_optional *opt, int on_device)
+{
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!calgo || !Ts_i || !t_zt || !qs_i || !q_zt || !U_zu || !Cd || !Ch || !Ce || !t_zu || !q_zu || !Ubzu)
+        return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_turb_ice: NULL mandatory argument");
+    const int ialgo = ice_algo_id(calgo);
+    if (!ialgo) return fail(AEROBULK_GPU_ERR_ALGO, "aerobulk_gpu_turb_ice: sea-ice bulk algorithm %s is unknown!!!", calgo);
+    const bool need_frice = (ialgo == abd::ICE_LU12 || ialgo == abd::ICE_LG15);
+    if (need_frice && !frice) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_turb_ice: turb_ice_%s needs frice", calgo);
+    if (ialgo == abd::ICE_EASY && !cxn) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_turb_ice: turb_ice_easy needs CdN, ChN, CeN");
+    if (Ni < 0 || Nj < 0) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_turb_ice: negative shape %d x %d", Ni, Nj);
+    int rc = ensure_device();
+    if (rc) return rc;
+    const long long n = (long long)Ni * Nj;
+    if (n == 0) return 0;
+    cudaStream_t cs_ = compute_stream();
+    rc = check_bad_flag(nullptr, nullptr);
+    if (rc) return rc;
+
+    double *optp[8] = {nullptr};
+    if (opt) {
+        optp[0] = opt->CdN; optp[1] = opt->ChN; optp[2] = opt->CeN; optp[3] = opt->xz0; optp[4] = opt->xu_star;
+        optp[5] = opt->xL; optp[6] = opt->xUN10; optp[7] = opt->CdN_frm;
+    }
+    const double *hin[6] = {Ts_i, t_zt, qs_i, q_zt, U_zu, need_frice ? frice : nullptr};
+    double *hout[14] = {Cd, Ch, Ce, t_zu, q_zu, Ubzu, optp[0], optp[1], optp[2], optp[3], optp[4], optp[5], optp[6], optp[7]};
+    const double *din[6];
+    double *dout[14];
+    if (on_device) {
+        for (int k = 0; k < 6; ++k) din[k] = hin[k];
+        for (int k = 0; k < 14; ++k) dout[k] = hout[k];
+    } else {
+        rc = ensure_turb_slab(n * 20);
+        if (rc) return rc;
+        double *p = g.d_turb;
+        for (int k = 0; k < 6; ++k) {
+            din[k] = hin[k] ? p : nullptr;
+            if (hin[k]) CUDA_TRY(cudaMemcpyAsync(p, hin[k], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs_));
+            p += n;
+        }
+        for (int k = 0; k < 14; ++k) {
+            dout[k] = hout[k] ? p : nullptr;
+            p += n;
+        }
+    }
+    abk::IceTurbArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Ts_i = din[0]; a.t_zt = din[1]; a.qs_i = din[2]; a.q_zt = din[3]; a.U_zu = din[4]; a.frice = din[5];
+    a.Cd = dout[0]; a.Ch = dout[1]; a.Ce = dout[2]; a.t_zu = dout[3]; a.q_zu = dout[4]; a.Ubzu = dout[5];
+    for (int k = 0; k < 8; ++k) a.opt[k] = dout[6 + k];
+    a.n = n;
+    a.form_index = g.ice_form_per_point ? -1 : n - 1;
+    a.u = make_ice_uniform(zt, zu, cxn);
+    a.bad_rough = g.d_bad + 1;
+    CUDA_TRY(abk::launch_ice_turb(ialgo, fabs(zu - zt) < 0.01, a, cs_));
+    g.launches += 1;
+    if (!on_device)
+        for (int k = 0; k < 14; ++k)
+            if (hout[k]) CUDA_TRY(cudaMemcpyAsync(hout[k], dout[k], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, cs_));
+    return finish_ice_call(cs_, "aerobulk_gpu_turb_ice");
+}
+
+int oce_ice_impl(const char *calgo_ice, const char *calgo_oce, double zt, double zu, long long n, const double *sit,
+                 const double *sst, const double *t_zt, const double *hum_zt, int hum_kind, const double *wind,
+                 const double *slp, const double *frice, const double *cxn, const aerobulk_gpu_oce_ice_out *out, int on_device)
+{
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!calgo_ice || !sit || !t_zt || !hum_zt || !wind || !slp || !frice || !out)
+        return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_oce_ice: NULL mandatory argument");
+    const int ialgo = ice_algo_id(calgo_ice);
+    if (!ialgo) return fail(AEROBULK_GPU_ERR_ALGO, "aerobulk_gpu_oce_ice: sea-ice bulk algorithm %s is unknown!!!", calgo_ice);
+    const int oalgo = calgo_oce ? algo_id(calgo_oce) : 0;
+    if (calgo_oce && !oalgo) return fail(AEROBULK_GPU_ERR_ALGO, "aerobulk_gpu_oce_ice: bulk algorithm %s is unknown!!!", calgo_oce);
+    if (oalgo && !sst) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_oce_ice: the leads need sst");
+    if (ialgo == abd::ICE_EASY && !cxn) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_oce_ice: turb_ice_easy needs CdN, ChN, CeN");
+    if (n < 0 || hum_kind < 0 || hum_kind > 2) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_oce_ice: bad n or hum_kind");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (n == 0) return 0;
+    cudaStream_t cs_ = compute_stream();
+    rc = check_bad_flag(nullptr, nullptr);
+    if (rc) return rc;
+
+    double *const hout[abk::NOCEICE_OUT] = {
+        out->Cd_i, out->Ch_i, out->Ce_i, out->theta_zu_i, out->q_zu_i, out->t_zu_i, out->Ub_i, out->RiB_i, out->z0_i,
+        out->u_star_i, out->L_i, out->UN10_i, out->rho_zu_i, out->Tau_i, out->QH_i, out->QL_i, out->Evap_i,
+        out->Cd_w, out->Ch_w, out->Ce_w, out->theta_zu_w, out->q_zu_w, out->Ub_w, out->z0_w, out->u_star_w, out->L_w,
+        out->UN10_w, out->Tau_w, out->QH_w, out->QL_w, out->Evap_w, out->Tau, out->QH, out->QL, out->Evap};
+    const double *hin[7] = {sit, oalgo ? sst : nullptr, t_zt, hum_zt, wind, slp, frice};
+    int nout = 0;
+    for (int k = 0; k < abk::NOCEICE_OUT; ++k) nout += hout[k] ? 1 : 0;
+    // scratch for the four ice fluxes the cell means need when the caller does not want them
+    int nscratch = 0;
+    if (oalgo)
+        for (int k = 0; k < 4; ++k) nscratch += hout[13 + k] ? 0 : 1;
+    rc = ensure_turb_slab(n * ((on_device ? 0 : 7 + nout) + nscratch));
+    if (rc) return rc;
+    double *p = g.d_turb;
+    const double *din[7];
+    double *dout[abk::NOCEICE_OUT];
+    if (on_device) {
+        for (int k = 0; k < 7; ++k) din[k] = hin[k];
+        for (int k = 0; k < abk::NOCEICE_OUT; ++k) dout[k] = hout[k];
+    } else {
+        for (int k = 0; k < 7; ++k) {
+            din[k] = hin[k] ? p : nullptr;
+            if (hin[k]) {
+                CUDA_TRY(cudaMemcpyAsync(p, hin[k], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs_));
+                p += n;
+            }
+        }
+        for (int k = 0; k < abk::NOCEICE_OUT; ++k) {
+            dout[k] = hout[k] ? p : nullptr;
+            if (hout[k]) p += n;
+        }
+    }
+    abk::OceIceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sit = din[0]; a.sst = din[1]; a.t_zt = din[2]; a.hum_zt = din[3]; a.wnd = din[4]; a.slp = din[5]; a.frice = din[6];
+    for (int k = 0; k < abk::NOCEICE_OUT; ++k) a.out[k] = dout[k];
+    if (oalgo)
+        for (int k = 0; k < 4; ++k) {
+            a.ice_flux[k] = dout[13 + k];
+            if (!a.ice_flux[k]) {
+                a.ice_flux[k] = p;
+                p += n;
+            }
+        }
+    a.n = n;
+    a.form_index = g.ice_form_per_point ? -1 : n - 1;
+    a.hum_kind = hum_kind;
+    a.ui = make_ice_uniform(zt, zu, cxn);
+    a.uo = make_uniform(zt, zu);
+    a.bad_tau = g.d_bad;
+    a.bad_rough = g.d_bad + 1;
+    const bool zteq = fabs(zu - zt) < 0.01;
+    CUDA_TRY(abk::launch_ice_flux(ialgo, zteq, a, cs_));
+    g.launches += 1;
+    if (oalgo) {
+        CUDA_TRY(abk::launch_leads(oalgo, zteq, a, cs_));
+        g.launches += 1;
+    }
+    if (!on_device)
+        for (int k = 0; k < abk::NOCEICE_OUT; ++k)
+            if (hout[k] && (oalgo || k < 17))
+                CUDA_TRY(cudaMemcpyAsync(hout[k], dout[k], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, cs_));
+    return finish_ice_call(cs_, "aerobulk_gpu_oce_ice");
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -1056,6 +1279,28 @@ int aerobulk_gpu_series_csv(const char *path_in, const char *path_out, const cha
     std::lock_guard<std::mutex> lk(g_mu);
     return series_csv_impl(path_in, path_out, calgo, zt, zu, l_use_skin);
 }
+
+int aerobulk_gpu_turb_ice(const char *calgo, double zt, double zu, int Ni, int Nj, const double *Ts_i, const double *t_zt,
+                          const double *qs_i, const double *q_zt, const double *U_zu, const double *frice,
+                          const double *CxN_easy, double *Cd, double *Ch, double *Ce, double *t_zu, double *q_zu,
+                          double *Ubzu, const aerobulk_gpu_turb_ice_optional *opt, int on_device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return turb_ice_impl(calgo, zt, zu, Ni, Nj, Ts_i, t_zt, qs_i, q_zt, U_zu, frice, CxN_easy, Cd, Ch, Ce, t_zu, q_zu, Ubzu,
+                         opt, on_device);
+}
+
+int aerobulk_gpu_oce_ice(const char *calgo_ice, const char *calgo_oce, double zt, double zu, long long n,
+                         const double *sit, const double *sst, const double *t_zt, const double *hum_zt, int hum_kind,
+                         const double *wind, const double *slp, const double *frice, const double *CxN_easy,
+                         const aerobulk_gpu_oce_ice_out *out, int on_device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return oce_ice_impl(calgo_ice, calgo_oce, zt, zu, n, sit, sst, t_zt, hum_zt, hum_kind, wind, slp, frice, CxN_easy, out,
+                        on_device);
+}
+
+void aerobulk_gpu_set_ice_form_drag_per_point(int on) { std::lock_guard<std::mutex> lk(g_mu); g.ice_form_per_point = on ? 1 : 0; }
 
 void aerobulk_gpu_set_nitend(int nitend) { std::lock_guard<std::mutex> lk(g_mu); g.nitend = nitend; }
 
@@ -1156,9 +1401,10 @@ void aerobulk_gpu_reset(void)
         if (g.d_turb) cudaFree(g.d_turb);
         g.d_turb = nullptr;
         g.cap_turb = 0;
-        if (g.h_bad) *g.h_bad = ~0ull;
-        if (g.d_bad) cudaMemset(g.d_bad, 0xFF, sizeof(unsigned long long));
+        if (g.h_bad) g.h_bad[0] = g.h_bad[1] = ~0ull;
+        if (g.d_bad) cudaMemset(g.d_bad, 0xFF, 2 * sizeof(unsigned long long));
     }
+    g.ice_form_per_point = 0;
     g.nb_iter = 5;
     g.nitend = 1;
     g.l_use_skin_schemes = false;

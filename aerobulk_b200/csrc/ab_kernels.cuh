@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "ab_device.cuh"
+#include "ab_ice.cuh"
 
 namespace abk {
 
@@ -64,6 +65,35 @@ struct SeriesArgs {
     unsigned long long *bad_index;   // first record*S + station whose stress exceeds 10 N/m^2, else ~0ull
 };
 cudaError_t launch_series(int algo, bool skin, bool zt_eq_zu, const SeriesArgs &a, cudaStream_t s);
+
+// Sea ice.  One launch = one TURB_ICE_* call (src/ice/mod_blk_ice_*.f90).
+struct IceTurbArgs {
+    const double *Ts_i, *t_zt, *qs_i, *q_zt, *U_zu, *frice;   // frice: lu12 / lg15 only (else NULL)
+    double *Cd, *Ch, *Ce, *t_zu, *q_zu, *Ubzu;
+    double *opt[8];                  // CdN ChN CeN xz0 xu_star xL xUN10 CdN_frm (NULL: not wanted)
+    long long n;
+    long long form_index;            // point whose ice fraction drives the LG15 form drag (reference: n-1), -1: each its own
+    abd::IceUniform u;
+    unsigned long long *bad_rough;   // first point where rough_leng_tq would ctl_stop, else ~0ull
+};
+cudaError_t launch_ice_turb(int ialgo, bool zt_eq_zu, const IceTurbArgs &a, cudaStream_t s);
+
+// Ice + leads workflow of src/ice/test_aerobulk_oce+ice.f90:225-412: ice_flux_kernel writes out[0..16], leads_kernel
+// out[17..34] (the cell means read the four ice fluxes back from `ice_flux`).
+constexpr int NOCEICE_OUT = 35;
+struct OceIceArgs {
+    const double *sit, *sst, *t_zt, *hum_zt, *wnd, *slp, *frice;
+    double *out[NOCEICE_OUT];
+    double *ice_flux[4];             // Tau, QH, QL, Evap over the ice (user arrays or scratch)
+    long long n;
+    long long form_index;
+    int hum_kind;
+    abd::IceUniform ui;
+    abd::Uniform uo;
+    unsigned long long *bad_tau, *bad_rough;
+};
+cudaError_t launch_ice_flux(int ialgo, bool zt_eq_zu, const OceIceArgs &a, cudaStream_t s);
+cudaError_t launch_leads(int oalgo, bool zt_eq_zu, const OceIceArgs &a, cudaStream_t s);
 
 // number of doubles in the statistics vector (see include/aerobulk_gpu.h)
 constexpr int NSTATS = 64;

@@ -74,6 +74,12 @@ def lib():
                                     [C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_void_p] * 3 + [C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_int])
     L.aerobulk_gpu_set_nitend.argtypes = [C.c_int]
+    L.aerobulk_gpu_turb_ice.restype = C.c_int
+    L.aerobulk_gpu_turb_ice.argtypes = ([C.c_char_p, C.c_double, C.c_double, C.c_int, C.c_int] + [C.c_void_p] * 14 + [C.c_int])
+    L.aerobulk_gpu_oce_ice.restype = C.c_int
+    L.aerobulk_gpu_oce_ice.argtypes = ([C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_longlong] + [C.c_void_p] * 4 +
+                                       [C.c_int] + [C.c_void_p] * 5 + [C.c_int])
+    L.aerobulk_gpu_set_ice_form_drag_per_point.argtypes = [C.c_int]
     L.aerobulk_gpu_series.restype = C.c_int
     L.aerobulk_gpu_series.argtypes = ([C.c_char_p, C.c_int, C.c_longlong, C.c_double, C.c_double] + [C.c_void_p] * 5 +
                                       [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int])
@@ -334,3 +340,59 @@ def series_csv(path_in: str, path_out: str, calgo: str, zt: float, zu: float, l_
     """One station, CSV in / CSV out (see include/aerobulk_gpu.h: aerobulk_gpu_series_csv)."""
     _check(lib().aerobulk_gpu_series_csv(os.fsencode(path_in), os.fsencode(path_out), calgo.encode(), float(zt),
                                          float(zu), int(bool(l_use_skin))))
+
+
+# ---------------------------------------------------------------------------
+# sea ice (SURVEY.md 8f row 4)
+# ---------------------------------------------------------------------------
+ICE_ALGORITHMS = ("nemo", "easy", "an05", "lu12", "lg15", "lg15_io")
+ICE_OPTIONAL = ("CdN", "ChN", "CeN", "xz0", "xu_star", "xL", "xUN10", "CdN_frm")
+OCE_ICE_OUT = tuple([k + "_i" for k in ("Cd", "Ch", "Ce", "theta_zu", "q_zu", "t_zu", "Ub", "RiB", "z0", "u_star", "L", "UN10",
+                                         "rho_zu", "Tau", "QH", "QL", "Evap")] +
+                    [k + "_w" for k in ("Cd", "Ch", "Ce", "theta_zu", "q_zu", "Ub", "z0", "u_star", "L", "UN10", "Tau", "QH",
+                                         "QL", "Evap")] + ["Tau", "QH", "QL", "Evap"])
+
+
+def set_ice_form_drag_per_point(on: bool):
+    lib().aerobulk_gpu_set_ice_form_drag_per_point(int(bool(on)))
+
+
+def turb_ice(calgo: str, zt: float, zu: float, Ts_i, t_zt, qs_i, q_zt, U_zu, frice=None, cxn=None, want=()) -> dict:
+    """Direct TURB_ICE_<calgo> call on HOST (numpy) arrays (src/ice/mod_blk_ice_*.f90).
+    Returns {"Cd","Ch","Ce","t_zu","q_zu","Ubzu"} plus the optional outputs named in `want`."""
+    L = lib()
+    Ts = _f64(Ts_i, np.shape(Ts_i))
+    shape = Ts.shape
+    Ni, Nj = _shape2(shape)
+    ins = [Ts] + [_f64(a, shape) for a in (t_zt, qs_i, q_zt, U_zu)] + [None if frice is None else _f64(frice, shape)]
+    cx = None if cxn is None else np.ascontiguousarray(cxn, dtype=np.float64)
+    outs = {k: np.empty(shape, dtype=np.float64, order="F") for k in ("Cd", "Ch", "Ce", "t_zu", "q_zu", "Ubzu")}
+    optv = {k: np.zeros(shape, dtype=np.float64, order="F") for k in want}
+    ptr = lambda a: None if a is None else a.ctypes.data
+    arr = (C.c_void_p * 8)(*[ptr(optv.get(k)) for k in ICE_OPTIONAL])
+    rc = L.aerobulk_gpu_turb_ice(calgo.encode(), float(zt), float(zu), Ni, Nj, *[ptr(a) for a in ins], ptr(cx),
+                                 *[ptr(outs[k]) for k in ("Cd", "Ch", "Ce", "t_zu", "q_zu", "Ubzu")],
+                                 C.cast(arr, C.c_void_p), 0)
+    _check(rc)
+    outs.update(optv)
+    return outs
+
+
+def oce_ice(calgo_ice: str, calgo_oce, zt: float, zu: float, sit, sst, t_zt, hum_zt, wind, slp, frice, hum_kind="q",
+            cxn=None, want=OCE_ICE_OUT) -> dict:
+    """Ice + leads fluxes on HOST (numpy) 1-D arrays: the computation of src/ice/test_aerobulk_oce+ice.f90:225-412.
+    `calgo_oce` None skips the leads.  Returns the series named in `want` (see OCE_ICE_OUT)."""
+    L = lib()
+    f = lambda a: None if a is None else np.ascontiguousarray(np.ravel(a, order="F"), dtype=np.float64)
+    ins = [f(a) for a in (sit, sst, t_zt, hum_zt, wind, slp, frice)]
+    n = ins[0].size
+    cx = None if cxn is None else np.ascontiguousarray(cxn, dtype=np.float64)
+    outs = {k: np.zeros(n, dtype=np.float64) for k in want}
+    ptr = lambda a: None if a is None else a.ctypes.data
+    arr = (C.c_void_p * len(OCE_ICE_OUT))(*[ptr(outs.get(k)) for k in OCE_ICE_OUT])
+    hk = HUM_KINDS[hum_kind] if isinstance(hum_kind, str) else int(hum_kind)
+    rc = L.aerobulk_gpu_oce_ice(calgo_ice.encode(), None if calgo_oce is None else calgo_oce.encode(), float(zt), float(zu),
+                                n, ptr(ins[0]), ptr(ins[1]), ptr(ins[2]), ptr(ins[3]), hk, ptr(ins[4]), ptr(ins[5]),
+                                ptr(ins[6]), ptr(cx), C.cast(arr, C.c_void_p), 0)
+    _check(rc)
+    return outs

@@ -129,3 +129,32 @@ def station_series(Nt: int, S: int, seed: int = SEED, humidity: str = "q", dt_s:
     c = lambda a: np.array(np.broadcast_to(a, (Nt, S)), dtype=np.float64, order="C")
     return dict(isecday_utc=isd, lon=lon, sst=c(sst), t_zt=c(t_zt), hum_zt=c(hum), wind=c(wind), slp=c(slp),
                 rad_sw=c(rad_sw), rad_lw=c(rad_lw))
+
+
+def ice_fields(n: int, seed: int = SEED, humidity: str = "q") -> dict:
+    """Synthetic polar forcing for the sea-ice algorithms: n points, 1-D arrays.
+    sit -35..-0.5 degC, leads at -1.9..0.5 degC, air-ice difference -6..+8 K (about half stable), RH 60..98 %, Rayleigh
+    wind capped at 28 m/s with 1 exact calm in 2048, ice fraction 0..1 with exact 0 and 1 occurrences."""
+    idx = np.arange(n, dtype=np.uint64)
+    u = lambda name, k=0: _u01(seed + 15485863 * (k + 1), _F[name], idx)
+    sit = 273.15 - 35.0 + 34.5 * u("sst")
+    sst = 273.15 - 1.9 + 2.4 * u("sst", 1)
+    t_zt = sit + (-6.0 + 14.0 * u("dT"))
+    slp = 100000.0 + 3500.0 * (u("slp") - 0.5)
+    rh = 60.0 + 38.0 * u("hum")
+    tc = t_zt - 273.15
+    esat = 611.2 * np.exp(17.67 * tc / (tc + 243.5))
+    if humidity in ("q", "sh"):
+        hum = 0.01 * rh * 0.622 * esat / slp
+    elif humidity == "rh":
+        hum = rh
+    elif humidity == "dp":
+        ln = np.log(0.01 * rh * esat / 611.2)
+        hum = 273.15 + 243.5 * ln / (17.67 - ln)
+    else:
+        raise ValueError(humidity)
+    wind = np.minimum(28.0, 7.0 * np.sqrt(-np.log(1.0 - u("wspd"))))
+    wind = np.where(u("calm") < 1.0 / 2048.0, 0.0, wind)
+    a = u("rsw")
+    frice = np.where(a < 0.02, 0.0, np.where(a > 0.9, 1.0, (a - 0.02) / 0.88))
+    return dict(sit=sit, sst=sst, t_zt=t_zt, hum_zt=hum, wind=wind, slp=slp, frice=frice)

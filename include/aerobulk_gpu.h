@@ -45,6 +45,7 @@ enum {
     AEROBULK_GPU_ERR_ALGO = 7,        /* unknown algorithm string    (mod_aerobulk_compute.f90:173-176) */
     AEROBULK_GPU_ERR_TAU = 8,         /* wind stress > 10 N/m^2      (mod_phymbl.f90:1250-1253)  */
     AEROBULK_GPU_ERR_STATE = 9,       /* warm-layer state (re)allocation (mod_blk_coare3p6.f90:82-83) */
+    AEROBULK_GPU_ERR_ICE_ROUGH = 10,  /* rough_leng_tq ctl_stop  (src/ice/mod_blk_ice_an05.f90:296-297) */
     AEROBULK_GPU_ERR_CUDA = 100,      /* CUDA runtime failure / no device                         */
     AEROBULK_GPU_ERR_ARG = 101,       /* NULL / inconsistent argument                             */
     AEROBULK_GPU_ERR_IO = 102         /* series CSV: file cannot be opened / parsed               */
@@ -160,6 +161,54 @@ int aerobulk_gpu_series(const char *calgo, int Nt, long long S, double zt, doubl
  * Returns 0, or an error code (AEROBULK_GPU_ERR_IO for file / format problems). */
 int aerobulk_gpu_series_csv(const char *path_in, const char *path_out, const char *calgo, double zt, double zu,
                             int l_use_skin);
+
+/* ---- sea ice (src/ice/) -------------------------------------------------------------------------------- */
+
+/* Optional outputs of the TURB_ICE_* routines; any member may be NULL.  CdN_frm: neutral FORM drag (lu12, lg15,
+ * lg15_io; 0 for the others). */
+typedef struct aerobulk_gpu_turb_ice_optional {
+    double *CdN, *ChN, *CeN, *xz0, *xu_star, *xL, *xUN10, *CdN_frm;
+} aerobulk_gpu_turb_ice_optional;
+
+/* Replaces TURB_ICE_NEMO / _EASY / _AN05 / _LU12 / _LG15 / _LG15_IO (src/ice/mod_blk_ice_nemo.f90:36-39,
+ * mod_blk_ice_easy.f90:35-38, mod_blk_ice_an05.f90:41-43, mod_blk_ice_lu12.f90:50-52, mod_blk_ice_lg15.f90:53-55,
+ * mod_blk_ice_lg15_io.f90:39-42 -- its over-ice outputs), selected by calgo = "nemo" | "easy" | "an05" | "lu12" | "lg15" |
+ * "lg15_io".  t_zt is the POTENTIAL air temperature, qs_i the saturation humidity over ice at Ts_i, U_zu the scalar wind.
+ * frice (ice fraction) is needed by lu12 / lg15 / lg15_io, CxN_easy[3] = CdN, ChN, CeN (host memory) by easy; NULL otherwise.
+ * Iterations: the nb_iter global.  Not provided: TURB_ICE_BEST (reads an unset array in the reference,
+ * mod_blk_ice_best.f90:154) and the over-water outputs of TURB_ICE_LG15_IO (never initialised there, :170-172).
+ * Reference behaviour kept by default: the LG15 form drag of EVERY point is computed from the ice fraction of the LAST
+ * point, because CdN_f_LG15_light assigns its whole result array inside the point loop (src/ice/mod_cdn_form_ice.f90:324);
+ * aerobulk_gpu_set_ice_form_drag_per_point(1) uses each point's own fraction instead.
+ * Error 10 where the reference's rough_leng_tq would ctl_stop (an05, roughness Reynolds number in ]2.49999, 2.5[). */
+int aerobulk_gpu_turb_ice(const char *calgo, double zt, double zu, int Ni, int Nj,
+                          const double *Ts_i, const double *t_zt, const double *qs_i, const double *q_zt,
+                          const double *U_zu, const double *frice, const double *CxN_easy,
+                          double *Cd, double *Ch, double *Ce, double *t_zu, double *q_zu, double *Ubzu,
+                          const aerobulk_gpu_turb_ice_optional *opt, int on_device);
+void aerobulk_gpu_set_ice_form_drag_per_point(int on);
+
+/* Outputs of aerobulk_gpu_oce_ice; any member may be NULL.  _i over the ice, _w over the leads, no suffix: the
+ * area-weighted cell mean A x_i + (1-A) x_w (the partition a model such as NEMO applies; the reference program prints the
+ * two sides only). */
+typedef struct aerobulk_gpu_oce_ice_out {
+    double *Cd_i, *Ch_i, *Ce_i, *theta_zu_i, *q_zu_i, *t_zu_i, *Ub_i, *RiB_i, *z0_i, *u_star_i, *L_i, *UN10_i, *rho_zu_i;
+    double *Tau_i, *QH_i, *QL_i, *Evap_i;
+    double *Cd_w, *Ch_w, *Ce_w, *theta_zu_w, *q_zu_w, *Ub_w, *z0_w, *u_star_w, *L_w, *UN10_w, *Tau_w, *QH_w, *QL_w, *Evap_w;
+    double *Tau, *QH, *QL, *Evap;
+} aerobulk_gpu_oce_ice_out;
+
+/* The ice + leads computation of src/ice/test_aerobulk_oce+ice.f90:225-412 (and test_aerobulk_ice.f90:186-370) on n
+ * points: sit ice surface temperature [K], sst temperature of the leads [K], t_zt ABSOLUTE air temperature [K], hum_zt
+ * (hum_kind 0 specific humidity, 1 dew-point [K], 2 RH [%]), wind [m/s], slp [Pa], frice ice fraction.  Over the ice:
+ * siq = q_sat(sit, l_ice), theta_zt = t_zt + gamma_moist zt, TURB_ICE_<calgo_ice>, Ri_b, t_zu, rho_zu,
+ * BULK_FORMULA(l_ice=.TRUE.) (sublimation heat, Evap = MIN(E, 0)).  Over the leads (calgo_oce NULL: skipped; the
+ * program uses "ecmwf"): ssq = 0.98 q_sat(sst) (the program evaluates it at sit, :213 -- not reproduced),
+ * TURB_<calgo_oce> without skin, BULK_FORMULA. */
+int aerobulk_gpu_oce_ice(const char *calgo_ice, const char *calgo_oce, double zt, double zu, long long n,
+                         const double *sit, const double *sst, const double *t_zt, const double *hum_zt, int hum_kind,
+                         const double *wind, const double *slp, const double *frice, const double *CxN_easy,
+                         const aerobulk_gpu_oce_ice_out *out, int on_device);
 
 /* Waits for the session stream and reports a deferred error (wind stress too strong). */
 int aerobulk_gpu_synchronize(void);

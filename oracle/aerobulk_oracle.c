@@ -1817,6 +1817,507 @@ int abo_series(abo_session *s, const char *calgo, int Nt, long S, double zt, dou
     return rc;
 }
 
+/* ================================================================== */
+/* SEA ICE: src/ice/mod_blk_ice_{nemo,easy,an05,lu12,lg15,lg15_io}.f90,                   */
+/* src/ice/mod_cdn_form_ice.f90 and the ice helpers of src/mod_phymbl.f90.                                        */
+/* Not restated: mod_blk_ice_best.f90 (reads sqrtCdn10 before it is ever set, :154 -- undefined in the reference) */
+/* and the over-water outputs of turb_ice_lg15_io (zCdN_s(:,:,2), zz0_s(:,:,2) are never initialised, :170-172).  */
+/* ================================================================== */
+static const double rtt0 = 273.16;            /* mod_const.f90:61 triple point */
+static const double rLsub = 2.834e+6;         /* :92 */
+static const double rCd_ice = 1.4e-3;         /* :118 */
+static const double wspd_thrshld_ice = 0.2;   /* :120 */
+
+/* e_sat_ice_sclr, mod_phymbl.f90:815-830 (Goff over ice) */
+static double e_sat_ice(double pTa)
+{
+    const double rAg_i = -9.09718, rBg_i = -3.56654, rCg_i = 0.876793;
+    const double rDg_i = 0.7858350313586662;    /* LOG10(6.1071_wp): a PARAMETER, folded (correctly rounded) by the compiler, :147 */
+    double zta = MAX(pTa, 180.);
+    double ztmp = rtt0 / zta;
+    double zle = rAg_i * (ztmp - 1.) + rBg_i * log10(ztmp) + rCg_i * (1. - zta / rtt0) + rDg_i;
+    return 100. * pow(10., zle);
+}
+/* q_sat_sclr with l_ice=.TRUE., :881-904 */
+static double q_sat_ice(double pTa, double pslp)
+{
+    double ze_s = e_sat_ice(pTa);
+    return reps0 * ze_s / (pslp - (1. - reps0) * ze_s);
+}
+/* Cd_from_z0 without ppsi, :1396-1414 */
+static double Cd_from_z0(double pzu, double pz0)
+{
+    double r = 1. / log(pzu / pz0);
+    return vkarmn2 * r * r;
+}
+/* f_m_louis_sclr :1419-1440, f_h_louis_sclr :1458-1479 (Louis 1979; rc_louis = 5, :149-153) */
+static double f_m_louis(double pzu, double pRib, double pCdn, double pz0)
+{
+    const double rc2_louis = 5. * 5., ram_louis = 2. * 5.;
+    double zstab = 0.5 + SIGN(0.5, pRib);
+    double ztu = pRib / (1. + 3. * rc2_louis * pCdn * sqrt(fabs(-pRib * (pzu / pz0 + 1.))));
+    double zts = pRib / sqrt(fabs(1. + pRib));
+    return (1. - zstab) * (1. - ram_louis * ztu) + zstab * 1. / (1. + ram_louis * zts);
+}
+static double f_h_louis(double pzu, double pRib, double pChn, double pz0)
+{
+    const double rc2_louis = 5. * 5., rah_louis = 3. * 5.;
+    double zstab = 0.5 + SIGN(0.5, pRib);
+    double ztu = pRib / (1. + 3. * rc2_louis * pChn * sqrt(fabs(-pRib * (pzu / pz0 + 1.))));
+    double zts = pRib / sqrt(fabs(1. + pRib));
+    return (1. - zstab) * (1. - rah_louis * ztu) + zstab * 1. / (1. + rah_louis * zts);
+}
+/* CdN10_f_LU13, mod_cdn_form_ice.f90:170-208: rCe_0 A**(mu-1) (1-A)**(nu + 1/(10 beta)), mu = nu = 1, beta = 1.4 */
+static double CdN10_f_LU13(double pfrice)
+{
+    const double rCe_0 = 2.23E-3, rNu_0 = 1., rMu_0 = 1., rbeta_0 = 1.4;
+    double zcoef = rNu_0 + 1. / (10. * rbeta_0);
+    return rCe_0 * pow(pfrice, rMu_0 - 1.) * pow(1. - pfrice, zcoef);
+}
+/* CdN_f_LG15_light, :299-330 (Eq.46).  NB: the reference assigns the WHOLE result array inside its point loop
+ * (`CdN_f_LG15_light(:,:) = ...`, :324), so every point ends up with the value of the LAST point (Ni,Nj): callers
+ * pass the ice fraction of the last point (see abo_turb_ice). */
+static double CdN_f_LG15_light(double pzu, double pfrice, double pz0w)
+{
+    const double rce10_i_0 = 3.46e-3, rbeta_0 = 1.4;
+    double ztmp = 1. / pz0w;
+    double zrlog = log(10. * ztmp) / log(pzu * ztmp);
+    return rce10_i_0 * zrlog * zrlog * pfrice * pow(1. - pfrice, rbeta_0);
+}
+/* psi_m_ice / psi_h_ice, mod_blk_ice_an05.f90:329-405 (same text in mod_blk_ice_easy.f90:213-289) */
+static double psi_m_ice(double pzeta)
+{
+    double zta = pzeta;
+    double zx = pow(fabs(1. - 16. * zta), .25);
+    double zpsi_u = log((1. + zx * zx) / 2.) + 2. * log((1. + zx) / 2.) - 2. * atan(zx) + 0.5 * rpi;
+    double zpsi_s = -(0.7 * zta + 0.75 * (zta - 14.3) * exp(-0.35 * zta) + 10.7);
+    double zstab = 0.5 + SIGN(0.5, zta);
+    return (1. - zstab) * zpsi_u + zstab * zpsi_s;
+}
+static double psi_h_ice(double pzeta)
+{
+    double zta = pzeta;
+    double zx = pow(fabs(1. - 16. * zta), .25);
+    double zpsi_u = 2. * log((1. + zx * zx) / 2.);
+    double zpsi_s = -(0.7 * zta + 0.75 * (zta - 14.3) * exp(-0.35 * zta) + 10.7);
+    double zstab = 0.5 + SIGN(0.5, zta);
+    return (1. - zstab) * zpsi_u + zstab * zpsi_s;
+}
+/* rough_leng_m, mod_blk_ice_an05.f90:247-268 (Andreas et al. 2005 Eq.19) */
+static double rough_leng_m(double pus, double pnua)
+{
+    double zus = MAX(pus, 1.E-9);
+    double zz = (zus - 0.18) / 0.1;
+    return 0.135 * pnua / zus + 0.035 * zus * zus / grav * (5. * exp(-zz * zz) + 1.);
+}
+/* rough_leng_tq, :270-325 (Andreas 1987 table); returns 1 when the reference would ctl_stop (:296-297: for
+ * 2.49999 < R* < 2.5 none of the three regimes is selected) */
+static int rough_leng_tq(double pz0, double pus, double pnua, double *z0t, double *z0q)
+{
+    double zz0 = pz0;
+    double zus = MAX(pus, 1.E-9);
+    double zre = MAX(zus * zz0 / pnua, 0.);
+    double zsmoot = 0.5 + SIGN(0.5, (0.135 - zre));
+    double ztrans = 0.5 + SIGN(0.5, (2.49999 - zre)) - zsmoot;
+    double zrough = 0.5 + SIGN(0.5, (zre - 2.5));
+    int bad = (zsmoot + ztrans + zrough > 1.001) || (zsmoot + ztrans + zrough < 0.999);
+    double zlog = log(zre);
+    double zlog2 = zlog * zlog;
+    double zb0 = zsmoot * 1.25 + ztrans * 0.149 + zrough * 0.317;
+    double zb1 = -ztrans * 0.550 - zrough * 0.565;
+    double zb2 = -zrough * 0.183;
+    *z0t = zz0 * exp(zb0 + zb1 * zlog + zb2 * zlog2);
+    zb0 = zsmoot * 1.61 + ztrans * 0.351 + zrough * 0.396;
+    zb1 = -ztrans * 0.628 - zrough * 0.512;
+    zb2 = -zrough * 0.180;
+    *z0q = zz0 * exp(zb0 + zb1 * zlog + zb2 * zlog2);
+    return bad;
+}
+
+typedef struct {
+    double Cd, Ch, Ce, t_zu, q_zu, Ub;
+    double CdN, ChN, CeN, z0, us, L, UN10, CdN_frm;
+} ice_out;
+
+static void ice_first_guess(double Ts_i, double t_zt, double qs_i, double q_zt, double U_zu, ice_out *o, double *dt, double *dq)
+{
+    o->Ub = MAX(U_zu, wspd_thrshld_ice);
+    o->t_zu = MAX(t_zt, 100.);
+    o->q_zu = MAX(q_zt, 0.1e-6);
+    *dt = o->t_zu - Ts_i; *dt = SIGN(MAX(fabs(*dt), 1.E-6), *dt);
+    *dq = o->q_zu - qs_i; *dq = SIGN(MAX(fabs(*dq), 1.E-9), *dq);
+}
+
+/* turb_ice_nemo, mod_blk_ice_nemo.f90:36-153 */
+static void turb_ice_nemo(double zt, double zu, double Ts_i, double t_zt, double qs_i, double q_zt, double U_zu, ice_out *o)
+{
+    (void)zt;
+    double dt, dq;
+    ice_first_guess(Ts_i, t_zt, qs_i, q_zt, U_zu, o, &dt, &dq);
+    o->Cd = o->Ch = o->Ce = rCd_ice;
+    o->CdN = o->ChN = o->CeN = rCd_ice;
+    o->z0 = z0_from_Cd_neutral(zu, o->Cd);
+    o->us = sqrt(rCd_ice) * o->Ub;
+    o->L = 1. / One_on_L(o->t_zu, o->q_zu, sqrt(rCd_ice) * o->Ub, rCd_ice / sqrt(rCd_ice) * dt, rCd_ice / sqrt(rCd_ice) * dq);
+    o->UN10 = sqrt(rCd_ice) * o->Ub / vkarmn * log(10. / z0_from_Cd_neutral(zu, o->Cd));
+    o->CdN_frm = 0.;
+}
+
+/* turb_ice_easy, mod_blk_ice_easy.f90:35-209 (CdN, ChN, CeN are scalar INPUTS) */
+static void turb_ice_easy(int nb_iter, double zt, double zu, double Ts_i, double t_zt, double qs_i, double q_zt, double U_zu,
+                          double CdN, double ChN, double CeN, ice_out *o)
+{
+    int l_zt_equal_zu = (fabs(zu - zt) < 0.01);
+    double zsqrtCDN = sqrt(CdN);
+    double zlog1 = log(zt / zu);
+    double zlog2 = log(zu / 10.);
+    o->Ub = MAX(U_zu, wspd_thrshld_ice);
+    o->t_zu = MAX(t_zt, 100.);
+    o->q_zu = MAX(q_zt, 0.1e-6);
+    o->Cd = CdN; o->Ch = ChN; o->Ce = CeN;
+    double u_star = 0., t_star = 0., q_star = 0., zeta_u = 0., zeta_t = 0.;
+    for (int jit = 1; jit <= nb_iter; jit++) {
+        double dt_zu = o->t_zu - Ts_i;
+        double dq_zu = o->q_zu - qs_i;
+        double ztmp0 = sqrt(o->Cd);
+        u_star = ztmp0 * o->Ub;
+        ztmp0 = 1. / MAX(ztmp0, 1.E-15);
+        t_star = o->Ch * dt_zu * ztmp0;
+        q_star = o->Ce * dq_zu * ztmp0;
+        ztmp0 = One_on_L(o->t_zu, o->q_zu, u_star, t_star, q_star);
+        ztmp0 = SIGN(MIN(fabs(ztmp0), 200.), ztmp0);
+        zeta_u = zu * ztmp0;
+        zeta_u = SIGN(MIN(fabs(zeta_u), 50.0), zeta_u);
+        if (!l_zt_equal_zu) {
+            zeta_t = zt * ztmp0;
+            zeta_t = SIGN(MIN(fabs(zeta_t), 50.0), zeta_t);
+        }
+        ztmp0 = 1. + zsqrtCDN / vkarmn * (zlog2 - psi_m_ice(zeta_u));
+        o->Cd = MIN(MAX(CdN / (ztmp0 * ztmp0), Cx_min), 1.9E-3);
+        ztmp0 = (zlog2 - psi_h_ice(zeta_u)) / vkarmn / zsqrtCDN;
+        double ztmp1 = sqrt(o->Cd) / zsqrtCDN;
+        o->Ch = MIN(MAX(ChN * ztmp1 / (1. + ChN * ztmp0), Cx_min), 1.9E-3);
+        o->Ce = MIN(MAX(CeN * ztmp1 / (1. + CeN * ztmp0), Cx_min), 1.9E-3);
+        if (!l_zt_equal_zu) {
+            ztmp0 = psi_h_ice(zeta_u) - psi_h_ice(zeta_t) + zlog1;
+            o->t_zu = t_zt - t_star / vkarmn * ztmp0;
+            o->q_zu = MAX(0., q_zt - q_star / vkarmn * ztmp0);
+        }
+    }
+    o->CdN = CdN; o->ChN = ChN; o->CeN = CeN;
+    o->z0 = z0_from_Cd_psi(zu, o->Cd, psi_m_ice(zeta_u));
+    o->us = u_star;
+    o->L = 1. / One_on_L(o->t_zu, o->q_zu, u_star, t_star, q_star);
+    o->UN10 = UN10_from_CD(zu, o->Ub, o->Cd, psi_m_ice(zeta_u));
+    o->CdN_frm = 0.;
+}
+
+/* turb_ice_an05, mod_blk_ice_an05.f90:41-243; returns 1 when rough_leng_tq would ctl_stop */
+static int turb_ice_an05(int nb_iter, double zt, double zu, double Ts_i, double t_zt, double qs_i, double q_zt, double U_zu, ice_out *o)
+{
+    int l_zt_equal_zu = (fabs(zu - zt) < 0.01);
+    double dt_zu, dq_zu;
+    int bad = 0;
+    ice_first_guess(Ts_i, t_zt, qs_i, q_zt, U_zu, o, &dt_zu, &dq_zu);
+    double znu_a = visc_air(o->t_zu);
+    double z0 = 8.0E-4;
+    double u_star = 0.035 * o->Ub * log(10. / z0) / log(zu / z0);
+    z0 = rough_leng_m(u_star, znu_a);
+    for (int jit = 1; jit <= 2; jit++) {
+        u_star = MAX(o->Ub * vkarmn / (log(zu) - log(z0)), 1.E-9);
+        z0 = rough_leng_m(u_star, znu_a);
+    }
+    double z0t, z0q;
+    bad |= rough_leng_tq(z0, u_star, znu_a, &z0t, &z0q);
+    double t_star = dt_zu * vkarmn / (log(zu / z0t));
+    double q_star = dq_zu * vkarmn / (log(zu / z0q));
+    for (int jit = 1; jit <= nb_iter; jit++) {
+        double ztmp0 = One_on_L(o->t_zu, o->q_zu, u_star, t_star, q_star);
+        ztmp0 = SIGN(MIN(fabs(ztmp0), 200.), ztmp0);
+        double zeta_u = zu * ztmp0, zeta_t = 0.;
+        zeta_u = SIGN(MIN(fabs(zeta_u), 50.0), zeta_u);
+        if (!l_zt_equal_zu) {
+            zeta_t = zt * ztmp0;
+            zeta_t = SIGN(MIN(fabs(zeta_t), 50.0), zeta_t);
+        }
+        z0 = rough_leng_m(u_star, znu_a);
+        bad |= rough_leng_tq(z0, u_star, znu_a, &z0t, &z0q);
+        ztmp0 = psi_h_ice(zeta_u);
+        t_star = dt_zu * vkarmn / (log(zu) - log(z0t) - ztmp0);
+        q_star = dq_zu * vkarmn / (log(zu) - log(z0q) - ztmp0);
+        u_star = MAX(o->Ub * vkarmn / (log(zu) - log(z0) - psi_m_ice(zeta_u)), 1.E-9);
+        if (!l_zt_equal_zu) {
+            double ztmp1 = log(zt / zu) + ztmp0 - psi_h_ice(zeta_t);
+            o->t_zu = t_zt - t_star / vkarmn * ztmp1;
+            o->q_zu = q_zt - q_star / vkarmn * ztmp1;
+            dt_zu = o->t_zu - Ts_i; dt_zu = SIGN(MAX(fabs(dt_zu), 1.E-6), dt_zu);
+            dq_zu = o->q_zu - qs_i; dq_zu = SIGN(MAX(fabs(dq_zu), 1.E-9), dq_zu);
+        }
+    }
+    double ztmp0 = u_star / o->Ub;
+    o->Cd = ztmp0 * ztmp0;
+    o->Ch = ztmp0 * t_star / dt_zu;
+    o->Ce = ztmp0 * q_star / dq_zu;
+    ztmp0 = 1. / log(zu / z0);
+    o->CdN = vkarmn2 * ztmp0 * ztmp0;
+    o->ChN = vkarmn2 * ztmp0 / log(zu / z0t);
+    o->CeN = vkarmn2 * ztmp0 / log(zu / z0q);
+    o->z0 = z0;
+    o->us = u_star;
+    o->L = 1. / One_on_L(o->t_zu, o->q_zu, u_star, t_star, q_star);
+    o->UN10 = u_star / vkarmn * log(10. / z0);
+    o->CdN_frm = 0.;
+    return bad;
+}
+
+/* turb_ice_lu12, mod_blk_ice_lu12.f90:50-214 ("Method #1": skin drag of z0 = 0.69e-3 m + LU13 form drag) */
+static void turb_ice_lu12(double zt, double zu, double Ts_i, double t_zt, double qs_i, double q_zt, double U_zu, double frice, ice_out *o)
+{
+    (void)zt;
+    const double rz0_i_s_0 = 0.69e-3;
+    double dt_zu, dq_zu;
+    ice_first_guess(Ts_i, t_zt, qs_i, q_zt, U_zu, o, &dt_zu, &dq_zu);
+    o->CdN_frm = CdN10_f_LU13(frice);
+    o->Cd = Cd_from_z0(zu, rz0_i_s_0) + o->CdN_frm;
+    o->Ch = o->Cd;
+    o->Ce = o->Cd;
+    o->CdN = o->Cd; o->ChN = o->Ch; o->CeN = o->Ce;
+    o->z0 = z0_from_Cd_neutral(zu, o->Cd);
+    o->us = sqrt(o->Cd) * o->Ub;
+    o->L = 1. / One_on_L(o->t_zu, o->q_zu, sqrt(o->Cd) * o->Ub, o->Cd / sqrt(o->Cd) * dt_zu, o->Cd / sqrt(o->Cd) * dq_zu);
+    o->UN10 = sqrt(o->Cd) * o->Ub / vkarmn * log(10. / z0_from_Cd_neutral(zu, o->Cd));
+}
+
+/* turb_ice_lg15, mod_blk_ice_lg15.f90:53-307 (== the over-ice part of turb_ice_lg15_io, mod_blk_ice_lg15_io.f90:39-370).
+ * frice_form is the ice fraction the form drag is computed from: the LAST point's in the reference (see CdN_f_LG15_light). */
+static void turb_ice_lg15(int nb_iter, double zt, double zu, double Ts_i, double t_zt, double qs_i, double q_zt, double U_zu,
+                          double frice_form, ice_out *o)
+{
+    const double ralpha_0 = 0.2, rz0_i_s_0 = 0.69e-3, rz0_i_f_0 = 4.54e-4;
+    int l_zt_equal_zu = (fabs(zu - zt) < 0.01);
+    double dt_zu, dq_zu;
+    ice_first_guess(Ts_i, t_zt, qs_i, q_zt, U_zu, o, &dt_zu, &dq_zu);
+    double zz0_s = rz0_i_s_0;
+    double zCdN_s = Cd_from_z0(zu, zz0_s);
+    double zChN_s = vkarmn2 / (log(zu / zz0_s) * log(zu / (ralpha_0 * zz0_s)));
+    double zz0_f = rz0_i_f_0;
+    double zCdN_f = CdN_f_LG15_light(zu, frice_form, zz0_f);
+    double zChN_f = zCdN_f / (1. + log(1. / ralpha_0) / vkarmn * sqrt(zCdN_f));
+    o->Cd = zCdN_s + zCdN_f;
+    o->Ch = zChN_s + zChN_f;
+    double RiB = Ri_bulk(zt, Ts_i, t_zt, qs_i, q_zt, o->Ub);
+    for (int jit = 1; jit <= nb_iter; jit++) {
+        double xtmp1, xtmp2;
+        if (!l_zt_equal_zu) {
+            xtmp1 = zCdN_s + zCdN_f;
+            xtmp2 = zz0_s + zz0_f;
+            xtmp1 = log(zt / zu) + f_h_louis(zu, RiB, xtmp1, xtmp2) - f_h_louis(zt, RiB, xtmp1, xtmp2);
+            xtmp2 = MAX(o->Ub + (sqrt(o->Cd) * o->Ub) * xtmp1, wspd_thrshld_ice);
+            xtmp2 = MIN(xtmp2, o->Ub);
+        } else {
+            xtmp2 = o->Ub;
+        }
+        RiB = Ri_bulk(zt, Ts_i, t_zt, qs_i, q_zt, xtmp2);
+        o->Cd = zCdN_s * f_m_louis(zu, RiB, zCdN_s, zz0_s);
+        o->Ch = zChN_s * f_h_louis(zu, RiB, zCdN_s, zz0_s);
+        o->Cd = o->Cd + zCdN_f * f_m_louis(zu, RiB, zCdN_f, zz0_f);
+        o->Ch = o->Ch + zChN_f * f_h_louis(zu, RiB, zCdN_f, zz0_f);
+        if (!l_zt_equal_zu) {
+            xtmp1 = zCdN_s + zCdN_f;
+            xtmp2 = zz0_s + zz0_f;
+            xtmp1 = log(zt / zu) + f_h_louis(zu, RiB, xtmp1, xtmp2) - f_h_louis(zt, RiB, xtmp1, xtmp2);
+            xtmp2 = 1. / sqrt(o->Cd);
+            o->t_zu = t_zt - (o->Ch * dt_zu * xtmp2) / vkarmn * xtmp1;
+            o->q_zu = q_zt - (o->Ch * dq_zu * xtmp2) / vkarmn * xtmp1;
+            o->q_zu = MAX(0., o->q_zu);
+            dt_zu = o->t_zu - Ts_i;
+            dq_zu = o->q_zu - qs_i;
+            dt_zu = SIGN(MAX(fabs(dt_zu), 1.E-6), dt_zu);
+            dq_zu = SIGN(MAX(fabs(dq_zu), 1.E-9), dq_zu);
+        }
+    }
+    o->Ce = o->Ch;
+    o->CdN_frm = zCdN_f;
+    o->CdN = zCdN_s + zCdN_f;
+    o->ChN = zChN_s + zChN_f;
+    o->CeN = zChN_s + zChN_f;
+    o->z0 = z0_from_Cd_neutral(zu, zCdN_s + zCdN_f);
+    o->us = sqrt(o->Cd) * o->Ub;
+    {
+        double x = sqrt(o->Cd);
+        o->L = 1. / One_on_L(o->t_zu, o->q_zu, x * o->Ub, o->Ch * dt_zu / x, o->Ce * dq_zu / x);
+    }
+    o->UN10 = sqrt(o->Cd) * o->Ub / vkarmn * log(10. / z0_from_Cd_neutral(zu, zCdN_s + zCdN_f));
+}
+
+enum { ABO_ICE_NEMO = 1, ABO_ICE_EASY = 2, ABO_ICE_AN05 = 3, ABO_ICE_LU12 = 4, ABO_ICE_LG15 = 5, ABO_ICE_LG15_IO = 6 };
+static int ice_algo_id(const char *c)
+{
+    if (!strcmp(c, "nemo")) return ABO_ICE_NEMO;
+    if (!strcmp(c, "easy")) return ABO_ICE_EASY;
+    if (!strcmp(c, "an05")) return ABO_ICE_AN05;
+    if (!strcmp(c, "lu12")) return ABO_ICE_LU12;
+    if (!strcmp(c, "lg15")) return ABO_ICE_LG15;
+    if (!strcmp(c, "lg15_io")) return ABO_ICE_LG15_IO;
+    return 0;
+}
+
+static int ice_point(int ialgo, int nb_iter, double zt, double zu, double Ts_i, double t_zt, double qs_i, double q_zt,
+                     double U_zu, double frice, double frice_form, const double *cxn, ice_out *o)
+{
+    switch (ialgo) {
+    case ABO_ICE_NEMO: turb_ice_nemo(zt, zu, Ts_i, t_zt, qs_i, q_zt, U_zu, o); return 0;
+    case ABO_ICE_EASY: turb_ice_easy(nb_iter, zt, zu, Ts_i, t_zt, qs_i, q_zt, U_zu, cxn[0], cxn[1], cxn[2], o); return 0;
+    case ABO_ICE_AN05: return turb_ice_an05(nb_iter, zt, zu, Ts_i, t_zt, qs_i, q_zt, U_zu, o);
+    case ABO_ICE_LU12: turb_ice_lu12(zt, zu, Ts_i, t_zt, qs_i, q_zt, U_zu, frice, o); return 0;
+    default: turb_ice_lg15(nb_iter, zt, zu, Ts_i, t_zt, qs_i, q_zt, U_zu, frice_form, o); return 0;
+    }
+}
+
+/*
+ * Direct TURB_ICE_* call on n points.  calgo: nemo | easy | an05 | lu12 | lg15 | lg15_io.  frice is needed by lu12 / lg15 /
+ * lg15_io; cxn[3] = CdN, ChN, CeN are the scalar inputs of `easy`.  per_point_form_drag = 0 reproduces the reference
+ * (lg15: the form drag of EVERY point comes from the ice fraction of the LAST point, see CdN_f_LG15_light), 1 uses each
+ * point's own fraction.  opt[8] (NULL = skip): CdN ChN CeN xz0 xu_star xL xUN10 CdN_frm.
+ */
+int abo_turb_ice(abo_session *s, const char *calgo, double zt, double zu, long n,
+                 const double *Ts_i, const double *t_zt, const double *qs_i, const double *q_zt, const double *U_zu,
+                 const double *frice, const double *cxn, int per_point_form_drag,
+                 double *Cd, double *Ch, double *Ce, double *t_zu, double *q_zu, double *Ubzu, double *const *opt)
+{
+    init_consts();
+    s->errmsg[0] = 0;
+    int ialgo = ice_algo_id(calgo);
+    if (!ialgo) { snprintf(s->errmsg, sizeof(s->errmsg), "unknown sea-ice algorithm %s", calgo); return ABO_ERR_ALGO; }
+    if (ialgo >= ABO_ICE_LU12 && !frice) { snprintf(s->errmsg, sizeof(s->errmsg), "turb_ice_%s needs frice", calgo); return ABO_ERR_ALGO; }
+    if (ialgo == ABO_ICE_EASY && !cxn) { snprintf(s->errmsg, sizeof(s->errmsg), "turb_ice_easy needs CdN, ChN, CeN"); return ABO_ERR_ALGO; }
+    long bad = n;   /* first point where rough_leng_tq would ctl_stop */
+    const int nb_iter = s->nb_iter;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(s->nthreads) schedule(static) reduction(min:bad)
+#endif
+    for (long i = 0; i < n; i++) {
+        ice_out o;
+        memset(&o, 0, sizeof(o));
+        double fr = frice ? frice[i] : 0.;
+        double frf = frice ? (per_point_form_drag ? frice[i] : frice[n - 1]) : 0.;
+        if (ice_point(ialgo, nb_iter, zt, zu, Ts_i[i], t_zt[i], qs_i[i], q_zt[i], U_zu[i], fr, frf, cxn, &o) && i < bad) bad = i;
+        Cd[i] = o.Cd; Ch[i] = o.Ch; Ce[i] = o.Ce; t_zu[i] = o.t_zu; q_zu[i] = o.q_zu; Ubzu[i] = o.Ub;
+        if (opt) {
+            const double v[8] = {o.CdN, o.ChN, o.CeN, o.z0, o.us, o.L, o.UN10, o.CdN_frm};
+            for (int k = 0; k < 8; k++)
+                if (opt[k]) opt[k][i] = v[k];
+        }
+    }
+    if (bad < n) {
+        snprintf(s->errmsg, sizeof(s->errmsg), " rough_leng_tq@mod_blk_ice_an05.f90 => something wrong with zsmoot, ztrans, zrough! (point %ld)", bad + 1);
+        return ABO_ERR_ICE_ROUGH;
+    }
+    return ABO_OK;
+}
+
+/* BULK_FORMULA_SCLR with l_ice = .TRUE., mod_phymbl.f90:1149-1203 */
+static void bulk_formula_ice(double pzu, double pts, double pqs, double pThta, double pqa, double pCd, double pCh, double pCe,
+                             double pwnd, double pUb, double pslp, double *pTau, double *pQsen, double *pQlat, double *pEvap)
+{
+    double zta = pThta - rgamma_dry * pzu;
+    double zrho = rho_air(zta, pqa, pslp);
+    zrho = rho_air(zta, pqa, pslp - zrho * grav * pzu);
+    double zUrho = pUb * MAX(zrho, 1.);
+    *pTau = zUrho * pCd * pwnd;
+    double zevap = zUrho * pCe * (pqa - pqs);
+    *pQsen = zUrho * pCh * (pThta - pts) * cp_air(pqa);
+    *pQlat = rLsub * zevap;
+    *pEvap = MIN(zevap, 0.);
+}
+
+/*
+ * Ice + leads workflow of src/ice/test_aerobulk_oce+ice.f90:225-412 (and test_aerobulk_ice.f90:186-370) on n points:
+ *   siq = q_sat(SIT, SLP, l_ice) (:212); ssq = 0.98 q_sat(SST, SLP) (the program evaluates it at SIT, :213 -- a slip of
+ *   the test program that is not reproduced); theta_zt = t_zt + gamma_moist zt (:262); over the leads
+ *   TURB_<calgo_oce>(no skin) + BULK_FORMULA (:297-304); over the ice TURB_ICE_<calgo_ice> (:332-351), Ri_b (:354),
+ *   t_zu by 4 lapse-rate passes at the mean layer temperature (:359-363), rho_zu (:384-387), BULK_FORMULA(l_ice) (:391).
+ * hum_kind 0 q, 1 dew-point [K], 2 RH [%].  out[35] (NULL = skip):
+ *   ice  0 Cd 1 Ch 2 Ce 3 theta_zu 4 q_zu 5 t_zu 6 Ub 7 RiB 8 z0 9 u* 10 L 11 UN10 12 rho_zu 13 Tau 14 QH 15 QL 16 Evap
+ *   water 17 Cd 18 Ch 19 Ce 20 theta_zu 21 q_zu 22 Ub 23 z0 24 u* 25 L 26 UN10 27 Tau 28 QH 29 QL 30 Evap
+ *   cell  31 Tau 32 QH 33 QL 34 Evap  = A ice + (1-A) water  (NEMO-style partition; not in the reference program)
+ */
+int abo_oce_ice(abo_session *s, const char *calgo_ice, const char *calgo_oce, double zt, double zu, long n,
+                const double *sit, const double *sst, const double *t_zt, const double *hum_zt, int hum_kind,
+                const double *wnd, const double *slp, const double *frice, const double *cxn, int per_point_form_drag,
+                double *const *out)
+{
+    init_consts();
+    s->errmsg[0] = 0;
+    int ialgo = ice_algo_id(calgo_ice);
+    if (!ialgo) { snprintf(s->errmsg, sizeof(s->errmsg), "unknown sea-ice algorithm %s", calgo_ice); return ABO_ERR_ALGO; }
+    int ioce = calgo_oce ? algo_id(calgo_oce) : 0;
+    if (calgo_oce && !ioce) { snprintf(s->errmsg, sizeof(s->errmsg), "unknown algorithm %s", calgo_oce); return ABO_ERR_ALGO; }
+    if (ialgo == ABO_ICE_EASY && !cxn) { snprintf(s->errmsg, sizeof(s->errmsg), "turb_ice_easy needs CdN, ChN, CeN"); return ABO_ERR_ALGO; }
+    long bad = n;
+    int badtau = 0;
+    const int nb_iter = s->nb_iter;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(s->nthreads) schedule(static) reduction(min:bad) reduction(|:badtau)
+#endif
+    for (long i = 0; i < n; i++) {
+        const double T = t_zt[i], P = slp[i];
+        double q;
+        if (hum_kind == 2) q = q_air_rh(hum_zt[i], T, P);
+        else if (hum_kind == 1) q = q_air_dp(hum_zt[i], P);
+        else q = hum_zt[i];
+        const double siq = q_sat_ice(sit[i], P);
+        const double tha = T + gamma_moist(T, q) * zt;
+        double v[35];
+        for (int k = 0; k < 35; k++) v[k] = 0.;
+        ice_out o;
+        memset(&o, 0, sizeof(o));
+        if (ice_point(ialgo, nb_iter, zt, zu, sit[i], tha, siq, q, wnd[i], frice[i],
+                      per_point_form_drag ? frice[i] : frice[n - 1], cxn, &o) && i < bad) bad = i;
+        double tz = o.t_zu;
+        for (int jq = 0; jq < 4; jq++) tz = o.t_zu - gamma_moist(0.5 * (tz + sit[i]), o.q_zu) * zu;
+        double rho = rho_air(tz, o.q_zu, P);
+        rho = rho_air(tz, o.q_zu, P - rho * grav * zu);
+        double tau, qh, ql, ev;
+        bulk_formula_ice(zu, sit[i], siq, o.t_zu, o.q_zu, o.Cd, o.Ch, o.Ce, wnd[i], o.Ub, P, &tau, &qh, &ql, &ev);
+        if (tau > 10.) badtau = 1;
+        v[0] = o.Cd; v[1] = o.Ch; v[2] = o.Ce; v[3] = o.t_zu; v[4] = o.q_zu; v[5] = tz; v[6] = o.Ub;
+        v[7] = Ri_bulk(zu, sit[i], o.t_zu, siq, o.q_zu, o.Ub);
+        v[8] = o.z0; v[9] = o.us; v[10] = o.L; v[11] = o.UN10; v[12] = rho; v[13] = tau; v[14] = qh; v[15] = ql; v[16] = ev;
+        if (ioce) {
+            turb_io w;
+            memset(&w, 0, sizeof(w));
+            w.T_s = sst[i];
+            w.q_s = rdct_qsat_salt * q_sat(sst[i], P);
+            skin_in sk;
+            memset(&sk, 0, sizeof(sk));
+            switch (ioce) {
+            case ABO_COARE3P0: turb_coare3p0(nb_iter, zt, zu, tha, q, wnd[i], &sk, &w); break;
+            case ABO_COARE3P6: turb_coare3p6(nb_iter, zt, zu, tha, q, wnd[i], &sk, &w); break;
+            case ABO_NCAR: turb_ncar(nb_iter, zt, zu, w.T_s, tha, w.q_s, q, wnd[i], &w); break;
+            case ABO_ECMWF: turb_ecmwf(nb_iter, zt, zu, tha, q, wnd[i], &sk, &w); break;
+            default: turb_andreas(nb_iter, zt, zu, w.T_s, tha, w.q_s, q, wnd[i], &w); break;
+            }
+            double tw, qhw, qlw, evw;
+            bulk_formula(zu, sst[i], w.q_s, w.t_zu, w.q_zu, w.Cd, w.Ch, w.Ce, wnd[i], w.Ubzu, P, &tw, &qhw, &qlw, &evw, NULL);
+            if (tw > 10.) badtau = 1;
+            v[17] = w.Cd; v[18] = w.Ch; v[19] = w.Ce; v[20] = w.t_zu; v[21] = w.q_zu; v[22] = w.Ubzu; v[23] = w.z0;
+            v[24] = w.us; v[25] = w.L; v[26] = w.UN10; v[27] = tw; v[28] = qhw; v[29] = qlw; v[30] = evw;
+            const double A = frice[i];
+            v[31] = A * tau + (1. - A) * tw; v[32] = A * qh + (1. - A) * qhw;
+            v[33] = A * ql + (1. - A) * qlw; v[34] = A * ev + (1. - A) * evw;
+        }
+        for (int k = 0; k < 35; k++)
+            if (out[k]) out[k][i] = v[k];
+    }
+    if (bad < n) {
+        snprintf(s->errmsg, sizeof(s->errmsg), " rough_leng_tq@mod_blk_ice_an05.f90 => something wrong with zsmoot, ztrans, zrough! (point %ld)", bad + 1);
+        return ABO_ERR_ICE_ROUGH;
+    }
+    if (badtau) { snprintf(s->errmsg, sizeof(s->errmsg), "wind stress too strong"); return ABO_ERR_TAU; }
+    return ABO_OK;
+}
+
 /* ------------------------------------------------------------------ */
 /* building blocks for unit tests                                      */
 /* ------------------------------------------------------------------ */
@@ -1828,6 +2329,16 @@ double abo_visc_air(double T) { init_consts(); return visc_air(T); }
 double abo_L_vap(double T) { init_consts(); return L_vap(T); }
 double abo_cp_air(double q) { init_consts(); return cp_air(q); }
 double abo_gamma_moist(double T, double q) { init_consts(); return gamma_moist(T, q); }
+double abo_e_sat_ice(double T) { init_consts(); return e_sat_ice(T); }
+double abo_q_sat_ice(double T, double p) { init_consts(); return q_sat_ice(T, p); }
+double abo_f_m_louis(double zu, double Rib, double Cdn, double z0) { init_consts(); return f_m_louis(zu, Rib, Cdn, z0); }
+double abo_f_h_louis(double zu, double Rib, double Chn, double z0) { init_consts(); return f_h_louis(zu, Rib, Chn, z0); }
+double abo_psi_m_ice(double zeta) { init_consts(); return psi_m_ice(zeta); }
+double abo_psi_h_ice(double zeta) { init_consts(); return psi_h_ice(zeta); }
+double abo_rough_leng_m(double us, double nua) { init_consts(); return rough_leng_m(us, nua); }
+int abo_rough_leng_tq(double z0, double us, double nua, double *z0t, double *z0q) { init_consts(); return rough_leng_tq(z0, us, nua, z0t, z0q); }
+double abo_CdN10_f_LU13(double A) { init_consts(); return CdN10_f_LU13(A); }
+double abo_CdN_f_LG15_light(double zu, double A, double z0w) { init_consts(); return CdN_f_LG15_light(zu, A, z0w); }
 double abo_alpha_sw(double T) { init_consts(); return alpha_sw(T); }
 double abo_qlw_net(double rlw, double Ts) { init_consts(); return qlw_net(rlw, Ts); }
 double abo_one_on_L(double tha, double qa, double us, double ts, double qs) { init_consts(); return One_on_L(tha, qa, us, ts, qs); }

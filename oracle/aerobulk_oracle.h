@@ -41,7 +41,8 @@ enum {
     ABO_ERR_UNITS = 6,         /* mod_phymbl.f90:1946-1950 */
     ABO_ERR_ALGO = 7,          /* mod_aerobulk_compute.f90:173-176 */
     ABO_ERR_TAU = 8,           /* mod_phymbl.f90:1250-1253 */
-    ABO_ERR_STATE = 9          /* double ALLOCATE of warm-layer state, mod_blk_coare3p6.f90:82-83 */
+    ABO_ERR_STATE = 9,         /* double ALLOCATE of warm-layer state, mod_blk_coare3p6.f90:82-83 */
+    ABO_ERR_ICE_ROUGH = 10     /* rough_leng_tq ctl_stop, src/ice/mod_blk_ice_an05.f90:296-297 */
 };
 
 typedef struct abo_session abo_session;
@@ -125,6 +126,28 @@ int abo_series(abo_session *s, const char *calgo, int Nt, long S, double zt, dou
                const int *isecday_utc, const double *lon,
                const double *sst, const double *t_zt, const double *hum_zt, int hum_kind, const double *wnd,
                const double *slp, const double *rad_sw, const double *rad_lw, int l_skin, double *const *out);
+
+/* ---- sea ice ("parity unpinned": the reference holds no ice fixture, see .c) ---- */
+double abo_e_sat_ice(double T);
+double abo_q_sat_ice(double T, double p);
+double abo_f_m_louis(double zu, double Rib, double Cdn, double z0);
+double abo_f_h_louis(double zu, double Rib, double Chn, double z0);
+double abo_psi_m_ice(double zeta);
+double abo_psi_h_ice(double zeta);
+double abo_rough_leng_m(double us, double nua);
+int abo_rough_leng_tq(double z0, double us, double nua, double *z0t, double *z0q);
+double abo_CdN10_f_LU13(double A);
+double abo_CdN_f_LG15_light(double zu, double A, double z0w);
+/* TURB_ICE_<nemo|easy|an05|lu12|lg15|lg15_io>; opt[8] = CdN ChN CeN xz0 xu_star xL xUN10 CdN_frm */
+int abo_turb_ice(abo_session *s, const char *calgo, double zt, double zu, long n,
+                 const double *Ts_i, const double *t_zt, const double *qs_i, const double *q_zt, const double *U_zu,
+                 const double *frice, const double *cxn, int per_point_form_drag,
+                 double *Cd, double *Ch, double *Ce, double *t_zu, double *q_zu, double *Ubzu, double *const *opt);
+/* ice + leads workflow of src/ice/test_aerobulk_oce+ice.f90; out[35], see .c */
+int abo_oce_ice(abo_session *s, const char *calgo_ice, const char *calgo_oce, double zt, double zu, long n,
+                const double *sit, const double *sst, const double *t_zt, const double *hum_zt, int hum_kind,
+                const double *wnd, const double *slp, const double *frice, const double *cxn, int per_point_form_drag,
+                double *const *out);
 
 /* test-only: reproduce the pre-drift COARE 3.0 viscosity line (see .c) */
 void abo_debug_coare3p0_visc_at_tzu(int on);

@@ -80,6 +80,20 @@ def lib():
         L.abo_series.restype = C.c_int
         L.abo_series.argtypes = ([C.c_void_p, C.c_char_p, C.c_int, C.c_long, C.c_double, C.c_double, C.POINTER(C.c_int), _dp] +
                                  [_dp] * 3 + [C.c_int] + [_dp] * 4 + [C.c_int, C.POINTER(_dp)])
+        L.abo_turb_ice.restype = C.c_int
+        L.abo_turb_ice.argtypes = ([C.c_void_p, C.c_char_p, C.c_double, C.c_double, C.c_long] + [_dp] * 7 + [C.c_int] +
+                                   [_dp] * 6 + [C.POINTER(_dp)])
+        L.abo_oce_ice.restype = C.c_int
+        L.abo_oce_ice.argtypes = ([C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_long] + [_dp] * 4 +
+                                  [C.c_int] + [_dp] * 4 + [C.c_int, C.POINTER(_dp)])
+        for name, nargs in (("abo_e_sat_ice", 1), ("abo_q_sat_ice", 2), ("abo_f_m_louis", 4), ("abo_f_h_louis", 4),
+                            ("abo_psi_m_ice", 1), ("abo_psi_h_ice", 1), ("abo_rough_leng_m", 2), ("abo_CdN10_f_LU13", 1),
+                            ("abo_CdN_f_LG15_light", 3)):
+            f = getattr(L, name)
+            f.restype = C.c_double
+            f.argtypes = [C.c_double] * nargs
+        L.abo_rough_leng_tq.restype = C.c_int
+        L.abo_rough_leng_tq.argtypes = [C.c_double] * 3 + [_dp, _dp]
         L.abo_gamma_moist.restype = C.c_double
         L.abo_gamma_moist.argtypes = [C.c_double, C.c_double]
         _lib = L
@@ -193,6 +207,46 @@ class OracleSession:
                                 isd.ctypes.data_as(C.POINTER(C.c_int)), _ptr(lon), _ptr(ins[0]), _ptr(ins[1]), _ptr(ins[2]),
                                 int(hum_kind), _ptr(ins[3]), _ptr(ins[4]), _ptr(ins[5]), _ptr(ins[6]),
                                 int(bool(l_use_skin)), arr)
+        if rc != 0:
+            raise OracleError(rc, self._L.abo_errmsg(self._s).decode())
+        return outs
+
+    ICE_OPT = ("CdN", "ChN", "CeN", "xz0", "xu_star", "xL", "xUN10", "CdN_frm")
+    OCE_ICE_OUT = tuple([k + "_i" for k in ("Cd", "Ch", "Ce", "theta_zu", "q_zu", "t_zu", "Ub", "RiB", "z0", "u_star", "L",
+                                             "UN10", "rho_zu", "Tau", "QH", "QL", "Evap")] +
+                        [k + "_w" for k in ("Cd", "Ch", "Ce", "theta_zu", "q_zu", "Ub", "z0", "u_star", "L", "UN10", "Tau",
+                                             "QH", "QL", "Evap")] + ["Tau", "QH", "QL", "Evap"])
+
+    def turb_ice(self, calgo, zt, zu, Ts_i, t_zt, qs_i, q_zt, U_zu, frice=None, cxn=None, per_point_form_drag=False,
+                 want=()):
+        """TURB_ICE_<calgo> on flat arrays; returns Cd Ch Ce t_zu q_zu Ubzu + wanted optionals."""
+        f = lambda a: None if a is None else np.ascontiguousarray(np.ravel(a, order="F"), dtype=np.float64)
+        ins = [f(a) for a in (Ts_i, t_zt, qs_i, q_zt, U_zu, frice)]
+        n = ins[0].size
+        cx = None if cxn is None else np.ascontiguousarray(cxn, dtype=np.float64)
+        outs = {k: np.zeros(n) for k in ("Cd", "Ch", "Ce", "t_zu", "q_zu", "Ubzu")}
+        optv = {k: np.zeros(n) for k in want}
+        arr = (_dp * 8)(*[_ptr(optv[k]) if k in optv else None for k in self.ICE_OPT])
+        rc = self._L.abo_turb_ice(self._s, calgo.encode(), float(zt), float(zu), n, *[_ptr(a) for a in ins], _ptr(cx),
+                                  int(bool(per_point_form_drag)), *[_ptr(outs[k]) for k in ("Cd", "Ch", "Ce", "t_zu", "q_zu", "Ubzu")],
+                                  arr)
+        if rc != 0:
+            raise OracleError(rc, self._L.abo_errmsg(self._s).decode())
+        outs.update(optv)
+        return outs
+
+    def oce_ice(self, calgo_ice, calgo_oce, zt, zu, sit, sst, t_zt, hum_zt, wind, slp, frice, hum_kind=0, cxn=None,
+                per_point_form_drag=False):
+        """Ice + leads workflow (abo_oce_ice); returns the 35 series of OCE_ICE_OUT."""
+        f = lambda a: None if a is None else np.ascontiguousarray(np.ravel(a, order="F"), dtype=np.float64)
+        ins = [f(a) for a in (sit, sst, t_zt, hum_zt, wind, slp, frice)]
+        n = ins[0].size
+        cx = None if cxn is None else np.ascontiguousarray(cxn, dtype=np.float64)
+        outs = {k: np.zeros(n) for k in self.OCE_ICE_OUT}
+        arr = (_dp * 35)(*[_ptr(outs[k]) for k in self.OCE_ICE_OUT])
+        rc = self._L.abo_oce_ice(self._s, calgo_ice.encode(), None if calgo_oce is None else calgo_oce.encode(), float(zt),
+                                 float(zu), n, _ptr(ins[0]), _ptr(ins[1]), _ptr(ins[2]), _ptr(ins[3]), int(hum_kind),
+                                 _ptr(ins[4]), _ptr(ins[5]), _ptr(ins[6]), _ptr(cx), int(bool(per_point_form_drag)), arr)
         if rc != 0:
             raise OracleError(rc, self._L.abo_errmsg(self._s).decode())
         return outs
