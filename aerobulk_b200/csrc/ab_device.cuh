@@ -35,6 +35,21 @@ namespace abd {
 #define ABD_HEAVY __device__ __forceinline__
 #endif
 
+// FP64 literals in the constant bank.  ptxas builds a double that does not fit a 32-bit immediate with two moves
+// (UMOV / IMAD.MOV): ~20 % of the instructions the COARE + skin kernel executed in the round-1b profile.  KC(x) puts
+// the value of the constant expression x into a __constant__ variable (one per distinct bit pattern; adjacent ones are
+// fetched in pairs by LDCU.128) -- doubles whose low word is zero (0.5, 16., 1.25 ...) stay immediates.
+// Wrap a WHOLE constant sub-expression, e.g. KC(1. / 0.014): the compiler cannot fold across a memory operand.
+template <unsigned long long B>
+static __constant__ double kc_bank = __builtin_bit_cast(double, B);
+template <unsigned long long B>
+__device__ __forceinline__ double kc_value()
+{
+    if constexpr ((B & 0xffffffffull) == 0ull) return __builtin_bit_cast(double, B);
+    else return kc_bank<B>;
+}
+#define KC(x) (::abd::kc_value<__builtin_bit_cast(unsigned long long, static_cast<double>(x))>())
+
 // ---------------------------------------------------------------------------
 // constants, reference src/mod_const.f90:38-120 (derived ones folded in FP64
 // operation by operation, as gfortran does for PARAMETERs)
@@ -82,8 +97,8 @@ enum Algo { COARE3P0 = 1, COARE3P6 = 2, NCAR = 3, ECMWF = 4, ANDREAS = 5 };
 // small helpers
 // ---------------------------------------------------------------------------
 // SIGN(MIN(ABS(x),lim),x) and SIGN(MAX(ABS(x),lo),x)
-ABD double clip_abs(double x, double lim) { return copysign(fmin(fabs(x), lim), x); }
-ABD double floor_abs(double x, double lo) { return copysign(fmax(fabs(x), lo), x); }
+ABD double clip_abs(double x, double lim) { return (fabs(x) <= lim) ? x : copysign(lim, x); }
+ABD double floor_abs(double x, double lo) { return (fabs(x) >= lo) ? x : copysign(lo, x); }
 // x**y for x >= 0 (0**y = 0 for y > 0); own exp/log/atan with constant-bank tables, see ab_math.cuh
 ABD double powr(double x, double y) { return abm::dpowr(x, y); }
 // zstab = 0.5 + SIGN(0.5, x) is 1 unless the sign bit of x is set
@@ -118,14 +133,14 @@ ABD double virt_temp(double T, double q) { return T * (1. + RCTV0 * q); }       
 ABD_HEAVY double e_sat(double T)
 {
     const double zta = fmax(T, 180.);
-    const double ztmp = fdiv(RT0, zta);
-    const double r = zta * (1. / RT0);
-    const double a = 10.79574 * (1. - ztmp) - 5.028 * abm::dlog10(r)
-                     + (1.50475 * 1.e-4) * (1. - abm::dexp10(-8.2969 * (r - 1.)))
-                     + (0.42873 * 1.e-3) * (abm::dexp10(4.76955 * (1. - ztmp)) - 1.) + 0.78614;
+    const double ztmp = fdiv(KC(RT0), zta);
+    const double r = zta * KC(1. / RT0);
+    const double a = KC(10.79574) * (1. - ztmp) - KC(5.028) * abm::dlog10(r)
+                     + KC(1.50475 * 1.e-4) * (1. - abm::dexp10(KC(-8.2969) * (r - 1.)))
+                     + KC(0.42873 * 1.e-3) * (abm::dexp10(KC(4.76955) * (1. - ztmp)) - 1.) + KC(0.78614);
     return 100. * abm::dexp10(a);
 }
-ABD double q_sat_from_e(double es, double p) { return fdiv(REPS0 * es, p - (1. - REPS0) * es); }  // :903
+ABD double q_sat_from_e(double es, double p) { return fdiv(KC(REPS0) * es, p - KC(1. - REPS0) * es); }  // :903
 ABD double q_sat(double T, double p) { return q_sat_from_e(e_sat(T), p); }                   // :881-904
 
 // Theta_from_z_P0_T_q, :283-318 + :163-187 + :343-365; e_sat(T) is loop-invariant
@@ -146,10 +161,10 @@ ABD double rho_air(double T, double q, double p) { return fmax(fdiv(p, R_DRY * T
 ABD double visc_air(double T)                                                                              // :549-563
 {
     const double tc = T - RT0, tc2 = tc * tc;
-    return 1.326e-5 * (1. + 6.542E-3 * tc + 8.301e-6 * tc2 - 4.84e-9 * tc2 * tc);
+    return KC(1.326e-5) * (1. + KC(6.542E-3) * tc + KC(8.301e-6) * tc2 - KC(4.84e-9) * tc2 * tc);
 }
-ABD double L_vap(double T) { return (2.501 - 0.00237 * (T - RT0)) * 1.e6; }                               // :579-592
-ABD double cp_air(double q) { return RCP_DRY + RCP_VAP * q; }                                             // :603-616
+ABD double L_vap(double T) { return (KC(2.501) - KC(0.00237) * (T - KC(RT0))) * 1.e6; }                               // :579-592
+ABD double cp_air(double q) { return KC(RCP_DRY) + KC(RCP_VAP) * q; }                                             // :603-616
 // moist adiabatic lapse rate [K/m], :627-649
 ABD double gamma_moist(double T, double q)
 {
@@ -161,13 +176,13 @@ ABD double gamma_moist(double T, double q)
     return fdiv(GRAV * (1. + Lv * wa * iRT), RCP_DRY + fdiv(Lv * Lv * wa * REPS0 * iRT, ta));
 }
 ABD double alpha_sw(double T) { return 2.1e-5 * powr(fmax(T - RT0 + 3.2, 0.), 0.79); }                    // :1267-1280
-ABD double qlw_net(double rlw, double Ts) { const double t2 = Ts * Ts; return EMISS_W * (rlw - STEFAN * t2 * t2); }  // :1291-1314
+ABD double qlw_net(double rlw, double Ts) { const double t2 = Ts * Ts; return KC(EMISS_W) * (rlw - KC(STEFAN) * t2 * t2); }  // :1291-1314
 
 // 1/L, :666-693
 ABD double one_on_L(double tha, double qa, double us, double ts, double qs)
 {
-    const double zqa = 1. + RCTV0 * qa;
-    const double r = fdiv(GRAV * VKARMN * (ts * zqa + RCTV0 * tha * qs), fmax(us * us * tha * zqa, 1.E-9));
+    const double zqa = 1. + KC(RCTV0) * qa;
+    const double r = fdiv(KC(GRAV * VKARMN) * (ts * zqa + KC(RCTV0) * tha * qs), fmax(us * us * tha * zqa, KC(1.E-9)));
     return clip_abs(r, 200.);
 }
 
@@ -204,10 +219,10 @@ struct AirZu {
 };
 ABD AirZu air_at_zu(double zu, double tha, double qa, double slp)
 {
-    const double ta = tha - RGAMMA_DRY * zu;
-    const double r = abm::fast_rcp(R_DRY * ta * (1. + RCTV0 * qa));     // rho_air = MAX(p / (R T (1 + rctv0 q)), 0.8)
-    double rho = fmax(slp * r, 0.8);
-    rho = fmax((slp - rho * GRAV * zu) * r, 0.8);
+    const double ta = tha - KC(RGAMMA_DRY) * zu;
+    const double r = abm::fast_rcp(KC(R_DRY) * ta * (1. + KC(RCTV0) * qa));     // rho_air = MAX(p / (R T (1 + rctv0 q)), 0.8)
+    double rho = fmax(slp * r, KC(0.8));
+    rho = fmax((slp - rho * KC(GRAV) * zu) * r, KC(0.8));
     AirZu a;
     a.rho = rho;
     a.rho1 = fmax(rho, 1.);
@@ -305,22 +320,22 @@ ABD double psi_h_ncar(double z) { return nonneg(z) ? -5. * z : psi_h_ncar_unstab
 // SIGN(0.5,+0.) selects the stable branch and the truncated literals do not cancel.
 ABD double psi_coare_convective(double phi_c)
 {
-    return 1.5 * abm::dlog((1. + phi_c + phi_c * phi_c) * (1. / 3.)) - 1.7320508 * abm::datan((1. + 2. * phi_c) * (1. / 1.7320508)) + 1.813799447;
+    return 1.5 * abm::dlog((1. + phi_c + phi_c * phi_c) * KC(1. / 3.)) - KC(1.7320508) * abm::datan((1. + 2. * phi_c) * KC(1. / 1.7320508)) + KC(1.813799447);
 }
 ABD PsiMH psi_mh_coare_stable(double z)
 {
-    const double e = abm::dexp(-fmin(50., 0.35 * z));
-    const double a = fabs(1. + 2. * z * (1. / 3.));
+    const double e = abm::dexp(-fmin(50., KC(0.35) * z));
+    const double a = fabs(1. + 2. * z * KC(1. / 3.));
     PsiMH r;
-    r.m = -(1. + 1. * z + 0.6667 * (z - 14.28) * e + 8.525);
-    r.h = -(a * sqrt(a) + .6667 * (z - 14.28) * e + 8.525);                      // **1.5
+    r.m = -(1. + 1. * z + KC(0.6667) * (z - KC(14.28)) * e + KC(8.525));
+    r.h = -(a * sqrt(a) + KC(.6667) * (z - KC(14.28)) * e + KC(8.525));                      // **1.5
     return r;
 }
 ABD double psi_h_coare_stable(double z)
 {
-    const double e = abm::dexp(-fmin(50., 0.35 * z));
-    const double a = fabs(1. + 2. * z * (1. / 3.));
-    return -(a * sqrt(a) + .6667 * (z - 14.28) * e + 8.525);
+    const double e = abm::dexp(-fmin(50., KC(0.35) * z));
+    const double a = fabs(1. + 2. * z * KC(1. / 3.));
+    return -(a * sqrt(a) + KC(.6667) * (z - KC(14.28)) * e + KC(8.525));
 }
 ABD PsiMH psi_mh_coare_unstable(double z)
 {
@@ -330,8 +345,8 @@ ABD PsiMH psi_mh_coare_unstable(double z)
     f = fdiv(f, 1. + f);
     const double km = 2. * abm::dlog((1. + phi_m) * 0.5) + abm::dlog((1. + phi_m * phi_m) * 0.5) - 2. * abm::datan(phi_m) + 0.5 * RPI;
     const double kh = 2. * abm::dlog((1. + phi_h) * 0.5);
-    const double cm = psi_coare_convective(powr(fabs(1. - 10.15 * z), .3333));
-    const double ch = psi_coare_convective(powr(fabs(1. - 34.15 * z), .3333));
+    const double cm = psi_coare_convective(powr(fabs(1. - KC(10.15) * z), KC(.3333)));
+    const double ch = psi_coare_convective(powr(fabs(1. - KC(34.15) * z), KC(.3333)));
     PsiMH r;
     r.m = (1. - f) * km + f * cm;
     r.h = (1. - f) * kh + f * ch;
@@ -343,7 +358,7 @@ ABD double psi_h_coare_unstable(double z)
     double f = z * z;
     f = fdiv(f, 1. + f);
     const double kh = 2. * abm::dlog((1. + phi_h) * 0.5);
-    const double ch = psi_coare_convective(powr(fabs(1. - 34.15 * z), .3333));
+    const double ch = psi_coare_convective(powr(fabs(1. - KC(34.15) * z), KC(.3333)));
     return (1. - f) * kh + f * ch;
 }
 // psi_m(zeta_u), psi_h(zeta_u), psi_h(zeta_t); zeta_t has the sign of zeta_u
@@ -402,7 +417,7 @@ ABD double psi_m_andreas_stable(double zeta)
 {
     const double z = fmin(zeta, 15.);
     const double zam = 5.;
-    const double x = cbrt(fabs(1. + z));
+    const double x = abm::fast_cbrt(fabs(1. + z));
     return -(3. * zam / ZBM_A * (x - 1.))
            + zam * ZBBM_A / (2. * ZBM_A)
                  * (2. * abm::dlog(fabs((x + ZBBM_A) * (1. / (1. + ZBBM_A))))
@@ -523,19 +538,19 @@ template <bool COARE_FORM>
 ABD double cool_skin_dT(double alpha, double Qsw, double Qnsol, double us, double Qlat)
 {
     // invariants of the five delta_skin_layer evaluations
-    const double usw = fmax(us, 1.E-4) * SQ_RADRW;
+    const double usw = fmax(us, KC(1.E-4)) * KC(SQ_RADRW);
     const double usw2 = usw * usw;
-    const double c_lamb = fdiv(alpha * RCST_CS, usw2 * usw2);
-    const double nu_o_usw = fdiv(RNU0_W, usw);
-    const double d_warm = fmin(6. * nu_o_usw, 0.007);
-    const double q_lat_term = COARE_FORM ? fdiv(0.026 * fmin(Qlat, 0.) * RCP0_W * (1. / RLEVAP), alpha) : 0.;
+    const double c_lamb = fdiv(alpha * KC(RCST_CS), usw2 * usw2);
+    const double nu_o_usw = fdiv(KC(RNU0_W), usw);
+    const double d_warm = fmin(6. * nu_o_usw, KC(0.007));
+    const double q_lat_term = COARE_FORM ? fdiv(KC(0.026) * fmin(Qlat, 0.) * KC(RCP0_W * (1. / RLEVAP)), alpha) : 0.;
 
     auto delta = [&](double Qd) -> double {
         const double zQd = COARE_FORM ? Qd + q_lat_term : Qd;
         if (nonneg(zQd)) return d_warm;                                  // warming of the viscous layer
         const double x = fmax(c_lamb * zQd, 0.);
-        const double x75 = sqrt(x) * sqrt(sqrt(x));                      // **0.75
-        return 6. * rcbrt(1. + x75) * nu_o_usw;                           // **(-1./3.)
+        const double x75 = abm::pow075(x);                               // **0.75
+        return 6. * abm::fast_rcbrt(1. + x75) * nu_o_usw;                 // **(-1./3.)
     };
 
     // delta(Qnsol), then 4 x { solar absorption fr(delta) -> Qabs -> delta(Qabs) }: one rolled loop so that
@@ -544,12 +559,12 @@ ABD double cool_skin_dT(double alpha, double Qsw, double Qnsol, double us, doubl
 #pragma unroll 1
     for (int jc = 0; jc < 5; ++jc) {
         if (jc > 0) {
-            const double fr = fmax((COARE_FORM ? 0.137 : 0.065) + 11. * d - fdiv(6.6E-5, d) * (1. - abm::dexp(-d * (1. / 8.E-4))), 0.01);
+            const double fr = fmax((COARE_FORM ? KC(0.137) : KC(0.065)) + 11. * d - fdiv(KC(6.6E-5), d) * (1. - abm::dexp(-d * KC(1. / 8.E-4))), KC(0.01));
             Qabs = Qnsol + fr * Qsw;
         }
         d = delta(Qabs);
     }
-    return Qabs * d * (1. / RK0_W);
+    return Qabs * d * KC(1. / RK0_W);
 }
 
 // ---------------------------------------------------------------------------
@@ -594,10 +609,10 @@ ABD double wl_coare_absorption(double H)   // solar absorption profile, :167-168
 {
     // 1 - EXP(-x) is exactly 1 in FP64 once EXP(-x) < 2**-54, i.e. x > 37.43: the two short-wave bands
     // are only evaluated for shallow layers (H <= 0.53 m, H <= 13.4 m) -- bit-identical, fewer exps
-    const double e1 = (H > 0.53) ? 0. : abm::dexp(-H * (1. / 0.014));
-    const double e2 = (H > 13.4) ? 0. : abm::dexp(-H * (1. / 0.357));
-    return 1. - fdiv(0.28 * 0.014 * (1. - e1) + 0.27 * 0.357 * (1. - e2)
-                     + 0.45 * 12.82 * (1 - abm::dexp(-H * (1. / 12.82))), H);
+    const double e1 = (H > KC(0.53)) ? 0. : abm::dexp(-H * KC(1. / 0.014));
+    const double e2 = (H > KC(13.4)) ? 0. : abm::dexp(-H * KC(1. / 0.357));
+    return 1. - fdiv(KC(0.28 * 0.014) * (1. - e1) + KC(0.27 * 0.357) * (1. - e2)
+                     + KC(0.45 * 12.82) * (1 - abm::dexp(-H * KC(1. / 12.82))), H);
 }
 // WL_COARE, src/mod_skin_coare.f90:97-250; `commit` is (iwait == 0)
 ABD void wl_coare(WarmLayer &w, const WlCoareCtx &c, double Qsw, double Qnsol, double Tau, double rdt,
@@ -626,12 +641,12 @@ ABD void wl_coare(WarmLayer &w, const WlCoareCtx &c, double Qsw, double Qnsol, d
             if (jl > 0) Qabs = wl_coare_absorption(H) * Qsw + Qnsol;   // jl == 0: H unchanged since the test above
             qac = w.Qac + Qabs * rdt;
             if (qac <= 0.) break;
-            H = fmax(fmin(Hwl_max, c.cd1 * tac * rsqrt(qac)), 0.1);
+            H = fmax(fmin(Hwl_max, c.cd1 * tac * abm::fast_rsqrt(qac)), 0.1);
         }
         if (qac <= 0.) {
             destroy = true;
         } else {
-            dT = fdiv(c.cd2 * (qac * sqrt(qac)), tac);                       // qac > 0 here: MAX(qac/ABS(qac),0) = 1   // **1.5
+            dT = fdiv(c.cd2 * (qac * (qac * abm::fast_rsqrt(qac))), tac);                       // qac > 0 here: MAX(qac/ABS(qac),0) = 1   // **1.5
             if (signbit(gdept - H)) dT = dT * fdiv(gdept, H);                       // flg = 0
         }
     }
@@ -654,7 +669,7 @@ ABD double phi_takaya(double z)
 {
     const double z2 = z * z;
     if (nonneg(z)) return 1. + fdiv(5. * z + 4. * z2, 1. + 3. * z + 0.25 * z2);
-    return rsqrt(1. - 16. * (-fabs(z)));
+    return abm::fast_rsqrt(1. - 16. * (-fabs(z)));
 }
 // WL_ECMWF, src/mod_skin_ecmwf.f90:113-230 -- advances dT_wl by rdt at EVERY call
 // quantities of WL_ECMWF that only depend on the (constant) layer depth: hoisted out of the bulk iteration
@@ -679,7 +694,7 @@ ABD void wl_ecmwf(WarmLayer &w, const WlEcmwfCtx &c, double alpha, double Qsw, d
 
     const double Qabs = c.fr * Qsw + Qnsol;
 
-    const double usw = fmax(us, 1.E-4) * SQ_RADRW;
+    const double usw = fmax(us, KC(1.E-4)) * KC(SQ_RADRW);
     const double usw2 = usw * usw;
     const bool warming = nonneg(Qabs);
 
@@ -792,7 +807,7 @@ ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p, Diag &dg)
     c.Cd = Cd; c.Ch = Ch; c.Ce = Ce; c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = p.sst; c.qs = p.ssq;
     // optional outputs, src/mod_blk_ncar.f90:229-235
     dg.CdN = CdN; dg.ChN = ChN; dg.CeN = CeN; dg.UN10 = Un10; dg.L = 1. / r1oL; dg.us = us;
-    dg.z0 = fmin(u.zu * abm::dexp(-VKARMN * rsqrt(CdN)), Z0_SEA_MAX);
+    dg.z0 = fmin(u.zu * abm::dexp(-VKARMN * abm::fast_rsqrt(CdN)), Z0_SEA_MAX);
     dg.dT_cs = 0.;
     return c;
 }
@@ -807,14 +822,14 @@ ABD double charn_coare3p0(double w)
     if (nonneg(w - 18.)) return 0.018;
     return 0.011 + (0.018 - 0.011) * (w - 10.) * (1. / (18. - 10.));
 }
-ABD double charn_coare3p6(double w) { return fmax(fmin(0.0017 * w - 0.005, 0.028), 0.); }
+ABD double charn_coare3p6(double w) { return fmax(fmin(KC(0.0017) * w - KC(0.005), KC(0.028)), 0.); }
 
 // CS / WL: l_use_cs / l_use_wl of the reference (aerobulk_model switches both on together)
 template <bool V36, bool CS, bool WL, bool ZTEQ>
 ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &dg)
 {
     constexpr bool SKIN = CS || WL;
-    const double zi0 = 600., Beta0 = V36 ? 1.2 : 1.25, zeta_abs_max = 50.;
+    constexpr double zi0 = 600., Beta0 = V36 ? 1.2 : 1.25, zeta_abs_max = 50.;
 
     double Ts = p.sst, qs_ = p.ssq;
     double alpha = 0.;
@@ -842,31 +857,31 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
         const double us2 = us * us;
         r1oL = one_on_L(t_zu, q_zu, us, ts, qst);    // already clipped to +-200
 
-        const double cv = cbrt(fmax(-zi0 * r1oL * INV_VKARMN, 0.));
-        const double gust2 = Beta0 * Beta0 * us2 * (cv * cv);       // **(2./3.)
-        Ub = fmax(sqrt(p.wnd * p.wnd + gust2), 0.2);
+        const double cv = abm::fast_cbrt(fmax(KC(-zi0 * INV_VKARMN) * r1oL, 0.));
+        const double gust2 = KC(Beta0 * Beta0) * us2 * (cv * cv);       // **(2./3.)
+        Ub = fmax(sqrt(p.wnd * p.wnd + gust2), KC(0.2));
 
         const double zeta_u = clip_abs(u.zu * r1oL, zeta_abs_max);
 
         const double Un10 = us * INV_VKARMN * (u.log_10 - log_z0);
         const double r_us = abm::fast_rcp(us);
-        z0 = (V36 ? charn_coare3p6(Un10) : charn_coare3p0(Un10)) * us2 * INV_GRAV + 0.11 * nu_a * r_us;
-        z0 = fmin(fmax(fabs(z0), 1.E-9), 1.);
+        z0 = (V36 ? charn_coare3p6(Un10) : charn_coare3p0(Un10)) * us2 * KC(INV_GRAV) + KC(0.11) * nu_a * r_us;
+        z0 = fmin(fmax(fabs(z0), KC(1.E-9)), 1.);
         log_z0 = abm::dlog(z0);
 
         // z0t = MIN(1.6e-4, 5.8e-5 (nu/(z0 u*))**0.72) [3.6] / MIN(1.1e-4, 5.5e-5 (..)**0.6) [3.0], floored at
         // 1e-9, is only needed as LOG(z0t): monotonic, so MIN / MAX act on the logarithms (no pow)
         const double log_rr = abm::dlog(nu_a * r_us) - log_z0;
-        log_z0t = V36 ? fmax(fmin(LOG_1P6EM4, LOG_5P8EM5 + 0.72 * log_rr), LOG_1EM9)
-                      : fmax(fmin(LOG_1P1EM4, LOG_5P5EM5 + 0.6 * log_rr), LOG_1EM9);
+        log_z0t = V36 ? fmax(fmin(KC(LOG_1P6EM4), KC(LOG_5P8EM5) + KC(0.72) * log_rr), KC(LOG_1EM9))
+                      : fmax(fmin(KC(LOG_1P1EM4), KC(LOG_5P5EM5) + KC(0.6) * log_rr), KC(LOG_1EM9));
 
         const double zeta_t = clip_abs(u.zt * r1oL, zeta_abs_max);
         double psi_m_u, psi_h_u, psi_h_t;
         psi3_coare<ZTEQ>(zeta_u, zeta_t, psi_m_u, psi_h_u, psi_h_t);
-        double tmp1 = fdiv(VKARMN, u.log_zu - log_z0t - psi_h_u);
+        double tmp1 = fdiv(KC(VKARMN), u.log_zu - log_z0t - psi_h_u);
         ts = dt * tmp1;
         qst = dq * tmp1;
-        us = fmax(fdiv(Ub * VKARMN, u.log_zu - log_z0 - psi_m_u), 1.E-9);
+        us = fmax(fdiv(Ub * KC(VKARMN), u.log_zu - log_z0 - psi_m_u), KC(1.E-9));
 
         if (!ZTEQ) {
             tmp1 = u.log_zt - u.log_zu + psi_h_u - psi_h_t;
@@ -894,12 +909,12 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
                     Ts = p.sst + wl.dT;
                     if (CS) Ts = Ts + dT_cs;
                 }
-                qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+                qs_ = KC(RDCT_QSAT_SALT) * q_sat(fmax(Ts, 200.), p.slp);
             }
         }
         if (SKIN || !ZTEQ || !V36) {
-            dt = floor_abs(t_zu - Ts, 1.E-09);
-            dq = floor_abs(q_zu - qs_, 1.E-12);
+            dt = floor_abs(t_zu - Ts, KC(1.E-09));
+            dq = floor_abs(q_zu - qs_, KC(1.E-12));
         }
     }
     Coeffs c;
@@ -1010,7 +1025,7 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
             psi_h_z0q = psi_h_ecmwf_unstable(z0q * r1oL);
         }
 
-        const double cv = cbrt(fmax(-zi0 * r1oL * INV_VKARMN, 0.));
+        const double cv = abm::fast_cbrt(fmax(-zi0 * r1oL * INV_VKARMN, 0.));
         tmp0 = Beta0 * Beta0 * us2 * (cv * cv);
         Ub = fmax(sqrt(p.wnd * p.wnd + tmp0), 0.2);
 
@@ -1116,7 +1131,7 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p, Diag &dg)
             if (adjust) psi_h_t = psi_h_andreas_unstable(zeta_t);
         }
         // z0 = MIN(zu EXP(-(k/SQRT(Cd) + psi_m)), z0_sea_max), kept together with its logarithm
-        const double log_z0 = fmin(u.log_zu - (VKARMN * rsqrt(Cd) + psi_m), LOG_Z0_SEA_MAX);
+        const double log_z0 = fmin(u.log_zu - (VKARMN * abm::fast_rsqrt(Cd) + psi_m), LOG_Z0_SEA_MAX);
         z0 = abm::dexp(log_z0);
 
         const double Rer = fdiv(z0 * u_star, visc_air(t_zu));

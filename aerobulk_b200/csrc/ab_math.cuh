@@ -35,6 +35,9 @@ static inline double make_double(int hi, int lo)
     double x; std::memcpy(&x, &b, 8); return x;
 }
 static inline double rcp_seed(double y) { return (double)(float)(1.0 / y); }   // ~24-bit seed like MUFU.RCP64H
+// seeds of the root functions, degraded to the worst accuracy the device versions may have (2^-21)
+static inline double rsqrt_seed(double y) { return (double)(float)(1.0 / std::sqrt(y)) * (1.0 + 0x1p-21); }
+static inline double pow_seed(double y, float p) { return (double)(float)std::pow(y, (double)p) * (1.0 - 0x1p-21); }
 }
 #else
 #include <cuda_runtime.h>
@@ -57,6 +60,23 @@ ABM_FN double rcp_seed(double y)
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));   // MUFU.RCP64H, rel. error <= 2^-23
     return r;
 }
+ABM_FN double rsqrt_seed(double y)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));   // MUFU.RSQ64H
+    return r;
+}
+// y**p for y in the normal FP32 range through the FP32 special-function unit (MUFU.LG2, MUFU.EX2): ~2^-22,
+// and off the FP64 pipe
+ABM_FN double pow_seed(double y, float p)
+{
+    float l, r;
+    const float f = (float)y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(f));
+    l *= p;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l));
+    return (double)r;
+}
 }
 #endif
 
@@ -71,8 +91,40 @@ ABM_FN double fast_rcp(double y)
 {
     const double r0 = rcp_seed(y);
     const double e = fma(-y, r0, 1.0);
-    const double r1 = fma(r0, e, r0);
-    return fma(r1, e * e, r1);
+    return fma(r0, fma(e, e, e), r0);            // r0 (1 + e + e^2): error e^3 <= 2^-69
+}
+
+// Roots: one seed of relative accuracy d <= 2^-21 and ONE step of cubic convergence.  With e = 1 - x y^n
+// (~ n d) the exact root is y (1-e)^(-1/n) = y (1 + e/n + (n+1) e^2 / (2 n^2) + O(e^3)); the neglected term is
+// below 2^-60.  About 1 ulp, for x > 0 in the normal range (callers guard zero).
+// CUDA's rsqrt / rcbrt / cbrt cost 28 / 47 / 49 instructions here (special-case handling, FP64 seeds).
+ABM_FN double fast_rsqrt(double x)              // x**(-1/2)
+{
+    const double y = rsqrt_seed(x);
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
+ABM_FN double fast_rcbrt(double x)              // x**(-1/3), x in the normal FP32 range
+{
+    const double y = pow_seed(x, -1.0f / 3.0f);
+    const double e = fma(-(x * y), y * y, 1.0);
+    return fma(y * e, fma(2.0 / 9.0, e, 1.0 / 3.0), y);
+}
+ABM_FN double fast_r4rt(double x)               // x**(-1/4), x in the normal FP32 range
+{
+    const double y = pow_seed(x, -0.25f);
+    const double y2 = y * y;
+    const double e = fma(-(x * y2), y2, 1.0);
+    return fma(y * e, fma(5.0 / 32.0, e, 0.25), y);
+}
+// x**0.75 and x**(1/3) for x >= 0; below 1e-30 (where the FP32 seed would leave its range) the result is 0:
+// the callers add it to 1 (delta_skin_layer) or to a squared wind speed (gustiness)
+ABM_FN double pow075(double x) { return (x > 1.e-30) ? x * fast_r4rt(x) : 0.; }
+ABM_FN double fast_cbrt(double x)
+{
+    if (!(x > 1.e-30)) return 0.;
+    const double r = fast_rcbrt(x);
+    return x * (r * r);
 }
 
 // p(r) ~ exp(r) on |r| <= ln2/2 (Estrin: depth 5 instead of 11 dependent FMAs), then * 2^k through

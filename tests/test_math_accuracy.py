@@ -100,3 +100,18 @@ def test_powr_and_rcp(abm):
     assert (abm(5, np.zeros(3), np.array([0.75, 0.79, 2.0 / 3.0])) == 0).all()   # 0**y = 0
     x = np.exp(RNG.uniform(-30, 30, N))
     assert _relerr(abm(6, x), x, lambda v: 1 / v) <= 2 * ULP
+
+
+def test_fast_roots(abm):
+    """x**(-1/2), x**(-1/3), x**(-1/4), x**0.75, x**(1/3): one seed (degraded to 2^-21 in the host build, the worst the
+    device seeds may have) and one cubic-convergence step."""
+    x = np.concatenate([np.exp(RNG.uniform(-60, 60, N)), RNG.uniform(0.5, 4.0, N), [1.0, 2.0, 8.0, 1e-29, 1e30]])
+    mp.mp.dps = 50
+    assert _relerr(abm(10, x), x, lambda v: 1 / mp.sqrt(v)) <= 2 * ULP
+    assert _relerr(abm(11, x), x, lambda v: v ** (mp.mpf(-1) / 3)) <= 2 * ULP
+    assert _relerr(abm(12, x), x, lambda v: v ** mp.mpf(-0.25)) <= 2 * ULP
+    assert _relerr(abm(13, x), x, lambda v: v ** mp.mpf(0.75)) <= 3 * ULP
+    assert _relerr(abm(14, x), x, lambda v: v ** (mp.mpf(1) / 3)) <= 3 * ULP
+    z = np.array([0.0, 1e-31, 1e-300])
+    assert (abm(13, z) == 0).all() and (abm(14, z) == 0).all()     # documented flush below 1e-30
+    assert _relerr(abm(6, x), x, lambda v: 1 / v) <= 2 * ULP       # 3-instruction reciprocal refinement
