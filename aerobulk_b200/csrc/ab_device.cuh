@@ -132,7 +132,7 @@ ABD double virt_temp(double T, double q) { return T * (1. + RCTV0 * q); }       
 // Goff (1957) saturation vapour pressure [Pa], :777-800 (rt0, not the triple point)
 ABD_HEAVY double e_sat(double T)
 {
-    const double zta = fmax(T, 180.);
+    const double zta = abm::dmax(T, 180.);
     const double ztmp = fdiv(KC(RT0), zta);
     const double r = zta * KC(1. / RT0);
     const double a = KC(10.79574) * (1. - ztmp) - KC(5.028) * abm::dlog10(r)
@@ -157,7 +157,7 @@ ABD double theta_from_z_P0_T_q(double z, double slp, double T, double q)
     return T * powr(fdiv(slp, pa), RPOISS_DRY);
 }
 
-ABD double rho_air(double T, double q, double p) { return fmax(fdiv(p, R_DRY * T * (1. + RCTV0 * q)), 0.8); }  // :522-537
+ABD double rho_air(double T, double q, double p) { return abm::dmax(fdiv(p, R_DRY * T * (1. + RCTV0 * q)), 0.8); }  // :522-537
 ABD double visc_air(double T)                                                                              // :549-563
 {
     const double tc = T - RT0, tc2 = tc * tc;
@@ -168,21 +168,21 @@ ABD double cp_air(double q) { return KC(RCP_DRY) + KC(RCP_VAP) * q; }           
 // moist adiabatic lapse rate [K/m], :627-649
 ABD double gamma_moist(double T, double q)
 {
-    const double ta = fmax(T, 180.);
-    const double qa = fmax(q, 1.E-6);
+    const double ta = abm::dmax(T, 180.);
+    const double qa = abm::dmax(q, 1.E-6);
     const double wa = fdiv(qa, 1. - qa);
     const double iRT = abm::fast_rcp(R_DRY * ta);
     const double Lv = L_vap(T);
     return fdiv(GRAV * (1. + Lv * wa * iRT), RCP_DRY + fdiv(Lv * Lv * wa * REPS0 * iRT, ta));
 }
-ABD double alpha_sw(double T) { return 2.1e-5 * powr(fmax(T - RT0 + 3.2, 0.), 0.79); }                    // :1267-1280
+ABD double alpha_sw(double T) { return 2.1e-5 * powr(abm::dmax(T - RT0 + 3.2, 0.), 0.79); }                    // :1267-1280
 ABD double qlw_net(double rlw, double Ts) { const double t2 = Ts * Ts; return KC(EMISS_W) * (rlw - KC(STEFAN) * t2 * t2); }  // :1291-1314
 
 // 1/L, :666-693
 ABD double one_on_L(double tha, double qa, double us, double ts, double qs)
 {
     const double zqa = 1. + KC(RCTV0) * qa;
-    const double r = fdiv(KC(GRAV * VKARMN) * (ts * zqa + KC(RCTV0) * tha * qs), fmax(us * us * tha * zqa, KC(1.E-9)));
+    const double r = fdiv(KC(GRAV * VKARMN) * (ts * zqa + KC(RCTV0) * tha * qs), abm::dmax(us * us * tha * zqa, KC(1.E-9)));
     return clip_abs(r, 200.);
 }
 
@@ -198,12 +198,12 @@ ABD double ri_bulk(double z, double sst, double tha, double ssq, double qa, doub
 ABD double q_air_rh(double rh, double T, double p)  // :963-985
 {
     const double ze = 0.01 * rh * e_sat(T);
-    return fdiv(ze * REPS0, fmax(p - (1. - REPS0) * ze, 1.));
+    return fdiv(ze * REPS0, abm::dmax(p - (1. - REPS0) * ze, 1.));
 }
 ABD double q_air_dp(double dp, double p)            // :990-1000
 {
-    const double e = fmax(e_sat(dp), 0.);
-    return fdiv(e * REPS0, fmax(p - (1. - REPS0) * e, 1.));
+    const double e = abm::dmax(e_sat(dp), 0.);
+    return fdiv(e * REPS0, abm::dmax(p - (1. - REPS0) * e, 1.));
 }
 
 struct Flux {
@@ -221,11 +221,11 @@ ABD AirZu air_at_zu(double zu, double tha, double qa, double slp)
 {
     const double ta = tha - KC(RGAMMA_DRY) * zu;
     const double r = abm::fast_rcp(KC(R_DRY) * ta * (1. + KC(RCTV0) * qa));     // rho_air = MAX(p / (R T (1 + rctv0 q)), 0.8)
-    double rho = fmax(slp * r, KC(0.8));
-    rho = fmax((slp - rho * KC(GRAV) * zu) * r, KC(0.8));
+    double rho = abm::dmax(slp * r, KC(0.8));
+    rho = abm::dmax((slp - rho * KC(GRAV) * zu) * r, KC(0.8));
     AirZu a;
     a.rho = rho;
-    a.rho1 = fmax(rho, 1.);
+    a.rho1 = abm::dmax(rho, 1.);
     a.cp = cp_air(qa);
     return a;
 }
@@ -283,7 +283,7 @@ ABD double log_z0tq_LKB(int iflag, double Rer, double log_Rer, double log_z0)
         else if (Rer <= 300.) { la = 0x1.d1d1701b4f5c8p+2; b = -2.682; }
         else { la = 0x1.935aebcc59706p+3; b = -3.616; }
     }
-    return fmin(fmax(la + (b - 1.) * log_Rer + log_z0, LOG_1EM9), LOG_0P05);
+    return abm::dmin(abm::dmax(la + (b - 1.) * log_Rer + log_z0, LOG_1EM9), LOG_0P05);
 }
 
 // ---------------------------------------------------------------------------
@@ -300,7 +300,7 @@ struct PsiMH {
 // Large & Yeager, src/mod_blk_ncar.f90:333-407
 ABD PsiMH psi_mh_ncar_unstable(double z)
 {
-    const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
+    const double x2 = abm::dmax(sqrt(fabs(1. - 16. * z)), 1.);
     const double x = sqrt(x2);
     const double l2 = abm::dlog((1. + x2) * 0.5);
     PsiMH r;
@@ -310,7 +310,7 @@ ABD PsiMH psi_mh_ncar_unstable(double z)
 }
 ABD double psi_h_ncar_unstable(double z)
 {
-    const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
+    const double x2 = abm::dmax(sqrt(fabs(1. - 16. * z)), 1.);
     return 2. * abm::dlog(0.5 * (1. + x2));
 }
 ABD double psi_m_ncar(double z) { return nonneg(z) ? -5. * z : psi_mh_ncar_unstable(z).m; }
@@ -324,7 +324,7 @@ ABD double psi_coare_convective(double phi_c)
 }
 ABD PsiMH psi_mh_coare_stable(double z)
 {
-    const double e = abm::dexp(-fmin(50., KC(0.35) * z));
+    const double e = abm::dexp(-abm::dmin(50., KC(0.35) * z));
     const double a = fabs(1. + 2. * z * KC(1. / 3.));
     PsiMH r;
     r.m = -(1. + 1. * z + KC(0.6667) * (z - KC(14.28)) * e + KC(8.525));
@@ -333,7 +333,7 @@ ABD PsiMH psi_mh_coare_stable(double z)
 }
 ABD double psi_h_coare_stable(double z)
 {
-    const double e = abm::dexp(-fmin(50., KC(0.35) * z));
+    const double e = abm::dexp(-abm::dmin(50., KC(0.35) * z));
     const double a = fabs(1. + 2. * z * KC(1. / 3.));
     return -(a * sqrt(a) + KC(.6667) * (z - KC(14.28)) * e + KC(8.525));
 }
@@ -380,7 +380,7 @@ ABD void psi3_coare(double zeta_u, double zeta_t, double &m_u, double &h_u, doub
 }
 
 // IFS, src/mod_blk_ecmwf.f90:441-564 (zeta capped to [-50, 5]; the cap keeps the sign)
-ABD double cap_zeta(double zeta) { return fmin(fmax(zeta, -50.), 5.); }
+ABD double cap_zeta(double zeta) { return abm::dmin(abm::dmax(zeta, -50.), 5.); }
 ABD PsiMH psi_mh_ecmwf_stable(double zeta)
 {
     const double zc = 5. / 0.35;
@@ -415,7 +415,7 @@ ABD double psi_h_ecmwf_unstable(double zeta)
 // Andreas et al. 2015 (Paulson unstable / Grachev 2007 stable), src/mod_blk_andreas.f90:307-410
 ABD double psi_m_andreas_stable(double zeta)
 {
-    const double z = fmin(zeta, 15.);
+    const double z = abm::dmin(zeta, 15.);
     const double zam = 5.;
     const double x = abm::fast_cbrt(fabs(1. + z));
     return -(3. * zam / ZBM_A * (x - 1.))
@@ -426,7 +426,7 @@ ABD double psi_m_andreas_stable(double zeta)
 }
 ABD double psi_h_andreas_stable(double zeta)
 {
-    const double z = fmin(zeta, 15.);
+    const double z = abm::dmin(zeta, 15.);
     const double zah = 5., zbh = 5., zch = 3.;
     const double zz = 2. * z + zch;
     return -(0.5 * zbh * abm::dlog(fabs(1. + zch * z + z * z)))
@@ -435,8 +435,8 @@ ABD double psi_h_andreas_stable(double zeta)
 }
 ABD PsiMH psi_mh_andreas_unstable(double zeta)
 {
-    const double z = fmin(zeta, 15.);
-    const double x2 = fmax(sqrt(fabs(1. - 16. * z)), 1.);
+    const double z = abm::dmin(zeta, 15.);
+    const double x2 = abm::dmax(sqrt(fabs(1. - 16. * z)), 1.);
     const double x = sqrt(x2);
     PsiMH r;
     r.m = 2. * abm::dlog(fabs((1. + x) * 0.5)) + abm::dlog(fabs((1. + x2) * 0.5)) - 2. * abm::datan(x) + RPI * 0.5;
@@ -445,7 +445,7 @@ ABD PsiMH psi_mh_andreas_unstable(double zeta)
 }
 ABD double psi_h_andreas_unstable(double zeta)
 {
-    const double x2 = fmax(sqrt(fabs(1. - 16. * fmin(zeta, 15.))), 1.);
+    const double x2 = abm::dmax(sqrt(fabs(1. - 16. * abm::dmin(zeta, 15.))), 1.);
     return 2. * abm::dlog(0.5 * (1. + x2));
 }
 
@@ -475,8 +475,8 @@ template <bool ZTEQ>
 ABD Guess first_guess_coare(const Uniform &u, double sst, double t_zt, double ssq, double q_zt, double wnd, double charn)
 {
     Guess g;
-    g.t_zu = fmax(t_zt, 180.);
-    g.q_zu = fmax(q_zt, 1.e-6);
+    g.t_zu = abm::dmax(t_zt, 180.);
+    g.q_zu = abm::dmax(q_zt, 1.e-6);
 
     double dt = floor_abs(g.t_zu - sst, 1.E-09);
     double dq = floor_abs(g.q_zu - ssq, 1.E-12);
@@ -486,7 +486,7 @@ ABD Guess first_guess_coare(const Uniform &u, double sst, double t_zt, double ss
     double us = u.fg_c_a * Ub;
 
     double z0 = charn * us * us * INV_GRAV + fdiv(0.11 * nu_a, us);
-    z0 = fmin(fmax(fabs(z0), 1.E-8), 1.);
+    z0 = abm::dmin(abm::dmax(fabs(z0), 1.E-8), 1.);
     const double log_z0 = abm::dlog(z0);
 
     const double sq = fdiv(VKARMN, u.log_zu - log_z0);
@@ -494,7 +494,7 @@ ABD Guess first_guess_coare(const Uniform &u, double sst, double t_zt, double ss
     const double r1_o_sqrt_Cd10 = (u.log_10 - log_z0) * INV_VKARMN;
 
     // z0t = 10 / EXP(k / (0.00115 r)) clipped to [1e-8, 1], only needed as LOG(z0t)
-    const double log_z0t = fmin(fmax(u.log_10 - fdiv(VKARMN, 0.00115 * r1_o_sqrt_Cd10), LOG_1EM8), 0.);
+    const double log_z0t = abm::dmin(abm::dmax(u.log_10 - fdiv(VKARMN, 0.00115 * r1_o_sqrt_Cd10), LOG_1EM8), 0.);
 
     const double Rib = ri_bulk(u.zu, sst, g.t_zu, ssq, g.q_zu, Ub);
 
@@ -505,7 +505,7 @@ ABD Guess first_guess_coare(const Uniform &u, double sst, double t_zt, double ss
     const double zeta_t = ZTEQ ? zeta_u : fdiv(u.zt * zeta_u, u.zu);
     double psi_m_u, psi_h_u, psi_h_t;
     psi3_coare<ZTEQ>(zeta_u, zeta_t, psi_m_u, psi_h_u, psi_h_t);
-    us = fmax(fdiv(Ub * VKARMN, u.log_zu - log_z0 - psi_m_u), 1.E-9);
+    us = abm::dmax(fdiv(Ub * VKARMN, u.log_zu - log_z0 - psi_m_u), 1.E-9);
     const double tmp = fdiv(VKARMN, u.log_zu - log_z0t - psi_h_u);
     double ts = dt * tmp;
     double qs = dq * tmp;
@@ -525,7 +525,7 @@ ABD Guess first_guess_coare(const Uniform &u, double sst, double t_zt, double ss
     g.qs = qs;
     g.Ub = Ub;
     z0 = charn * us * us * INV_GRAV + fdiv(0.11 * nu_a, us);
-    g.z0 = fmin(fmax(fabs(z0), 1.E-8), 1.);
+    g.z0 = abm::dmin(abm::dmax(fabs(z0), 1.E-8), 1.);
     return g;
 }
 
@@ -538,17 +538,17 @@ template <bool COARE_FORM>
 ABD double cool_skin_dT(double alpha, double Qsw, double Qnsol, double us, double Qlat)
 {
     // invariants of the five delta_skin_layer evaluations
-    const double usw = fmax(us, KC(1.E-4)) * KC(SQ_RADRW);
+    const double usw = abm::dmax(us, KC(1.E-4)) * KC(SQ_RADRW);
     const double usw2 = usw * usw;
     const double c_lamb = fdiv(alpha * KC(RCST_CS), usw2 * usw2);
     const double nu_o_usw = fdiv(KC(RNU0_W), usw);
-    const double d_warm = fmin(6. * nu_o_usw, KC(0.007));
-    const double q_lat_term = COARE_FORM ? fdiv(KC(0.026) * fmin(Qlat, 0.) * KC(RCP0_W * (1. / RLEVAP)), alpha) : 0.;
+    const double d_warm = abm::dmin(6. * nu_o_usw, KC(0.007));
+    const double q_lat_term = COARE_FORM ? fdiv(KC(0.026) * abm::dmin(Qlat, 0.) * KC(RCP0_W * (1. / RLEVAP)), alpha) : 0.;
 
     auto delta = [&](double Qd) -> double {
         const double zQd = COARE_FORM ? Qd + q_lat_term : Qd;
         if (nonneg(zQd)) return d_warm;                                  // warming of the viscous layer
-        const double x = fmax(c_lamb * zQd, 0.);
+        const double x = abm::dmax(c_lamb * zQd, 0.);
         const double x75 = abm::pow075(x);                               // **0.75
         return 6. * abm::fast_rcbrt(1. + x75) * nu_o_usw;                 // **(-1./3.)
     };
@@ -559,7 +559,7 @@ ABD double cool_skin_dT(double alpha, double Qsw, double Qnsol, double us, doubl
 #pragma unroll 1
     for (int jc = 0; jc < 5; ++jc) {
         if (jc > 0) {
-            const double fr = fmax((COARE_FORM ? KC(0.137) : KC(0.065)) + 11. * d - fdiv(KC(6.6E-5), d) * (1. - abm::dexp(-d * KC(1. / 8.E-4))), KC(0.01));
+            const double fr = abm::dmax((COARE_FORM ? KC(0.137) : KC(0.065)) + 11. * d - fdiv(KC(6.6E-5), d) * (1. - abm::dexp(-d * KC(1. / 8.E-4))), KC(0.01));
             Qabs = Qnsol + fr * Qsw;
         }
         d = delta(Qabs);
@@ -620,7 +620,7 @@ ABD void wl_coare(WarmLayer &w, const WlCoareCtx &c, double Qsw, double Qnsol, d
 {
     const double Hwl_max = 20.;
     double dT = w.dT;
-    double H = fmax(fmin(w.Hz, Hwl_max), 0.1);
+    double H = abm::dmax(abm::dmin(w.Hz, Hwl_max), 0.1);
     double qac = w.Qac;
     double tac = w.Tac;
     bool l_exit = c.dawn, destroy = c.dawn;
@@ -635,13 +635,13 @@ ABD void wl_coare(WarmLayer &w, const WlCoareCtx &c, double Qsw, double Qnsol, d
         destroy = true;
     }
     if (!l_exit) {
-        tac = w.Tac + fmax(.002, Tau) * rdt;
+        tac = w.Tac + abm::dmax(.002, Tau) * rdt;
 #pragma unroll 1
         for (int jl = 0; jl < 5; ++jl) {
             if (jl > 0) Qabs = wl_coare_absorption(H) * Qsw + Qnsol;   // jl == 0: H unchanged since the test above
             qac = w.Qac + Qabs * rdt;
             if (qac <= 0.) break;
-            H = fmax(fmin(Hwl_max, c.cd1 * tac * abm::fast_rsqrt(qac)), 0.1);
+            H = abm::dmax(abm::dmin(Hwl_max, c.cd1 * tac * abm::fast_rsqrt(qac)), 0.1);
         }
         if (qac <= 0.) {
             destroy = true;
@@ -690,11 +690,11 @@ ABD void wl_ecmwf(WarmLayer &w, const WlEcmwfCtx &c, double alpha, double Qsw, d
     const double RhoCp_w = RHO0_W * RCP0_W;
     const double H = w.Hz;
     const double tcorr = c.tcorr;
-    const double dT_b = fmax(w.dT * c.r_tcorr, 0.);
+    const double dT_b = abm::dmax(w.dT * c.r_tcorr, 0.);
 
     const double Qabs = c.fr * Qsw + Qnsol;
 
-    const double usw = fmax(us, KC(1.E-4)) * KC(SQ_RADRW);
+    const double usw = abm::dmax(us, KC(1.E-4)) * KC(SQ_RADRW);
     const double usw2 = usw * usw;
     const bool warming = nonneg(Qabs);
 
@@ -711,7 +711,7 @@ ABD void wl_ecmwf(WarmLayer &w, const WlEcmwfCtx &c, double alpha, double Qsw, d
         dT_n = 0.5 * (dT_n + dT_b);
         const double zeta = warming ? H * L2 : H * sqrt(dT_n * cst2);
         const double B = fdiv(cst3, phi_takaya(zeta));
-        dT_n = fmax(dT_b + A + B * dT_n, 0.);
+        dT_n = abm::dmax(dT_b + A + B * dT_n, 0.);
     }
     w.dT = dT_n * tcorr;
 }
@@ -742,22 +742,22 @@ ABD double cd_n10_ncar(double w)
     w6 = w6 * w6;
     const double r = nonneg(w - 33.) ? 1.e-3 * 2.34
                                      : 1.e-3 * (fdiv(2.7, w) + 0.142 + w * (1. / 13.09) - 3.14807E-10 * w6);
-    return fmax(r, CX_MIN);
+    return abm::dmax(r, CX_MIN);
 }
 
 template <bool ZTEQ>
 ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p, Diag &dg)
 {
-    const double Ub = fmax(0.5, p.wnd);
+    const double Ub = abm::dmax(0.5, p.wnd);
     const bool stable0 = nonneg(virt_temp(p.theta_zt, p.q_zt) - virt_temp(p.sst, p.ssq));
     double CdN = cd_n10_ncar(Ub);
     double sqrt_CdN = sqrt(CdN);
     double Cd = CdN;
-    double Ce = fmax(1.e-3 * (34.6 * sqrt_CdN), CX_MIN);
-    double Ch = fmax(1.e-3 * sqrt_CdN * (stable0 ? 18. : 32.7), CX_MIN);
+    double Ce = abm::dmax(1.e-3 * (34.6 * sqrt_CdN), CX_MIN);
+    double Ch = abm::dmax(1.e-3 * sqrt_CdN * (stable0 ? 18. : 32.7), CX_MIN);
     double sqrt_Cd = sqrt_CdN;
-    double t_zu = fmax(p.theta_zt, 180.);
-    double q_zu = fmax(p.q_zt, 1.e-6);
+    double t_zu = abm::dmax(p.theta_zt, 180.);
+    double q_zu = abm::dmax(p.q_zt, 1.e-6);
     double us = 0., r1oL = 0., Un10 = 0., ChN = 0., CeN = 0.;
 
 #pragma unroll 1
@@ -785,29 +785,29 @@ ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p, Diag &dg)
         if (!ZTEQ) {
             const double tmp = u.log_ztu + psi_h_u - psi_h_t;
             t_zu = p.theta_zt - ts * INV_VKARMN * tmp;
-            q_zu = fmax(0., p.q_zt - qs * INV_VKARMN * tmp);
+            q_zu = abm::dmax(0., p.q_zt - qs * INV_VKARMN * tmp);
         }
         // UN10_from_CD (mod_phymbl.f90:1532-1547) with z0_from_Cd(zu, Cd, psi) (:1335-1352); SQRT(Cd) is sqrt_Cd
         // z0 = zu EXP(-(k/SQRT(Cd) + psi_m)) only enters as LOG(10/z0) = k/SQRT(Cd) + psi_m - LOG(zu/10)
-        Un10 = fmax(0.25, sqrt_Cd * Ub * INV_VKARMN * (VKARMN * r_sqrt_Cd + psi_m - u.log_zu10));
+        Un10 = abm::dmax(0.25, sqrt_Cd * Ub * INV_VKARMN * (VKARMN * r_sqrt_Cd + psi_m - u.log_zu10));
         CdN = cd_n10_ncar(Un10);
         sqrt_CdN = sqrt(CdN);
         double tmp = 1. + sqrt_CdN * INV_VKARMN * (u.log_zu10 - psi_m);
-        Cd = fmax(fdiv(CdN, tmp * tmp), CX_MIN);
+        Cd = abm::dmax(fdiv(CdN, tmp * tmp), CX_MIN);
         sqrt_Cd = sqrt(Cd);
         const double r_sqrt_CdN = abm::fast_rcp(sqrt_CdN);
         tmp = (u.log_zu10 - psi_h_u) * INV_VKARMN * r_sqrt_CdN;
         const double tmp2 = sqrt_Cd * r_sqrt_CdN;
         ChN = 1.e-3 * sqrt_CdN * (nonneg(zeta_u) ? 18. : 32.7);
         CeN = 1.e-3 * (34.6 * sqrt_CdN);
-        Ch = fmax(fdiv(ChN * tmp2, 1. + ChN * tmp), CX_MIN);
-        Ce = fmax(fdiv(CeN * tmp2, 1. + CeN * tmp), CX_MIN);
+        Ch = abm::dmax(fdiv(ChN * tmp2, 1. + ChN * tmp), CX_MIN);
+        Ce = abm::dmax(fdiv(CeN * tmp2, 1. + CeN * tmp), CX_MIN);
     }
     Coeffs c;
     c.Cd = Cd; c.Ch = Ch; c.Ce = Ce; c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = p.sst; c.qs = p.ssq;
     // optional outputs, src/mod_blk_ncar.f90:229-235
     dg.CdN = CdN; dg.ChN = ChN; dg.CeN = CeN; dg.UN10 = Un10; dg.L = 1. / r1oL; dg.us = us;
-    dg.z0 = fmin(u.zu * abm::dexp(-VKARMN * abm::fast_rsqrt(CdN)), Z0_SEA_MAX);
+    dg.z0 = abm::dmin(u.zu * abm::dexp(-VKARMN * abm::fast_rsqrt(CdN)), Z0_SEA_MAX);
     dg.dT_cs = 0.;
     return c;
 }
@@ -822,7 +822,7 @@ ABD double charn_coare3p0(double w)
     if (nonneg(w - 18.)) return 0.018;
     return 0.011 + (0.018 - 0.011) * (w - 10.) * (1. / (18. - 10.));
 }
-ABD double charn_coare3p6(double w) { return fmax(fmin(KC(0.0017) * w - KC(0.005), KC(0.028)), 0.); }
+ABD double charn_coare3p6(double w) { return abm::dmax(abm::dmin(KC(0.0017) * w - KC(0.005), KC(0.028)), 0.); }
 
 // CS / WL: l_use_cs / l_use_wl of the reference (aerobulk_model switches both on together)
 template <bool V36, bool CS, bool WL, bool ZTEQ>
@@ -836,7 +836,7 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
     WlCoareCtx wc = {};
     if (SKIN) {
         if (CS) Ts = Ts - 0.25;
-        qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+        qs_ = RDCT_QSAT_SALT * q_sat(abm::dmax(Ts, 200.), p.slp);
         alpha = alpha_sw(p.sst);
         if (WL) wc = wl_coare_ctx(alpha, p.has_lon ? wl_coare_dawn(p.lon, u.isd) : (u.dawn != 0));
     }
@@ -857,23 +857,23 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
         const double us2 = us * us;
         r1oL = one_on_L(t_zu, q_zu, us, ts, qst);    // already clipped to +-200
 
-        const double cv = abm::fast_cbrt(fmax(KC(-zi0 * INV_VKARMN) * r1oL, 0.));
+        const double cv = abm::fast_cbrt(abm::dmax(KC(-zi0 * INV_VKARMN) * r1oL, 0.));
         const double gust2 = KC(Beta0 * Beta0) * us2 * (cv * cv);       // **(2./3.)
-        Ub = fmax(sqrt(p.wnd * p.wnd + gust2), KC(0.2));
+        Ub = abm::dmax(sqrt(p.wnd * p.wnd + gust2), KC(0.2));
 
         const double zeta_u = clip_abs(u.zu * r1oL, zeta_abs_max);
 
         const double Un10 = us * INV_VKARMN * (u.log_10 - log_z0);
         const double r_us = abm::fast_rcp(us);
         z0 = (V36 ? charn_coare3p6(Un10) : charn_coare3p0(Un10)) * us2 * KC(INV_GRAV) + KC(0.11) * nu_a * r_us;
-        z0 = fmin(fmax(fabs(z0), KC(1.E-9)), 1.);
+        z0 = abm::dmin(abm::dmax(fabs(z0), KC(1.E-9)), 1.);
         log_z0 = abm::dlog(z0);
 
         // z0t = MIN(1.6e-4, 5.8e-5 (nu/(z0 u*))**0.72) [3.6] / MIN(1.1e-4, 5.5e-5 (..)**0.6) [3.0], floored at
         // 1e-9, is only needed as LOG(z0t): monotonic, so MIN / MAX act on the logarithms (no pow)
         const double log_rr = abm::dlog(nu_a * r_us) - log_z0;
-        log_z0t = V36 ? fmax(fmin(KC(LOG_1P6EM4), KC(LOG_5P8EM5) + KC(0.72) * log_rr), KC(LOG_1EM9))
-                      : fmax(fmin(KC(LOG_1P1EM4), KC(LOG_5P5EM5) + KC(0.6) * log_rr), KC(LOG_1EM9));
+        log_z0t = V36 ? abm::dmax(abm::dmin(KC(LOG_1P6EM4), KC(LOG_5P8EM5) + KC(0.72) * log_rr), KC(LOG_1EM9))
+                      : abm::dmax(abm::dmin(KC(LOG_1P1EM4), KC(LOG_5P5EM5) + KC(0.6) * log_rr), KC(LOG_1EM9));
 
         const double zeta_t = clip_abs(u.zt * r1oL, zeta_abs_max);
         double psi_m_u, psi_h_u, psi_h_t;
@@ -881,7 +881,7 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
         double tmp1 = fdiv(KC(VKARMN), u.log_zu - log_z0t - psi_h_u);
         ts = dt * tmp1;
         qst = dq * tmp1;
-        us = fmax(fdiv(Ub * KC(VKARMN), u.log_zu - log_z0 - psi_m_u), KC(1.E-9));
+        us = abm::dmax(fdiv(Ub * KC(VKARMN), u.log_zu - log_z0 - psi_m_u), KC(1.E-9));
 
         if (!ZTEQ) {
             tmp1 = u.log_zt - u.log_zu + psi_h_u - psi_h_t;
@@ -909,7 +909,7 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
                     Ts = p.sst + wl.dT;
                     if (CS) Ts = Ts + dT_cs;
                 }
-                qs_ = KC(RDCT_QSAT_SALT) * q_sat(fmax(Ts, 200.), p.slp);
+                qs_ = KC(RDCT_QSAT_SALT) * q_sat(abm::dmax(Ts, 200.), p.slp);
             }
         }
         if (SKIN || !ZTEQ || !V36) {
@@ -919,14 +919,14 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
     }
     Coeffs c;
     const double r = fdiv(us, Ub);
-    c.Cd = fmax(r * r, CX_MIN);
-    c.Ch = fmax(fdiv(r * ts, dt), CX_MIN);
-    c.Ce = fmax(fdiv(r * qst, dq), CX_MIN);
+    c.Cd = abm::dmax(r * r, CX_MIN);
+    c.Ch = abm::dmax(fdiv(r * ts, dt), CX_MIN);
+    c.Ce = abm::dmax(fdiv(r * qst, dq), CX_MIN);
     c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = Ts; c.qs = qs_;
     // optional outputs, src/mod_blk_coare3p6.f90:391-401
     const double t0 = 1. / (u.log_zu - log_z0);
-    dg.CdN = fmax(VKARMN2 * t0 * t0, CX_MIN);
-    dg.ChN = dg.CeN = fmax(VKARMN2 * t0 / (u.log_zu - log_z0t), CX_MIN);
+    dg.CdN = abm::dmax(VKARMN2 * t0 * t0, CX_MIN);
+    dg.ChN = dg.CeN = abm::dmax(VKARMN2 * t0 / (u.log_zu - log_z0t), CX_MIN);
     dg.z0 = z0; dg.us = us; dg.L = 1. / r1oL; dg.UN10 = us * INV_VKARMN * (u.log_10 - log_z0);
     dg.dT_cs = dT_cs;
     return c;
@@ -946,7 +946,7 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
     WlEcmwfCtx wec = {};
     if (SKIN) {
         if (CS) Ts = Ts - 0.25;
-        qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+        qs_ = RDCT_QSAT_SALT * q_sat(abm::dmax(Ts, 200.), p.slp);
         alpha = alpha_sw(p.sst);
         if (WL) wec = wl_ecmwf_ctx(wl.Hz, u.gdept);
     }
@@ -962,8 +962,8 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
 
     double r1oL = one_on_L(t_zu, q_zu, us, ts, qst);
     const double x0 = fdiv(VKARMN, fdiv(0.00115, fdiv(VKARMN, u.log_10 - log_z0)));
-    double z0t = fmin(fmax(10. * abm::dexp(-x0), 1.E-9), 1.);
-    double log_z0t = fmin(fmax(u.log_10 - x0, LOG_1EM9), 0.);
+    double z0t = abm::dmin(abm::dmax(10. * abm::dexp(-x0), 1.E-9), 1.);
+    double log_z0t = abm::dmin(abm::dmax(u.log_10 - x0, LOG_1EM9), 0.);
 
     double Fm, Fh, psi_h_u;
     if (nonneg(r1oL)) {
@@ -1006,13 +1006,13 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
         us = fdiv(Ub * VKARMN, Fm);
         const double us2 = us * us;
         double tmp0 = fdiv(nu_a, us);
-        z0 = fmin(fabs(alpha_M * tmp0 + charn0 * us2 * INV_GRAV), 0.001);
-        z0t = fmin(fabs(alpha_H * tmp0), 0.001);
-        const double z0q = fmin(fabs(alpha_Q * tmp0), 0.001);
+        z0 = abm::dmin(fabs(alpha_M * tmp0 + charn0 * us2 * INV_GRAV), 0.001);
+        z0t = abm::dmin(fabs(alpha_H * tmp0), 0.001);
+        const double z0q = abm::dmin(fabs(alpha_Q * tmp0), 0.001);
         log_z0 = abm::dlog(z0);
         const double log_t0 = abm::dlog(fabs(tmp0));          // LOG(alpha nu/u*) = LOG(alpha) + LOG(nu/u*)
-        log_z0t = fmin(LOG_0P40 + log_t0, LOG_1EM3);
-        log_z0q = fmin(LOG_0P62 + log_t0, LOG_1EM3);
+        log_z0t = abm::dmin(LOG_0P40 + log_t0, LOG_1EM3);
+        log_z0q = abm::dmin(LOG_0P62 + log_t0, LOG_1EM3);
 
         double psi_m_z0, psi_h_z0t;
         if (stable) {
@@ -1025,9 +1025,9 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
             psi_h_z0q = psi_h_ecmwf_unstable(z0q * r1oL);
         }
 
-        const double cv = abm::fast_cbrt(fmax(-zi0 * r1oL * INV_VKARMN, 0.));
+        const double cv = abm::fast_cbrt(abm::dmax(-zi0 * r1oL * INV_VKARMN, 0.));
         tmp0 = Beta0 * Beta0 * us2 * (cv * cv);
-        Ub = fmax(sqrt(p.wnd * p.wnd + tmp0), 0.2);
+        Ub = abm::dmax(sqrt(p.wnd * p.wnd + tmp0), 0.2);
 
         tmp0 = psi_h_u - psi_h_z0t;
         double tmp1 = fdiv(VKARMN, u.log_zu - log_z0t - tmp0);
@@ -1043,9 +1043,9 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
         qst = dq * tmp1;
         if (!ZTEQ) {
             tmp1 = u.log_ztu + tmp0 - psi_h_t + psi_h_z0q;
-            q_zu = fmax(p.q_zt - qst * INV_VKARMN * tmp1, 0.);
+            q_zu = abm::dmax(p.q_zt - qst * INV_VKARMN * tmp1, 0.);
         } else {
-            q_zu = fmax(p.q_zt, 0.);
+            q_zu = abm::dmax(p.q_zt, 0.);
         }
 
         Fm = u.log_zu - log_z0 - psi_m_u + psi_m_z0;
@@ -1067,7 +1067,7 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
                     Ts = p.sst + wl.dT;
                     if (CS) Ts = Ts + dT_cs;
                 }
-                qs_ = RDCT_QSAT_SALT * q_sat(fmax(Ts, 200.), p.slp);
+                qs_ = RDCT_QSAT_SALT * q_sat(abm::dmax(Ts, 200.), p.slp);
             }
         }
         dt = floor_abs(t_zu - Ts, 1.E-09);
@@ -1076,14 +1076,14 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
     Coeffs c;
     const double Fq = u.log_zu - log_z0q - psi_h_u + psi_h_z0q;
     const double k2_o_Fm = fdiv(VKARMN2, Fm);
-    c.Cd = fmax(fdiv(k2_o_Fm, Fm), CX_MIN);
-    c.Ch = fmax(fdiv(k2_o_Fm, Fh), CX_MIN);
-    c.Ce = fmax(fdiv(k2_o_Fm, Fq), CX_MIN);
+    c.Cd = abm::dmax(fdiv(k2_o_Fm, Fm), CX_MIN);
+    c.Ch = abm::dmax(fdiv(k2_o_Fm, Fh), CX_MIN);
+    c.Ce = abm::dmax(fdiv(k2_o_Fm, Fq), CX_MIN);
     c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = Ts; c.qs = qs_;
     // optional outputs, src/mod_blk_ecmwf.f90:361-371
     const double t0 = 1. / (u.log_zu - log_z0);
-    dg.CdN = fmax(VKARMN2 * t0 * t0, CX_MIN);
-    dg.ChN = dg.CeN = fmax(VKARMN2 * t0 / (u.log_zu - log_z0t), CX_MIN);
+    dg.CdN = abm::dmax(VKARMN2 * t0 * t0, CX_MIN);
+    dg.ChN = dg.CeN = abm::dmax(VKARMN2 * t0 / (u.log_zu - log_z0t), CX_MIN);
     dg.z0 = z0; dg.us = us; dg.L = 1. / r1oL; dg.UN10 = us * INV_VKARMN * (u.log_10 - log_z0);
     dg.dT_cs = dT_cs;
     return c;
@@ -1096,7 +1096,7 @@ template <bool ZTEQ>
 ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p, Diag &dg)
 {
     const double rRi_max = 0.15, rCs_min = 0.35E-3;
-    const double Ub = fmax(0.25, p.wnd);
+    const double Ub = abm::dmax(0.25, p.wnd);
     const double r_Ub = abm::fast_rcp(Ub);
     double UN10 = Ub;
     double t_zu = p.theta_zt, q_zu = p.q_zt;
@@ -1116,11 +1116,11 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p, Diag &dg)
         }
         zeta_u = u.zu * one_on_L(t_zu, q_zu, u_star, t_star, q_star);
         const double r = u_star * r_Ub;
-        const double Cd = fmax(r * r, CX_MIN);
+        const double Cd = abm::dmax(r * r, CX_MIN);
         const double zeta_t = fdiv(zeta_u, u.zu) * u.zt;
         const bool adjust = !ZTEQ && jit > 1;
         double psi_h_u, psi_h_t = 0.;
-        if (nonneg(fmin(zeta_u, 15.))) {
+        if (nonneg(abm::dmin(zeta_u, 15.))) {
             psi_m = psi_m_andreas_stable(zeta_u);
             psi_h_u = psi_h_andreas_stable(zeta_u);
             if (adjust) psi_h_t = psi_h_andreas_stable(zeta_t);
@@ -1131,11 +1131,11 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p, Diag &dg)
             if (adjust) psi_h_t = psi_h_andreas_unstable(zeta_t);
         }
         // z0 = MIN(zu EXP(-(k/SQRT(Cd) + psi_m)), z0_sea_max), kept together with its logarithm
-        const double log_z0 = fmin(u.log_zu - (VKARMN * abm::fast_rsqrt(Cd) + psi_m), LOG_Z0_SEA_MAX);
+        const double log_z0 = abm::dmin(u.log_zu - (VKARMN * abm::fast_rsqrt(Cd) + psi_m), LOG_Z0_SEA_MAX);
         z0 = abm::dexp(log_z0);
 
         const double Rer = fdiv(z0 * u_star, visc_air(t_zu));
-        const double log_Rer = abm::dlog(fmax(Rer, 1.E-300));
+        const double log_Rer = abm::dlog(abm::dmax(Rer, 1.E-300));
         const double log_z0t = log_z0tq_LKB(1, Rer, log_Rer, log_z0);
         const double log_z0q = log_z0tq_LKB(2, Rer, log_Rer, log_z0);
 
@@ -1148,22 +1148,22 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p, Diag &dg)
             q_zu = p.q_zt - q_star * INV_VKARMN * tmp;
             RiB = ri_bulk(u.zu, p.sst, t_zu, p.ssq, q_zu, Ub);
         }
-        UN10 = fmax(0.1, Ub - u_star * INV_VKARMN * (u.log_zu10 - psi_m));   // UN10_from_ustar, mod_phymbl.f90:1498-1510
+        UN10 = abm::dmax(0.1, Ub - u_star * INV_VKARMN * (u.log_zu10 - psi_m));   // UN10_from_ustar, mod_phymbl.f90:1498-1510
     }
     Coeffs c;
     const double r = u_star * r_Ub;
-    c.Cd = fmax(r * r, CX_MIN);
+    c.Cd = abm::dmax(r * r, CX_MIN);
     const double d1 = floor_abs(t_zu - p.sst, 1.E-6);
     const double d2 = floor_abs(q_zu - p.ssq, 1.E-9);
-    c.Ch = fmax(fdiv(r * t_star, d1), rCs_min);
-    c.Ce = fmax(fdiv(r * q_star, d2), rCs_min);
+    c.Ch = abm::dmax(fdiv(r * t_star, d1), rCs_min);
+    c.Ce = abm::dmax(fdiv(r * q_star, d2), rCs_min);
     c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = p.sst; c.qs = p.ssq;
     // optional outputs, src/mod_blk_andreas.f90:256-267
     const double log_z0 = abm::dlog(z0);
     const double t0 = 1. / (u.log_zu - log_z0);
-    dg.CdN = fmax(VKARMN2 * t0 * t0, CX_MIN);
+    dg.CdN = abm::dmax(VKARMN2 * t0 * t0, CX_MIN);
     const double Rer = z0 * u_star / visc_air(t_zu);
-    const double log_Rer = abm::dlog(fmax(Rer, 1.E-300));
+    const double log_Rer = abm::dlog(abm::dmax(Rer, 1.E-300));
     dg.ChN = VKARMN2 * t0 / (u.log_zu - log_z0tq_LKB(1, Rer, log_Rer, log_z0));
     dg.CeN = VKARMN2 * t0 / (u.log_zu - log_z0tq_LKB(2, Rer, log_Rer, log_z0));
     dg.z0 = z0; dg.us = u_star; dg.L = u.zu / zeta_u;

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(ICE_BLOCK, ICE_MIN_BLOCKS) ice_flux_kernel(con
     const double evap = Urho * o.Ce * (o.q_zu - siq);
     const double qsen = Urho * o.Ch * (o.t_zu - sit) * air.cp;
     const double qlat = RLSUB * evap;
-    const double ev = fmin(evap, 0.);
+    const double ev = abm::dmin(evap, 0.);
     if (tau > 10.) atomicMin(a.bad_tau, (unsigned long long)i);
     const double v[17] = {o.Cd, o.Ch, o.Ce, o.t_zu, o.q_zu, tz, o.Ub, ri_bulk(a.ui.zu, sit, o.t_zu, siq, o.q_zu, o.Ub),
                           o.z0, o.us, o.L, o.UN10, rho, tau, qsen, qlat, ev};

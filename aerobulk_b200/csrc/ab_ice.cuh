@@ -23,7 +23,7 @@ constexpr double LOG_5 = 0x1.9c041f7ed8d33p+0;          // LOG(1./0.2)
 // Goff over ice, mod_phymbl.f90:815-830; q_sat(l_ice=.TRUE.), :881-904
 ABD double e_sat_ice(double T)
 {
-    const double zta = fmax(T, 180.);
+    const double zta = abm::dmax(T, 180.);
     const double ztmp = fdiv(RTT0, zta);
     const double zle = -9.09718 * (ztmp - 1.) + -3.56654 * abm::dlog10(ztmp) + 0.876793 * (1. - zta * (1. / RTT0)) + RDG_I;
     return 100. * abm::dexp10(zle);
@@ -65,7 +65,7 @@ ABD double psi_h_ice(double z)
 // Andreas et al. 2005 Eq.19, mod_blk_ice_an05.f90:247-268
 ABD double rough_leng_m(double us, double nua)
 {
-    const double zus = fmax(us, 1.E-9);
+    const double zus = abm::dmax(us, 1.E-9);
     const double zz = (zus - 0.18) * 10.;
     return fdiv(0.135 * nua, zus) + 0.035 * zus * zus * INV_GRAV * (5. * abm::dexp(-zz * zz) + 1.);
 }
@@ -73,8 +73,8 @@ ABD double rough_leng_m(double us, double nua)
 // `bad` is raised where the reference would ctl_stop (:296-297: no regime selected for 2.49999 < R* < 2.5).
 ABD void log_rough_leng_tq(double z0, double log_z0, double us, double nua, double &log_z0t, double &log_z0q, bool &bad)
 {
-    const double zus = fmax(us, 1.E-9);
-    const double zre = fmax(fdiv(zus * z0, nua), 0.);
+    const double zus = abm::dmax(us, 1.E-9);
+    const double zre = abm::dmax(fdiv(zus * z0, nua), 0.);
     const double zlog = abm::dlog(zre), zlog2 = zlog * zlog;
     double t0, t1, t2, q0, q1, q2;
     if (zre <= 0.135) {
@@ -116,9 +116,9 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
     IceOut o;
     o.bad = false;
     o.CdN_frm = 0.;
-    o.Ub = fmax(U_zu, WSPD_THRSHLD_ICE);
-    o.t_zu = fmax(t_zt, 100.);
-    o.q_zu = fmax(q_zt, 0.1e-6);
+    o.Ub = abm::dmax(U_zu, WSPD_THRSHLD_ICE);
+    o.t_zu = abm::dmax(t_zt, 100.);
+    o.q_zu = abm::dmax(q_zt, 0.1e-6);
     double dt = floor_abs(o.t_zu - Ts, 1.E-6);
     double dq = floor_abs(o.q_zu - qs, 1.E-9);
 
@@ -149,7 +149,7 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
             const double dt_zu = o.t_zu - Ts, dq_zu = o.q_zu - qs;       // no floor here (:148-149)
             const double sq = sqrt(o.Cd);
             us = sq * o.Ub;
-            const double r = abm::fast_rcp(fmax(sq, 1.E-15));
+            const double r = abm::fast_rcp(abm::dmax(sq, 1.E-15));
             ts = o.Ch * dt_zu * r;
             qst = o.Ce * dq_zu * r;
             const double r1oL = one_on_L(o.t_zu, o.q_zu, us, ts, qst);
@@ -157,16 +157,16 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
             psim_u = psi_m_ice(zeta_u);
             const double psih_u = psi_h_ice(zeta_u);
             double x = 1. + u.sqrt_cdn * INV_VKARMN * (u.log_zu10 - psim_u);
-            o.Cd = fmin(fmax(fdiv(CdN, x * x), CX_MIN), 1.9E-3);
+            o.Cd = abm::dmin(abm::dmax(fdiv(CdN, x * x), CX_MIN), 1.9E-3);
             x = fdiv((u.log_zu10 - psih_u) * INV_VKARMN, u.sqrt_cdn);
             const double y = fdiv(sqrt(o.Cd), u.sqrt_cdn);
-            o.Ch = fmin(fmax(fdiv(ChN * y, 1. + ChN * x), CX_MIN), 1.9E-3);
-            o.Ce = fmin(fmax(fdiv(CeN * y, 1. + CeN * x), CX_MIN), 1.9E-3);
+            o.Ch = abm::dmin(abm::dmax(fdiv(ChN * y, 1. + ChN * x), CX_MIN), 1.9E-3);
+            o.Ce = abm::dmin(abm::dmax(fdiv(CeN * y, 1. + CeN * x), CX_MIN), 1.9E-3);
             if (!ZTEQ) {
                 const double zeta_t = clip_abs(u.zt * r1oL, 50.0);
                 const double c = psih_u - psi_h_ice(zeta_t) + u.log_ztu;
                 o.t_zu = t_zt - ts * INV_VKARMN * c;
-                o.q_zu = fmax(0., q_zt - qst * INV_VKARMN * c);
+                o.q_zu = abm::dmax(0., q_zt - qst * INV_VKARMN * c);
             }
         }
         o.CdN = CdN; o.ChN = ChN; o.CeN = CeN;
@@ -185,7 +185,7 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
         double log_z0 = abm::dlog(z0);
 #pragma unroll 1
         for (int jit = 1; jit <= 2; ++jit) {
-            us = fmax(fdiv(o.Ub * VKARMN, u.log_zu - log_z0), 1.E-9);
+            us = abm::dmax(fdiv(o.Ub * VKARMN, u.log_zu - log_z0), 1.E-9);
             z0 = rough_leng_m(us, nu);
             log_z0 = abm::dlog(z0);
         }
@@ -203,7 +203,7 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
             const double psih_u = psi_h_ice(zeta_u);
             ts = fdiv(dt * VKARMN, u.log_zu - log_z0t - psih_u);
             qst = fdiv(dq * VKARMN, u.log_zu - log_z0q - psih_u);
-            us = fmax(fdiv(o.Ub * VKARMN, u.log_zu - log_z0 - psi_m_ice(zeta_u)), 1.E-9);
+            us = abm::dmax(fdiv(o.Ub * VKARMN, u.log_zu - log_z0 - psi_m_ice(zeta_u)), 1.E-9);
             if (!ZTEQ) {
                 const double zeta_t = clip_abs(u.zt * r1oL, 50.0);
                 const double c = u.log_ztu + psih_u - psi_h_ice(zeta_t);
@@ -243,7 +243,7 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
             double wnd_zt = o.Ub;
             if (!ZTEQ) {
                 const double c = u.log_ztu + f_h_louis(u.zu, RiB, CdN, z0_tot) - f_h_louis(u.zt, RiB, CdN, z0_tot);
-                wnd_zt = fmin(fmax(o.Ub + (sqrt(o.Cd) * o.Ub) * c, WSPD_THRSHLD_ICE), o.Ub);
+                wnd_zt = abm::dmin(abm::dmax(o.Ub + (sqrt(o.Cd) * o.Ub) * c, WSPD_THRSHLD_ICE), o.Ub);
             }
             RiB = ri_bulk(u.zt, Ts, t_zt, qs, q_zt, wnd_zt);
             o.Cd = CdN_s * f_m_louis(u.zu, RiB, CdN_s, z0_s);
@@ -254,7 +254,7 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
                 const double c = u.log_ztu + f_h_louis(u.zu, RiB, CdN, z0_tot) - f_h_louis(u.zt, RiB, CdN, z0_tot);
                 const double r = abm::fast_rcp(sqrt(o.Cd));
                 o.t_zu = t_zt - (o.Ch * dt * r) * INV_VKARMN * c;
-                o.q_zu = fmax(0., q_zt - (o.Ch * dq * r) * INV_VKARMN * c);
+                o.q_zu = abm::dmax(0., q_zt - (o.Ch * dq * r) * INV_VKARMN * c);
                 dt = floor_abs(o.t_zu - Ts, 1.E-6);
                 dq = floor_abs(o.q_zu - qs, 1.E-9);
             }

@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(FLUX_BLOCK, AB_MIN_BLOCKS) flux_kernel(const F
     p.slp = slp;
     // humidity -> specific humidity (mod_aerobulk_compute.f90:99-108); slp floored at 5e4 Pa by the caller
     if (a.ihum == 0) p.q_zt = hum;
-    else if (a.ihum == 1) p.q_zt = q_air_dp(hum, fmax(slp, 50000.));
-    else p.q_zt = q_air_rh(hum, t_air, fmax(slp, 50000.));
+    else if (a.ihum == 1) p.q_zt = q_air_dp(hum, abm::dmax(slp, 50000.));
+    else p.q_zt = q_air_rh(hum, t_air, abm::dmax(slp, 50000.));
     // :111 -- no FMA contraction here: U*U+V*V must not depend on the order of the components
     p.wnd = sqrt(__dadd_rn(__dmul_rn(U, U), __dmul_rn(V, V)));
     p.ssq = RDCT_QSAT_SALT * q_sat(sst, slp);                      // :114

@@ -35,6 +35,8 @@ static inline double make_double(int hi, int lo)
     double x; std::memcpy(&x, &b, 8); return x;
 }
 static inline double rcp_seed(double y) { return (double)(float)(1.0 / y); }   // ~24-bit seed like MUFU.RCP64H
+static inline double dmax(double a, double b) { return (a > b) ? a : b; }
+static inline double dmin(double a, double b) { return (a < b) ? a : b; }
 // seeds of the root functions, degraded to the worst accuracy the device versions may have (2^-21)
 static inline double rsqrt_seed(double y) { return (double)(float)(1.0 / std::sqrt(y)) * (1.0 + 0x1p-21); }
 static inline double pow_seed(double y, float p) { return (double)(float)std::pow(y, (double)p) * (1.0 - 0x1p-21); }
@@ -59,6 +61,22 @@ ABM_FN double rcp_seed(double y)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));   // MUFU.RCP64H, rel. error <= 2^-23
     return r;
+}
+// MAX / MIN as the Fortran intrinsics define them (a > b ? a : b): one DSETP and two FSEL.  CUDA's fmax / fmin return
+// the non-NaN operand, which ptxas lowers to 8-9 instructions per call (DSETP.MAX with a NaN predicate, moves, a
+// predicated LOP3 that quiets the NaN ...): 8 % of what the COARE + skin kernel executed.  The setp / selp pair is
+// written in PTX because NVVM canonicalises the C++ ternary back into max.f64.
+ABM_FN double dmax(double a, double b)
+{
+    double d;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(d) : "d"(a), "d"(b));
+    return d;
+}
+ABM_FN double dmin(double a, double b)
+{
+    double d;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(d) : "d"(a), "d"(b));
+    return d;
 }
 ABM_FN double rsqrt_seed(double y)
 {

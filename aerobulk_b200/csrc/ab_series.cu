@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(SERIES_BLOCK, SERIES_MIN_BLOCKS) series_kernel
         u.isd = __ldg(a.isd + jt);
 
         double q = hum;
-        if (a.hum_kind == 2) q = q_air_rh(fmin(99.999, hum), T, slp);
+        if (a.hum_kind == 2) q = q_air_rh(abm::dmin(99.999, hum), T, slp);
         else if (a.hum_kind == 1) q = q_air_dp(hum, slp);
 
         PointIn p;
