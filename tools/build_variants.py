@@ -4,6 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from aerobulk_b200 import build as B
 VARIANTS = {
     "smemtab": ["ABM_SMEM_TABLES=1"],
+    "b128x6": ["AB_FLUX_BLOCK=128", "AB_MIN_BLOCKS=6"],
+    "b128x7": ["AB_FLUX_BLOCK=128", "AB_MIN_BLOCKS=7"],
+    "b128x8": ["AB_FLUX_BLOCK=128", "AB_MIN_BLOCKS=8"],
+    "b256x4": ["AB_FLUX_BLOCK=256", "AB_MIN_BLOCKS=4"],
     "ser64x1": ["AB_SERIES_MIN_BLOCKS=1"],
     "ser64x8": ["AB_SERIES_MIN_BLOCKS=8"],
     "ser128x6": ["AB_SERIES_BLOCK=128", "AB_SERIES_MIN_BLOCKS=6"],
