@@ -31,8 +31,50 @@
 
 namespace {
 
-constexpr int MAX_CHUNKS = 6;
+constexpr int MAX_CHUNKS = 12;          // capacity; the number used is chunk_limit() (default 6, measured best)
 constexpr long long MIN_CHUNK_POINTS = 200000;
+
+// tuning knobs of the host-array pipeline (experiments: tools/diag_e2e.py)
+int chunk_limit()
+{
+    static int v = [] {
+        const char *e = getenv("AEROBULK_GPU_MAX_CHUNKS");
+        int k = e ? atoi(e) : 6;
+        return k < 1 ? 1 : (k > MAX_CHUNKS ? MAX_CHUNKS : k);
+    }();
+    return v;
+}
+// AEROBULK_GPU_TRACE=1: GPU timeline of every host-array call (H2D / kernel / D2H end of each chunk) on stderr
+bool trace_on()
+{
+    static bool v = [] { const char *e = getenv("AEROBULK_GPU_TRACE"); return e && atoi(e) != 0; }();
+    return v;
+}
+cudaEvent_t tr_t0 = nullptr, tr_in[MAX_CHUNKS] = {}, tr_k[MAX_CHUNKS] = {}, tr_out[MAX_CHUNKS] = {};
+void trace_init()
+{
+    if (tr_t0) return;
+    cudaEventCreate(&tr_t0);
+    for (int i = 0; i < MAX_CHUNKS; ++i) {
+        cudaEventCreate(&tr_in[i]);
+        cudaEventCreate(&tr_k[i]);
+        cudaEventCreate(&tr_out[i]);
+    }
+}
+int chunk_shape()   // 0: sizes decrease linearly (K..1), 1: equal, 2: small first chunk then equal
+{
+    static int v = [] { const char *e = getenv("AEROBULK_GPU_CHUNK_SHAPE"); return e ? atoi(e) : 0; }();
+    return v;
+}
+long long min_chunk_points()
+{
+    static long long v = [] {
+        const char *e = getenv("AEROBULK_GPU_MIN_CHUNK_POINTS");
+        long long k = e ? atoll(e) : MIN_CHUNK_POINTS;
+        return k < 2048 ? 2048 : k;
+    }();
+    return v;
+}
 
 struct Session {
     // ---- module globals of mod_const.f90:22-33
@@ -69,6 +111,7 @@ struct Session {
     unsigned short *d_perm = nullptr;
     long long cap_perm = 0;
     int sort_points = 1;   // 0 never, 1 auto (where it measured faster), 2 always
+    bool pitched_ok = true;       // pitched (2-D) staging copies allowed, see copy_fields
     int ice_form_per_point = 0;   // 0: LG15 form drag from the LAST point's ice fraction (reference), 1: per point
     // ---- statistics + deferred wind-stress flag
     double *d_partials = nullptr, *d_stats = nullptr;
@@ -187,20 +230,63 @@ int alloc_ecmwf_state(long long n)
     return 0;
 }
 
+// Moves elements [s0, s0+len) of `nf` fields between host and device staging.  Consecutive fields whose HOST arrays are
+// equally spaced in memory (a caller that keeps its fields in one slab) go in ONE pitched copy: with H2D and D2H running
+// concurrently in 0.4-3 MB pieces the DMA engines reach 62 GB/s aggregate, with one pitched copy per chunk 72 GB/s
+// (tools/probes/duplex_probe.cu on this pool's B200: 1.86 -> 1.62 ms per 1 M-point skin call).
+int copy_fields(int nf, double *const *dev, double *const *host, long long dev_pitch, long long s0, long long len, bool h2d,
+                cudaStream_t st)
+{
+    const long long MAX_PITCH_BYTES = 0x7fffffffLL;   // cudaDevAttrMaxPitch
+    int k = 0;
+    while (k < nf) {
+        if (!host[k]) { ++k; continue; }
+        int run = 1;
+        if (k + 1 < nf && host[k + 1]) {
+            const long long d = host[k + 1] - host[k];
+            if (d >= len && d * 8 <= MAX_PITCH_BYTES && dev_pitch * 8 <= MAX_PITCH_BYTES)
+                while (k + run < nf && host[k + run] && host[k + run] - host[k + run - 1] == d) ++run;
+        }
+        if (run > 1 && g.pitched_ok) {
+            const size_t hp = (size_t)(host[k + 1] - host[k]) * 8, dp = (size_t)dev_pitch * 8, w = (size_t)len * 8;
+            const cudaError_t e =
+                h2d ? cudaMemcpy2DAsync(dev[k] + s0, dp, host[k] + s0, hp, w, (size_t)run, cudaMemcpyHostToDevice, st)
+                    : cudaMemcpy2DAsync(host[k] + s0, hp, dev[k] + s0, dp, w, (size_t)run, cudaMemcpyDeviceToHost, st);
+            if (e == cudaErrorInvalidValue) {
+                // equally spaced but SEPARATE pinned allocations: the driver refuses a pitched copy that spans them.
+                // Nothing was enqueued; use plain copies from now on.
+                cudaGetLastError();
+                g.pitched_ok = false;
+                continue;
+            }
+            CUDA_TRY(e);
+        } else if (run > 1) {
+            for (int j = k; j < k + run; ++j) {
+                if (h2d) CUDA_TRY(cudaMemcpyAsync(dev[j] + s0, host[j] + s0, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, st));
+                else CUDA_TRY(cudaMemcpyAsync(host[j] + s0, dev[j] + s0, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, st));
+            }
+        } else {
+            if (h2d) CUDA_TRY(cudaMemcpyAsync(dev[k] + s0, host[k] + s0, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, st));
+            else CUDA_TRY(cudaMemcpyAsync(host[k] + s0, dev[k] + s0, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, st));
+        }
+        k += run;
+    }
+    return 0;
+}
+
 int ensure_staging(long long n)
 {
     if (n <= g.cap) return 0;
-    for (int k = 0; k < 8; ++k) {
-        if (g.d_in[k]) cudaFree(g.d_in[k]);
-        g.d_in[k] = nullptr;
-    }
-    for (int k = 0; k < 6; ++k) {
-        if (g.d_out[k]) cudaFree(g.d_out[k]);
-        g.d_out[k] = nullptr;
-    }
+    // one slab, fields equally spaced (pitch = cap doubles): a run of equally spaced caller arrays then moves with ONE
+    // pitched copy per chunk (see copy_fields)
+    if (g.d_in[0]) cudaFree(g.d_in[0]);
+    for (int k = 0; k < 8; ++k) g.d_in[k] = nullptr;
+    for (int k = 0; k < 6; ++k) g.d_out[k] = nullptr;
     g.cap = 0;
-    for (int k = 0; k < 8; ++k) CUDA_TRY(cudaMalloc(&g.d_in[k], sizeof(double) * (size_t)n));
-    for (int k = 0; k < 6; ++k) CUDA_TRY(cudaMalloc(&g.d_out[k], sizeof(double) * (size_t)n));
+    double *slab = nullptr;
+    CUDA_TRY(cudaMalloc(&slab, sizeof(double) * (size_t)n * 14));
+    for (int k = 0; k < 8; ++k) g.d_in[k] = slab + (long long)k * n;
+    for (int k = 0; k < 6; ++k) g.d_out[k] = slab + (long long)(8 + k) * n;
     g.cap = n;
     return 0;
 }
@@ -402,7 +488,8 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         if (rc) return rc;
     }
 
-    const double *in_h[8] = {sst, t_zt, hum_zt, U_zu, V_zu, slp, lsrad ? rad_sw : nullptr, lsrad ? rad_lw : nullptr};
+    // rad_lw before rad_sw: a caller slab [sst .. slp, rad_lw] with a per-step rad_sw elsewhere is one run + one array
+    const double *in_h[8] = {sst, t_zt, hum_zt, U_zu, V_zu, slp, lsrad ? rad_lw : nullptr, lsrad ? rad_sw : nullptr};
     const double *in_d[8];
     double *out_h[6] = {QL, QH, Tau_x, Tau_y, Evap, lsrad ? T_s : nullptr};
     double *out_d[6];
@@ -414,17 +501,21 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     // (Two copy-in streams were measured slower: 2.3 vs 2.0 ms per 1M-point call.)
     int nchunks = 1;
     if (!device_ptrs) {
-        nchunks = (int)(n / MIN_CHUNK_POINTS);
-        nchunks = nchunks < 1 ? 1 : (nchunks > MAX_CHUNKS ? MAX_CHUNKS : nchunks);
+        nchunks = (int)(n / min_chunk_points());
+        nchunks = nchunks < 1 ? 1 : (nchunks > chunk_limit() ? chunk_limit() : nchunks);
     }
     long long cstart[MAX_CHUNKS + 1];
     {
-        const long long wsum = (long long)nchunks * (nchunks + 1) / 2;
-        long long acc = 0;
+        double w[MAX_CHUNKS], wsum = 0.;
+        for (int c = 0; c < nchunks; ++c) {
+            w[c] = chunk_shape() == 0 ? (double)(nchunks - c) : (chunk_shape() == 2 && c == 0 ? 0.5 : 1.);
+            wsum += w[c];
+        }
+        double acc = 0.;
         cstart[0] = 0;
         for (int c = 0; c < nchunks; ++c) {
-            acc += nchunks - c;
-            long long s0 = (long long)((double)n * (double)acc / (double)wsum);
+            acc += w[c];
+            long long s0 = (long long)((double)n * acc / wsum);
             s0 = (s0 + 2047) / 2048 * 2048;   // whole sort windows / thread blocks
             cstart[c + 1] = s0 > n ? n : s0;
         }
@@ -439,14 +530,19 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         if (rc) return rc;
         for (int k = 0; k < 8; ++k) in_d[k] = in_h[k] ? g.d_in[k] : nullptr;
         for (int k = 0; k < 6; ++k) out_d[k] = out_h[k] ? g.d_out[k] : nullptr;
+        if (trace_on()) {
+            trace_init();
+            cudaEventRecord(tr_t0, g.in_stream);
+        }
         // H2D, chunk by chunk, on the copy-in stream
         for (int c = 0; c < nchunks; ++c) {
             const long long s0 = cstart[c], len = cstart[c + 1] - s0;
-            for (int k = 0; k < 8 && len > 0; ++k)
-                if (in_h[k])
-                    CUDA_TRY(cudaMemcpyAsync(g.d_in[k] + s0, in_h[k] + s0, sizeof(double) * (size_t)len,
-                                             cudaMemcpyHostToDevice, g.in_stream));
+            if (len > 0) {
+                rc = copy_fields(8, g.d_in, const_cast<double *const *>(in_h), g.cap, s0, len, true, g.in_stream);
+                if (rc) return rc;
+            }
             CUDA_TRY(cudaEventRecord(g.ev_in[c], g.in_stream));
+            if (trace_on()) cudaEventRecord(tr_in[c], g.in_stream);
         }
     }
 
@@ -459,7 +555,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
             if (!device_ptrs) CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_in[nchunks - 1], 0));
             if (n > 0) {
                 // :248 -- prsw=rad_lw: rad_lw is checked against both radiation ranges, rad_sw never
-                rc = local_stats(n, in_d[0], in_d[1], in_d[2], in_d[3], in_d[4], in_d[5], lsrad ? in_d[7] : nullptr, cs, st);
+                rc = local_stats(n, in_d[0], in_d[1], in_d[2], in_d[3], in_d[4], in_d[5], lsrad ? in_d[6] : nullptr, cs, st);
                 if (rc) return rc;
             } else {
                 memset(st, 0, sizeof(st));
@@ -527,8 +623,8 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         if (len <= 0) continue;
         a.sst = in_d[0] + s0; a.t_zt = in_d[1] + s0; a.hum_zt = in_d[2] + s0;
         a.U_zu = in_d[3] + s0; a.V_zu = in_d[4] + s0; a.slp = in_d[5] + s0;
-        a.rad_sw = in_d[6] ? in_d[6] + s0 : nullptr;
-        a.rad_lw = in_d[7] ? in_d[7] + s0 : nullptr;
+        a.rad_lw = in_d[6] ? in_d[6] + s0 : nullptr;
+        a.rad_sw = in_d[7] ? in_d[7] + s0 : nullptr;
         a.lon = nullptr;
         a.QL = out_d[0] + s0; a.QH = out_d[1] + s0; a.Tau_x = out_d[2] + s0; a.Tau_y = out_d[3] + s0;
         a.Evap = out_d[4] + s0;
@@ -555,11 +651,11 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         g.launches += 1;
         if (!device_ptrs) {
             CUDA_TRY(cudaEventRecord(g.ev_k[c], cs));
+            if (trace_on()) cudaEventRecord(tr_k[c], cs);
             CUDA_TRY(cudaStreamWaitEvent(g.out_stream, g.ev_k[c], 0));
-            for (int k = 0; k < 6; ++k)
-                if (out_h[k])
-                    CUDA_TRY(cudaMemcpyAsync(out_h[k] + s0, g.d_out[k] + s0, sizeof(double) * (size_t)len,
-                                             cudaMemcpyDeviceToHost, g.out_stream));
+            rc = copy_fields(6, g.d_out, out_h, g.cap, s0, len, false, g.out_stream);
+            if (rc) return rc;
+            if (trace_on()) cudaEventRecord(tr_out[c], g.out_stream);
         }
     }
     CUDA_TRY(cudaMemcpyAsync(g.h_bad, g.d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs));
@@ -574,6 +670,16 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         CUDA_TRY(cudaStreamSynchronize(cs));
         if (!device_ptrs) CUDA_TRY(cudaStreamSynchronize(g.out_stream));
         rc = check_bad_flag(device_ptrs ? nullptr : Tau_x, device_ptrs ? nullptr : Tau_y);
+        if (!device_ptrs && trace_on()) {
+            fprintf(stderr, "[aerobulk_gpu trace] jt=%d chunks=%d  (ms since the first H2D: in | kernel | out)\n", jt, nchunks);
+            for (int c = 0; c < nchunks; ++c) {
+                float a = 0.f, b = 0.f, d = 0.f;
+                cudaEventElapsedTime(&a, tr_t0, tr_in[c]);
+                cudaEventElapsedTime(&b, tr_t0, tr_k[c]);
+                cudaEventElapsedTime(&d, tr_t0, tr_out[c]);
+                fprintf(stderr, "   chunk %d  %7lld pts  %6.3f | %6.3f | %6.3f\n", c, cstart[c + 1] - cstart[c], a, b, d);
+            }
+        }
     }
 
     // kt == nitend -> *_EXIT frees the state (mod_blk_coare3p6.f90:411); jt == Nt -> AEROBULK_BYE (:267)
@@ -1392,8 +1498,9 @@ void aerobulk_gpu_reset(void)
         cudaDeviceSynchronize();
         free_coare_state();
         free_ecmwf_state();
-        for (int k = 0; k < 8; ++k) { if (g.d_in[k]) cudaFree(g.d_in[k]); g.d_in[k] = nullptr; }
-        for (int k = 0; k < 6; ++k) { if (g.d_out[k]) cudaFree(g.d_out[k]); g.d_out[k] = nullptr; }
+        if (g.d_in[0]) cudaFree(g.d_in[0]);   // one slab, see ensure_staging
+        for (int k = 0; k < 8; ++k) g.d_in[k] = nullptr;
+        for (int k = 0; k < 6; ++k) g.d_out[k] = nullptr;
         g.cap = 0;
         if (g.d_perm) cudaFree(g.d_perm);
         g.d_perm = nullptr;
@@ -1405,6 +1512,7 @@ void aerobulk_gpu_reset(void)
         if (g.d_bad) cudaMemset(g.d_bad, 0xFF, 2 * sizeof(unsigned long long));
     }
     g.ice_form_per_point = 0;
+    g.pitched_ok = true;
     g.nb_iter = 5;
     g.nitend = 1;
     g.l_use_skin_schemes = false;

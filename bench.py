@@ -201,7 +201,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         t.numpy()[:] = np.ravel(a, order="F")
         return t
 
-    host = {k: pinned(f[k]) for k in IN_KEYS + ("rad_lw",)}
+    # the model keeps its step-invariant fields in ONE pinned slab (sst .. slp, rad_lw) and its outputs in another:
+    # the library then moves each pipeline chunk with one pitched copy per slab ("faster paths")
+    in_slab = torch.empty((len(IN_KEYS) + 1, n), dtype=torch.float64).pin_memory()
+    host = {}
+    for i, k in enumerate(IN_KEYS + ("rad_lw",)):
+        in_slab[i].numpy()[:] = np.ravel(f[k], order="F")
+        host[k] = in_slab[i]
     host_rsw = [pinned(a) for a in rsw_h]
     # two device copies of the step-invariant inputs, used alternately, so that consecutive calls never
     # re-read the same lines (per call: 8 inputs + 6 outputs + 4 state arrays R/W = 150 MB > 126 MB L2)
@@ -271,7 +277,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     value = world * n * NT * args.steps / (ms * 1e-3)
 
     # ---------------- end to end through the host-array API (`e2e`): pinned host inputs, H2D + D2H inside
-    host_out = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k in OUT_KEYS}
+    out_slab = torch.empty((len(OUT_KEYS), n), dtype=torch.float64).pin_memory()
+    host_out = {k: out_slab[i] for i, k in enumerate(OUT_KEYS)}
     np_in = {k: v.numpy().reshape((NI, NJ), order="F") for k, v in host.items()}
     np_rsw = [t.numpy().reshape((NI, NJ), order="F") for t in host_rsw]
     np_out = {k: v.numpy().reshape((NI, NJ), order="F") for k, v in host_out.items()}
@@ -326,7 +333,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                    "sharding": "latitude row blocks, one rank per GPU, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "grid points/s", "h2d_bytes_per_step": 8 * 8 * n * NT,
                 "d2h_bytes_per_step": 6 * 8 * n * NT,
-                "how": "aerobulk_gpu_model (host-array C ABI) with pinned host buffers, chunked H2D|kernel|D2H pipeline"},
+                "how": "aerobulk_gpu_model (host-array C ABI) with pinned host buffers (inputs in one slab, outputs in another: one pitched copy per chunk and slab), chunked H2D|kernel|D2H pipeline"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -261,3 +261,34 @@ def test_deferred_wind_stress_error_on_device_api(ab):
         ab.synchronize()
     assert e.value.code == 8
     ab.reset()
+
+
+def test_fields_in_one_slab_use_pitched_copies_and_agree(ab):
+    """A caller that keeps its fields equally spaced in one slab gets one pitched copy per pipeline chunk
+    (copy_fields in ab_api.cu); results are bit-identical to separate arrays -- pageable and pinned slabs."""
+    import torch
+    Ni, Nj = 640, 400                      # 256 000 points: 1 chunk; plus a 3-chunk case below
+    for (ni, nj) in ((Ni, Nj), (1440, 500)):
+        n = ni * nj
+        f = synth.fields(ni, nj)
+        keys = ("sst", "t_zt", "hum_zt", "U_zu", "V_zu", "slp", "rad_lw")
+        ab.reset()
+        ref = ab.aerobulk_model(1, 1, "coare3p6", 2.0, 10.0, *[f[k] for k in keys[:6]], Niter=5, l_use_skin=True,
+                                rad_sw=f["rad_sw"], rad_lw=f["rad_lw"])
+        for pinned in (False, True):
+            slab = torch.empty((7, n), dtype=torch.float64)
+            oslab = torch.empty((6, n), dtype=torch.float64)
+            if pinned:
+                slab, oslab = slab.pin_memory(), oslab.pin_memory()
+            view = {}
+            for i, k in enumerate(keys):
+                slab[i].numpy()[:] = np.ravel(f[k], order="F")
+                view[k] = slab[i].numpy().reshape((ni, nj), order="F")
+            names = ("QL", "QH", "Tau_x", "Tau_y", "Evap", "T_s")
+            out = {k: oslab[i].numpy().reshape((ni, nj), order="F") for i, k in enumerate(names)}
+            ab.reset()
+            got = ab.aerobulk_model(1, 1, "coare3p6", 2.0, 10.0, *[view[k] for k in keys[:6]], Niter=5, l_use_skin=True,
+                                    rad_sw=f["rad_sw"], rad_lw=view["rad_lw"], out=out)
+            for k in names:
+                assert np.array_equal(got[k], ref[k]), (ni, pinned, k)
+                assert np.array_equal(out[k], ref[k]), (ni, pinned, k)
