@@ -17,6 +17,9 @@ MODULE mod_aerobulk_gpu
 
    PUBLIC :: aerobulk_gpu_model, aerobulk_gpu_synchronize,                       &
       &      aerobulk_gpu_turb, aerobulk_gpu_turb_optional, aerobulk_gpu_set_nitend, &
+      &      aerobulk_gpu_series, aerobulk_gpu_series_out, aerobulk_gpu_series_csv,  &
+      &      aerobulk_gpu_turb_ice, aerobulk_gpu_turb_ice_optional,                  &
+      &      aerobulk_gpu_oce_ice, aerobulk_gpu_oce_ice_out, aerobulk_gpu_set_ice_form_drag_per_point, &
       &      aerobulk_gpu_set_rdt, aerobulk_gpu_set_gdept, aerobulk_gpu_set_nb_iter, &
       &      aerobulk_gpu_get_nb_iter, aerobulk_gpu_get_use_skin,                 &
       &      aerobulk_gpu_set_device, aerobulk_gpu_set_verbose, aerobulk_gpu_reset,  &
@@ -28,6 +31,35 @@ MODULE mod_aerobulk_gpu
       TYPE(c_ptr) :: xz0 = C_NULL_PTR, xu_star = C_NULL_PTR, xL = C_NULL_PTR, xUN10 = C_NULL_PTR
       TYPE(c_ptr) :: pdT_cs = C_NULL_PTR, pdT_wl = C_NULL_PTR, pHz_wl = C_NULL_PTR
    END TYPE aerobulk_gpu_turb_optional
+
+   !! output series of aerobulk_gpu_series (struct aerobulk_gpu_series_out), each [Nt][S]; C_NULL_PTR = not wanted
+   TYPE, BIND(C) :: aerobulk_gpu_series_out
+      TYPE(c_ptr) :: rho_zu = C_NULL_PTR, QL = C_NULL_PTR, QH = C_NULL_PTR, Qlw = C_NULL_PTR, QNS = C_NULL_PTR
+      TYPE(c_ptr) :: Qsw = C_NULL_PTR, dT_cs = C_NULL_PTR, dT_wl = C_NULL_PTR, TAU = C_NULL_PTR, dT = C_NULL_PTR
+      TYPE(c_ptr) :: Hz_wl = C_NULL_PTR, Qnt_ac = C_NULL_PTR, Tau_ac = C_NULL_PTR
+      TYPE(c_ptr) :: Cd = C_NULL_PTR, Ce = C_NULL_PTR, Ch = C_NULL_PTR
+      TYPE(c_ptr) :: theta_zu = C_NULL_PTR, q_zu = C_NULL_PTR, t_zu = C_NULL_PTR, RiB = C_NULL_PTR, z0 = C_NULL_PTR
+      TYPE(c_ptr) :: u_star = C_NULL_PTR, L = C_NULL_PTR, UN10 = C_NULL_PTR, Ts = C_NULL_PTR, Evap = C_NULL_PTR
+      TYPE(c_ptr) :: q_zt = C_NULL_PTR, theta_zt = C_NULL_PTR
+   END TYPE aerobulk_gpu_series_out
+
+   !! optional outputs of the TURB_ICE_* routines (struct aerobulk_gpu_turb_ice_optional)
+   TYPE, BIND(C) :: aerobulk_gpu_turb_ice_optional
+      TYPE(c_ptr) :: CdN = C_NULL_PTR, ChN = C_NULL_PTR, CeN = C_NULL_PTR
+      TYPE(c_ptr) :: xz0 = C_NULL_PTR, xu_star = C_NULL_PTR, xL = C_NULL_PTR, xUN10 = C_NULL_PTR, CdN_frm = C_NULL_PTR
+   END TYPE aerobulk_gpu_turb_ice_optional
+
+   !! outputs of aerobulk_gpu_oce_ice (struct aerobulk_gpu_oce_ice_out): _i over the ice, _w over the leads, cell means
+   TYPE, BIND(C) :: aerobulk_gpu_oce_ice_out
+      TYPE(c_ptr) :: Cd_i = C_NULL_PTR, Ch_i = C_NULL_PTR, Ce_i = C_NULL_PTR, theta_zu_i = C_NULL_PTR, q_zu_i = C_NULL_PTR
+      TYPE(c_ptr) :: t_zu_i = C_NULL_PTR, Ub_i = C_NULL_PTR, RiB_i = C_NULL_PTR, z0_i = C_NULL_PTR, u_star_i = C_NULL_PTR
+      TYPE(c_ptr) :: L_i = C_NULL_PTR, UN10_i = C_NULL_PTR, rho_zu_i = C_NULL_PTR
+      TYPE(c_ptr) :: Tau_i = C_NULL_PTR, QH_i = C_NULL_PTR, QL_i = C_NULL_PTR, Evap_i = C_NULL_PTR
+      TYPE(c_ptr) :: Cd_w = C_NULL_PTR, Ch_w = C_NULL_PTR, Ce_w = C_NULL_PTR, theta_zu_w = C_NULL_PTR, q_zu_w = C_NULL_PTR
+      TYPE(c_ptr) :: Ub_w = C_NULL_PTR, z0_w = C_NULL_PTR, u_star_w = C_NULL_PTR, L_w = C_NULL_PTR, UN10_w = C_NULL_PTR
+      TYPE(c_ptr) :: Tau_w = C_NULL_PTR, QH_w = C_NULL_PTR, QL_w = C_NULL_PTR, Evap_w = C_NULL_PTR
+      TYPE(c_ptr) :: Tau = C_NULL_PTR, QH = C_NULL_PTR, QL = C_NULL_PTR, Evap = C_NULL_PTR
+   END TYPE aerobulk_gpu_oce_ice_out
 
    INTERFACE
 
@@ -71,6 +103,72 @@ MODULE mod_aerobulk_gpu
          INTEGER(c_int), VALUE :: on_device
          INTEGER(c_int)        :: ierr
       END FUNCTION aerobulk_gpu_turb
+
+      !! Station time series (time loop of src/tests/test_aerobulk_buoy_series_oce.f90:364-537 for S stations);
+      !! records are [Nt][S], i.e. Fortran arrays dimensioned (S,Nt); pisd: C_LOC of INTEGER(c_int) isecday_utc(Nt);
+      !! pout: C_LOC of a TYPE(aerobulk_gpu_series_out); hum_kind 0 q / 1 dew-point [K] / 2 RH [%].
+      FUNCTION aerobulk_gpu_series( calgo, Nt, S, zt, zu, pisd, plon, psst, pt_zt, phum_zt, hum_kind, pwind, pslp,   &
+         &                          prad_sw, prad_lw, l_use_skin, pout, on_device )                                  &
+         &     BIND(C, NAME='aerobulk_gpu_series') RESULT(ierr)
+         IMPORT :: c_int, c_long_long, c_double, c_char, c_ptr
+         CHARACTER(KIND=c_char), DIMENSION(*), INTENT(in) :: calgo
+         INTEGER(c_int),       VALUE :: Nt
+         INTEGER(c_long_long), VALUE :: S
+         REAL(c_double),       VALUE :: zt, zu
+         TYPE(c_ptr),          VALUE :: pisd, plon, psst, pt_zt, phum_zt
+         INTEGER(c_int),       VALUE :: hum_kind
+         TYPE(c_ptr),          VALUE :: pwind, pslp, prad_sw, prad_lw
+         INTEGER(c_int),       VALUE :: l_use_skin
+         TYPE(c_ptr),          VALUE :: pout
+         INTEGER(c_int),       VALUE :: on_device
+         INTEGER(c_int)              :: ierr
+      END FUNCTION aerobulk_gpu_series
+
+      !! One station, CSV in / CSV out (the buoy-series program with text files for NetCDF)
+      FUNCTION aerobulk_gpu_series_csv( path_in, path_out, calgo, zt, zu, l_use_skin ) &
+         &     BIND(C, NAME='aerobulk_gpu_series_csv') RESULT(ierr)
+         IMPORT :: c_int, c_double, c_char
+         CHARACTER(KIND=c_char), DIMENSION(*), INTENT(in) :: path_in, path_out, calgo   !: NUL-terminated
+         REAL(c_double), VALUE :: zt, zu
+         INTEGER(c_int), VALUE :: l_use_skin
+         INTEGER(c_int)        :: ierr
+      END FUNCTION aerobulk_gpu_series_csv
+
+      !! TURB_ICE_NEMO / _EASY / _AN05 / _LU12 / _LG15 / _LG15_IO (src/ice/mod_blk_ice_*.f90), selected by calgo;
+      !! pfrice: lu12 / lg15 only, pCxN_easy: C_LOC of REAL(c_double) (/CdN,ChN,CeN/) for easy; C_NULL_PTR otherwise
+      FUNCTION aerobulk_gpu_turb_ice( calgo, zt, zu, Ni, Nj, pTs_i, pt_zt, pqs_i, pq_zt, pU_zu, pfrice, pCxN_easy,   &
+         &                            pCd, pCh, pCe, pt_zu, pq_zu, pUbzu, popt, on_device )                          &
+         &     BIND(C, NAME='aerobulk_gpu_turb_ice') RESULT(ierr)
+         IMPORT :: c_int, c_double, c_char, c_ptr
+         CHARACTER(KIND=c_char), DIMENSION(*), INTENT(in) :: calgo
+         REAL(c_double), VALUE :: zt, zu
+         INTEGER(c_int), VALUE :: Ni, Nj
+         TYPE(c_ptr),    VALUE :: pTs_i, pt_zt, pqs_i, pq_zt, pU_zu, pfrice, pCxN_easy
+         TYPE(c_ptr),    VALUE :: pCd, pCh, pCe, pt_zu, pq_zu, pUbzu, popt
+         INTEGER(c_int), VALUE :: on_device
+         INTEGER(c_int)        :: ierr
+      END FUNCTION aerobulk_gpu_turb_ice
+
+      !! Ice + leads fluxes (src/ice/test_aerobulk_oce+ice.f90:225-412) on n points; calgo_oce: C_NULL_CHAR-terminated
+      !! ocean algorithm for the leads; pout: C_LOC of a TYPE(aerobulk_gpu_oce_ice_out)
+      FUNCTION aerobulk_gpu_oce_ice( calgo_ice, calgo_oce, zt, zu, n, psit, psst, pt_zt, phum_zt, hum_kind, pwind,   &
+         &                           pslp, pfrice, pCxN_easy, pout, on_device )                                      &
+         &     BIND(C, NAME='aerobulk_gpu_oce_ice') RESULT(ierr)
+         IMPORT :: c_int, c_long_long, c_double, c_char, c_ptr
+         CHARACTER(KIND=c_char), DIMENSION(*), INTENT(in) :: calgo_ice, calgo_oce
+         REAL(c_double),       VALUE :: zt, zu
+         INTEGER(c_long_long), VALUE :: n
+         TYPE(c_ptr),          VALUE :: psit, psst, pt_zt, phum_zt
+         INTEGER(c_int),       VALUE :: hum_kind
+         TYPE(c_ptr),          VALUE :: pwind, pslp, pfrice, pCxN_easy, pout
+         INTEGER(c_int),       VALUE :: on_device
+         INTEGER(c_int)              :: ierr
+      END FUNCTION aerobulk_gpu_oce_ice
+
+      SUBROUTINE aerobulk_gpu_set_ice_form_drag_per_point( on ) BIND(C, NAME='aerobulk_gpu_set_ice_form_drag_per_point')
+         IMPORT :: c_int
+         INTEGER(c_int), VALUE :: on
+      END SUBROUTINE aerobulk_gpu_set_ice_form_drag_per_point
 
       SUBROUTINE aerobulk_gpu_set_nitend( knitend ) BIND(C, NAME='aerobulk_gpu_set_nitend')
          IMPORT :: c_int
