@@ -597,7 +597,9 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     // Stability sort (classify_kernel).  Measured on B200 (tools/kbench.py, round 1): a gain for ANDREAS
     // and the COARE / ECMWF kernels without skin schemes, a loss for NCAR (too little work per point)
     // and for the skin kernels (instruction-cache bound: homogeneous blocks run different code regions)
-    const bool do_sort = g.sort_points == 2 || (g.sort_points == 1 && !use_skin && ialgo != abd::NCAR);
+    // auto policy = where it measured faster (tools/kbench.py, KBENCH_SORT=0/2): not NCAR (+10 %), not ECMWF + skin (+1 %);
+    // COARE + skin: -7 % at night, neutral by day
+    const bool do_sort = g.sort_points == 2 || (g.sort_points == 1 && ialgo != abd::NCAR && !(use_skin && ialgo == abd::ECMWF));
     if (do_sort) {
         // every chunk is padded to whole sort windows
         const long long need = n + (long long)(nchunks + 1) * abk::sort_window();
@@ -1563,6 +1565,7 @@ long aerobulk_gpu_set_state(int which, const double *host_in, long n)
     std::lock_guard<std::mutex> lk(g_mu);
     long long have = 0;
     double *p = state_ptr(which, &have);
+    if (host_in && !p && g.n_ecmwf && which == 1 && n == have) return n;   // Hz_wl of ECMWF is the constant 3 m: nothing to restore
     if (!host_in || !p || n != have) return 0;
     cudaSetDevice(g.device);
     cudaStreamSynchronize(compute_stream());
