@@ -300,8 +300,8 @@ struct PsiMH {
 // Large & Yeager, src/mod_blk_ncar.f90:333-407
 ABD PsiMH psi_mh_ncar_unstable(double z)
 {
-    const double x2 = abm::dmax(sqrt(fabs(1. - 16. * z)), 1.);
-    const double x = sqrt(x2);
+    const double x2 = abm::dmax(abm::fast_sqrt(fabs(1. - 16. * z)), 1.);
+    const double x = abm::fast_sqrt(x2);
     const double l2 = abm::dlog((1. + x2) * 0.5);
     PsiMH r;
     r.m = 2. * abm::dlog((1. + x) * 0.5) + l2 - 2. * abm::datan(x) + RPI * 0.5;
@@ -310,7 +310,7 @@ ABD PsiMH psi_mh_ncar_unstable(double z)
 }
 ABD double psi_h_ncar_unstable(double z)
 {
-    const double x2 = abm::dmax(sqrt(fabs(1. - 16. * z)), 1.);
+    const double x2 = abm::dmax(abm::fast_sqrt(fabs(1. - 16. * z)), 1.);
     return 2. * abm::dlog(0.5 * (1. + x2));
 }
 ABD double psi_m_ncar(double z) { return nonneg(z) ? -5. * z : psi_mh_ncar_unstable(z).m; }
@@ -328,19 +328,19 @@ ABD PsiMH psi_mh_coare_stable(double z)
     const double a = fabs(1. + 2. * z * KC(1. / 3.));
     PsiMH r;
     r.m = -(1. + 1. * z + KC(0.6667) * (z - KC(14.28)) * e + KC(8.525));
-    r.h = -(a * sqrt(a) + KC(.6667) * (z - KC(14.28)) * e + KC(8.525));                      // **1.5
+    r.h = -(a * abm::fast_sqrt(a) + KC(.6667) * (z - KC(14.28)) * e + KC(8.525));                      // **1.5
     return r;
 }
 ABD double psi_h_coare_stable(double z)
 {
     const double e = abm::dexp(-abm::dmin(50., KC(0.35) * z));
     const double a = fabs(1. + 2. * z * KC(1. / 3.));
-    return -(a * sqrt(a) + KC(.6667) * (z - KC(14.28)) * e + KC(8.525));
+    return -(a * abm::fast_sqrt(a) + KC(.6667) * (z - KC(14.28)) * e + KC(8.525));
 }
 ABD PsiMH psi_mh_coare_unstable(double z)
 {
-    const double phi_h = sqrt(fabs(1. - 15. * z));                               // **.5
-    const double phi_m = sqrt(phi_h);                                            // **.25
+    const double phi_h = abm::fast_sqrt(fabs(1. - 15. * z));                               // **.5
+    const double phi_m = abm::fast_sqrt(phi_h);                                            // **.25
     double f = z * z;
     f = fdiv(f, 1. + f);
     const double km = 2. * abm::dlog((1. + phi_m) * 0.5) + abm::dlog((1. + phi_m * phi_m) * 0.5) - 2. * abm::datan(phi_m) + 0.5 * RPI;
@@ -354,7 +354,7 @@ ABD PsiMH psi_mh_coare_unstable(double z)
 }
 ABD double psi_h_coare_unstable(double z)
 {
-    const double phi_h = sqrt(fabs(1. - 15. * z));
+    const double phi_h = abm::fast_sqrt(fabs(1. - 15. * z));
     double f = z * z;
     f = fdiv(f, 1. + f);
     const double kh = 2. * abm::dlog((1. + phi_h) * 0.5);
@@ -389,14 +389,14 @@ ABD PsiMH psi_mh_ecmwf_stable(double zeta)
     const double a = fabs(1. + 2. / 3. * z);
     PsiMH r;
     r.m = -t - z - 2. / 3. * zc;
-    r.h = -t - a * sqrt(a) - 2. / 3. * zc + 1.;
+    r.h = -t - a * abm::fast_sqrt(a) - 2. / 3. * zc + 1.;
     return r;
 }
 ABD PsiMH psi_mh_ecmwf_unstable(double zeta)
 {
     const double z = cap_zeta(zeta);
-    const double x2 = sqrt(fabs(1. - 16. * z));
-    const double x = sqrt(x2);
+    const double x2 = abm::fast_sqrt(fabs(1. - 16. * z));
+    const double x = abm::fast_sqrt(x2);
     const double t = 1. + x;
     PsiMH r;
     r.m = abm::dlog(0.125 * t * t * (1. + x2)) - 2. * abm::datan(x) + 0.5 * RPI;
@@ -408,7 +408,7 @@ ABD double psi_h_ecmwf_stable(double zeta) { return psi_mh_ecmwf_stable(zeta).h;
 ABD double psi_m_ecmwf_unstable(double zeta) { return psi_mh_ecmwf_unstable(zeta).m; }
 ABD double psi_h_ecmwf_unstable(double zeta)
 {
-    const double x2 = sqrt(fabs(1. - 16. * cap_zeta(zeta)));
+    const double x2 = abm::fast_sqrt(fabs(1. - 16. * cap_zeta(zeta)));
     return 2. * abm::dlog(0.5 * (1. + x2));
 }
 
@@ -436,8 +436,8 @@ ABD double psi_h_andreas_stable(double zeta)
 ABD PsiMH psi_mh_andreas_unstable(double zeta)
 {
     const double z = abm::dmin(zeta, 15.);
-    const double x2 = abm::dmax(sqrt(fabs(1. - 16. * z)), 1.);
-    const double x = sqrt(x2);
+    const double x2 = abm::dmax(abm::fast_sqrt(fabs(1. - 16. * z)), 1.);
+    const double x = abm::fast_sqrt(x2);
     PsiMH r;
     r.m = 2. * abm::dlog(fabs((1. + x) * 0.5)) + abm::dlog(fabs((1. + x2) * 0.5)) - 2. * abm::datan(x) + RPI * 0.5;
     r.h = 2. * abm::dlog(0.5 * (1. + x2));
@@ -445,7 +445,7 @@ ABD PsiMH psi_mh_andreas_unstable(double zeta)
 }
 ABD double psi_h_andreas_unstable(double zeta)
 {
-    const double x2 = abm::dmax(sqrt(fabs(1. - 16. * abm::dmin(zeta, 15.))), 1.);
+    const double x2 = abm::dmax(abm::fast_sqrt(fabs(1. - 16. * abm::dmin(zeta, 15.))), 1.);
     return 2. * abm::dlog(0.5 * (1. + x2));
 }
 
@@ -709,7 +709,7 @@ ABD void wl_ecmwf(WarmLayer &w, const WlEcmwfCtx &c, double alpha, double Qsw, d
 #pragma unroll 1
     for (int jc = 0; jc < 10; ++jc) {
         dT_n = 0.5 * (dT_n + dT_b);
-        const double zeta = warming ? H * L2 : H * sqrt(dT_n * cst2);
+        const double zeta = warming ? H * L2 : H * abm::fast_sqrt(dT_n * cst2);
         const double B = fdiv(cst3, phi_takaya(zeta));
         dT_n = abm::dmax(dT_b + A + B * dT_n, 0.);
     }
@@ -751,7 +751,7 @@ ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p, Diag &dg)
     const double Ub = abm::dmax(0.5, p.wnd);
     const bool stable0 = nonneg(virt_temp(p.theta_zt, p.q_zt) - virt_temp(p.sst, p.ssq));
     double CdN = cd_n10_ncar(Ub);
-    double sqrt_CdN = sqrt(CdN);
+    double sqrt_CdN = abm::fast_sqrt(CdN);
     double Cd = CdN;
     double Ce = abm::dmax(1.e-3 * (34.6 * sqrt_CdN), CX_MIN);
     double Ch = abm::dmax(1.e-3 * sqrt_CdN * (stable0 ? 18. : 32.7), CX_MIN);
@@ -791,10 +791,10 @@ ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p, Diag &dg)
         // z0 = zu EXP(-(k/SQRT(Cd) + psi_m)) only enters as LOG(10/z0) = k/SQRT(Cd) + psi_m - LOG(zu/10)
         Un10 = abm::dmax(0.25, sqrt_Cd * Ub * INV_VKARMN * (VKARMN * r_sqrt_Cd + psi_m - u.log_zu10));
         CdN = cd_n10_ncar(Un10);
-        sqrt_CdN = sqrt(CdN);
+        sqrt_CdN = abm::fast_sqrt(CdN);
         double tmp = 1. + sqrt_CdN * INV_VKARMN * (u.log_zu10 - psi_m);
         Cd = abm::dmax(fdiv(CdN, tmp * tmp), CX_MIN);
-        sqrt_Cd = sqrt(Cd);
+        sqrt_Cd = abm::fast_sqrt(Cd);
         const double r_sqrt_CdN = abm::fast_rcp(sqrt_CdN);
         tmp = (u.log_zu10 - psi_h_u) * INV_VKARMN * r_sqrt_CdN;
         const double tmp2 = sqrt_Cd * r_sqrt_CdN;
@@ -859,7 +859,7 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
 
         const double cv = abm::fast_cbrt(abm::dmax(KC(-zi0 * INV_VKARMN) * r1oL, 0.));
         const double gust2 = KC(Beta0 * Beta0) * us2 * (cv * cv);       // **(2./3.)
-        Ub = abm::dmax(sqrt(p.wnd * p.wnd + gust2), KC(0.2));
+        Ub = abm::dmax(abm::fast_sqrt(p.wnd * p.wnd + gust2), KC(0.2));
 
         const double zeta_u = clip_abs(u.zu * r1oL, zeta_abs_max);
 
@@ -1027,7 +1027,7 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
 
         const double cv = abm::fast_cbrt(abm::dmax(-zi0 * r1oL * INV_VKARMN, 0.));
         tmp0 = Beta0 * Beta0 * us2 * (cv * cv);
-        Ub = abm::dmax(sqrt(p.wnd * p.wnd + tmp0), 0.2);
+        Ub = abm::dmax(abm::fast_sqrt(p.wnd * p.wnd + tmp0), 0.2);
 
         tmp0 = psi_h_u - psi_h_z0t;
         double tmp1 = fdiv(VKARMN, u.log_zu - log_z0t - tmp0);
@@ -1110,9 +1110,9 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p, Diag &dg)
     for (int jit = 1; jit <= u.nb_iter; ++jit) {
         if (RiB < rRi_max) {
             const double za = UN10 - 8.271;
-            u_star = 0.239 + 0.0433 * (za + sqrt(0.12 * za * za + 0.181));   // :275-293
+            u_star = 0.239 + 0.0433 * (za + abm::fast_sqrt(0.12 * za * za + 0.181));   // :275-293
         } else {
-            u_star = sqrt(CX_MIN) * Ub;
+            u_star = abm::fast_sqrt(CX_MIN) * Ub;
         }
         zeta_u = u.zu * one_on_L(t_zu, q_zu, u_star, t_star, q_star);
         const double r = u_star * r_Ub;

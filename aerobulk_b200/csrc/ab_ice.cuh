@@ -33,8 +33,8 @@ ABD double q_sat_ice(double T, double p) { return q_sat_from_e(e_sat_ice(T), p);
 // Louis (1979) stability functions, mod_phymbl.f90:1419-1479 (rc_louis = 5); only the selected side is evaluated
 ABD double f_louis(double ra, double zu, double Rib, double Cxn, double z0)
 {
-    if (nonneg(Rib)) return abm::fast_rcp(1. + ra * fdiv(Rib, sqrt(fabs(1. + Rib))));
-    const double ztu = fdiv(Rib, 1. + 3. * 25. * Cxn * sqrt(fabs(-Rib * (fdiv(zu, z0) + 1.))));
+    if (nonneg(Rib)) return abm::fast_rcp(1. + ra * fdiv(Rib, abm::fast_sqrt(fabs(1. + Rib))));
+    const double ztu = fdiv(Rib, 1. + 3. * 25. * Cxn * abm::fast_sqrt(fabs(-Rib * (fdiv(zu, z0) + 1.))));
     return 1. - ra * ztu;
 }
 ABD double f_m_louis(double zu, double Rib, double Cdn, double z0) { return f_louis(10., zu, Rib, Cdn, z0); }
@@ -52,13 +52,13 @@ ABD double psi_ice_stable(double z) { return -(0.7 * z + 0.75 * (z - 14.3) * abm
 ABD double psi_m_ice(double z)
 {
     if (nonneg(z)) return psi_ice_stable(z);
-    const double x2 = sqrt(fabs(1. - 16. * z)), x = sqrt(x2);
+    const double x2 = abm::fast_sqrt(fabs(1. - 16. * z)), x = abm::fast_sqrt(x2);
     return abm::dlog((1. + x2) * 0.5) + 2. * abm::dlog((1. + x) * 0.5) - 2. * abm::datan(x) + 0.5 * RPI;
 }
 ABD double psi_h_ice(double z)
 {
     if (nonneg(z)) return psi_ice_stable(z);
-    const double x2 = sqrt(fabs(1. - 16. * z));
+    const double x2 = abm::fast_sqrt(fabs(1. - 16. * z));
     return 2. * abm::dlog((1. + x2) * 0.5);
 }
 
@@ -130,7 +130,7 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
             Cd = u.cdn_s + o.CdN_frm;
         }
         o.Cd = o.Ch = o.Ce = o.CdN = o.ChN = o.CeN = Cd;
-        const double sq = sqrt(Cd);
+        const double sq = abm::fast_sqrt(Cd);
         o.z0 = u.zu * abm::dexp(-fdiv(VKARMN, sq));
         o.us = sq * o.Ub;
         const double cs = fdiv(Cd, sq);
@@ -147,7 +147,7 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
 #pragma unroll 1
         for (int jit = 1; jit <= u.nb_iter; ++jit) {
             const double dt_zu = o.t_zu - Ts, dq_zu = o.q_zu - qs;       // no floor here (:148-149)
-            const double sq = sqrt(o.Cd);
+            const double sq = abm::fast_sqrt(o.Cd);
             us = sq * o.Ub;
             const double r = abm::fast_rcp(abm::dmax(sq, 1.E-15));
             ts = o.Ch * dt_zu * r;
@@ -159,7 +159,7 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
             double x = 1. + u.sqrt_cdn * INV_VKARMN * (u.log_zu10 - psim_u);
             o.Cd = abm::dmin(abm::dmax(fdiv(CdN, x * x), CX_MIN), 1.9E-3);
             x = fdiv((u.log_zu10 - psih_u) * INV_VKARMN, u.sqrt_cdn);
-            const double y = fdiv(sqrt(o.Cd), u.sqrt_cdn);
+            const double y = fdiv(abm::fast_sqrt(o.Cd), u.sqrt_cdn);
             o.Ch = abm::dmin(abm::dmax(fdiv(ChN * y, 1. + ChN * x), CX_MIN), 1.9E-3);
             o.Ce = abm::dmin(abm::dmax(fdiv(CeN * y, 1. + CeN * x), CX_MIN), 1.9E-3);
             if (!ZTEQ) {
@@ -170,10 +170,10 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
             }
         }
         o.CdN = CdN; o.ChN = ChN; o.CeN = CeN;
-        o.z0 = u.zu * abm::dexp(-(fdiv(VKARMN, sqrt(o.Cd)) + psim_u));
+        o.z0 = u.zu * abm::dexp(-(fdiv(VKARMN, abm::fast_sqrt(o.Cd)) + psim_u));
         o.us = us;
         o.L = abm::fast_rcp(one_on_L(o.t_zu, o.q_zu, us, ts, qst));
-        o.UN10 = sqrt(o.Cd) * o.Ub * INV_VKARMN * abm::dlog(fdiv(10., o.z0));
+        o.UN10 = abm::fast_sqrt(o.Cd) * o.Ub * INV_VKARMN * abm::dlog(fdiv(10., o.z0));
         return o;
     }
 
@@ -233,7 +233,7 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
         const double z0_s = RZ0_I_S_0, z0_f = RZ0_I_F_0;
         const double CdN_s = u.cdn_s, ChN_s = u.chn_s;
         const double CdN_f = CdN_f_LG15_light(u.lg15_log_ratio, frice_form);
-        const double ChN_f = fdiv(CdN_f, 1. + LOG_5 * INV_VKARMN * sqrt(CdN_f));
+        const double ChN_f = fdiv(CdN_f, 1. + LOG_5 * INV_VKARMN * abm::fast_sqrt(CdN_f));
         const double CdN = CdN_s + CdN_f, z0_tot = z0_s + z0_f;
         o.Cd = CdN;
         o.Ch = ChN_s + ChN_f;
@@ -243,7 +243,7 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
             double wnd_zt = o.Ub;
             if (!ZTEQ) {
                 const double c = u.log_ztu + f_h_louis(u.zu, RiB, CdN, z0_tot) - f_h_louis(u.zt, RiB, CdN, z0_tot);
-                wnd_zt = abm::dmin(abm::dmax(o.Ub + (sqrt(o.Cd) * o.Ub) * c, WSPD_THRSHLD_ICE), o.Ub);
+                wnd_zt = abm::dmin(abm::dmax(o.Ub + (abm::fast_sqrt(o.Cd) * o.Ub) * c, WSPD_THRSHLD_ICE), o.Ub);
             }
             RiB = ri_bulk(u.zt, Ts, t_zt, qs, q_zt, wnd_zt);
             o.Cd = CdN_s * f_m_louis(u.zu, RiB, CdN_s, z0_s);
@@ -252,7 +252,7 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
             o.Ch = o.Ch + ChN_f * f_h_louis(u.zu, RiB, CdN_f, z0_f);
             if (!ZTEQ) {
                 const double c = u.log_ztu + f_h_louis(u.zu, RiB, CdN, z0_tot) - f_h_louis(u.zt, RiB, CdN, z0_tot);
-                const double r = abm::fast_rcp(sqrt(o.Cd));
+                const double r = abm::fast_rcp(abm::fast_sqrt(o.Cd));
                 o.t_zu = t_zt - (o.Ch * dt * r) * INV_VKARMN * c;
                 o.q_zu = abm::dmax(0., q_zt - (o.Ch * dq * r) * INV_VKARMN * c);
                 dt = floor_abs(o.t_zu - Ts, 1.E-6);
@@ -263,8 +263,8 @@ ABD IceOut solve_ice(const IceUniform &u, double Ts, double t_zt, double qs, dou
         o.CdN_frm = CdN_f;
         o.CdN = CdN;
         o.ChN = o.CeN = ChN_s + ChN_f;
-        o.z0 = u.zu * abm::dexp(-fdiv(VKARMN, sqrt(CdN)));
-        const double sq = sqrt(o.Cd);
+        o.z0 = u.zu * abm::dexp(-fdiv(VKARMN, abm::fast_sqrt(CdN)));
+        const double sq = abm::fast_sqrt(o.Cd);
         o.us = sq * o.Ub;
         o.L = abm::fast_rcp(one_on_L(o.t_zu, o.q_zu, sq * o.Ub, fdiv(o.Ch * dt, sq), fdiv(o.Ce * dq, sq)));
         o.UN10 = sq * o.Ub * INV_VKARMN * abm::dlog(fdiv(10., o.z0));

@@ -21,6 +21,7 @@ void abm_eval(int fn, const double *x, const double *y, double *out, long n)
         case 12: out[i] = abm::fast_r4rt(x[i]); break;
         case 13: out[i] = abm::pow075(x[i]); break;
         case 14: out[i] = abm::fast_cbrt(x[i]); break;
+        case 15: out[i] = abm::fast_sqrt(x[i]); break;
         }
     }
 }

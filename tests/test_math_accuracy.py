@@ -112,6 +112,8 @@ def test_fast_roots(abm):
     assert _relerr(abm(12, x), x, lambda v: v ** mp.mpf(-0.25)) <= 2 * ULP
     assert _relerr(abm(13, x), x, lambda v: v ** mp.mpf(0.75)) <= 3 * ULP
     assert _relerr(abm(14, x), x, lambda v: v ** (mp.mpf(1) / 3)) <= 3 * ULP
+    assert _relerr(abm(15, x), x, mp.sqrt) <= 2 * ULP
     z = np.array([0.0, 1e-31, 1e-300])
     assert (abm(13, z) == 0).all() and (abm(14, z) == 0).all()     # documented flush below 1e-30
+    assert (abm(15, np.array([0.0, 1e-300])) == 0).all()
     assert _relerr(abm(6, x), x, lambda v: 1 / v) <= 2 * ULP       # 3-instruction reciprocal refinement
