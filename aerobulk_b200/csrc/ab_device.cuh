@@ -103,15 +103,11 @@ ABD double floor_abs(double x, double lo) { return (fabs(x) >= lo) ? x : copysig
 ABD double powr(double x, double y) { return abm::dpowr(x, y); }
 // zstab = 0.5 + SIGN(0.5, x) is 1 unless the sign bit of x is set
 ABD bool nonneg(double x) { return !signbit(x); }
-// a / b for normal-range operands: MUFU.RCP64H seed, Newton, one residual correction (<= 1 ulp).
-// CUDA's IEEE division spends as many non-FP64 instructions on its special-case guard as FP64 ones
-// on the quotient; the physics never feeds it denormals, infinities or zero denominators.
-ABD double fdiv(double a, double b)
-{
-    const double r = abm::fast_rcp(b);
-    const double q = a * r;
-    return fma(fma(-b, q, a), r, q);
-}
+// a / b for normal-range operands: a * (1/b) with the reciprocal from MUFU.RCP64H + one refinement (<= 1.5 ulp; a
+// residual correction to <= 1 ulp cost two more FP64 instructions per quotient, 5 % of the kernel's FP64 work, for
+// nothing the 1e-10 parity metric can see).  CUDA's IEEE division spends as many non-FP64 instructions on its
+// special-case guard as FP64 ones on the quotient; the physics never feeds it denormals, infinities or zero denominators.
+ABD double fdiv(double a, double b) { return a * abm::fast_rcp(b); }
 // natural logs of literals of the reference (glibc values), for roughness lengths handled in log space
 constexpr double LOG_1EM9 = -0x1.4b927f32bffb8p+4;   // LOG(1.E-9)
 constexpr double LOG_1EM8 = -18.420680743952367;     // LOG(1.E-8)
@@ -136,9 +132,9 @@ ABD_HEAVY double e_sat(double T)
     const double ztmp = fdiv(KC(RT0), zta);
     const double r = zta * KC(1. / RT0);
     const double a = KC(10.79574) * (1. - ztmp) - KC(5.028) * abm::dlog10(r)
-                     + KC(1.50475 * 1.e-4) * (1. - abm::dexp10(KC(-8.2969) * (r - 1.)))
-                     + KC(0.42873 * 1.e-3) * (abm::dexp10(KC(4.76955) * (1. - ztmp)) - 1.) + KC(0.78614);
-    return 100. * abm::dexp10(a);
+                     + KC(1.50475 * 1.e-4) * (1. - abm::dexp10_b(KC(-8.2969) * (r - 1.)))
+                     + KC(0.42873 * 1.e-3) * (abm::dexp10_b(KC(4.76955) * (1. - ztmp)) - 1.) + KC(0.78614);
+    return 100. * abm::dexp10_b(a);   // T is floored at 180 K: every exponent of this function is inside [-4, 4]
 }
 ABD double q_sat_from_e(double es, double p) { return fdiv(KC(REPS0) * es, p - KC(1. - REPS0) * es); }  // :903
 ABD double q_sat(double T, double p) { return q_sat_from_e(e_sat(T), p); }                   // :881-904
@@ -152,7 +148,7 @@ ABD double theta_from_z_P0_T_q(double z, double slp, double T, double q)
     for (int it = 0; it < 3; ++it) {
         const double f = fdiv(q, q_sat_from_e(es, pa));
         const double xm = (1. - f) * RMM_DRYAIR + f * RMM_WATER;
-        pa = slp * abm::dexp(fdiv(-GRAV * xm * z, R_GAS * T));
+        pa = slp * abm::dexp_b(fdiv(-GRAV * xm * z, R_GAS * T));
     }
     return T * powr(fdiv(slp, pa), RPOISS_DRY);
 }
@@ -324,7 +320,7 @@ ABD double psi_coare_convective(double phi_c)
 }
 ABD PsiMH psi_mh_coare_stable(double z)
 {
-    const double e = abm::dexp(-abm::dmin(50., KC(0.35) * z));
+    const double e = abm::dexp_b(-abm::dmin(50., KC(0.35) * z));   // stable branch: z >= 0
     const double a = fabs(1. + 2. * z * KC(1. / 3.));
     PsiMH r;
     r.m = -(1. + 1. * z + KC(0.6667) * (z - KC(14.28)) * e + KC(8.525));
@@ -333,7 +329,7 @@ ABD PsiMH psi_mh_coare_stable(double z)
 }
 ABD double psi_h_coare_stable(double z)
 {
-    const double e = abm::dexp(-abm::dmin(50., KC(0.35) * z));
+    const double e = abm::dexp_b(-abm::dmin(50., KC(0.35) * z));   // stable branch: z >= 0
     const double a = fabs(1. + 2. * z * KC(1. / 3.));
     return -(a * abm::fast_sqrt(a) + KC(.6667) * (z - KC(14.28)) * e + KC(8.525));
 }
@@ -385,7 +381,7 @@ ABD PsiMH psi_mh_ecmwf_stable(double zeta)
 {
     const double zc = 5. / 0.35;
     const double z = cap_zeta(zeta);
-    const double t = 2. / 3. * (z - zc) * abm::dexp(-0.35 * z);
+    const double t = 2. / 3. * (z - zc) * abm::dexp_b(-0.35 * z);   // zeta is capped to [-50, 5]
     const double a = fabs(1. + 2. / 3. * z);
     PsiMH r;
     r.m = -t - z - 2. / 3. * zc;
@@ -609,10 +605,10 @@ ABD double wl_coare_absorption(double H)   // solar absorption profile, :167-168
 {
     // 1 - EXP(-x) is exactly 1 in FP64 once EXP(-x) < 2**-54, i.e. x > 37.43: the two short-wave bands
     // are only evaluated for shallow layers (H <= 0.53 m, H <= 13.4 m) -- bit-identical, fewer exps
-    const double e1 = (H > KC(0.53)) ? 0. : abm::dexp(-H * KC(1. / 0.014));
-    const double e2 = (H > KC(13.4)) ? 0. : abm::dexp(-H * KC(1. / 0.357));
+    const double e1 = (H > KC(0.53)) ? 0. : abm::dexp_b(-H * KC(1. / 0.014));   // 0.1 <= H <= 20 (callers clamp)
+    const double e2 = (H > KC(13.4)) ? 0. : abm::dexp_b(-H * KC(1. / 0.357));
     return 1. - fdiv(KC(0.28 * 0.014) * (1. - e1) + KC(0.27 * 0.357) * (1. - e2)
-                     + KC(0.45 * 12.82) * (1 - abm::dexp(-H * KC(1. / 12.82))), H);
+                     + KC(0.45 * 12.82) * (1 - abm::dexp_b(-H * KC(1. / 12.82))), H);
 }
 // WL_COARE, src/mod_skin_coare.f90:97-250; `commit` is (iwait == 0)
 ABD void wl_coare(WarmLayer &w, const WlCoareCtx &c, double Qsw, double Qnsol, double Tau, double rdt,
@@ -807,7 +803,7 @@ ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p, Diag &dg)
     c.Cd = Cd; c.Ch = Ch; c.Ce = Ce; c.t_zu = t_zu; c.q_zu = q_zu; c.Ub = Ub; c.Ts = p.sst; c.qs = p.ssq;
     // optional outputs, src/mod_blk_ncar.f90:229-235
     dg.CdN = CdN; dg.ChN = ChN; dg.CeN = CeN; dg.UN10 = Un10; dg.L = 1. / r1oL; dg.us = us;
-    dg.z0 = abm::dmin(u.zu * abm::dexp(-VKARMN * abm::fast_rsqrt(CdN)), Z0_SEA_MAX);
+    dg.z0 = abm::dmin(u.zu * abm::dexp_b(-VKARMN * abm::fast_rsqrt(CdN)), Z0_SEA_MAX);
     dg.dT_cs = 0.;
     return c;
 }

@@ -48,7 +48,7 @@ ABD double CdN_f_LG15_light(double log_ratio, double A)   // log_ratio = LOG(10/
 }
 
 // psi_m_ice / psi_h_ice, mod_blk_ice_an05.f90:329-405 == mod_blk_ice_easy.f90:213-289 (Paulson with 16 / Holtslag-De Bruin)
-ABD double psi_ice_stable(double z) { return -(0.7 * z + 0.75 * (z - 14.3) * abm::dexp(-0.35 * z) + 10.7); }
+ABD double psi_ice_stable(double z) { return -(0.7 * z + 0.75 * (z - 14.3) * abm::dexp_b(-0.35 * z) + 10.7); }   // 0 <= z <= 50
 ABD double psi_m_ice(double z)
 {
     if (nonneg(z)) return psi_ice_stable(z);

@@ -258,6 +258,17 @@ ABM_BIG double dexp_table(double x)
     const double v = expt_core(r, k);
     return (x < -700.) ? 0. : v;
 }
+// the same without the underflow guard, for call sites whose argument is provably inside [-700, 700]
+ABM_BIG double dexp_table_bounded(double x)
+{
+    const double MAGIC = 6755399441055744.0;
+    const double t = fma(x, MATH_K[K_L2E64], MAGIC);
+    const int k = lo_word(t);
+    const double kf = t - MAGIC;
+    double r = fma(kf, -MATH_K[K_LN2_64_HI], x);
+    r = fma(kf, -MATH_K[K_LN2_64_LO], r);
+    return expt_core(r, k);
+}
 ABM_BIG double dexp10_table(double x)
 {
     const double MAGIC = 6755399441055744.0;
@@ -268,6 +279,16 @@ ABM_BIG double dexp10_table(double x)
     r = fma(kf, -MATH_K[K_LG2_64_LO], r);
     const double v = expt_core(r * MATH_K[K_LN10], k);
     return (x < -304.) ? 0. : v;
+}
+ABM_BIG double dexp10_table_bounded(double x)   // |x| <= 300 guaranteed by the caller
+{
+    const double MAGIC = 6755399441055744.0;
+    const double t = fma(x, MATH_K[K_L2T64], MAGIC);
+    const int k = lo_word(t);
+    const double kf = t - MAGIC;
+    double r = fma(kf, -MATH_K[K_LG2_64_HI], x);
+    r = fma(kf, -MATH_K[K_LG2_64_LO], r);
+    return expt_core(r * MATH_K[K_LN10], k);
 }
 // log(x) = e ln2 + lc_j + log1p(m rc_j - 1), m in [0.708, 1.416) (so that x ~ 1 has e = 0 and the exact
 // entry c = 1), j = interval of m's hi word
@@ -293,10 +314,14 @@ ABM_BIG double dlog_table(double x)
 #if defined(ABM_POLY_MATH) && ABM_POLY_MATH
 ABM_FN double dexp(double x) { return dexp_poly(x); }
 ABM_FN double dexp10(double x) { return dexp10_poly(x); }
+ABM_FN double dexp_b(double x) { return dexp_poly(x); }
+ABM_FN double dexp10_b(double x) { return dexp10_poly(x); }
 ABM_FN double dlog(double x) { return dlog_poly(x); }
 #else
 ABM_FN double dexp(double x) { return dexp_table(x); }
 ABM_FN double dexp10(double x) { return dexp10_table(x); }
+ABM_FN double dexp_b(double x) { return dexp_table_bounded(x); }      // argument inside [-700, 700]
+ABM_FN double dexp10_b(double x) { return dexp10_table_bounded(x); }  // argument inside [-300, 300]
 ABM_FN double dlog(double x) { return dlog_table(x); }
 #endif
 
