@@ -554,11 +554,15 @@ ABD double cool_skin_dT(double alpha, double Qsw, double Qnsol, double us, doubl
     double Qabs = Qnsol, d = 0.;
 #pragma unroll 1
     for (int jc = 0; jc < 5; ++jc) {
+        const double d_prev = d;
         if (jc > 0) {
             const double fr = abm::dmax((COARE_FORM ? KC(0.137) : KC(0.065)) + 11. * d - fdiv(KC(6.6E-5), d) * (1. - abm::dexp(-d * KC(1. / 8.E-4))), KC(0.01));
             Qabs = Qnsol + fr * Qsw;
         }
         d = delta(Qabs);
+        // fixed point reached (typically d == d_warm while the skin warms): the remaining passes would reproduce
+        // Qabs and d bit for bit
+        if (jc > 0 && d == d_prev) break;
     }
     return Qabs * d * KC(1. / RK0_W);
 }
@@ -637,7 +641,9 @@ ABD void wl_coare(WarmLayer &w, const WlCoareCtx &c, double Qsw, double Qnsol, d
             if (jl > 0) Qabs = wl_coare_absorption(H) * Qsw + Qnsol;   // jl == 0: H unchanged since the test above
             qac = w.Qac + Qabs * rdt;
             if (qac <= 0.) break;
+            const double H_prev = H;
             H = abm::dmax(abm::dmin(Hwl_max, c.cd1 * tac * abm::fast_rsqrt(qac)), 0.1);
+            if (H == H_prev) break;   // fixed point (usually a clamp): further passes are bit-identical
         }
         if (qac <= 0.) {
             destroy = true;
