@@ -707,13 +707,16 @@ ABD void wl_ecmwf(WarmLayer &w, const WlEcmwfCtx &c, double alpha, double Qsw, d
     const double A = cst0 * Qabs * (1. / (rNuwl0 * RhoCp_w));
     const double cst3 = -cst0 * VKARMN * usw * FLA_ECMWF;
 
+    // while the layer warms zeta = H L2 does not depend on dT: B is the same in all ten passes
+    const double B_warm = warming ? fdiv(cst3, phi_takaya(H * L2)) : 0.;
     double dT_n = dT_b;
 #pragma unroll 1
     for (int jc = 0; jc < 10; ++jc) {
+        const double prev = dT_n;
         dT_n = 0.5 * (dT_n + dT_b);
-        const double zeta = warming ? H * L2 : H * abm::fast_sqrt(dT_n * cst2);
-        const double B = fdiv(cst3, phi_takaya(zeta));
+        const double B = warming ? B_warm : fdiv(cst3, phi_takaya(H * abm::fast_sqrt(dT_n * cst2)));
         dT_n = abm::dmax(dT_b + A + B * dT_n, 0.);
+        if (dT_n == prev) break;   // fixed point of the pass (e.g. 0 at night): the remaining passes are bit-identical
     }
     w.dT = dT_n * tcorr;
 }
