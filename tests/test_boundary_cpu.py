@@ -113,3 +113,13 @@ def test_cpp_api_links_and_reports(ab, tmp_path):
     else:
         # fail-stop like the reference's ctl_stop: message on stdout, process ends (exit status 1)
         assert r.returncode == 1 and "E R R O R" in r.stdout and "no CUDA device" in r.stdout, r.stdout + r.stderr
+
+
+def test_series_cli_arguments():
+    """Argument handling of the series CLI needs no GPU (it mirrors the prompts of the reference program)."""
+    r = subprocess.run([sys.executable, "-m", "aerobulk_b200.series_cli", "a.csv", "b.csv", "--zu", "150"], cwd=ROOT,
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "Be reasonable" in r.stderr
+    r = subprocess.run([sys.executable, "-m", "aerobulk_b200.series_cli", "a.csv", "b.csv", "--algo", "coare9"], cwd=ROOT,
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "invalid choice" in r.stderr

@@ -181,3 +181,29 @@ def test_series_errors(ab):
     with pytest.raises(ab.AerobulkError) as e:
         ab.series_csv("/nonexistent/in.csv", "/tmp/out.csv", "ncar", 2.0, 10.0)
     assert e.value.code == 102
+
+
+def test_series_cli(ab, tmp_path):
+    """python -m aerobulk_b200.series_cli == aerobulk_gpu_series_csv with the program's nb_iter = 20."""
+    import subprocess
+    import sys
+    Nt = 12
+    d = synth.station_series(Nt, 1)
+    fin, fout, fref = tmp_path / "in.csv", tmp_path / "out.csv", tmp_path / "ref.csv"
+    with open(fin, "w") as f:
+        f.write("time,lon,sst,t_air,q_air,wndspd,msl,ssrd,strd\n")
+        for jt in range(Nt):
+            f.write(f"2020/01/01-{jt:02d}:00,10.0," + ",".join(repr(float(d[k][jt, 0])) for k in
+                    ("sst", "t_zt", "hum_zt", "wind", "slp", "rad_sw", "rad_lw")) + "\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "aerobulk_b200.series_cli", str(fin), str(fout), "--algo", "ecmwf"],
+                       cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ab.reset()
+    ab.set_nb_iter(20)
+    ab.series_csv(str(fin), str(fref), "ecmwf", 2.0, 10.0, True)
+    assert open(fout).read() == open(fref).read()
+    r = subprocess.run([sys.executable, "-m", "aerobulk_b200.series_cli", str(tmp_path / "missing.csv"), str(fout)],
+                       cwd=root, capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stderr
+    ab.reset()
