@@ -256,30 +256,19 @@ ABD_HEAVY void update_qnsol_tau(const AirZu &air, double Ts, double qs, double t
 // Liu-Katsaros-Businger z0t / z0q, :1635-1701 (iflag 1: temperature, 2: humidity), in log space:
 // LOG(z0t) = LOG(XA) + (XB - 1) LOG(Rer) + LOG(z0), clipped to [LOG(1e-9), LOG(0.05)]; Rer outside
 // ]0,1000[ gives the reference's ABS(-999.) -> 0.05.  (One log of Rer instead of two pow and two log.)
+static __constant__ double LKB_T[2][8][2] = {
+    {{-0x1.bb4a804765594p+0, 0.}, {0x1.46d750d6da9dbp-2, 0.929}, {0x1.a48a553637bd3p-6, -0.599}, {0x1.f128f5faf06edp-2, -1.018},
+     {0x1.8a0afa79b6d2dp+0, -1.475}, {0x1.c6bba4d3499efp+1, -2.067}, {0x1.dacf2c5c04d22p+2, -2.907}, {0x1.a91a7a7897e05p+3, -3.935}},
+    {{-0x1.3b22e9abd04f9p+0, 0.}, {0x1.2f37a01050599p-1, 0.826}, {0x1.536a2b94647bcp-2, -0.528}, {0x1.57806929d28c9p-1, -0.870},
+     {0x1.9bb56ebf3d3b9p+0, -1.297}, {0x1.b657d7f0668f0p+1, -1.845}, {0x1.d1d1701b4f5c8p+2, -2.682}, {0x1.935aebcc59706p+3, -3.616}}};
 ABD double log_z0tq_LKB(int iflag, double Rer, double log_Rer, double log_z0)
 {
     if (!(Rer > 0. && Rer < 1000.)) return LOG_0P05;
-    double la, b;
-    if (iflag == 1) {
-        if (Rer <= 0.11) { la = -0x1.bb4a804765594p+0; b = 0.; }
-        else if (Rer <= 0.825) { la = 0x1.46d750d6da9dbp-2; b = 0.929; }
-        else if (Rer <= 3.0) { la = 0x1.a48a553637bd3p-6; b = -0.599; }
-        else if (Rer <= 10.0) { la = 0x1.f128f5faf06edp-2; b = -1.018; }
-        else if (Rer <= 30.0) { la = 0x1.8a0afa79b6d2dp+0; b = -1.475; }
-        else if (Rer <= 100.) { la = 0x1.c6bba4d3499efp+1; b = -2.067; }
-        else if (Rer <= 300.) { la = 0x1.dacf2c5c04d22p+2; b = -2.907; }
-        else { la = 0x1.a91a7a7897e05p+3; b = -3.935; }
-    } else {
-        if (Rer <= 0.11) { la = -0x1.3b22e9abd04f9p+0; b = 0.; }
-        else if (Rer <= 0.825) { la = 0x1.2f37a01050599p-1; b = 0.826; }
-        else if (Rer <= 3.0) { la = 0x1.536a2b94647bcp-2; b = -0.528; }
-        else if (Rer <= 10.0) { la = 0x1.57806929d28c9p-1; b = -0.870; }
-        else if (Rer <= 30.0) { la = 0x1.9bb56ebf3d3b9p+0; b = -1.297; }
-        else if (Rer <= 100.) { la = 0x1.b657d7f0668f0p+1; b = -1.845; }
-        else if (Rer <= 300.) { la = 0x1.d1d1701b4f5c8p+2; b = -2.682; }
-        else { la = 0x1.935aebcc59706p+3; b = -3.616; }
-    }
-    return abm::dmin(abm::dmax(la + (b - 1.) * log_Rer + log_z0, LOG_1EM9), LOG_0P05);
+    // interval of the table (upper bounds 0.11 0.825 3 10 30 100 300 1000) and its {LOG(XA), XB} from the constant bank
+    int k = 0;
+    k += (Rer > KC(0.11)) + (Rer > KC(0.825)) + (Rer > 3.0) + (Rer > 10.0) + (Rer > 30.0) + (Rer > 100.) + (Rer > 300.);
+    const double la = LKB_T[iflag == 1 ? 0 : 1][k][0], b = LKB_T[iflag == 1 ? 0 : 1][k][1];
+    return abm::dmin(abm::dmax(la + (b - 1.) * log_Rer + log_z0, KC(LOG_1EM9)), KC(LOG_0P05));
 }
 
 // ---------------------------------------------------------------------------
@@ -745,9 +734,9 @@ ABD double cd_n10_ncar(double w)
 {
     double w6 = w * w * w;
     w6 = w6 * w6;
-    const double r = nonneg(w - 33.) ? 1.e-3 * 2.34
-                                     : 1.e-3 * (fdiv(2.7, w) + 0.142 + w * (1. / 13.09) - 3.14807E-10 * w6);
-    return abm::dmax(r, CX_MIN);
+    const double r = nonneg(w - 33.) ? KC(1.e-3 * 2.34)
+                                     : KC(1.e-3) * (fdiv(KC(2.7), w) + KC(0.142) + w * KC(1. / 13.09) - KC(3.14807E-10) * w6);
+    return abm::dmax(r, KC(CX_MIN));
 }
 
 template <bool ZTEQ>
@@ -1114,8 +1103,8 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p, Diag &dg)
 #pragma unroll 1
     for (int jit = 1; jit <= u.nb_iter; ++jit) {
         if (RiB < rRi_max) {
-            const double za = UN10 - 8.271;
-            u_star = 0.239 + 0.0433 * (za + abm::fast_sqrt(0.12 * za * za + 0.181));   // :275-293
+            const double za = UN10 - KC(8.271);
+            u_star = KC(0.239) + KC(0.0433) * (za + abm::fast_sqrt(KC(0.12) * za * za + KC(0.181)));   // :275-293
         } else {
             u_star = abm::fast_sqrt(CX_MIN) * Ub;
         }

@@ -122,18 +122,18 @@ ABM_FN double fast_rsqrt(double x)              // x**(-1/2)
     const double e = fma(-(x * y), y, 1.0);
     return fma(y * e, fma(0.375, e, 0.5), y);
 }
-// sqrt for x >= 0 in the normal range (0 and below 1e-290 -> 0): CUDA's sqrt is 12 instructions inline but up to 34
+// sqrt for x >= 0 in the normal range (0 and below 2^-962 -> 0): CUDA's sqrt is 12 instructions inline but up to 34
 // where ptxas keeps its slow-path call (10 % of the ECMWF + skin kernel was the sqrt of the warm-layer inner loop)
 ABM_FN double fast_sqrt(double x)
 {
     const double r = fast_rsqrt(x);
-    return (x > 1.e-290) ? x * r : 0.;
+    return (hi_word(x) >= 0x03d00000) ? x * r : 0.;   // x >= 2^-962
 }
 ABM_FN double fast_rcbrt(double x)              // x**(-1/3), x in the normal FP32 range
 {
     const double y = pow_seed(x, -1.0f / 3.0f);
     const double e = fma(-(x * y), y * y, 1.0);
-    return fma(y * e, fma(2.0 / 9.0, e, 1.0 / 3.0), y);
+    return fma(y * e, fma(MATH_K[K_TWO_NINTHS], e, MATH_K[K_ONE_THIRD]), y);
 }
 ABM_FN double fast_r4rt(double x)               // x**(-1/4), x in the normal FP32 range
 {
@@ -142,12 +142,13 @@ ABM_FN double fast_r4rt(double x)               // x**(-1/4), x in the normal FP
     const double e = fma(-(x * y2), y2, 1.0);
     return fma(y * e, fma(5.0 / 32.0, e, 0.25), y);
 }
-// x**0.75 and x**(1/3) for x >= 0; below 1e-30 (where the FP32 seed would leave its range) the result is 0:
+// x**0.75 and x**(1/3) for x >= 0; below 2^-100 (where the FP32 seed would leave its range) the result is 0:
 // the callers add it to 1 (delta_skin_layer) or to a squared wind speed (gustiness)
-ABM_FN double pow075(double x) { return (x > 1.e-30) ? x * fast_r4rt(x) : 0.; }
+// (the guards compare the high word: x > 2^-100 without an FP64 compare or a 64-bit literal)
+ABM_FN double pow075(double x) { return (hi_word(x) >= 0x39b00000) ? x * fast_r4rt(x) : 0.; }
 ABM_FN double fast_cbrt(double x)
 {
-    if (!(x > 1.e-30)) return 0.;
+    if (hi_word(x) < 0x39b00000) return 0.;
     const double r = fast_rcbrt(x);
     return x * (r * r);
 }
@@ -332,9 +333,9 @@ ABM_BIG double datan(double x)
 {
     const double ax = fabs(x);
     double num = ax, den = 1.0, bhi = 0., blo = 0.;
-    if (ax > 2.414213562373095) {
+    if (ax > MATH_K[K_TAN3PIO8]) {
         num = -1.0; den = ax; bhi = MATH_K[K_PIO2_HI]; blo = MATH_K[K_PIO2_LO];
-    } else if (ax > 0.4142135623730950) {
+    } else if (ax > MATH_K[K_TANPIO8]) {
         num = ax - 1.0; den = ax + 1.0; bhi = MATH_K[K_PIO4_HI]; blo = MATH_K[K_PIO4_LO];
     }
     const double t = num * fast_rcp(den);
