@@ -1296,6 +1296,46 @@ int oce_ice_impl(const char *calgo_ice, const char *calgo_oce, double zt, double
     return finish_ice_call(cs_, "aerobulk_gpu_oce_ice");
 }
 
+// ---------------------------------------------------------------------------
+// flux diagnostics (the optional global reduction)
+// ---------------------------------------------------------------------------
+int diag_impl(long long n, const double *const *fields, double *stats, int on_device)
+{
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!stats || n < 0) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_flux_diagnostics: bad argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaStream_t cs_ = compute_stream();
+    abk::DiagArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n;
+    a.partials = g.d_partials;
+    a.out = g.d_stats;
+    if (on_device) {
+        for (int f = 0; f < abk::NDIAG_FIELDS; ++f) a.field[f] = fields[f];
+    } else {
+        int nf = 0;
+        for (int f = 0; f < abk::NDIAG_FIELDS; ++f) nf += fields[f] ? 1 : 0;
+        rc = ensure_turb_slab(n * nf);
+        if (rc) return rc;
+        double *p = g.d_turb;
+        for (int f = 0; f < abk::NDIAG_FIELDS; ++f) {
+            if (!fields[f] || n == 0) continue;
+            CUDA_TRY(cudaMemcpyAsync(p, fields[f], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs_));
+            a.field[f] = p;
+            p += n;
+        }
+    }
+    const long long want = (n + 255) / 256;
+    const int nblocks = (int)(want < 1 ? 1 : (want > abk::stats_max_blocks() ? abk::stats_max_blocks() : want));
+    CUDA_TRY(abk::launch_diag(a, nblocks, cs_));
+    g.launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(stats, g.d_stats, sizeof(double) * abk::NDIAG, cudaMemcpyDeviceToHost, cs_));
+    CUDA_TRY(cudaStreamSynchronize(cs_));
+    return 0;
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -1409,6 +1449,16 @@ int aerobulk_gpu_oce_ice(const char *calgo_ice, const char *calgo_oce, double zt
 }
 
 void aerobulk_gpu_set_ice_form_drag_per_point(int on) { std::lock_guard<std::mutex> lk(g_mu); g.ice_form_per_point = on ? 1 : 0; }
+
+int aerobulk_gpu_flux_diagnostics(long long n, const double *QL, const double *QH, const double *Tau_x, const double *Tau_y,
+                                  const double *Evap, const double *T_s, double *stats, int on_device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    const double *fields[abk::NDIAG_FIELDS] = {QL, QH, Tau_x, Tau_y, Evap, T_s};
+    return diag_impl(n, fields, stats, on_device);
+}
+
+int aerobulk_gpu_diag_reduce_op(int i) { return (i <= 0 || i >= abk::NDIAG) ? 0 : (i - 1) % 3; }
 
 void aerobulk_gpu_set_nitend(int nitend) { std::lock_guard<std::mutex> lk(g_mu); g.nitend = nitend; }
 

@@ -479,6 +479,71 @@ cudaError_t launch_stats(const StatsArgs &a, int nblocks, cudaStream_t s)
 }
 
 // ---------------------------------------------------------------------------
+// flux diagnostics: sum / min / max of the output fields (the optional global reduction of SURVEY.md 8e)
+// ---------------------------------------------------------------------------
+__host__ __device__ inline int diag_op(int k) { return k == 0 ? 0 : (k - 1) % 3; }   // 0 sum, 1 min, 2 max
+
+__global__ void __launch_bounds__(STATS_BLOCK) diag_kernel(const DiagArgs a)
+{
+    double acc[NDIAG];
+    acc[0] = 0.;
+#pragma unroll
+    for (int f = 0; f < NDIAG_FIELDS; ++f) {
+        acc[1 + 3 * f] = 0.;
+        acc[2 + 3 * f] = DBL_MAX;
+        acc[3 + 3 * f] = -DBL_MAX;
+    }
+    const long long stride = (long long)gridDim.x * STATS_BLOCK;
+    for (long long i = (long long)blockIdx.x * STATS_BLOCK + threadIdx.x; i < a.n; i += stride) {
+        acc[0] += 1.;
+#pragma unroll
+        for (int f = 0; f < NDIAG_FIELDS; ++f) {
+            if (!a.field[f]) continue;
+            const double v = __ldg(a.field[f] + i);
+            acc[1 + 3 * f] += v;
+            acc[2 + 3 * f] = fmin(acc[2 + 3 * f], v);
+            acc[3 + 3 * f] = fmax(acc[3 + 3 * f], v);
+        }
+    }
+    __shared__ double sm[STATS_BLOCK / 32][NDIAG];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NDIAG; ++k) {
+        const double r = warp_reduce(acc[k], diag_op(k));
+        if (lane == 0) sm[w][k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < NDIAG) {
+        const int k = threadIdx.x, op = diag_op(k);
+        double r = sm[0][k];
+        for (int j = 1; j < STATS_BLOCK / 32; ++j) r = (op == 0) ? r + sm[j][k] : (op == 1) ? fmin(r, sm[j][k]) : fmax(r, sm[j][k]);
+        a.partials[(long long)blockIdx.x * NDIAG + k] = r;
+    }
+}
+
+__global__ void __launch_bounds__(32 * NDIAG) diag_final(const double *partials, int nblocks, double *out)
+{
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int op = diag_op(k);
+    double r = (op == 0) ? 0. : (op == 1) ? DBL_MAX : -DBL_MAX;
+    for (int b = lane; b < nblocks; b += 32) {
+        const double w = partials[(long long)b * NDIAG + k];
+        r = (op == 0) ? r + w : (op == 1) ? fmin(r, w) : fmax(r, w);
+    }
+    r = warp_reduce(r, op);
+    if (lane == 0) out[k] = r;
+}
+
+cudaError_t launch_diag(const DiagArgs &a, int nblocks, cudaStream_t s)
+{
+    diag_kernel<<<nblocks, STATS_BLOCK, 0, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    diag_final<<<1, 32 * NDIAG, 0, s>>>(a.partials, nblocks, a.out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // FP64 peak: 8 independent dependent-DFMA chains per thread
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b)

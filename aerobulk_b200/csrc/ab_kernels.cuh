@@ -106,6 +106,18 @@ struct StatsArgs {
     double *out;        // [NSTATS]
 };
 
+// Global flux diagnostics (the optional reduction): sum / min / max of up to 6 fields.
+// out[1 + 3 f + {0,1,2}] = sum, min, max of field f; out[0] = number of points.  Fixed-order reduction (deterministic).
+constexpr int NDIAG_FIELDS = 6;
+constexpr int NDIAG = 1 + 3 * NDIAG_FIELDS;
+struct DiagArgs {
+    const double *field[NDIAG_FIELDS];   // NULL: skipped (sum 0, min +DBL_MAX, max -DBL_MAX)
+    long long n;
+    double *partials;                    // [gridDim.x][NDIAG]
+    double *out;                         // [NDIAG]
+};
+cudaError_t launch_diag(const DiagArgs &a, int nblocks, cudaStream_t s);
+
 cudaError_t launch_flux(int algo, bool skin, bool zt_eq_zu, const FluxArgs &a, cudaStream_t s);
 // block size / register info for reports
 int flux_block_size();

@@ -80,6 +80,10 @@ def lib():
     L.aerobulk_gpu_oce_ice.argtypes = ([C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_longlong] + [C.c_void_p] * 4 +
                                        [C.c_int] + [C.c_void_p] * 5 + [C.c_int])
     L.aerobulk_gpu_set_ice_form_drag_per_point.argtypes = [C.c_int]
+    L.aerobulk_gpu_flux_diagnostics.restype = C.c_int
+    L.aerobulk_gpu_flux_diagnostics.argtypes = [C.c_longlong] + [C.c_void_p] * 6 + [_dp, C.c_int]
+    L.aerobulk_gpu_diag_reduce_op.restype = C.c_int
+    L.aerobulk_gpu_diag_reduce_op.argtypes = [C.c_int]
     L.aerobulk_gpu_series.restype = C.c_int
     L.aerobulk_gpu_series.argtypes = ([C.c_char_p, C.c_int, C.c_longlong, C.c_double, C.c_double] + [C.c_void_p] * 5 +
                                       [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int])
@@ -396,3 +400,50 @@ def oce_ice(calgo_ice: str, calgo_oce, zt: float, zu: float, sit, sst, t_zt, hum
                                 ptr(ins[6]), ptr(cx), C.cast(arr, C.c_void_p), 0)
     _check(rc)
     return outs
+
+
+# ---------------------------------------------------------------------------
+# optional global flux diagnostics
+# ---------------------------------------------------------------------------
+NDIAG = 19
+DIAG_FIELDS = ("QL", "QH", "Tau_x", "Tau_y", "Evap", "T_s")
+
+
+def flux_diagnostics(fields: dict) -> np.ndarray:
+    """Row-block sum / min / max of the flux fields named in DIAG_FIELDS (numpy arrays or CUDA torch tensors; missing
+    ones are skipped): the 19-double vector of aerobulk_gpu_flux_diagnostics, to be combined across ranks with
+    :func:`diag_reduce_ops` (0 sum, 1 min, 2 max)."""
+    L = lib()
+    present = [fields[k] for k in DIAG_FIELDS if k in fields and fields[k] is not None]
+    on_dev = bool(present) and hasattr(present[0], "data_ptr")
+    keep, ptrs, n = [], [], 0
+    for k in DIAG_FIELDS:
+        a = fields.get(k)
+        if a is None:
+            ptrs.append(None)
+        elif on_dev:
+            ptrs.append(a.data_ptr())
+            n = a.numel()
+        else:
+            a = np.ascontiguousarray(np.ravel(a, order="F"), dtype=np.float64)
+            keep.append(a)
+            ptrs.append(a.ctypes.data)
+            n = a.size
+    st = np.zeros(NDIAG, dtype=np.float64)
+    _check(L.aerobulk_gpu_flux_diagnostics(n, *ptrs, st.ctypes.data_as(_dp), int(on_dev)))
+    return st
+
+
+def diag_reduce_ops() -> np.ndarray:
+    L = lib()
+    return np.array([L.aerobulk_gpu_diag_reduce_op(i) for i in range(NDIAG)], dtype=np.int64)
+
+
+def diagnostics_summary(st: np.ndarray) -> dict:
+    """{"n": count, field: {"mean", "min", "max"}} from a (combined) diagnostics vector."""
+    out = {"n": int(st[0])}
+    for f, k in enumerate(DIAG_FIELDS):
+        s_, lo, hi = st[1 + 3 * f: 4 + 3 * f]
+        if hi >= lo:
+            out[k] = {"mean": float(s_ / max(st[0], 1.0)), "min": float(lo), "max": float(hi)}
+    return out

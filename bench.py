@@ -302,6 +302,21 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * n * NT * args.steps / float(e2e_s.item())
 
+    # ---------------- optional global diagnostics of the last device-resident step (outside every timed region):
+    # row-block sums / minima / maxima on the device, combined across ranks by NCCL all-reduces of 19 doubles
+    dvec = torch.from_numpy(abm.flux_diagnostics(out)).to(dev)
+    if world > 1:
+        dop = torch.from_numpy(abm.diag_reduce_ops()).to(dev)
+        big = torch.full_like(dvec, float("inf"))
+        d_sum = torch.where(dop == 0, dvec, torch.zeros_like(dvec))
+        d_min = torch.where(dop == 1, dvec, big)
+        d_max = torch.where(dop == 2, dvec, -big)
+        dist.all_reduce(d_sum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(d_min, op=dist.ReduceOp.MIN)
+        dist.all_reduce(d_max, op=dist.ReduceOp.MAX)
+        dvec = torch.where(dop == 0, d_sum, torch.where(dop == 1, d_min, d_max))
+    diagnostics = abm.diagnostics_summary(dvec.cpu().numpy())
+
     # ---------------- rooflines
     hbm_peak, hbm_src = measured_peaks()
     bytes_pt = ab.bytes_per_point(ALGO, SKIN)
@@ -336,6 +351,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 "how": "aerobulk_gpu_model (host-array C ABI) with pinned host buffers (inputs in one slab, outputs in another: one pitched copy per chunk and slab), chunked H2D|kernel|D2H pipeline"},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "diagnostics": diagnostics,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": traffic,
                      "kernel": "flux_kernel<COARE3P6,skin,zt!=zu>", "avg_launch_ms": kern_ms,

@@ -213,6 +213,19 @@ int aerobulk_gpu_oce_ice(const char *calgo_ice, const char *calgo_oce, double zt
 /* Waits for the session stream and reports a deferred error (wind stress too strong). */
 int aerobulk_gpu_synchronize(void);
 
+/* ---- optional global flux diagnostics for sharded grids ---------------------------------------------- */
+#define AEROBULK_GPU_NDIAG 19
+/* Sum / min / max of the flux fields of this process's row block (any pointer may be NULL): stats[0] = number of points,
+ * stats[1 + 3 f + {0,1,2}] = sum, min, max of field f in the order QL, QH, Tau_x, Tau_y, Evap, T_s (a skipped field
+ * gives 0, +DBL_MAX, -DBL_MAX).  Deterministic (fixed-order) reduction on the device.  Ranks combine their vectors
+ * element-wise with the operation aerobulk_gpu_diag_reduce_op(i) gives (0 sum, 1 min, 2 max): the one place a
+ * collective (NCCL / MPI all-reduce of 19 doubles) appears besides the AEROBULK_INIT statistics below.  The reference
+ * has no counterpart (its callers compute such diagnostics themselves). */
+int aerobulk_gpu_flux_diagnostics(long long n, const double *QL, const double *QH, const double *Tau_x,
+                                  const double *Tau_y, const double *Evap, const double *T_s, double *stats,
+                                  int on_device);
+int aerobulk_gpu_diag_reduce_op(int i);
+
 /* ---- AEROBULK_INIT split for row-block sharded grids (one process per GPU) ---- */
 
 #define AEROBULK_GPU_NSTATS 64

@@ -59,6 +59,7 @@ def test_pure_host_entry_points(ab):
     assert ab.nb_iter() == 7
     ab.reset()
     assert ab.nb_iter() == 5
+    assert list(ab.diag_reduce_ops()) == [0] + [0, 1, 2] * 6          # count, then sum / min / max of the six flux fields
     ops = [L.aerobulk_gpu_stats_reduce_op(i) for i in range(64)]
     assert ops[:2] == [0, 0] and ops[2:7] == [0, 1, 2, 1, 2] and ops[47:] == [0] * 17
 

@@ -292,3 +292,34 @@ def test_fields_in_one_slab_use_pitched_copies_and_agree(ab):
             for k in names:
                 assert np.array_equal(got[k], ref[k]), (ni, pinned, k)
                 assert np.array_equal(out[k], ref[k]), (ni, pinned, k)
+
+
+def test_flux_diagnostics_match_numpy_and_combine_like_one_domain(ab):
+    """aerobulk_gpu_flux_diagnostics: device sums / minima / maxima of the flux fields; two row blocks combined with
+    aerobulk_gpu_diag_reduce_op equal the whole domain (min / max exactly, sums to rounding)."""
+    Ni, Nj = 300, 200
+    f = synth.fields(Ni, Nj)
+    keys = ("sst", "t_zt", "hum_zt", "U_zu", "V_zu", "slp")
+    ab.reset()
+    r = ab.aerobulk_model(1, 1, "ecmwf", 2.0, 10.0, *[f[k] for k in keys], Niter=4, l_use_skin=True,
+                          rad_sw=f["rad_sw"], rad_lw=f["rad_lw"])
+    st = ab.flux_diagnostics(r)
+    ops = ab.diag_reduce_ops()
+    assert st[0] == Ni * Nj and list(ops[:4]) == [0, 0, 1, 2]
+    for i, k in enumerate(("QL", "QH", "Tau_x", "Tau_y", "Evap", "T_s")):
+        assert st[1 + 3 * i] == pytest.approx(r[k].sum(), rel=1e-12)
+        assert st[2 + 3 * i] == r[k].min() and st[3 + 3 * i] == r[k].max()
+    assert np.array_equal(ab.flux_diagnostics(r), st)                     # deterministic
+    half = Nj // 2
+    a = ab.flux_diagnostics({k: v[:, :half] for k, v in r.items()})
+    b = ab.flux_diagnostics({k: v[:, half:] for k, v in r.items()})
+    comb = np.where(ops == 0, a + b, np.where(ops == 1, np.minimum(a, b), np.maximum(a, b)))
+    assert np.allclose(comb, st, rtol=1e-12, atol=0) and np.array_equal(comb[ops != 0], st[ops != 0])
+    s = ab.diagnostics_summary(comb)
+    assert s["n"] == Ni * Nj and s["QH"]["min"] == r["QH"].min() and abs(s["T_s"]["mean"] - r["T_s"].mean()) < 1e-9
+    # a subset of the fields, on the device
+    import torch
+    t = {"QL": torch.from_numpy(np.ravel(r["QL"], order="F").copy()).cuda()}
+    d = ab.flux_diagnostics(t)
+    assert d[1] == pytest.approx(r["QL"].sum(), rel=1e-12) and d[4] == 0.0 and d[5] > 1e300 and d[6] < -1e300
+    assert "QH" not in ab.diagnostics_summary(d)
