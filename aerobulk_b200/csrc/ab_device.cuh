@@ -891,19 +891,29 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
             // quirk 1); rolled so that UPDATE_QNSOL_TAU and q_sat exist once in the loop body
             const AirZu air = air_at_zu(u.zu, t_zu, q_zu, p.slp);
 #pragma unroll 1
+            // WL_COARE only touches its state when iwait == 0 (mod_skin_coare.f90:239-248) and has no other output: at
+            // the other iterations the reference computes it for nothing, here it is not called (nor the
+            // UPDATE_QNSOL_TAU that feeds it).  T_s is still re-assembled in the warm-layer order of operations, and
+            // q_s recomputed only if that changed a bit of T_s.
+            const bool commit = (u.nb_iter % jit) == 0;
             for (int pass = CS ? 0 : 1; pass < (WL ? 2 : 1); ++pass) {
-                double Qns, Tau, Qlat;
-                update_qnsol_tau(air, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.rlw, Qns, Tau, Qlat);
+                const double Ts_q = Ts;
                 if (CS && pass == 0) {
+                    double Qns, Tau, Qlat;
+                    update_qnsol_tau(air, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.rlw, Qns, Tau, Qlat);
                     dT_cs = cool_skin_dT<true>(alpha, p.Qsw, Qns, us, Qlat);
                     Ts = p.sst + dT_cs;
                     if (WL) Ts = Ts + wl.dT;
                 } else {
-                    wl_coare(wl, wc, p.Qsw, Qns, Tau, u.rdt, u.gdept, (u.nb_iter % jit) == 0);
+                    if (commit) {
+                        double Qns, Tau, Qlat;
+                        update_qnsol_tau(air, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.rlw, Qns, Tau, Qlat);
+                        wl_coare(wl, wc, p.Qsw, Qns, Tau, u.rdt, u.gdept, true);
+                    }
                     Ts = p.sst + wl.dT;
                     if (CS) Ts = Ts + dT_cs;
                 }
-                qs_ = KC(RDCT_QSAT_SALT) * q_sat(abm::dmax(Ts, 200.), p.slp);
+                if (Ts != Ts_q) qs_ = KC(RDCT_QSAT_SALT) * q_sat(abm::dmax(Ts, 200.), p.slp);
             }
         }
         if (SKIN || !ZTEQ || !V36) {
