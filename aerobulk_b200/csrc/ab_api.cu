@@ -428,6 +428,9 @@ abd::Uniform make_uniform(double zt, double zu)
     u.rdt = g.rdt;
     u.gdept = g.gdept;
     u.nb_iter = g.nb_iter;
+    u.wl_commit_mask = 0ull;
+    for (int jit = 1; jit < 64 && jit <= g.nb_iter; ++jit)
+        if (g.nb_iter % jit == 0) u.wl_commit_mask |= 1ull << jit;
     u.isd = 12;   // aerobulk_compute passes isecday_utc=12 (seconds), mod_aerobulk_compute.f90:136,146
     u.dawn = abd::wl_coare_dawn(0., u.isd) ? 1 : 0;   // longitude fixed to 0, mod_aerobulk_compute.f90:126
     return u;

@@ -444,6 +444,7 @@ struct Uniform {
     double fg_1_o_Ribcu;                               // -0.004*600*1.2**3/zu              :108,:140
     double rdt, gdept;                                 // mod_const.f90:31-32
     int nb_iter;
+    unsigned long long wl_commit_mask;                 // bit jit set iff MOD(nb_iter, jit) == 0, jit < 64 (host-computed)
     int isd;                                           // seconds since 00h UTC (12 in aerobulk_compute)
     int dawn;                                          // WL_COARE dawn reset for longitude 0 (host-computed)
 };
@@ -895,7 +896,9 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
             // the other iterations the reference computes it for nothing, here it is not called (nor the
             // UPDATE_QNSOL_TAU that feeds it).  T_s is still re-assembled in the warm-layer order of operations, and
             // q_s recomputed only if that changed a bit of T_s.
-            const bool commit = (u.nb_iter % jit) == 0;
+            // iwait = MOD(nb_iter, jit) == 0 (mod_blk_coare3p6.f90:370), from a host-computed bit mask: the integer
+            // division cost 1.2 % of the kernel
+            const bool commit = (jit < 64) ? ((u.wl_commit_mask >> jit) & 1ull) != 0ull : (u.nb_iter % jit) == 0;
             for (int pass = CS ? 0 : 1; pass < (WL ? 2 : 1); ++pass) {
                 const double Ts_q = Ts;
                 if (CS && pass == 0) {
