@@ -33,6 +33,9 @@ namespace {
 
 constexpr int MAX_CHUNKS = 12;          // capacity; the number used is chunk_limit() (default 6, measured best)
 constexpr long long MIN_CHUNK_POINTS = 200000;
+#ifndef AEROBULK_GPU_ZEROCOPY_DEFAULT
+#define AEROBULK_GPU_ZEROCOPY_DEFAULT 3
+#endif
 
 // tuning knobs of the host-array pipeline (experiments: tools/diag_e2e.py)
 int chunk_limit()
@@ -65,6 +68,29 @@ int chunk_shape()   // 0: sizes decrease linearly (K..1), 1: equal, 2: small fir
 {
     static int v = [] { const char *e = getenv("AEROBULK_GPU_CHUNK_SHAPE"); return e ? atoi(e) : 0; }();
     return v;
+}
+// Zero-copy host-array calls.  When EVERY array of a call is pinned host memory (cudaHostAlloc / cudaHostRegister: it has a
+// device alias under unified virtual addressing) the flux kernel loads its inputs from and stores its outputs to the
+// caller's arrays directly: each byte crosses PCIe once, both directions busy for the whole launch, no staging, no
+// copy-engine granularity.  Measured 1.54 ms per 1 M-point skin call against 1.75-1.85 ms for the staged pipeline
+// (tools/e2e_probe.py).  AEROBULK_GPU_ZEROCOPY=0 disables it; 1 / 2 select one direction only (experiments: outputs
+// alone 1.77 ms, inputs alone 2.27 ms).  Not used at jt == 1 when AEROBULK_INIT needs the field statistics (the inputs
+// would cross PCIe twice), nor together with the stability sort (a gather / scatter across PCIe: 4.7 ms).
+int zerocopy_mode()
+{
+    static int v = [] { const char *e = getenv("AEROBULK_GPU_ZEROCOPY"); return e ? atoi(e) : AEROBULK_GPU_ZEROCOPY_DEFAULT; }();
+    return v;
+}
+// device alias of a pinned (page-locked, device-mapped) host pointer, or nullptr
+const double *device_alias(const double *p)
+{
+    if (!p) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return (a.type == cudaMemoryTypeHost && a.devicePointer) ? static_cast<const double *>(a.devicePointer) : nullptr;
 }
 long long min_chunk_points()
 {
@@ -502,8 +528,21 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     // is H2D(all) + kernel(last chunk) + D2H(last chunk): chunk sizes DEcrease linearly (weights K..1) to
     // keep the exposed tail short while the early pieces stay large enough for full PCIe efficiency.
     // (Two copy-in streams were measured slower: 2.3 vs 2.0 ms per 1M-point call.)
+    // zero-copy legs (host-array calls whose arrays are ALL pinned): see zerocopy_mode()
+    bool zc_in = false, zc_out = false;
+    const double *in_alias[8] = {};
+    double *out_alias[6] = {};
+    if (!device_ptrs && n > 0 && zerocopy_mode() != 0 && !(jt == 1 && !g.preinit_done)) {
+        zc_in = (zerocopy_mode() & 2) != 0;
+        zc_out = (zerocopy_mode() & 1) != 0;
+        for (int k = 0; k < 8 && zc_in; ++k)
+            if (in_h[k] && !(in_alias[k] = device_alias(in_h[k]))) zc_in = false;
+        for (int k = 0; k < 6 && zc_out; ++k)
+            if (out_h[k] && !(out_alias[k] = const_cast<double *>(device_alias(out_h[k])))) zc_out = false;
+        if (zerocopy_mode() == 3 && !(zc_in && zc_out)) zc_in = zc_out = false;   // all arrays pinned, or the staged pipeline
+    }
     int nchunks = 1;
-    if (!device_ptrs) {
+    if (!device_ptrs && !zc_in) {
         nchunks = (int)(n / min_chunk_points());
         nchunks = nchunks < 1 ? 1 : (nchunks > chunk_limit() ? chunk_limit() : nchunks);
     }
@@ -529,10 +568,12 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         for (int k = 0; k < 8; ++k) in_d[k] = in_h[k];
         for (int k = 0; k < 6; ++k) out_d[k] = out_h[k];
     } else {
-        rc = ensure_staging(n);
-        if (rc) return rc;
-        for (int k = 0; k < 8; ++k) in_d[k] = in_h[k] ? g.d_in[k] : nullptr;
-        for (int k = 0; k < 6; ++k) out_d[k] = out_h[k] ? g.d_out[k] : nullptr;
+        if (!(zc_in && zc_out)) {
+            rc = ensure_staging(n);
+            if (rc) return rc;
+        }
+        for (int k = 0; k < 8; ++k) in_d[k] = in_h[k] ? (zc_in ? in_alias[k] : g.d_in[k]) : nullptr;
+        for (int k = 0; k < 6; ++k) out_d[k] = out_h[k] ? (zc_out ? out_alias[k] : g.d_out[k]) : nullptr;
         if (trace_on()) {
             trace_init();
             cudaEventRecord(tr_t0, g.in_stream);
@@ -540,7 +581,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         // H2D, chunk by chunk, on the copy-in stream
         for (int c = 0; c < nchunks; ++c) {
             const long long s0 = cstart[c], len = cstart[c + 1] - s0;
-            if (len > 0) {
+            if (len > 0 && !zc_in) {
                 rc = copy_fields(8, g.d_in, const_cast<double *const *>(in_h), g.cap, s0, len, true, g.in_stream);
                 if (rc) return rc;
             }
@@ -602,7 +643,8 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     // and for the skin kernels (instruction-cache bound: homogeneous blocks run different code regions)
     // auto policy = where it measured faster (tools/kbench.py, KBENCH_SORT=0/2): not NCAR (+10 %), not ECMWF + skin (+1 %);
     // COARE + skin: -7 % at night, neutral by day
-    const bool do_sort = g.sort_points == 2 || (g.sort_points == 1 && ialgo != abd::NCAR && !(use_skin && ialgo == abd::ECMWF));
+    // (never with zero-copy inputs: the gather through the permutation would cross PCIe at sector granularity)
+    const bool do_sort = !zc_in && !zc_out && (g.sort_points == 2 || (g.sort_points == 1 && ialgo != abd::NCAR && !(use_skin && ialgo == abd::ECMWF)));
     if (do_sort) {
         // every chunk is padded to whole sort windows
         const long long need = n + (long long)(nchunks + 1) * abk::sort_window();
@@ -658,8 +700,10 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
             CUDA_TRY(cudaEventRecord(g.ev_k[c], cs));
             if (trace_on()) cudaEventRecord(tr_k[c], cs);
             CUDA_TRY(cudaStreamWaitEvent(g.out_stream, g.ev_k[c], 0));
-            rc = copy_fields(6, g.d_out, out_h, g.cap, s0, len, false, g.out_stream);
-            if (rc) return rc;
+            if (!zc_out) {
+                rc = copy_fields(6, g.d_out, out_h, g.cap, s0, len, false, g.out_stream);
+                if (rc) return rc;
+            }
             if (trace_on()) cudaEventRecord(tr_out[c], g.out_stream);
         }
     }

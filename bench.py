@@ -348,7 +348,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                    "sharding": "latitude row blocks, one rank per GPU, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "grid points/s", "h2d_bytes_per_step": 8 * 8 * n * NT,
                 "d2h_bytes_per_step": 6 * 8 * n * NT,
-                "how": "aerobulk_gpu_model (host-array C ABI) with pinned host buffers (inputs in one slab, outputs in another: one pitched copy per chunk and slab), chunked H2D|kernel|D2H pipeline"},
+                "how": "aerobulk_gpu_model (host-array C ABI) with pinned host buffers: the kernel loads its inputs from and stores its outputs to them directly over PCIe (zero-copy, every byte crosses once per call); jt=1 of each session goes through the staged chunked H2D|kernel|D2H pipeline"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "diagnostics": diagnostics,

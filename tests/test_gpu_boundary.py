@@ -323,3 +323,48 @@ def test_flux_diagnostics_match_numpy_and_combine_like_one_domain(ab):
     d = ab.flux_diagnostics(t)
     assert d[1] == pytest.approx(r["QL"].sum(), rel=1e-12) and d[4] == 0.0 and d[5] > 1e300 and d[6] < -1e300
     assert "QH" not in ab.diagnostics_summary(d)
+
+
+def test_pinned_arrays_take_the_zero_copy_path_and_agree(ab):
+    """When every array of a host-array call is pinned, the kernel reads / writes the caller's arrays directly (zero-copy,
+    no stability sort); pageable arrays go through the staged pipeline.  Bit-identical over a state-carrying session."""
+    import torch
+    Ni, Nj, Nt = 512, 300, 4
+    n = Ni * Nj
+    f = synth.fields(Ni, Nj)
+    keys = ("sst", "t_zt", "hum_zt", "U_zu", "V_zu", "slp", "rad_lw", "rad_sw")
+    names = ("QL", "QH", "Tau_x", "Tau_y", "Evap", "T_s")
+
+    def run(pinned):
+        src, out = {}, {}
+        hold = []
+        for k in keys:
+            t = torch.empty(n, dtype=torch.float64)
+            t = t.pin_memory() if pinned else t
+            t.numpy()[:] = np.ravel(f[k], order="F")
+            hold.append(t)
+            src[k] = t.numpy().reshape((Ni, Nj), order="F")
+        for k in names:
+            t = torch.zeros(n, dtype=torch.float64)
+            t = t.pin_memory() if pinned else t
+            hold.append(t)
+            out[k] = t.numpy().reshape((Ni, Nj), order="F")
+        ab.reset()
+        res, launches = [], []
+        for jt in range(1, Nt + 1):
+            ab.lib().aerobulk_gpu_reset_launch_count()
+            ab.aerobulk_model(jt, Nt, "coare3p6", 2.0, 10.0, *[src[k] for k in keys[:6]], Niter=5, l_use_skin=True,
+                              rad_sw=src["rad_sw"], rad_lw=src["rad_lw"], out=out)
+            res.append({k: out[k].copy() for k in names})
+            launches.append(ab.launch_count())
+        return res, launches
+
+    a, la = run(False)
+    b, lb = run(True)
+    for jt in range(Nt):
+        for k in names:
+            assert np.array_equal(a[jt][k], b[jt][k]), (jt, k)
+    # pageable: classify + flux per call (+ the two statistics kernels at jt == 1); pinned: jt == 1 is staged as well
+    # (AEROBULK_INIT needs the statistics), afterwards ONE flux launch per call and no classify
+    assert la[1:] == [2] * (Nt - 1) and lb[1:] == [1] * (Nt - 1) and la[0] == lb[0] == 4
+    ab.reset()

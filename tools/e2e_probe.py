@@ -29,6 +29,8 @@ else:
 np_in = {k: v.numpy().reshape((NI, NJ), order="F") for k, v in host.items()}
 np_out = {k: v.numpy().reshape((NI, NJ), order="F") for k, v in hout.items()}
 ab.reset(); ab.set_verbose(False)
+if os.environ.get("E2E_SORT"):
+    ab.set_sort(int(os.environ["E2E_SORT"]))
 best = []
 for s in range(4):
     ts = []
@@ -38,4 +40,6 @@ for s in range(4):
                           rad_sw=np_in["rad_sw"], rad_lw=np_in["rad_lw"], out=np_out)
         ts.append((time.perf_counter() - t0) * 1e3)
     best.append(np.median(ts[2:-1]))
+    if os.environ.get("E2E_SORT"):
+        ab.set_sort(int(os.environ["E2E_SORT"]))
 print(f"slab={os.environ.get('E2E_SLAB','1')} chunks={os.environ.get('AEROBULK_GPU_MAX_CHUNKS','6')} minpts={os.environ.get('AEROBULK_GPU_MIN_CHUNK_POINTS','200000')}: median per call {min(best):.3f} ms  ({n / min(best) / 1e3:.0f} Mpt/s)")
