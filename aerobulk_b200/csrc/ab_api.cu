@@ -92,6 +92,16 @@ const double *device_alias(const double *p)
     }
     return (a.type == cudaMemoryTypeHost && a.devicePointer) ? static_cast<const double *>(a.devicePointer) : nullptr;
 }
+// aliases of n host pointers (NULL entries stay NULL); false unless every non-NULL one is pinned
+bool alias_all(int n, const double *const *h, const double **d)
+{
+    if (zerocopy_mode() != 3) return false;
+    for (int k = 0; k < n; ++k) {
+        d[k] = nullptr;
+        if (h[k] && !(d[k] = device_alias(h[k]))) return false;
+    }
+    return true;
+}
 long long min_chunk_points()
 {
     static long long v = [] {
@@ -1464,6 +1474,18 @@ int aerobulk_gpu_series(const char *calgo, int Nt, long long S, double zt, doubl
                         int l_use_skin, const aerobulk_gpu_series_out *out, int on_device)
 {
     std::lock_guard<std::mutex> lk(g_mu);
+    if (!on_device && out && lon && sst && t_zt && hum_zt && wind && slp && rad_sw && rad_lw && ensure_device() == 0) {
+        // every array pinned: the kernel works on the caller's memory directly (zero-copy, see zerocopy_mode)
+        const double *h[8 + AEROBULK_GPU_SERIES_NOUT] = {lon, sst, t_zt, hum_zt, wind, slp, rad_sw, rad_lw};
+        memcpy(h + 8, out, sizeof(double *) * AEROBULK_GPU_SERIES_NOUT);
+        const double *d[8 + AEROBULK_GPU_SERIES_NOUT];
+        if (alias_all(8 + AEROBULK_GPU_SERIES_NOUT, h, d)) {
+            aerobulk_gpu_series_out od;
+            memcpy(&od, d + 8, sizeof(od));
+            return series_impl(calgo, Nt, S, zt, zu, isecday_utc, d[0], d[1], d[2], d[3], hum_kind, d[4], d[5], d[6], d[7],
+                               l_use_skin, &od, 1);
+        }
+    }
     return series_impl(calgo, Nt, S, zt, zu, isecday_utc, lon, sst, t_zt, hum_zt, hum_kind, wind, slp, rad_sw, rad_lw,
                        l_use_skin, out, on_device);
 }
@@ -1491,6 +1513,18 @@ int aerobulk_gpu_oce_ice(const char *calgo_ice, const char *calgo_oce, double zt
                          const aerobulk_gpu_oce_ice_out *out, int on_device)
 {
     std::lock_guard<std::mutex> lk(g_mu);
+    if (!on_device && out && sit && t_zt && hum_zt && wind && slp && frice && ensure_device() == 0) {
+        const double *h[7 + 35] = {sit, sst, t_zt, hum_zt, wind, slp, frice};
+        static_assert(sizeof(aerobulk_gpu_oce_ice_out) == 35 * sizeof(double *), "35 output pointers");
+        memcpy(h + 7, out, sizeof(aerobulk_gpu_oce_ice_out));
+        const double *d[7 + 35];
+        if (alias_all(7 + 35, h, d)) {
+            aerobulk_gpu_oce_ice_out od;
+            memcpy(&od, d + 7, sizeof(od));
+            return oce_ice_impl(calgo_ice, calgo_oce, zt, zu, n, d[0], d[1], d[2], d[3], hum_kind, d[4], d[5], d[6], CxN_easy,
+                                &od, 1);
+        }
+    }
     return oce_ice_impl(calgo_ice, calgo_oce, zt, zu, n, sit, sst, t_zt, hum_zt, hum_kind, wind, slp, frice, CxN_easy, out,
                         on_device);
 }

@@ -7,8 +7,8 @@
 // The time recursion of the warm layer is sequential per station, so the parallelism is across stations only; the
 // warm-layer state never leaves the registers between records and there is one launch for the whole series instead
 // of Nt.  Small blocks (64 threads) spread few stations over many SMs; 8 blocks per SM (16 warps, <= 128 registers)
-// measured best over 64x1 / 64x8 / 64x12 / 128x6 both for one station (latency: 110 us per record at nb_iter = 20) and
-// for 300 k stations (3.0e8 station-records/s device-resident), profiles/series_bench_r01.txt.
+// measured best over 64x1 / 64x8 / 64x12 / 128x6 both for one station (latency: 60 us per record at nb_iter = 20) and
+// for 300 k stations, profiles/series_bench_r01i.txt.
 #include "ab_kernels.cuh"
 
 namespace abk {

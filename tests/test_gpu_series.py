@@ -207,3 +207,39 @@ def test_series_cli(ab, tmp_path):
                        cwd=root, capture_output=True, text=True)
     assert r.returncode == 1 and "cannot open" in r.stderr
     ab.reset()
+
+
+def test_series_and_ice_with_pinned_arrays_zero_copy(ab):
+    """Pinned host arrays: the series / ice kernels work on the caller's memory directly; same bits as pageable arrays."""
+    import ctypes as C
+    import torch
+    Nt, S = 24, 300
+    d = synth.station_series(Nt, S)
+    ab.reset()
+    ab.set_nb_iter(6)
+    ref = ab.series("coare3p6", 2.0, 10.0, **d)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory()
+    keep = {k: pin(v) for k, v in d.items() if k != "isecday_utc"}
+    outs = {k: torch.zeros((Nt, S), dtype=torch.float64).pin_memory() for k in ab.SERIES_OUT}
+    arr = (C.c_void_p * len(ab.SERIES_OUT))(*[outs[k].data_ptr() for k in ab.SERIES_OUT])
+    isd = np.ascontiguousarray(d["isecday_utc"], dtype=np.int32)
+    ab.lib().aerobulk_gpu_reset_launch_count()
+    rc = ab.lib().aerobulk_gpu_series(b"coare3p6", Nt, S, 2.0, 10.0, isd.ctypes.data, keep["lon"].data_ptr(),
+                                      keep["sst"].data_ptr(), keep["t_zt"].data_ptr(), keep["hum_zt"].data_ptr(), 0,
+                                      keep["wind"].data_ptr(), keep["slp"].data_ptr(), keep["rad_sw"].data_ptr(),
+                                      keep["rad_lw"].data_ptr(), 1, C.cast(arr, C.c_void_p), 0)
+    assert rc == 0, ab.last_error()
+    for k in ab.SERIES_OUT:
+        assert np.array_equal(outs[k].numpy(), ref[k]), k
+    f = synth.ice_fields(5000)
+    refi = ab.oce_ice("lg15", "ecmwf", 2.0, 10.0, **f)
+    fk = {k: pin(v) for k, v in f.items()}
+    oi = {k: torch.zeros(5000, dtype=torch.float64).pin_memory() for k in ab.OCE_ICE_OUT}
+    arr2 = (C.c_void_p * len(ab.OCE_ICE_OUT))(*[oi[k].data_ptr() for k in ab.OCE_ICE_OUT])
+    rc = ab.lib().aerobulk_gpu_oce_ice(b"lg15", b"ecmwf", 2.0, 10.0, 5000, fk["sit"].data_ptr(), fk["sst"].data_ptr(),
+                                       fk["t_zt"].data_ptr(), fk["hum_zt"].data_ptr(), 0, fk["wind"].data_ptr(),
+                                       fk["slp"].data_ptr(), fk["frice"].data_ptr(), None, C.cast(arr2, C.c_void_p), 0)
+    assert rc == 0, ab.last_error()
+    for k in ab.OCE_ICE_OUT:
+        assert np.array_equal(oi[k].numpy(), refi[k]), k
+    ab.reset()
