@@ -891,7 +891,6 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
             // pass 0: cool skin, pass 1: warm layer (state committed whenever jit divides nb_iter, SURVEY 8a
             // quirk 1); rolled so that UPDATE_QNSOL_TAU and q_sat exist once in the loop body
             const AirZu air = air_at_zu(u.zu, t_zu, q_zu, p.slp);
-#pragma unroll 1
             // WL_COARE only touches its state when iwait == 0 (mod_skin_coare.f90:239-248) and has no other output: at
             // the other iterations the reference computes it for nothing, here it is not called (nor the
             // UPDATE_QNSOL_TAU that feeds it).  T_s is still re-assembled in the warm-layer order of operations, and
@@ -899,6 +898,7 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
             // iwait = MOD(nb_iter, jit) == 0 (mod_blk_coare3p6.f90:370), from a host-computed bit mask: the integer
             // division cost 1.2 % of the kernel
             const bool commit = (jit < 64) ? ((u.wl_commit_mask >> jit) & 1ull) != 0ull : (u.nb_iter % jit) == 0;
+#pragma unroll 1
             for (int pass = CS ? 0 : 1; pass < (WL ? 2 : 1); ++pass) {
                 const double Ts_q = Ts;
                 if (CS && pass == 0) {
