@@ -1464,6 +1464,25 @@ int aerobulk_gpu_turb(const char *calgo, int kt, double zt, double zu, int Ni, i
                       const aerobulk_gpu_turb_optional *opt, int on_device)
 {
     std::lock_guard<std::mutex> lk(g_mu);
+    if (!on_device && T_s && q_s && ensure_device() == 0) {
+        // every array pinned: zero-copy (see zerocopy_mode); the device-pointer path is asynchronous, hence the wait
+        const double *h[25] = {T_s, q_s, t_zt, q_zt, U_zu, Qsw, rad_lw, slp, plong, Cd, Ch, Ce, t_zu, q_zu, Ubzu};
+        static_assert(sizeof(aerobulk_gpu_turb_optional) == 10 * sizeof(double *), "10 optional outputs");
+        if (opt) memcpy(h + 15, opt, sizeof(*opt));
+        else memset(h + 15, 0, 10 * sizeof(double *));
+        const double *d[25];
+        if (alias_all(25, h, d)) {
+            aerobulk_gpu_turb_optional od;
+            memcpy(&od, d + 15, sizeof(od));
+            auto w = [](const double *p) { return const_cast<double *>(p); };
+            const int rc = turb_impl(calgo, kt, zt, zu, Ni, Nj, w(d[0]), d[2], w(d[1]), d[3], d[4], l_use_cs, l_use_wl, w(d[9]),
+                                     w(d[10]), w(d[11]), w(d[12]), w(d[13]), w(d[14]), d[5], d[6], d[7], isecday_utc, d[8],
+                                     opt ? &od : nullptr, 1);
+            if (rc) return rc;
+            CUDA_TRY(cudaStreamSynchronize(compute_stream()));
+            return 0;
+        }
+    }
     return turb_impl(calgo, kt, zt, zu, Ni, Nj, T_s, t_zt, q_s, q_zt, U_zu, l_use_cs, l_use_wl, Cd, Ch, Ce, t_zu, q_zu,
                      Ubzu, Qsw, rad_lw, slp, isecday_utc, plong, opt, on_device);
 }
@@ -1503,6 +1522,20 @@ int aerobulk_gpu_turb_ice(const char *calgo, double zt, double zu, int Ni, int N
                           double *Ubzu, const aerobulk_gpu_turb_ice_optional *opt, int on_device)
 {
     std::lock_guard<std::mutex> lk(g_mu);
+    if (!on_device && Ts_i && ensure_device() == 0) {
+        const double *h[20] = {Ts_i, t_zt, qs_i, q_zt, U_zu, frice, Cd, Ch, Ce, t_zu, q_zu, Ubzu};
+        static_assert(sizeof(aerobulk_gpu_turb_ice_optional) == 8 * sizeof(double *), "8 optional outputs");
+        if (opt) memcpy(h + 12, opt, sizeof(*opt));
+        else memset(h + 12, 0, 8 * sizeof(double *));
+        const double *d[20];
+        if (alias_all(20, h, d)) {
+            aerobulk_gpu_turb_ice_optional od;
+            memcpy(&od, d + 12, sizeof(od));
+            auto w = [](const double *p) { return const_cast<double *>(p); };
+            return turb_ice_impl(calgo, zt, zu, Ni, Nj, d[0], d[1], d[2], d[3], d[4], d[5], CxN_easy, w(d[6]), w(d[7]), w(d[8]),
+                                 w(d[9]), w(d[10]), w(d[11]), opt ? &od : nullptr, 1);
+        }
+    }
     return turb_ice_impl(calgo, zt, zu, Ni, Nj, Ts_i, t_zt, qs_i, q_zt, U_zu, frice, CxN_easy, Cd, Ch, Ce, t_zu, q_zu, Ubzu,
                          opt, on_device);
 }

@@ -110,3 +110,36 @@ def test_turb_argument_errors(ab):
         ab.turb("coare3p6", 2, 2.0, 10.0, f["sst"], theta, ssq, f["hum_zt"], wnd, l_use_wl=True, Qsw=f["rad_sw"], rad_lw=f["rad_lw"], slp=f["slp"], plong=lon)
     assert e.value.code == 9
     ab.reset()
+
+
+def test_turb_and_turb_ice_with_pinned_arrays_zero_copy(ab):
+    """Pinned arrays: aerobulk_gpu_turb / aerobulk_gpu_turb_ice work on the caller's memory directly; same bits."""
+    import ctypes as C
+    import torch
+    Ni, Nj = 160, 90
+    n = Ni * Nj
+    f, ssq, theta, wnd, lon = _inputs(Ni, Nj)
+    ab.reset()
+    ab.set_nb_iter(6)
+    ab.set_nitend(1)
+    ref = ab.turb("coare3p6", 1, 2.0, 10.0, f["sst"], theta, ssq, f["hum_zt"], wnd, l_use_cs=True, l_use_wl=True,
+                  Qsw=0.934 * f["rad_sw"], rad_lw=f["rad_lw"], slp=f["slp"], isecday_utc=43200, plong=lon, want=("xu_star", "pdT_cs"))
+    pin = lambda a: torch.from_numpy(np.ravel(a, order="F").copy()).pin_memory()
+    t = {k: pin(v) for k, v in dict(Ts=f["sst"], qs=ssq, th=theta, q=f["hum_zt"], w=wnd, Qsw=0.934 * f["rad_sw"],
+                                     rlw=f["rad_lw"], slp=f["slp"], lon=lon).items()}
+    o = {k: torch.zeros(n, dtype=torch.float64).pin_memory() for k in ("Cd", "Ch", "Ce", "t_zu", "q_zu", "Ubzu", "us", "dTcs")}
+    opt = (C.c_void_p * 10)(None, None, None, None, o["us"].data_ptr(), None, None, o["dTcs"].data_ptr(), None, None)
+    ab.reset()
+    ab.set_nb_iter(6)
+    ab.set_nitend(1)
+    p = lambda x: x.data_ptr()
+    rc = ab.lib().aerobulk_gpu_turb(b"coare3p6", 1, 2.0, 10.0, Ni, Nj, p(t["Ts"]), p(t["th"]), p(t["qs"]), p(t["q"]), p(t["w"]),
+                                    1, 1, p(o["Cd"]), p(o["Ch"]), p(o["Ce"]), p(o["t_zu"]), p(o["q_zu"]), p(o["Ubzu"]),
+                                    p(t["Qsw"]), p(t["rlw"]), p(t["slp"]), 43200, p(t["lon"]), C.cast(opt, C.c_void_p), 0)
+    assert rc == 0, ab.last_error()
+    flat = lambda a: np.ravel(a, order="F")
+    for k, r in (("Cd", "Cd"), ("Ch", "Ch"), ("Ce", "Ce"), ("t_zu", "t_zu"), ("q_zu", "q_zu"), ("Ubzu", "Ubzu"),
+                 ("us", "xu_star"), ("dTcs", "pdT_cs")):
+        assert np.array_equal(o[k].numpy(), flat(ref[r])), k
+    assert np.array_equal(t["Ts"].numpy(), flat(ref["T_s"])) and np.array_equal(t["qs"].numpy(), flat(ref["q_s"]))
+    ab.reset()
