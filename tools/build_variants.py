@@ -8,6 +8,8 @@ VARIANTS = {
     "b128x7": ["AB_FLUX_BLOCK=128", "AB_MIN_BLOCKS=7"],
     "b128x8": ["AB_FLUX_BLOCK=128", "AB_MIN_BLOCKS=8"],
     "b256x4": ["AB_FLUX_BLOCK=256", "AB_MIN_BLOCKS=4"],
+    "b256x2": ["AB_FLUX_BLOCK=256", "AB_MIN_BLOCKS=2"],
+    "b128x5": ["AB_FLUX_BLOCK=128", "AB_MIN_BLOCKS=5"],
     "ser64x1": ["AB_SERIES_MIN_BLOCKS=1"],
     "ser64x8": ["AB_SERIES_MIN_BLOCKS=8"],
     "ser128x6": ["AB_SERIES_BLOCK=128", "AB_SERIES_MIN_BLOCKS=6"],
