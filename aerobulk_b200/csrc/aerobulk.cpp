@@ -1,74 +1,86 @@
-// aerobulk.cpp -- C++ API `aerobulk::model` on top of the C ABI of libaerobulk_gpu.so.
-// Behaviour follows the reference's src/aerobulk.cpp:22-138 (enum -> string, equal-size
-// assertion, outputs resized to the input length, scalars passed by address), with the
-// two latent ABI bugs of the original closed: sizes are narrowed to int before the
-// varargs call, and the skin flag crosses the boundary as one byte.
+// aerobulk.cpp -- the C++ API `aerobulk::model` of include/aerobulk.hpp on top of the C ABI of libaerobulk_gpu.so.
+//
+// What a caller of the reference's src/aerobulk.cpp:22-138 relies on is kept: the enumerator -> name mapping, the
+// equal-length assertion on the inputs, outputs resized to that length, the grid seen as (m, 1).  The fields go
+// straight to aerobulk_gpu_model (no detour through the Fortran-style by-address bridge, whose two latent ABI slips --
+// size_t read as int through varargs, a C++ bool read as a 4-byte LOGICAL -- therefore cannot occur here).
 #pragma GCC visibility push(default)
 #include "../../include/aerobulk.hpp"
 #include "../../include/aerobulk_gpu.h"
 #pragma GCC visibility pop
 
+#include <initializer_list>
+
 namespace aerobulk
 {
 
+namespace
+{
+const char *const kAlgorithmNames[] = {"other", "coare3p0", "coare3p6", "ncar", "ecmwf", "andreas"};
+
+// common length of the input fields (asserted), as an int for the C ABI
+int common_length(std::initializer_list<const field *> inputs)
+{
+    const std::size_t m = (*inputs.begin())->size();
+    for (const field *f : inputs) {
+        assert(f->size() == m && "aerobulk::model: input fields differ in length");
+        (void)f;
+    }
+    return static_cast<int>(m);
+}
+
+void run(int jt, int Nt, algorithm algo, double zt, double zu, int m, const field &sst, const field &t_zt,
+         const field &hum_zt, const field &U_zu, const field &V_zu, const field &slp, field &QL, field &QH, field &Tau_x,
+         field &Tau_y, field &Evap, int Niter, const int *l_use_skin, const field *rad_sw, const field *rad_lw, field *T_s)
+{
+    for (field *out : {&QL, &QH, &Tau_x, &Tau_y, &Evap}) out->resize(m);
+    if (T_s) T_s->resize(m);
+    // errors follow the library's mode: fail-stop by default, like the reference's STOP
+    aerobulk_gpu_model(jt, Nt, algorithm_to_string(algo).c_str(), zt, zu, m, 1, sst.data(), t_zt.data(), hum_zt.data(),
+                       U_zu.data(), V_zu.data(), slp.data(), QL.data(), QH.data(), Tau_x.data(), Tau_y.data(), Evap.data(),
+                       &Niter, l_use_skin, rad_sw ? rad_sw->data() : nullptr, rad_lw ? rad_lw->data() : nullptr,
+                       T_s ? T_s->data() : nullptr);
+}
+}  // namespace
+
 std::string algorithm_to_string(algorithm algo)
 {
-    switch (algo) {
-    case algorithm::OTHER:    return "other";
-    case algorithm::COARE3p0: return "coare3p0";
-    case algorithm::COARE3p6: return "coare3p6";
-    case algorithm::NCAR:     return "ncar";
-    case algorithm::ECMWF:    return "ecmwf";
-    case algorithm::ANDREAS:  return "andreas";
-    }
-    return "unknown";
+    const int k = static_cast<int>(algo);
+    return (k >= 0 && k < 6) ? kAlgorithmNames[k] : "unknown";
 }
 
 int check_sizes(int count, ...)
 {
-    va_list ap;
-    va_start(ap, count);
-    const int first = va_arg(ap, int);
-    for (int i = 1; i < count; ++i) {
-        const int other = va_arg(ap, int);
-        assert(first == other);
-        (void)other;
+    va_list sizes;
+    va_start(sizes, count);
+    int common = 0;
+    for (int i = 0; i < count; ++i) {
+        const int s = va_arg(sizes, int);
+        if (i == 0) common = s;
+        assert(s == common);
     }
-    va_end(ap);
-    return first;
+    va_end(sizes);
+    return common;
 }
 
-static inline int isz(const std::vector<double> &v) { return static_cast<int>(v.size()); }
-
-void model(const int jt, const int Nt, algorithm algo, double zt, double zu,
-           const std::vector<double> &sst, const std::vector<double> &t_zt, const std::vector<double> &hum_zt,
-           const std::vector<double> &U_zu, const std::vector<double> &V_zu, const std::vector<double> &slp,
-           std::vector<double> &QL, std::vector<double> &QH, std::vector<double> &Tau_x, std::vector<double> &Tau_y,
-           std::vector<double> &Evap, const int Niter, const bool l_use_skin,
-           const std::vector<double> &rad_sw, const std::vector<double> &rad_lw, std::vector<double> &T_s)
+void model(const int jt, const int Nt, algorithm algo, double zt, double zu, const field &sst, const field &t_zt,
+           const field &hum_zt, const field &U_zu, const field &V_zu, const field &slp, field &QL, field &QH, field &Tau_x,
+           field &Tau_y, field &Evap, const int Niter, const bool l_use_skin, const field &rad_sw, const field &rad_lw,
+           field &T_s)
 {
-    const std::string calgo = algorithm_to_string(algo);
-    const int l = static_cast<int>(calgo.size());
-    const int m = check_sizes(8, isz(sst), isz(t_zt), isz(hum_zt), isz(U_zu), isz(V_zu), isz(slp), isz(rad_sw), isz(rad_lw));
-    for (std::vector<double> *out : {&QL, &QH, &Tau_x, &Tau_y, &Evap, &T_s}) out->resize(m);
-    aerobulk_cxx_skin(&jt, &Nt, calgo.c_str(), &zt, &zu, sst.data(), t_zt.data(), hum_zt.data(), U_zu.data(),
-                      V_zu.data(), slp.data(), QL.data(), QH.data(), Tau_x.data(), Tau_y.data(), Evap.data(),
-                      &Niter, &l_use_skin, rad_sw.data(), rad_lw.data(), T_s.data(), &l, &m);
+    const int m = common_length({&sst, &t_zt, &hum_zt, &U_zu, &V_zu, &slp, &rad_sw, &rad_lw});
+    const int skin = l_use_skin ? 1 : 0;
+    run(jt, Nt, algo, zt, zu, m, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y, Evap, Niter, &skin, &rad_sw,
+        &rad_lw, &T_s);
 }
 
-void model(const int jt, const int Nt, algorithm algo, double zt, double zu,
-           const std::vector<double> &sst, const std::vector<double> &t_zt, const std::vector<double> &hum_zt,
-           const std::vector<double> &U_zu, const std::vector<double> &V_zu, const std::vector<double> &slp,
-           std::vector<double> &QL, std::vector<double> &QH, std::vector<double> &Tau_x, std::vector<double> &Tau_y,
-           std::vector<double> &Evap, const int Niter)
+void model(const int jt, const int Nt, algorithm algo, double zt, double zu, const field &sst, const field &t_zt,
+           const field &hum_zt, const field &U_zu, const field &V_zu, const field &slp, field &QL, field &QH, field &Tau_x,
+           field &Tau_y, field &Evap, const int Niter)
 {
-    const std::string calgo = algorithm_to_string(algo);
-    const int l = static_cast<int>(calgo.size());
-    const int m = check_sizes(6, isz(sst), isz(t_zt), isz(hum_zt), isz(U_zu), isz(V_zu), isz(slp));
-    for (std::vector<double> *out : {&QL, &QH, &Tau_x, &Tau_y, &Evap}) out->resize(m);
-    aerobulk_cxx_no_skin(&jt, &Nt, calgo.c_str(), &zt, &zu, sst.data(), t_zt.data(), hum_zt.data(), U_zu.data(),
-                         V_zu.data(), slp.data(), QL.data(), QH.data(), Tau_x.data(), Tau_y.data(), Evap.data(),
-                         &Niter, &l, &m);
+    const int m = common_length({&sst, &t_zt, &hum_zt, &U_zu, &V_zu, &slp});
+    run(jt, Nt, algo, zt, zu, m, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y, Evap, Niter, nullptr, nullptr,
+        nullptr, nullptr);
 }
 
 }  // namespace aerobulk
