@@ -168,3 +168,22 @@ def test_readme_toy_table_coarse(golden_dir):
         assert r["QL"][0] == pytest.approx(t["rows"]["QL"][i], rel=3e-3)
         assert r["QH"][0] == pytest.approx(t["rows"]["QH"][i], rel=3e-3)
         assert 1e3 * r["Tau_x"][0] == pytest.approx(t["rows"]["Wind stress"][i], rel=3e-3)
+
+
+def test_oracle_regression_fixtures():
+    """The oracle still produces the numbers frozen in tests/golden/oracle_regression.json for the paths without a
+    reference fixture (sea ice, station series, TURB_* optional outputs).  Oracle-generated values: they guard against
+    accidental edits of oracle/, they do not pin parity with the reference."""
+    import importlib.util
+    import json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_regression", os.path.join(here, "make_regression.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(here, "oracle_regression.json")))["cases"]
+    got = mod.cases()
+    assert set(got) == set(want)
+    for name, vals in want.items():
+        for k, v in vals.items():
+            a, b = np.atleast_1d(np.array(got[name][k], dtype=float)), np.atleast_1d(np.array(v, dtype=float))
+            assert np.allclose(a, b, rtol=1e-13, atol=1e-300, equal_nan=True), (name, k, a, b)
