@@ -117,3 +117,11 @@ def test_fast_roots(abm):
     assert (abm(13, z) == 0).all() and (abm(14, z) == 0).all()     # documented flush below 1e-30
     assert (abm(15, np.array([0.0, 1e-300])) == 0).all()
     assert _relerr(abm(6, x), x, lambda v: 1 / v) <= 2 * ULP       # 3-instruction reciprocal refinement
+
+
+def test_generated_tables_are_up_to_date():
+    """aerobulk_b200/csrc/ab_math_tables.cuh is exactly what tools/gen_math_tables.py generates (mpmath, 50 digits)."""
+    import sys
+    root = os.path.dirname(HERE)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_math_tables.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
