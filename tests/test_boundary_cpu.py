@@ -76,6 +76,18 @@ def test_compute_fails_loudly_without_device(ab):
     with pytest.raises(ab.AerobulkError) as e:
         ab.aerobulk_model(1, 1, "ncar", 2.0, 10.0, x, x, x * 0 + 0.01, x * 0 + 5, x * 0, x * 0 + 101000.0)
     assert e.value.code == 100 and "no CPU fallback" in e.value.message
+    # every compute entry point, not only aerobulk_model
+    from aerobulk_b200 import synth
+    d = synth.station_series(3, 2)
+    one = np.ones(3)
+    for call in (lambda: ab.series("ncar", 2.0, 10.0, **d),
+                 lambda: ab.oce_ice("nemo", None, 2.0, 10.0, **synth.ice_fields(4)),
+                 lambda: ab.turb_ice("nemo", 2.0, 10.0, one * 270, one * 271, one * 1e-3, one * 1e-3, one * 3),
+                 lambda: ab.turb("ncar", 1, 2.0, 10.0, one * 290, one * 289, one * 1e-2, one * 8e-3, one * 5),
+                 lambda: ab.flux_diagnostics({"QL": one})):
+        with pytest.raises(ab.AerobulkError) as e:
+            call()
+        assert e.value.code == 100
     # argument errors are detected before any device work
     with pytest.raises(ab.AerobulkError) as e:
         ab.aerobulk_model(0, 1, "ncar", 2.0, 10.0, x, x, x, x, x, x)
