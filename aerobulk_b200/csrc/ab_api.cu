@@ -1574,6 +1574,40 @@ int aerobulk_gpu_flux_diagnostics(long long n, const double *QL, const double *Q
 
 int aerobulk_gpu_diag_reduce_op(int i) { return (i <= 0 || i >= abk::NDIAG) ? 0 : (i - 1) % 3; }
 
+int aerobulk_gpu_host_register(void *ptr, size_t bytes)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!ptr || bytes == 0) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_host_register: NULL pointer or empty range");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) {
+        cudaGetLastError();   // not sticky: the session stays usable
+        return fail(AEROBULK_GPU_ERR_CUDA, "aerobulk_gpu_host_register: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+int aerobulk_gpu_host_unregister(void *ptr)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!ptr) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_host_unregister: NULL pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaSetDevice(g.device);
+    cudaDeviceSynchronize();   // nothing in flight may still touch the range
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(AEROBULK_GPU_ERR_CUDA, "aerobulk_gpu_host_unregister: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
 void aerobulk_gpu_set_nitend(int nitend) { std::lock_guard<std::mutex> lk(g_mu); g.nitend = nitend; }
 
 int aerobulk_gpu_synchronize(void)

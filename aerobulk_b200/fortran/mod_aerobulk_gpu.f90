@@ -23,7 +23,7 @@ MODULE mod_aerobulk_gpu
       &      aerobulk_gpu_set_rdt, aerobulk_gpu_set_gdept, aerobulk_gpu_set_nb_iter, &
       &      aerobulk_gpu_get_nb_iter, aerobulk_gpu_get_use_skin,                 &
       &      aerobulk_gpu_set_device, aerobulk_gpu_set_verbose, aerobulk_gpu_reset,  &
-      &      aerobulk_gpu_get_state, aerobulk_gpu_set_state
+      &      aerobulk_gpu_get_state, aerobulk_gpu_set_state, aerobulk_gpu_host_register, aerobulk_gpu_host_unregister
 
    !! optional outputs of the TURB_* routines (struct aerobulk_gpu_turb_optional); C_NULL_PTR = not wanted
    TYPE, BIND(C) :: aerobulk_gpu_turb_optional
@@ -169,6 +169,19 @@ MODULE mod_aerobulk_gpu
          IMPORT :: c_int
          INTEGER(c_int), VALUE :: on
       END SUBROUTINE aerobulk_gpu_set_ice_form_drag_per_point
+
+      !! page-lock / release an existing array: ierr = aerobulk_gpu_host_register( C_LOC(sst), INT(8*SIZE(sst), c_size_t) )
+      FUNCTION aerobulk_gpu_host_register( ptr, nbytes ) BIND(C, NAME='aerobulk_gpu_host_register') RESULT(ierr)
+         IMPORT :: c_int, c_ptr, c_size_t
+         TYPE(c_ptr),       VALUE :: ptr
+         INTEGER(c_size_t), VALUE :: nbytes
+         INTEGER(c_int)           :: ierr
+      END FUNCTION aerobulk_gpu_host_register
+      FUNCTION aerobulk_gpu_host_unregister( ptr ) BIND(C, NAME='aerobulk_gpu_host_unregister') RESULT(ierr)
+         IMPORT :: c_int, c_ptr
+         TYPE(c_ptr), VALUE :: ptr
+         INTEGER(c_int)     :: ierr
+      END FUNCTION aerobulk_gpu_host_unregister
 
       SUBROUTINE aerobulk_gpu_set_nitend( knitend ) BIND(C, NAME='aerobulk_gpu_set_nitend')
          IMPORT :: c_int

@@ -84,6 +84,10 @@ def lib():
     L.aerobulk_gpu_flux_diagnostics.argtypes = [C.c_longlong] + [C.c_void_p] * 6 + [_dp, C.c_int]
     L.aerobulk_gpu_diag_reduce_op.restype = C.c_int
     L.aerobulk_gpu_diag_reduce_op.argtypes = [C.c_int]
+    L.aerobulk_gpu_host_register.restype = C.c_int
+    L.aerobulk_gpu_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.aerobulk_gpu_host_unregister.restype = C.c_int
+    L.aerobulk_gpu_host_unregister.argtypes = [C.c_void_p]
     L.aerobulk_gpu_series.restype = C.c_int
     L.aerobulk_gpu_series.argtypes = ([C.c_char_p, C.c_int, C.c_longlong, C.c_double, C.c_double] + [C.c_void_p] * 5 +
                                       [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int])
@@ -447,3 +451,13 @@ def diagnostics_summary(st: np.ndarray) -> dict:
         if hi >= lo:
             out[k] = {"mean": float(s_ / max(st[0], 1.0)), "min": float(lo), "max": float(hi)}
     return out
+
+
+def host_register(a: np.ndarray):
+    """Page-lock an existing numpy array so that host-array calls take the zero-copy path (release with host_unregister
+    before the array is freed)."""
+    _check(lib().aerobulk_gpu_host_register(a.ctypes.data, a.nbytes))
+
+
+def host_unregister(a: np.ndarray):
+    _check(lib().aerobulk_gpu_host_unregister(a.ctypes.data))

@@ -221,6 +221,14 @@ int aerobulk_gpu_oce_ice(const char *calgo_ice, const char *calgo_oce, double zt
 /* Waits for the session stream and reports a deferred error (wind stress too strong). */
 int aerobulk_gpu_synchronize(void);
 
+/* ---- pinning helpers ------------------------------------------------------------------------------------ */
+/* Page-lock / release an EXISTING host array (cudaHostRegister / cudaHostUnregister) so that callers that do not link
+ * the CUDA runtime themselves (Fortran, ctypes ...) can give their fields the zero-copy path described at the top of
+ * this file.  Register once, before the time loop; release before the array is freed.  Returns 0 or
+ * AEROBULK_GPU_ERR_CUDA. */
+int aerobulk_gpu_host_register(void *ptr, size_t bytes);
+int aerobulk_gpu_host_unregister(void *ptr);
+
 /* ---- optional global flux diagnostics for sharded grids ---------------------------------------------- */
 #define AEROBULK_GPU_NDIAG 19
 /* Sum / min / max of the flux fields of this process's row block (any pointer may be NULL): stats[0] = number of points,

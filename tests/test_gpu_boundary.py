@@ -368,3 +368,35 @@ def test_pinned_arrays_take_the_zero_copy_path_and_agree(ab):
     # (AEROBULK_INIT needs the statistics), afterwards ONE flux launch per call and no classify
     assert la[1:] == [2] * (Nt - 1) and lb[1:] == [1] * (Nt - 1) and la[0] == lb[0] == 4
     ab.reset()
+
+
+def test_host_register_gives_plain_arrays_the_pinned_path(ab):
+    """aerobulk_gpu_host_register on ordinary numpy arrays: same results as the pageable path, and the arrays can be
+    released and used again."""
+    ni, nj = 96, 50
+    f = synth.fields(ni, nj, seed=77)
+    names = ("sst", "t_zt", "hum_zt", "U_zu", "V_zu", "slp", "rad_sw", "rad_lw")
+    arrs = {k: np.array(f[k], order="F") for k in names}
+    outs = {k: np.zeros((ni, nj), order="F") for k in ("QL", "QH", "Tau_x", "Tau_y", "Evap", "T_s")}
+
+    def session():
+        ab.reset()
+        for jt in (1, 2, 3):
+            ab.aerobulk_model(jt, 3, "ecmwf", 2., 10., *[arrs[k] for k in names[:6]], Niter=6, l_use_skin=True,
+                              rad_sw=arrs["rad_sw"], rad_lw=arrs["rad_lw"], out=outs)
+        return {k: v.copy() for k, v in outs.items()}
+
+    plain = session()
+    for v in list(arrs.values()) + list(outs.values()):
+        ab.host_register(v)
+    try:
+        pinned = session()
+    finally:
+        for v in list(arrs.values()) + list(outs.values()):
+            ab.host_unregister(v)
+    again = session()
+    for k in plain:
+        assert np.array_equal(plain[k], pinned[k]), k
+        assert np.array_equal(plain[k], again[k]), k
+    with pytest.raises(ab.AerobulkError):
+        ab.host_unregister(arrs["sst"])  # not registered any more
