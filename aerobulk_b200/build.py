@@ -24,7 +24,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompil
 # -fmad=true (default): FMA contraction is part of the documented GPU arithmetic
 
 SOURCES = ["ab_kernels.cu", "ab_series.cu", "ab_ice.cu", "ab_api.cu", "aerobulk.cpp"]
-HEADERS = [os.path.join(CSRC, h) for h in ("ab_device.cuh", "ab_ice.cuh", "ab_kernels.cuh", "ab_math.cuh", "ab_math_tables.cuh")] + [
+HEADERS = [os.path.join(CSRC, h) for h in ("ab_device.cuh", "ab_ice.cuh", "ab_kernels.cuh", "ab_math.cuh", "ab_math_tables.cuh", "ab_copy_pool.hpp")] + [
     os.path.join(ROOT, "include", h) for h in ("aerobulk_gpu.h", "aerobulk.hpp")]
 
 

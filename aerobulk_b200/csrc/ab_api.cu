@@ -22,17 +22,24 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <fstream>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
+#include "ab_copy_pool.hpp"
 #include "ab_kernels.cuh"
 
 namespace {
 
-constexpr int MAX_CHUNKS = 12;          // capacity; the number used is chunk_limit() (default 6, measured best)
+constexpr int MAX_CHUNKS = 16;          // capacity; the number used is chunk_limit() (default 6, measured best)
 constexpr long long MIN_CHUNK_POINTS = 200000;
+#ifndef AEROBULK_GPU_COPY_STREAMING_DEFAULT
+#define AEROBULK_GPU_COPY_STREAMING_DEFAULT 1
+#endif
 #ifndef AEROBULK_GPU_ZEROCOPY_DEFAULT
 #define AEROBULK_GPU_ZEROCOPY_DEFAULT 3
 #endif
@@ -112,6 +119,54 @@ long long min_chunk_points()
     return v;
 }
 
+
+// ---------------------------------------------------------------------------
+// Host bounce path for PAGEABLE caller arrays (the plain relink case: Fortran / numpy arrays nobody pinned).
+// cudaMemcpyAsync from pageable memory is staged by the driver on ONE thread (measured 8.3 ms per 1 M-point skin call,
+// 14 GB/s).  Instead a few persistent host threads move each row-block chunk between the caller's arrays and a pinned
+// slab owned by the library, and the flux kernel works on that slab zero-copy: chunk c+1 is copied in and chunk c-1
+// copied out while the kernel runs on chunk c.  AEROBULK_GPU_BOUNCE=0 restores the driver-staged copies,
+// AEROBULK_GPU_HOST_THREADS sets the number of copy threads (default: half the hardware threads, at most 8).
+// ---------------------------------------------------------------------------
+using abpool::CopyPiece;
+using abpool::CopyPool;
+int host_threads()
+{
+    static int v = [] {
+        const char *e = getenv("AEROBULK_GPU_HOST_THREADS");
+        int k = e ? atoi(e) : (int)(std::thread::hardware_concurrency() / 2);
+        if (!e && k > 8) k = 8;
+        return k < 1 ? 1 : (k > 64 ? 64 : k);
+    }();
+    return v;
+}
+CopyPool &copy_pool()
+{
+    static CopyPool *p = new CopyPool(host_threads(), [] { const char *e = getenv("AEROBULK_GPU_COPY_STREAMING"); return e ? atoi(e) != 0 : AEROBULK_GPU_COPY_STREAMING_DEFAULT != 0; }());   // never destroyed: its threads outlive static destructors
+    return *p;
+}
+bool bounce_on()
+{
+    static int v = [] { const char *e = getenv("AEROBULK_GPU_BOUNCE"); return e ? atoi(e) : 1; }();
+    return v != 0;
+}
+long long bounce_chunk_points()
+{
+    static long long v = [] {
+        const char *e = getenv("AEROBULK_GPU_BOUNCE_CHUNK_POINTS");
+        long long k = e ? atoll(e) : 180224;
+        return k < 2048 ? 2048 : k;
+    }();
+    return v;
+}
+int bounce_lag()   // chunks the GPU keeps queued before the host turns to copying results home
+{
+    static int v = [] { const char *e = getenv("AEROBULK_GPU_BOUNCE_LAG"); int k = e ? atoi(e) : 2; return k < 1 ? 1 : k; }();
+    return v;
+}
+constexpr long long BOUNCE_MIN_POINTS = 65536;   // below this the driver-staged copies are as fast
+constexpr size_t COPY_PIECE_BYTES = 128 * 1024;
+
 struct Session {
     // ---- module globals of mod_const.f90:22-33
     int nb_iter = 5;
@@ -140,6 +195,9 @@ struct Session {
     // ---- staging for host-array calls
     long long cap = 0;
     double *d_in[8] = {}, *d_out[6] = {};
+    // ---- pinned bounce slab for pageable caller arrays (14 fields, pitch cap_hb) and its device alias
+    double *hb = nullptr, *hb_dev = nullptr;
+    long long cap_hb = 0;
     // ---- staging of aerobulk_gpu_turb host-array calls (one slab, grow-only)
     double *d_turb = nullptr;
     long long cap_turb = 0;
@@ -325,6 +383,39 @@ int ensure_staging(long long n)
     for (int k = 0; k < 6; ++k) g.d_out[k] = slab + (long long)(8 + k) * n;
     g.cap = n;
     return 0;
+}
+
+void free_bounce()
+{
+    if (g.hb) cudaFreeHost(g.hb);
+    g.hb = g.hb_dev = nullptr;
+    g.cap_hb = 0;
+}
+int ensure_bounce(long long n)
+{
+    if (n <= g.cap_hb) return 0;
+    free_bounce();
+    CUDA_TRY(cudaHostAlloc(&g.hb, sizeof(double) * (size_t)n * 14, cudaHostAllocPortable | cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer(&g.hb_dev, g.hb, 0));
+    g.cap_hb = n;
+    return 0;
+}
+// copy points [s0, s0+len) of nf fields between the caller's arrays and the bounce slab rows row0.., on the copy threads
+void bounce_copy(int nf, double *const *user, int row0, long long s0, long long len, bool to_slab)
+{
+    static thread_local std::vector<CopyPiece> pieces;
+    pieces.clear();
+    const long long step = (long long)(COPY_PIECE_BYTES / sizeof(double));
+    for (int k = 0; k < nf; ++k) {
+        if (!user[k]) continue;
+        double *slab = g.hb + (long long)(row0 + k) * g.cap_hb;
+        for (long long o = 0; o < len; o += step) {
+            const long long m = len - o < step ? len - o : step;
+            double *u = user[k] + s0 + o, *b = slab + s0 + o;
+            pieces.push_back(to_slab ? CopyPiece{b, u, sizeof(double) * (size_t)m} : CopyPiece{u, b, sizeof(double) * (size_t)m});
+        }
+    }
+    copy_pool().run(pieces.data(), (int)pieces.size());
 }
 
 int algo_id(const char *calgo)
@@ -551,8 +642,21 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
             if (out_h[k] && !(out_alias[k] = const_cast<double *>(device_alias(out_h[k])))) zc_out = false;
         if (zerocopy_mode() == 3 && !(zc_in && zc_out)) zc_in = zc_out = false;   // all arrays pinned, or the staged pipeline
     }
+    // pageable caller arrays: bounce through the library's pinned slab on the copy threads (see CopyPool)
+    const bool bounce = !device_ptrs && !zc_in && !zc_out && bounce_on() && zerocopy_mode() == 3 && n >= BOUNCE_MIN_POINTS &&
+                        !(jt == 1 && !g.preinit_done);
+    if (bounce) {
+        rc = ensure_bounce(n);
+        if (rc) return rc;
+        for (int k = 0; k < 8; ++k) in_alias[k] = in_h[k] ? g.hb_dev + (long long)k * g.cap_hb : nullptr;
+        for (int k = 0; k < 6; ++k) out_alias[k] = out_h[k] ? g.hb_dev + (long long)(8 + k) * g.cap_hb : nullptr;
+        zc_in = zc_out = true;
+    }
     int nchunks = 1;
-    if (!device_ptrs && !zc_in) {
+    if (bounce) {
+        nchunks = (int)((n + bounce_chunk_points() - 1) / bounce_chunk_points());
+        nchunks = nchunks > MAX_CHUNKS ? MAX_CHUNKS : nchunks;
+    } else if (!device_ptrs && !zc_in) {
         nchunks = (int)(n / min_chunk_points());
         nchunks = nchunks < 1 ? 1 : (nchunks > chunk_limit() ? chunk_limit() : nchunks);
     }
@@ -560,7 +664,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     {
         double w[MAX_CHUNKS], wsum = 0.;
         for (int c = 0; c < nchunks; ++c) {
-            w[c] = chunk_shape() == 0 ? (double)(nchunks - c) : (chunk_shape() == 2 && c == 0 ? 0.5 : 1.);
+            w[c] = bounce ? 1. : chunk_shape() == 0 ? (double)(nchunks - c) : (chunk_shape() == 2 && c == 0 ? 0.5 : 1.);
             wsum += w[c];
         }
         double acc = 0.;
@@ -675,6 +779,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     a.bad_index = g.d_bad;
     const bool zteq = fabs(zu - zt) < 0.01;
 
+    int launched[MAX_CHUNKS], n_launched = 0, n_home = 0;
     for (int c = 0; c < nchunks; ++c) {
         const long long s0 = cstart[c], len = cstart[c + 1] - s0;
         if (len <= 0) continue;
@@ -696,6 +801,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         }
         a.n = len;
         a.index_offset = s0;
+        if (bounce) bounce_copy(8, const_cast<double *const *>(in_h), 0, s0, len, true);
         if (!device_ptrs) CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_in[c], 0));
         a.perm = nullptr;
         if (do_sort) {
@@ -715,7 +821,20 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
                 if (rc) return rc;
             }
             if (trace_on()) cudaEventRecord(tr_out[c], g.out_stream);
+            if (bounce) {   // results of an earlier chunk go home while the GPU has bounce_lag() chunks queued
+                launched[n_launched++] = c;
+                if (n_launched - n_home > bounce_lag()) {
+                    const int h = launched[n_home++];
+                    CUDA_TRY(cudaEventSynchronize(g.ev_k[h]));
+                    bounce_copy(6, out_h, 8, cstart[h], cstart[h + 1] - cstart[h], false);
+                }
+            }
         }
+    }
+    while (bounce && n_home < n_launched) {
+        const int h = launched[n_home++];
+        CUDA_TRY(cudaEventSynchronize(g.ev_k[h]));
+        bounce_copy(6, out_h, 8, cstart[h], cstart[h + 1] - cstart[h], false);
     }
     CUDA_TRY(cudaMemcpyAsync(g.h_bad, g.d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaEventRecord(g.ev_bad, cs));
@@ -1574,6 +1693,28 @@ int aerobulk_gpu_flux_diagnostics(long long n, const double *QL, const double *Q
 
 int aerobulk_gpu_diag_reduce_op(int i) { return (i <= 0 || i >= abk::NDIAG) ? 0 : (i - 1) % 3; }
 
+int aerobulk_gpu_selftest_host_copy(long long n, int rounds)
+{
+    // no device needed: exercises the copy threads of the pageable-array path on host memory alone
+    if (n < 1 || rounds < 1) return -1;
+    std::vector<double> src((size_t)n), mid((size_t)n), dst((size_t)n);
+    const long long step = (long long)(COPY_PIECE_BYTES / sizeof(double));
+    int bad = 0;
+    for (int r = 0; r < rounds; ++r) {
+        for (long long i = 0; i < n; ++i) src[(size_t)i] = (double)(i * 31 + r);
+        std::vector<CopyPiece> there, back;
+        for (long long o = 0; o < n; o += step) {
+            const size_t m = (size_t)(n - o < step ? n - o : step);
+            there.push_back(CopyPiece{mid.data() + o, src.data() + o, sizeof(double) * m});
+            back.push_back(CopyPiece{dst.data() + o, mid.data() + o, sizeof(double) * m});
+        }
+        copy_pool().run(there.data(), (int)there.size());
+        copy_pool().run(back.data(), (int)back.size());
+        bad += memcmp(src.data(), dst.data(), sizeof(double) * (size_t)n) != 0;
+    }
+    return bad;
+}
+
 int aerobulk_gpu_host_register(void *ptr, size_t bytes)
 {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1698,6 +1839,7 @@ void aerobulk_gpu_reset(void)
         cudaDeviceSynchronize();
         free_coare_state();
         free_ecmwf_state();
+        free_bounce();
         if (g.d_in[0]) cudaFree(g.d_in[0]);   // one slab, see ensure_staging
         for (int k = 0; k < 8; ++k) g.d_in[k] = nullptr;
         for (int k = 0; k < 6; ++k) g.d_out[k] = nullptr;

@@ -24,12 +24,15 @@
  * There is NO CPU fallback: without a CUDA device every compute entry point fails.
  *
  * Host arrays (on_device = 0, and aerobulk_gpu_model / aerobulk_cxx_*): pageable memory is staged through device
- * buffers (aerobulk_gpu_model: chunked H2D | kernel | D2H pipeline).  When EVERY array of a call is pinned
+ * buffers; aerobulk_gpu_model on 65536 points or more moves it instead through a pinned slab of its own on a few
+ * persistent host threads, chunk by chunk around the kernel.  When EVERY array of a call is pinned
  * (cudaHostAlloc / cudaHostRegister) the kernels read and write the caller's memory directly over PCIe ("zero-copy":
  * same results, ~20 % faster end to end, no staging memory).
  * Environment: AEROBULK_GPU_DEVICE (or LOCAL_RANK) device ordinal; AEROBULK_GPU_ZEROCOPY=0 staged copies even for pinned
  * arrays; AEROBULK_GPU_MAX_CHUNKS / AEROBULK_GPU_MIN_CHUNK_POINTS / AEROBULK_GPU_CHUNK_SHAPE pipeline tuning;
- * AEROBULK_GPU_TRACE=1 GPU timeline of every staged call on stderr.
+ * AEROBULK_GPU_TRACE=1 GPU timeline of every staged call on stderr; pageable arrays: AEROBULK_GPU_BOUNCE=0 driver-staged
+ * copies, AEROBULK_GPU_HOST_THREADS copy threads (default: half the hardware threads, at most 8),
+ * AEROBULK_GPU_BOUNCE_CHUNK_POINTS, AEROBULK_GPU_COPY_STREAMING=0 plain instead of non-temporal stores.
  */
 #ifndef AEROBULK_GPU_H
 #define AEROBULK_GPU_H
@@ -228,6 +231,9 @@ int aerobulk_gpu_synchronize(void);
  * AEROBULK_GPU_ERR_CUDA. */
 int aerobulk_gpu_host_register(void *ptr, size_t bytes);
 int aerobulk_gpu_host_unregister(void *ptr);
+/* Self-test of the host copy threads used for PAGEABLE caller arrays (needs no device): copies n doubles through the
+ * thread pool and back, `rounds` times; returns the number of rounds whose data came back changed (0 = pass). */
+int aerobulk_gpu_selftest_host_copy(long long n, int rounds);
 
 /* ---- optional global flux diagnostics for sharded grids ---------------------------------------------- */
 #define AEROBULK_GPU_NDIAG 19

@@ -136,3 +136,25 @@ def test_series_cli_arguments():
     r = subprocess.run([sys.executable, "-m", "aerobulk_b200.series_cli", "a.csv", "b.csv", "--algo", "coare9"], cwd=ROOT,
                        capture_output=True, text=True)
     assert r.returncode == 2 and "invalid choice" in r.stderr
+
+
+def test_host_copy_threads_selftest(ab):
+    """The copy threads behind the pageable-array path move data faithfully (many back-to-back jobs, odd sizes)."""
+    L = ab.lib()
+    L.aerobulk_gpu_selftest_host_copy.restype = C.c_int
+    L.aerobulk_gpu_selftest_host_copy.argtypes = [C.c_longlong, C.c_int]
+    assert L.aerobulk_gpu_selftest_host_copy(1, 3) == 0
+    assert L.aerobulk_gpu_selftest_host_copy(16384 * 37 + 5, 50) == 0
+    assert L.aerobulk_gpu_selftest_host_copy(1_000_003, 20) == 0
+
+
+def test_host_copy_pool_under_thread_sanitizer(tmp_path):
+    """aerobulk_b200/csrc/ab_copy_pool.hpp built with -fsanitize=thread: 400 back-to-back jobs, no race, no lost piece."""
+    exe = str(tmp_path / "cp_tsan")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-pthread",
+                        os.path.join(ROOT, "tests", "copy_pool_tsan.cpp"), "-o", exe], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime here: " + r.stderr[-200:])
+    for args in ([], ["streaming-stores"]):
+        r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "bad=0" in r.stdout and "ThreadSanitizer" not in r.stderr, r.stderr[-2000:]

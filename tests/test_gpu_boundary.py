@@ -327,7 +327,7 @@ def test_flux_diagnostics_match_numpy_and_combine_like_one_domain(ab):
 
 def test_pinned_arrays_take_the_zero_copy_path_and_agree(ab):
     """When every array of a host-array call is pinned, the kernel reads / writes the caller's arrays directly (zero-copy,
-    no stability sort); pageable arrays go through the staged pipeline.  Bit-identical over a state-carrying session."""
+    no stability sort); pageable arrays go through the library's pinned slab (copy threads).  Bit-identical over a state-carrying session."""
     import torch
     Ni, Nj, Nt = 512, 300, 4
     n = Ni * Nj
@@ -364,16 +364,18 @@ def test_pinned_arrays_take_the_zero_copy_path_and_agree(ab):
     for jt in range(Nt):
         for k in names:
             assert np.array_equal(a[jt][k], b[jt][k]), (jt, k)
-    # pageable: classify + flux per call (+ the two statistics kernels at jt == 1); pinned: jt == 1 is staged as well
-    # (AEROBULK_INIT needs the statistics), afterwards ONE flux launch per call and no classify
-    assert la[1:] == [2] * (Nt - 1) and lb[1:] == [1] * (Nt - 1) and la[0] == lb[0] == 4
+    # jt == 1 is staged either way (AEROBULK_INIT needs the statistics): two statistics kernels, classify, flux.
+    # Afterwards no classify: pinned arrays are used in place (ONE flux launch), pageable ones of this size go through
+    # the library's pinned slab in row-block chunks (one flux launch per chunk; one chunk here)
+    assert la[1:] == [1] * (Nt - 1) and lb[1:] == [1] * (Nt - 1) and la[0] == lb[0] == 4
     ab.reset()
 
 
-def test_host_register_gives_plain_arrays_the_pinned_path(ab):
-    """aerobulk_gpu_host_register on ordinary numpy arrays: same results as the pageable path, and the arrays can be
-    released and used again."""
-    ni, nj = 96, 50
+@pytest.mark.parametrize("ni,nj", [(96, 50), (512, 300), (1031, 257)])
+def test_host_register_gives_plain_arrays_the_pinned_path(ab, ni, nj):
+    """aerobulk_gpu_host_register on ordinary numpy arrays: same results as the pageable path (driver-staged copies for
+    the small grid, the library's copy threads + pinned slab for the larger ones), and the arrays can be released and
+    used again."""
     f = synth.fields(ni, nj, seed=77)
     names = ("sst", "t_zt", "hum_zt", "U_zu", "V_zu", "slp", "rad_sw", "rad_lw")
     arrs = {k: np.array(f[k], order="F") for k in names}

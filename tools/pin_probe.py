@@ -35,5 +35,5 @@ same = all(np.array_equal(ref[k], np_out[k]) for k in OUT)
 for v in list(np_in.values()) + list(np_out.values()):
     ab.host_unregister(v)
 c = session()
-print(f"pageable {a:.3f} ms/call ({n / a / 1e3:.0f} Mpt/s) | registered {b:.3f} ms/call ({n / b / 1e3:.0f} Mpt/s), "
+print(f"bounce={os.environ.get('AEROBULK_GPU_BOUNCE','1')} threads={os.environ.get('AEROBULK_GPU_HOST_THREADS','auto')} chunk={os.environ.get('AEROBULK_GPU_BOUNCE_CHUNK_POINTS','180224')}: pageable {a:.3f} ms/call ({n / a / 1e3:.0f} Mpt/s) | registered {b:.3f} ms/call ({n / b / 1e3:.0f} Mpt/s), "
       f"one-off registration of 14 arrays {treg:.1f} ms, results identical: {same} | after unregister {c:.3f} ms/call")
