@@ -624,6 +624,28 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     double *out_h[6] = {QL, QH, Tau_x, Tau_y, Evap, lsrad ? T_s : nullptr};
     double *out_d[6];
 
+    // jt == 1 with PAGEABLE arrays (AEROBULK_INIT wants the statistics of the whole fields on the device before any flux
+    // is computed, so the chunk-by-chunk bounce below does not apply): the copy threads bring the inputs into the pinned
+    // slab in one go, the staged pipeline then runs from / to the slab, and the results go home at the end
+    double *user_out[6] = {};
+    bool bounce_first = false;
+    if (!device_ptrs && jt == 1 && !g.preinit_done && bounce_on() && zerocopy_mode() == 3 && n >= BOUNCE_MIN_POINTS) {
+        bool pinned = true;
+        for (int k = 0; k < 8 && pinned; ++k) pinned = !in_h[k] || device_alias(in_h[k]);
+        for (int k = 0; k < 6 && pinned; ++k) pinned = !out_h[k] || device_alias(out_h[k]);
+        if (!pinned) {
+            rc = ensure_bounce(n);
+            if (rc) return rc;
+            bounce_copy(8, const_cast<double *const *>(in_h), 0, 0, n, true);
+            for (int k = 0; k < 8; ++k) in_h[k] = in_h[k] ? g.hb + (long long)k * g.cap_hb : nullptr;
+            for (int k = 0; k < 6; ++k) {
+                user_out[k] = out_h[k];
+                out_h[k] = out_h[k] ? g.hb + (long long)(8 + k) * g.cap_hb : nullptr;
+            }
+            bounce_first = true;
+        }
+    }
+
     // Chunk plan of the host-array pipeline: contiguous row blocks of the flattened fields.  The pipeline is
     // H2D-bound (PCIe ~50 GB/s per direction measured, vs. >150 GB/s consumed by the kernel), so its length
     // is H2D(all) + kernel(last chunk) + D2H(last chunk): chunk sizes DEcrease linearly (weights K..1) to
@@ -847,6 +869,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     if (!device_ptrs || last || jt == 1) {
         CUDA_TRY(cudaStreamSynchronize(cs));
         if (!device_ptrs) CUDA_TRY(cudaStreamSynchronize(g.out_stream));
+        if (bounce_first) bounce_copy(6, user_out, 8, 0, n, false);
         rc = check_bad_flag(device_ptrs ? nullptr : Tau_x, device_ptrs ? nullptr : Tau_y);
         if (!device_ptrs && trace_on()) {
             fprintf(stderr, "[aerobulk_gpu trace] jt=%d chunks=%d  (ms since the first H2D: in | kernel | out)\n", jt, nchunks);
