@@ -198,6 +198,9 @@ struct Session {
     // ---- pinned bounce slab for pageable caller arrays (14 fields, pitch cap_hb) and its device alias
     double *hb = nullptr, *hb_dev = nullptr;
     long long cap_hb = 0;
+    // ---- the same for the other host-array entry points (turb, series, ice): arrays packed back to back
+    double *hx = nullptr, *hx_dev = nullptr;
+    long long cap_hx = 0;
     // ---- staging of aerobulk_gpu_turb host-array calls (one slab, grow-only)
     double *d_turb = nullptr;
     long long cap_turb = 0;
@@ -390,6 +393,9 @@ void free_bounce()
     if (g.hb) cudaFreeHost(g.hb);
     g.hb = g.hb_dev = nullptr;
     g.cap_hb = 0;
+    if (g.hx) cudaFreeHost(g.hx);
+    g.hx = g.hx_dev = nullptr;
+    g.cap_hx = 0;
 }
 int ensure_bounce(long long n)
 {
@@ -416,6 +422,78 @@ void bounce_copy(int nf, double *const *user, int row0, long long s0, long long 
         }
     }
     copy_pool().run(pieces.data(), (int)pieces.size());
+}
+
+
+// Host arrays of the entry points other than aerobulk_gpu_model (turb, series, turb_ice, oce_ice).  Every array pinned:
+// device aliases (zero-copy).  Otherwise, from BOUNCE_MIN_POINTS elements per array up, the copy threads pack the
+// inputs into a pinned slab, the kernel works on the slab zero-copy, and bounce_finish() brings the outputs home
+// (pageable cudaMemcpy is staged by the driver on one thread at ~14 GB/s; the copy threads move 55-70 GB/s).
+struct HostBounce {
+    int cnt = 0;
+    double *user[64];
+    long long len[64], off[64];
+    unsigned char dir[64];   // bit 0: input, bit 1: output
+    bool active = false;
+};
+void bounce_run(const HostBounce &hb, unsigned char which, bool to_slab)
+{
+    static thread_local std::vector<CopyPiece> pieces;
+    pieces.clear();
+    const long long step = (long long)(COPY_PIECE_BYTES / sizeof(double));
+    for (int k = 0; k < hb.cnt; ++k) {
+        if (!hb.user[k] || !(hb.dir[k] & which)) continue;
+        for (long long o = 0; o < hb.len[k]; o += step) {
+            const long long m = hb.len[k] - o < step ? hb.len[k] - o : step;
+            double *u = hb.user[k] + o, *b = g.hx + hb.off[k] + o;
+            pieces.push_back(to_slab ? CopyPiece{b, u, sizeof(double) * (size_t)m} : CopyPiece{u, b, sizeof(double) * (size_t)m});
+        }
+    }
+    copy_pool().run(pieces.data(), (int)pieces.size());
+}
+// 0: use the staged path of the entry point; 1: d = aliases of the caller's pinned arrays; 2: d = aliases of slab rows
+// holding copies of the inputs (call bounce_finish after the launch); < 0: -error code
+int alias_or_bounce(int cnt, const double *const *h, const long long *len, const unsigned char *dir, const double **d,
+                    HostBounce &hb)
+{
+    hb.active = false;
+    if (alias_all(cnt, h, d)) return 1;
+    if (!bounce_on() || zerocopy_mode() != 3 || cnt > 64) return 0;
+    long long total = 0, longest = 0;
+    for (int k = 0; k < cnt; ++k) {
+        hb.user[k] = const_cast<double *>(h[k]);
+        hb.len[k] = h[k] ? len[k] : 0;
+        hb.dir[k] = dir[k];
+        hb.off[k] = total;
+        total += (hb.len[k] + 63) / 64 * 64;   // rows start on 512-byte boundaries
+        longest = hb.len[k] > longest ? hb.len[k] : longest;
+    }
+    hb.cnt = cnt;
+    if (longest < BOUNCE_MIN_POINTS) return 0;
+    if (total > g.cap_hx) {
+        if (g.hx) cudaFreeHost(g.hx);
+        g.hx = g.hx_dev = nullptr;
+        g.cap_hx = 0;
+        if (cudaHostAlloc(&g.hx, sizeof(double) * (size_t)total, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(&g.hx_dev, g.hx, 0) != cudaSuccess) {
+            cudaGetLastError();   // no pinned memory to spare: the staged path still works
+            if (g.hx) cudaFreeHost(g.hx);
+            g.hx = g.hx_dev = nullptr;
+            return 0;
+        }
+        g.cap_hx = total;
+    }
+    bounce_run(hb, 1, true);
+    for (int k = 0; k < cnt; ++k) d[k] = h[k] ? g.hx_dev + hb.off[k] : nullptr;
+    hb.active = true;
+    return 2;
+}
+int bounce_finish(const HostBounce &hb, int rc)
+{
+    if (!hb.active || rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(compute_stream()));
+    bounce_run(hb, 2, false);
+    return 0;
 }
 
 int algo_id(const char *calgo)
@@ -1613,7 +1691,15 @@ int aerobulk_gpu_turb(const char *calgo, int kt, double zt, double zu, int Ni, i
         if (opt) memcpy(h + 15, opt, sizeof(*opt));
         else memset(h + 15, 0, 10 * sizeof(double *));
         const double *d[25];
-        if (alias_all(25, h, d)) {
+        long long len[25];
+        unsigned char dir[25];
+        const unsigned char io = (l_use_cs || l_use_wl) ? 3 : 1;   // T_s, q_s come back only from the skin schemes
+        for (int k = 0; k < 25; ++k) {
+            len[k] = (long long)Ni * Nj;
+            dir[k] = k < 2 ? io : (k < 9 ? 1 : 2);
+        }
+        HostBounce hb;
+        if (alias_or_bounce(25, h, len, dir, d, hb)) {
             aerobulk_gpu_turb_optional od;
             memcpy(&od, d + 15, sizeof(od));
             auto w = [](const double *p) { return const_cast<double *>(p); };
@@ -1622,7 +1708,7 @@ int aerobulk_gpu_turb(const char *calgo, int kt, double zt, double zu, int Ni, i
                                      opt ? &od : nullptr, 1);
             if (rc) return rc;
             CUDA_TRY(cudaStreamSynchronize(compute_stream()));
-            return 0;
+            return bounce_finish(hb, 0);
         }
     }
     return turb_impl(calgo, kt, zt, zu, Ni, Nj, T_s, t_zt, q_s, q_zt, U_zu, l_use_cs, l_use_wl, Cd, Ch, Ce, t_zu, q_zu,
@@ -1640,11 +1726,18 @@ int aerobulk_gpu_series(const char *calgo, int Nt, long long S, double zt, doubl
         const double *h[8 + AEROBULK_GPU_SERIES_NOUT] = {lon, sst, t_zt, hum_zt, wind, slp, rad_sw, rad_lw};
         memcpy(h + 8, out, sizeof(double *) * AEROBULK_GPU_SERIES_NOUT);
         const double *d[8 + AEROBULK_GPU_SERIES_NOUT];
-        if (alias_all(8 + AEROBULK_GPU_SERIES_NOUT, h, d)) {
+        long long len[8 + AEROBULK_GPU_SERIES_NOUT];
+        unsigned char dir[8 + AEROBULK_GPU_SERIES_NOUT];
+        for (int k = 0; k < 8 + AEROBULK_GPU_SERIES_NOUT; ++k) {
+            len[k] = k == 0 ? S : (long long)(Nt < 0 ? 0 : Nt) * (S < 0 ? 0 : S);   // lon is per station
+            dir[k] = k < 8 ? 1 : 2;
+        }
+        HostBounce hb;
+        if (alias_or_bounce(8 + AEROBULK_GPU_SERIES_NOUT, h, len, dir, d, hb)) {
             aerobulk_gpu_series_out od;
             memcpy(&od, d + 8, sizeof(od));
-            return series_impl(calgo, Nt, S, zt, zu, isecday_utc, d[0], d[1], d[2], d[3], hum_kind, d[4], d[5], d[6], d[7],
-                               l_use_skin, &od, 1);
+            return bounce_finish(hb, series_impl(calgo, Nt, S, zt, zu, isecday_utc, d[0], d[1], d[2], d[3], hum_kind, d[4], d[5],
+                                                 d[6], d[7], l_use_skin, &od, 1));
         }
     }
     return series_impl(calgo, Nt, S, zt, zu, isecday_utc, lon, sst, t_zt, hum_zt, hum_kind, wind, slp, rad_sw, rad_lw,
@@ -1670,12 +1763,19 @@ int aerobulk_gpu_turb_ice(const char *calgo, double zt, double zu, int Ni, int N
         if (opt) memcpy(h + 12, opt, sizeof(*opt));
         else memset(h + 12, 0, 8 * sizeof(double *));
         const double *d[20];
-        if (alias_all(20, h, d)) {
+        long long len[20];
+        unsigned char dir[20];
+        for (int k = 0; k < 20; ++k) {
+            len[k] = (long long)Ni * Nj;
+            dir[k] = k < 6 ? 1 : 2;
+        }
+        HostBounce hb;
+        if (alias_or_bounce(20, h, len, dir, d, hb)) {
             aerobulk_gpu_turb_ice_optional od;
             memcpy(&od, d + 12, sizeof(od));
             auto w = [](const double *p) { return const_cast<double *>(p); };
-            return turb_ice_impl(calgo, zt, zu, Ni, Nj, d[0], d[1], d[2], d[3], d[4], d[5], CxN_easy, w(d[6]), w(d[7]), w(d[8]),
-                                 w(d[9]), w(d[10]), w(d[11]), opt ? &od : nullptr, 1);
+            return bounce_finish(hb, turb_ice_impl(calgo, zt, zu, Ni, Nj, d[0], d[1], d[2], d[3], d[4], d[5], CxN_easy, w(d[6]),
+                                                   w(d[7]), w(d[8]), w(d[9]), w(d[10]), w(d[11]), opt ? &od : nullptr, 1));
         }
     }
     return turb_ice_impl(calgo, zt, zu, Ni, Nj, Ts_i, t_zt, qs_i, q_zt, U_zu, frice, CxN_easy, Cd, Ch, Ce, t_zu, q_zu, Ubzu,
@@ -1693,11 +1793,18 @@ int aerobulk_gpu_oce_ice(const char *calgo_ice, const char *calgo_oce, double zt
         static_assert(sizeof(aerobulk_gpu_oce_ice_out) == 35 * sizeof(double *), "35 output pointers");
         memcpy(h + 7, out, sizeof(aerobulk_gpu_oce_ice_out));
         const double *d[7 + 35];
-        if (alias_all(7 + 35, h, d)) {
+        long long len[7 + 35];
+        unsigned char dir[7 + 35];
+        for (int k = 0; k < 7 + 35; ++k) {
+            len[k] = n < 0 ? 0 : n;
+            dir[k] = k < 7 ? 1 : ((calgo_oce || k < 7 + 17) ? 2 : 0);   // the over-water outputs exist only with leads
+        }
+        HostBounce hb;
+        if (alias_or_bounce(7 + 35, h, len, dir, d, hb)) {
             aerobulk_gpu_oce_ice_out od;
             memcpy(&od, d + 7, sizeof(od));
-            return oce_ice_impl(calgo_ice, calgo_oce, zt, zu, n, d[0], d[1], d[2], d[3], hum_kind, d[4], d[5], d[6], CxN_easy,
-                                &od, 1);
+            return bounce_finish(hb, oce_ice_impl(calgo_ice, calgo_oce, zt, zu, n, d[0], d[1], d[2], d[3], hum_kind, d[4], d[5],
+                                                  d[6], CxN_easy, &od, 1));
         }
     }
     return oce_ice_impl(calgo_ice, calgo_oce, zt, zu, n, sit, sst, t_zt, hum_zt, hum_kind, wind, slp, frice, CxN_easy, out,
