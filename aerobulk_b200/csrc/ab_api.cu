@@ -17,6 +17,9 @@
 #include <cuda_runtime.h>
 
 #include <math.h>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -134,8 +137,19 @@ int host_threads()
 {
     static int v = [] {
         const char *e = getenv("AEROBULK_GPU_HOST_THREADS");
-        int k = e ? atoi(e) : (int)(std::thread::hardware_concurrency() / 2);
-        if (!e && k > 8) k = 8;
+        int k;
+        if (e) {
+            k = atoi(e);
+        } else {
+            // the CPUs this process may run on (an MPI rank bound to a few cores must not spin 8 threads on them)
+            int cpus = (int)std::thread::hardware_concurrency();
+#if defined(__linux__)
+            cpu_set_t set;
+            if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
+#endif
+            k = cpus / 2;
+            if (k > 8) k = 8;
+        }
         return k < 1 ? 1 : (k > 64 ? 64 : k);
     }();
     return v;
