@@ -178,6 +178,14 @@ int bounce_lag()   // chunks the GPU keeps queued before the host turns to copyi
     static int v = [] { const char *e = getenv("AEROBULK_GPU_BOUNCE_LAG"); int k = e ? atoi(e) : 2; return k < 1 ? 1 : k; }();
     return v;
 }
+size_t bounce_max_bytes()   // larger slabs are not worth pinning: the driver-staged copies take over
+{
+    static size_t v = [] {
+        const char *e = getenv("AEROBULK_GPU_BOUNCE_MAX_MB");
+        return (size_t)(e ? atoll(e) : 4096) << 20;
+    }();
+    return v;
+}
 constexpr long long BOUNCE_MIN_POINTS = 65536;   // below this the driver-staged copies are as fast
 constexpr size_t COPY_PIECE_BYTES = 128 * 1024;
 
@@ -411,14 +419,22 @@ void free_bounce()
     g.hx = g.hx_dev = nullptr;
     g.cap_hx = 0;
 }
-int ensure_bounce(long long n)
+// false (and the session stays usable) when the host has no pinned memory to spare: the caller then keeps the
+// driver-staged copies
+bool ensure_bounce(long long n)
 {
-    if (n <= g.cap_hb) return 0;
+    if (n <= g.cap_hb) return true;
+    if (sizeof(double) * (size_t)n * 14 > bounce_max_bytes()) return false;
     free_bounce();
-    CUDA_TRY(cudaHostAlloc(&g.hb, sizeof(double) * (size_t)n * 14, cudaHostAllocPortable | cudaHostAllocMapped));
-    CUDA_TRY(cudaHostGetDevicePointer(&g.hb_dev, g.hb, 0));
+    if (cudaHostAlloc(&g.hb, sizeof(double) * (size_t)n * 14, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&g.hb_dev, g.hb, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (g.hb) cudaFreeHost(g.hb);
+        g.hb = g.hb_dev = nullptr;
+        return false;
+    }
     g.cap_hb = n;
-    return 0;
+    return true;
 }
 // copy points [s0, s0+len) of nf fields between the caller's arrays and the bounce slab rows row0.., on the copy threads
 void bounce_copy(int nf, double *const *user, int row0, long long s0, long long len, bool to_slab)
@@ -483,7 +499,7 @@ int alias_or_bounce(int cnt, const double *const *h, const long long *len, const
         longest = hb.len[k] > longest ? hb.len[k] : longest;
     }
     hb.cnt = cnt;
-    if (longest < BOUNCE_MIN_POINTS) return 0;
+    if (longest < BOUNCE_MIN_POINTS || sizeof(double) * (size_t)total > bounce_max_bytes()) return 0;
     if (total > g.cap_hx) {
         if (g.hx) cudaFreeHost(g.hx);
         g.hx = g.hx_dev = nullptr;
@@ -725,9 +741,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         bool pinned = true;
         for (int k = 0; k < 8 && pinned; ++k) pinned = !in_h[k] || device_alias(in_h[k]);
         for (int k = 0; k < 6 && pinned; ++k) pinned = !out_h[k] || device_alias(out_h[k]);
-        if (!pinned) {
-            rc = ensure_bounce(n);
-            if (rc) return rc;
+        if (!pinned && ensure_bounce(n)) {
             bounce_copy(8, const_cast<double *const *>(in_h), 0, 0, n, true);
             for (int k = 0; k < 8; ++k) in_h[k] = in_h[k] ? g.hb + (long long)k * g.cap_hb : nullptr;
             for (int k = 0; k < 6; ++k) {
@@ -758,10 +772,8 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     }
     // pageable caller arrays: bounce through the library's pinned slab on the copy threads (see CopyPool)
     const bool bounce = !device_ptrs && !zc_in && !zc_out && bounce_on() && zerocopy_mode() == 3 && n >= BOUNCE_MIN_POINTS &&
-                        !(jt == 1 && !g.preinit_done);
+                        !(jt == 1 && !g.preinit_done) && ensure_bounce(n);
     if (bounce) {
-        rc = ensure_bounce(n);
-        if (rc) return rc;
         for (int k = 0; k < 8; ++k) in_alias[k] = in_h[k] ? g.hb_dev + (long long)k * g.cap_hb : nullptr;
         for (int k = 0; k < 6; ++k) out_alias[k] = out_h[k] ? g.hb_dev + (long long)(8 + k) * g.cap_hb : nullptr;
         zc_in = zc_out = true;

@@ -102,3 +102,43 @@ def test_series_large_pageable_arrays(ab, algo):
     lo, hi = run(slice(0, S // 2)), run(slice(S // 2, S))
     for k in whole:
         assert np.array_equal(whole[k], np.concatenate([lo[k], hi[k]], axis=1), equal_nan=True), k
+
+
+_KNOB_SCRIPT = r"""
+import hashlib, sys
+import numpy as np
+import aerobulk_b200 as ab
+from aerobulk_b200 import synth
+ni, nj, nt = 640, 250, 3
+f = synth.fields(ni, nj, seed=11)
+names = ("sst", "t_zt", "hum_zt", "U_zu", "V_zu", "slp")
+outs = {k: np.zeros((ni, nj), order="F") for k in ("QL", "QH", "Tau_x", "Tau_y", "Evap", "T_s")}
+ab.set_verbose(False)
+h = hashlib.sha256()
+for jt in range(1, nt + 1):
+    ab.aerobulk_model(jt, nt, "coare3p6", 2., 10., *[f[k] for k in names], Niter=5, l_use_skin=True,
+                      rad_sw=f["rad_sw"], rad_lw=f["rad_lw"], out=outs)
+    for k in sorted(outs):
+        h.update(outs[k].tobytes())
+g = synth.ice_fields(ni * nj, seed=3)
+r = ab.oce_ice("nemo", "ncar", 2.0, 10.0, **g, want=("Tau", "QH", "QL"))
+for k in sorted(r):
+    h.update(r[k].tobytes())
+print("HASH", h.hexdigest())
+"""
+
+
+def test_pageable_path_knobs_do_not_change_results():
+    """The environment knobs of the pageable-array path (read once per process, hence subprocesses): driver-staged copies,
+    a pinned-slab budget too small for the grid (fallback), one copy thread, plain stores, small chunks -- same bits."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hashes = {}
+    for tag, env in {"default": {}, "no bounce": {"AEROBULK_GPU_BOUNCE": "0"}, "slab budget 1 MB": {"AEROBULK_GPU_BOUNCE_MAX_MB": "1"},
+                     "1 thread, plain stores": {"AEROBULK_GPU_HOST_THREADS": "1", "AEROBULK_GPU_COPY_STREAMING": "0"},
+                     "small chunks, 3 threads": {"AEROBULK_GPU_BOUNCE_CHUNK_POINTS": "20000", "AEROBULK_GPU_HOST_THREADS": "3"}}.items():
+        r = subprocess.run([sys.executable, "-c", _KNOB_SCRIPT], cwd=root, env={**os.environ, **env}, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, (tag, r.stderr[-2000:])
+        hashes[tag] = [l for l in r.stdout.splitlines() if l.startswith("HASH")][0]
+    assert len(set(hashes.values())) == 1, hashes
