@@ -1600,6 +1600,70 @@ int oce_ice_impl(const char *calgo_ice, const char *calgo_oce, double zt, double
 }
 
 // ---------------------------------------------------------------------------
+// sea-ice station series (src/ice/test_aerobulk_buoy_series_ice.f90): one launch for all records
+// ---------------------------------------------------------------------------
+int series_ice_impl(const char *calgo, double zt, double zu, long long n, const double *sic, const double *sit,
+                    const double *t_zt, const double *hum_zt, int hum_kind, const double *wind, const double *slp,
+                    const double *rad_sw, const double *rad_lw, const aerobulk_gpu_series_ice_out *out, int on_device)
+{
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!calgo || !sic || !sit || !t_zt || !hum_zt || !wind || !slp || !rad_sw || !rad_lw || !out)
+        return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_series_ice: NULL mandatory argument");
+    const int ialgo = ice_algo_id(calgo);
+    if (ialgo != abd::ICE_NEMO && ialgo != abd::ICE_AN05 && ialgo != abd::ICE_LU12 && ialgo != abd::ICE_LG15)
+        return fail(AEROBULK_GPU_ERR_ALGO, "UNKNOWN algo: %s !!!", calgo);   // test_aerobulk_buoy_series_ice.f90:413-415
+    if (n < 0 || hum_kind < 0 || hum_kind > 2) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_series_ice: bad n or hum_kind");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (n == 0) return 0;
+    cudaStream_t cs_ = compute_stream();
+    rc = check_bad_flag(nullptr, nullptr);
+    if (rc) return rc;
+
+    static_assert(sizeof(aerobulk_gpu_series_ice_out) == abk::NICESERIES_OUT * sizeof(double *), "21 output pointers");
+    double *hout[abk::NICESERIES_OUT];
+    memcpy(hout, out, sizeof(hout));
+    const double *hin[8] = {sic, sit, t_zt, hum_zt, wind, slp, rad_sw, rad_lw};
+    const double *din[8];
+    double *dout[abk::NICESERIES_OUT];
+    if (on_device) {
+        for (int k = 0; k < 8; ++k) din[k] = hin[k];
+        for (int k = 0; k < abk::NICESERIES_OUT; ++k) dout[k] = hout[k];
+    } else {
+        int nout = 0;
+        for (int k = 0; k < abk::NICESERIES_OUT; ++k) nout += hout[k] ? 1 : 0;
+        rc = ensure_turb_slab(n * (8 + nout));
+        if (rc) return rc;
+        double *p = g.d_turb;
+        for (int k = 0; k < 8; ++k, p += n) {
+            din[k] = p;
+            CUDA_TRY(cudaMemcpyAsync(p, hin[k], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs_));
+        }
+        for (int k = 0; k < abk::NICESERIES_OUT; ++k) {
+            dout[k] = hout[k] ? p : nullptr;
+            if (hout[k]) p += n;
+        }
+    }
+    abk::IceSeriesArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sic = din[0]; a.sit = din[1]; a.t_zt = din[2]; a.hum_zt = din[3]; a.wnd = din[4]; a.slp = din[5];
+    a.rad_sw = din[6]; a.rad_lw = din[7];
+    for (int k = 0; k < abk::NICESERIES_OUT; ++k) a.out[k] = dout[k];
+    a.n = n;
+    a.hum_kind = hum_kind;
+    a.ui = make_ice_uniform(zt, zu, nullptr);
+    a.bad_tau = g.d_bad;
+    a.bad_rough = g.d_bad + 1;
+    CUDA_TRY(abk::launch_ice_series(ialgo, fabs(zu - zt) < 0.01, a, cs_));
+    g.launches += 1;
+    if (!on_device)
+        for (int k = 0; k < abk::NICESERIES_OUT; ++k)
+            if (hout[k]) CUDA_TRY(cudaMemcpyAsync(hout[k], dout[k], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, cs_));
+    return finish_ice_call(cs_, "aerobulk_gpu_series_ice");
+}
+
+// ---------------------------------------------------------------------------
 // flux diagnostics (the optional global reduction)
 // ---------------------------------------------------------------------------
 int diag_impl(long long n, const double *const *fields, double *stats, int on_device)
@@ -1835,6 +1899,33 @@ int aerobulk_gpu_oce_ice(const char *calgo_ice, const char *calgo_oce, double zt
     }
     return oce_ice_impl(calgo_ice, calgo_oce, zt, zu, n, sit, sst, t_zt, hum_zt, hum_kind, wind, slp, frice, CxN_easy, out,
                         on_device);
+}
+
+int aerobulk_gpu_series_ice(const char *calgo, double zt, double zu, long long n, const double *sic, const double *sit,
+                            const double *t_zt, const double *hum_zt, int hum_kind, const double *wind, const double *slp,
+                            const double *rad_sw, const double *rad_lw, const aerobulk_gpu_series_ice_out *out, int on_device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!on_device && out && sic && sit && t_zt && hum_zt && wind && slp && rad_sw && rad_lw && ensure_device() == 0) {
+        constexpr int NO = abk::NICESERIES_OUT;
+        const double *h[8 + NO] = {sic, sit, t_zt, hum_zt, wind, slp, rad_sw, rad_lw};
+        memcpy(h + 8, out, sizeof(double *) * NO);
+        const double *d[8 + NO];
+        long long len[8 + NO];
+        unsigned char dir[8 + NO];
+        for (int k = 0; k < 8 + NO; ++k) {
+            len[k] = n < 0 ? 0 : n;
+            dir[k] = k < 8 ? 1 : 2;
+        }
+        HostBounce hb;
+        if (alias_or_bounce(8 + NO, h, len, dir, d, hb)) {
+            aerobulk_gpu_series_ice_out od;
+            memcpy(&od, d + 8, sizeof(od));
+            return bounce_finish(hb, series_ice_impl(calgo, zt, zu, n, d[0], d[1], d[2], d[3], hum_kind, d[4], d[5], d[6], d[7],
+                                                     &od, 1));
+        }
+    }
+    return series_ice_impl(calgo, zt, zu, n, sic, sit, t_zt, hum_zt, hum_kind, wind, slp, rad_sw, rad_lw, out, on_device);
 }
 
 void aerobulk_gpu_set_ice_form_drag_per_point(int on) { std::lock_guard<std::mutex> lk(g_mu); g.ice_form_per_point = on ? 1 : 0; }

@@ -84,6 +84,49 @@ __global__ void __launch_bounds__(ICE_BLOCK, ICE_MIN_BLOCKS) ice_flux_kernel(con
     if (a.ice_flux[3] && a.ice_flux[3] != a.out[16]) a.ice_flux[3][i] = ev;
 }
 
+// One record of the sea-ice station series (src/ice/test_aerobulk_buoy_series_ice.f90:326-470): RiB at zt and the net
+// solar flux for every record; TURB_ICE_*, RiB at zu, BULK_FORMULA(l_ice), net long-wave and non-solar flux only where
+// the ice concentration exceeds 0.01 (:388) -- the other records read 0 (the program leaves them unset).  The program's
+// arrays are 1 x 1, so the LG15 form drag follows the record's own concentration.
+template <int IALGO, bool ZTEQ>
+__global__ void __launch_bounds__(ICE_BLOCK, ICE_MIN_BLOCKS) ice_series_kernel(const IceSeriesArgs a)
+{
+    abm::load_tables();
+    const long long i = (long long)blockIdx.x * ICE_BLOCK + threadIdx.x;
+    if (i >= a.n) return;
+    const double sit = __ldg(a.sit + i), T = __ldg(a.t_zt + i), slp = __ldg(a.slp + i), wnd = __ldg(a.wnd + i);
+    const double sic = __ldg(a.sic + i);
+    const double q = humidity_to_q(a.hum_kind, __ldg(a.hum_zt + i), T, slp);
+    const double siq = q_sat_ice(sit, slp);
+    const double tha = T + gamma_moist(T, q) * a.ui.zt;
+    double v[NICESERIES_OUT];
+#pragma unroll
+    for (int k = 0; k < NICESERIES_OUT; ++k) v[k] = 0.;
+    v[12] = ri_bulk(a.ui.zt, sit, tha, siq, q, abm::dmax(wnd, WSPD_THRSHLD_ICE));   // :380
+    v[5] = (1. - RICE_ALB0) * __ldg(a.rad_sw + i);                                  // :384
+    if (sic > 0.01) {
+        const IceOut o = solve_ice<IALGO, ZTEQ>(a.ui, sit, tha, siq, q, wnd, sic, sic);
+        if (IALGO == ICE_AN05 && o.bad) atomicMin(a.bad_rough, (unsigned long long)i);
+        // BULK_FORMULA_SCLR with l_ice, pEvap, prhoa: mod_phymbl.f90:1149-1203
+        const AirZu air = air_at_zu(a.ui.zu, o.t_zu, o.q_zu, slp);
+        const double Urho = o.Ub * air.rho1;
+        const double tau = Urho * o.Cd * wnd;
+        const double evap = Urho * o.Ce * (o.q_zu - siq);
+        const double qsen = Urho * o.Ch * (o.t_zu - sit) * air.cp;
+        const double qlat = RLSUB * evap;
+        if (tau > 10.) atomicMin(a.bad_tau, (unsigned long long)i);
+        const double t2 = sit * sit;
+        const double qlw = EMISS_I * (__ldg(a.rad_lw + i) - STEFAN * t2 * t2);      // qlw_net(l_ice), :1306-1312
+        v[0] = air.rho; v[1] = qlat; v[2] = qsen; v[3] = qlw; v[4] = qsen + qlat + qlw; v[6] = tau; v[7] = abm::dmin(evap, 0.);
+        v[8] = o.Cd; v[9] = o.Ch; v[10] = o.Ce; v[11] = o.z0;
+        v[13] = ri_bulk(a.ui.zu, sit, o.t_zu, siq, o.q_zu, o.Ub);
+        v[14] = o.CdN; v[15] = o.us; v[16] = o.L; v[17] = o.UN10; v[18] = o.t_zu; v[19] = o.q_zu; v[20] = o.Ub;
+    }
+#pragma unroll
+    for (int k = 0; k < NICESERIES_OUT; ++k)
+        if (a.out[k]) a.out[k][i] = v[k];
+}
+
 template <int OALGO, bool ZTEQ>
 __global__ void __launch_bounds__(ICE_BLOCK, ICE_MIN_BLOCKS) leads_kernel(const OceIceArgs a)
 {
@@ -148,6 +191,25 @@ static cudaError_t ice_flux_zt(bool zteq, const OceIceArgs &a, cudaStream_t s)
     else ice_flux_kernel<IALGO, false><<<nblocks(a.n), ICE_BLOCK, 0, s>>>(a);
     return cudaGetLastError();
 }
+template <int IALGO>
+static cudaError_t ice_series_zt(bool zteq, const IceSeriesArgs &a, cudaStream_t s)
+{
+    if (zteq) ice_series_kernel<IALGO, true><<<nblocks(a.n), ICE_BLOCK, 0, s>>>(a);
+    else ice_series_kernel<IALGO, false><<<nblocks(a.n), ICE_BLOCK, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_ice_series(int ialgo, bool zteq, const IceSeriesArgs &a, cudaStream_t s)
+{
+    if (a.n <= 0) return cudaSuccess;
+    switch (ialgo) {
+    case ICE_NEMO: return ice_series_zt<ICE_NEMO>(zteq, a, s);
+    case ICE_AN05: return ice_series_zt<ICE_AN05>(zteq, a, s);
+    case ICE_LU12: return ice_series_zt<ICE_LU12>(zteq, a, s);
+    case ICE_LG15: return ice_series_zt<ICE_LG15>(zteq, a, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 cudaError_t launch_ice_flux(int ialgo, bool zteq, const OceIceArgs &a, cudaStream_t s)
 {
     if (a.n <= 0) return cudaSuccess;

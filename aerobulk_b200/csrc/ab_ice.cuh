@@ -16,6 +16,8 @@ constexpr double RTT0 = 273.16;             // mod_const.f90:61
 constexpr double RLSUB = 2.834e+6;          // :92
 constexpr double RCD_ICE = 1.4e-3;          // :118
 constexpr double WSPD_THRSHLD_ICE = 0.2;    // :120
+constexpr double RICE_ALB0 = 0.8;           // mod_const.f90:51
+constexpr double EMISS_I = 0.996;           // mod_const.f90:56
 constexpr double RDG_I = 0.7858350313586662;            // LOG10(6.1071)   mod_phymbl.f90:147
 constexpr double RZ0_I_S_0 = 0.69e-3, RZ0_I_F_0 = 4.54e-4, RALPHA_0 = 0.2;   // mod_blk_ice_lg15.f90:37-41
 constexpr double LOG_5 = 0x1.9c041f7ed8d33p+0;          // LOG(1./0.2)

@@ -93,6 +93,20 @@ struct OceIceArgs {
     unsigned long long *bad_tau, *bad_rough;
 };
 cudaError_t launch_ice_flux(int ialgo, bool zt_eq_zu, const OceIceArgs &a, cudaStream_t s);
+
+// Sea-ice station series (src/ice/test_aerobulk_buoy_series_ice.f90:326-470), one thread per record.
+// out: 0 rho_zu 1 QL 2 QH 3 Qlw 4 QNS 5 Qsw 6 TAU 7 SBLM 8 Cd_i 9 Ch_i 10 Ce_i 11 z0 12 RiB_zt 13 RiB_zu 14 CdN 15 u_star 16 L
+//      17 UN10 18 theta_zu 19 q_zu 20 Ublk
+constexpr int NICESERIES_OUT = 21;
+struct IceSeriesArgs {
+    const double *sic, *sit, *t_zt, *hum_zt, *wnd, *slp, *rad_sw, *rad_lw;
+    double *out[NICESERIES_OUT];
+    long long n;
+    int hum_kind;
+    abd::IceUniform ui;
+    unsigned long long *bad_tau, *bad_rough;
+};
+cudaError_t launch_ice_series(int ialgo, bool zt_eq_zu, const IceSeriesArgs &a, cudaStream_t s);
 cudaError_t launch_leads(int oalgo, bool zt_eq_zu, const OceIceArgs &a, cudaStream_t s);
 
 // number of doubles in the statistics vector (see include/aerobulk_gpu.h)

@@ -20,6 +20,7 @@ MODULE mod_aerobulk_gpu
       &      aerobulk_gpu_series, aerobulk_gpu_series_out, aerobulk_gpu_series_csv,  &
       &      aerobulk_gpu_turb_ice, aerobulk_gpu_turb_ice_optional,                  &
       &      aerobulk_gpu_oce_ice, aerobulk_gpu_oce_ice_out, aerobulk_gpu_set_ice_form_drag_per_point, &
+      &      aerobulk_gpu_series_ice, aerobulk_gpu_series_ice_out,                   &
       &      aerobulk_gpu_set_rdt, aerobulk_gpu_set_gdept, aerobulk_gpu_set_nb_iter, &
       &      aerobulk_gpu_get_nb_iter, aerobulk_gpu_get_use_skin,                 &
       &      aerobulk_gpu_set_device, aerobulk_gpu_set_verbose, aerobulk_gpu_reset,  &
@@ -31,6 +32,16 @@ MODULE mod_aerobulk_gpu
       TYPE(c_ptr) :: xz0 = C_NULL_PTR, xu_star = C_NULL_PTR, xL = C_NULL_PTR, xUN10 = C_NULL_PTR
       TYPE(c_ptr) :: pdT_cs = C_NULL_PTR, pdT_wl = C_NULL_PTR, pHz_wl = C_NULL_PTR
    END TYPE aerobulk_gpu_turb_optional
+
+   !! output series of aerobulk_gpu_series_ice (struct aerobulk_gpu_series_ice_out), n values each; C_NULL_PTR = not wanted
+   TYPE, BIND(C) :: aerobulk_gpu_series_ice_out
+      TYPE(c_ptr) :: rho_zu = C_NULL_PTR, QL = C_NULL_PTR, QH = C_NULL_PTR, Qlw = C_NULL_PTR, QNS = C_NULL_PTR
+      TYPE(c_ptr) :: Qsw = C_NULL_PTR, TAU = C_NULL_PTR, SBLM = C_NULL_PTR
+      TYPE(c_ptr) :: Cd_i = C_NULL_PTR, Ch_i = C_NULL_PTR, Ce_i = C_NULL_PTR, z0 = C_NULL_PTR
+      TYPE(c_ptr) :: RiB_zt = C_NULL_PTR, RiB_zu = C_NULL_PTR, CdN = C_NULL_PTR
+      TYPE(c_ptr) :: u_star = C_NULL_PTR, L = C_NULL_PTR, UN10 = C_NULL_PTR
+      TYPE(c_ptr) :: theta_zu = C_NULL_PTR, q_zu = C_NULL_PTR, Ublk = C_NULL_PTR
+   END TYPE aerobulk_gpu_series_ice_out
 
    !! output series of aerobulk_gpu_series (struct aerobulk_gpu_series_out), each [Nt][S]; C_NULL_PTR = not wanted
    TYPE, BIND(C) :: aerobulk_gpu_series_out
@@ -169,6 +180,22 @@ MODULE mod_aerobulk_gpu
          IMPORT :: c_int
          INTEGER(c_int), VALUE :: on
       END SUBROUTINE aerobulk_gpu_set_ice_form_drag_per_point
+
+      !! sea-ice station series (src/ice/test_aerobulk_buoy_series_ice.f90) on n records; hum_kind 0 q, 1 dew-point, 2 RH
+      FUNCTION aerobulk_gpu_series_ice( calgo, zt, zu, n, psic, psit, pt_zt, phum_zt, hum_kind, pwind, pslp,  &
+         &                              prad_sw, prad_lw, pout, on_device )                                  &
+         &     BIND(C, NAME='aerobulk_gpu_series_ice') RESULT(ierr)
+         IMPORT :: c_int, c_long_long, c_double, c_char, c_ptr
+         CHARACTER(KIND=c_char), DIMENSION(*), INTENT(in) :: calgo      !! NUL-terminated
+         REAL(c_double),       VALUE :: zt, zu
+         INTEGER(c_long_long), VALUE :: n
+         TYPE(c_ptr),          VALUE :: psic, psit, pt_zt, phum_zt      !! C_LOC of the (host or device) arrays
+         INTEGER(c_int),       VALUE :: hum_kind
+         TYPE(c_ptr),          VALUE :: pwind, pslp, prad_sw, prad_lw
+         TYPE(c_ptr),          VALUE :: pout                            !! C_LOC of a TYPE(aerobulk_gpu_series_ice_out)
+         INTEGER(c_int),       VALUE :: on_device
+         INTEGER(c_int)              :: ierr
+      END FUNCTION aerobulk_gpu_series_ice
 
       !! page-lock / release an existing array: ierr = aerobulk_gpu_host_register( C_LOC(sst), INT(8*SIZE(sst), c_size_t) )
       FUNCTION aerobulk_gpu_host_register( ptr, nbytes ) BIND(C, NAME='aerobulk_gpu_host_register') RESULT(ierr)

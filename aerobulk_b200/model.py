@@ -88,6 +88,9 @@ def lib():
     L.aerobulk_gpu_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.aerobulk_gpu_host_unregister.restype = C.c_int
     L.aerobulk_gpu_host_unregister.argtypes = [C.c_void_p]
+    L.aerobulk_gpu_series_ice.restype = C.c_int
+    L.aerobulk_gpu_series_ice.argtypes = ([C.c_char_p, C.c_double, C.c_double, C.c_longlong] + [C.c_void_p] * 4 + [C.c_int] +
+                                          [C.c_void_p] * 4 + [C.c_void_p, C.c_int])
     L.aerobulk_gpu_series.restype = C.c_int
     L.aerobulk_gpu_series.argtypes = ([C.c_char_p, C.c_int, C.c_longlong, C.c_double, C.c_double] + [C.c_void_p] * 5 +
                                       [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int])
@@ -404,6 +407,31 @@ def oce_ice(calgo_ice: str, calgo_oce, zt: float, zu: float, sit, sst, t_zt, hum
                                 ptr(ins[6]), ptr(cx), C.cast(arr, C.c_void_p), 0)
     _check(rc)
     return outs
+
+
+SERIES_ICE_OUT = ("rho_zu", "QL", "QH", "Qlw", "QNS", "Qsw", "TAU", "SBLM", "Cd_i", "Ch_i", "Ce_i", "z0", "RiB_zt", "RiB_zu", "CdN",
+                  "u_star", "L", "UN10", "theta_zu", "q_zu", "Ublk")
+
+
+def series_ice(calgo: str, zt: float, zu: float, sic, sit, t_zt, hum_zt, wind, slp, rad_sw, rad_lw, hum_kind="q",
+               want=SERIES_ICE_OUT) -> dict:
+    """Sea-ice station series on HOST (numpy) arrays of any common shape: the per-record computation of
+    src/ice/test_aerobulk_buoy_series_ice.f90:326-470 (records without ice read 0).  Returns the series named in `want`."""
+    L = lib()
+    shape = np.shape(sic)
+    f = lambda a: np.ascontiguousarray(np.ravel(a), dtype=np.float64)
+    ins = [f(a) for a in (sic, sit, t_zt, hum_zt, wind, slp, rad_sw, rad_lw)]
+    n = ins[0].size
+    if any(a.size != n for a in ins):
+        raise ValueError("series_ice inputs differ in size")
+    outs = {k: np.zeros(n, dtype=np.float64) for k in want}
+    ptr = lambda a: None if a is None else a.ctypes.data
+    arr = (C.c_void_p * len(SERIES_ICE_OUT))(*[ptr(outs.get(k)) for k in SERIES_ICE_OUT])
+    hk = HUM_KINDS[hum_kind] if isinstance(hum_kind, str) else int(hum_kind)
+    rc = L.aerobulk_gpu_series_ice(calgo.encode(), float(zt), float(zu), n, *[ptr(a) for a in ins[:4]], hk,
+                                   *[ptr(a) for a in ins[4:]], C.cast(arr, C.c_void_p), 0)
+    _check(rc)
+    return {k: v.reshape(shape) for k, v in outs.items()}
 
 
 # ---------------------------------------------------------------------------

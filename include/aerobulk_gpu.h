@@ -223,6 +223,26 @@ int aerobulk_gpu_oce_ice(const char *calgo_ice, const char *calgo_oce, double zt
                          const double *wind, const double *slp, const double *frice, const double *CxN_easy,
                          const aerobulk_gpu_oce_ice_out *out, int on_device);
 
+/* Outputs of aerobulk_gpu_series_ice, each n values; any member may be NULL. */
+typedef struct aerobulk_gpu_series_ice_out {
+    double *rho_zu, *QL, *QH, *Qlw, *QNS, *Qsw, *TAU, *SBLM;     /* SBLM: sublimation, kg/m^2/s (the program prints mm/day) */
+    double *Cd_i, *Ch_i, *Ce_i, *z0, *RiB_zt, *RiB_zu, *CdN;
+    double *u_star, *L, *UN10, *theta_zu, *q_zu, *Ublk;
+} aerobulk_gpu_series_ice_out;
+
+/* The sea-ice station series of src/ice/test_aerobulk_buoy_series_ice.f90:326-470 on n records (stations x time,
+ * any order: nothing is carried from one record to the next): sic ice concentration, sit ice surface temperature [K],
+ * t_zt ABSOLUTE air temperature [K], hum_zt (hum_kind as above), wind [m/s], slp [Pa], rad_sw / rad_lw downwelling
+ * radiation [W/m^2].  calgo: "nemo", "an05", "lu12", "lg15" (the program's four choices; lg15 with the record's own
+ * concentration, as its 1 x 1 arrays imply).  RiB_zt and Qsw = (1 - 0.8) rad_sw for every record; the bulk algorithm,
+ * RiB_zu, BULK_FORMULA(l_ice), Qlw = 0.996 (rad_lw - sigma sit^4) and QNS = QH + QL + Qlw only where sic > 0.01 -- the
+ * program skips the other records and leaves their values unset; here they are 0.  Iterations: the nb_iter global
+ * (the program uses 20). */
+int aerobulk_gpu_series_ice(const char *calgo, double zt, double zu, long long n, const double *sic, const double *sit,
+                            const double *t_zt, const double *hum_zt, int hum_kind, const double *wind, const double *slp,
+                            const double *rad_sw, const double *rad_lw, const aerobulk_gpu_series_ice_out *out,
+                            int on_device);
+
 /* Waits for the session stream and reports a deferred error (wind stress too strong). */
 int aerobulk_gpu_synchronize(void);
 

@@ -2318,6 +2318,80 @@ int abo_oce_ice(abo_session *s, const char *calgo_ice, const char *calgo_oce, do
     return ABO_OK;
 }
 
+/*
+ * Sea-ice station series: the per-record computation of src/ice/test_aerobulk_buoy_series_ice.f90:326-470 on n records
+ * (no state is carried between records; the program's nx = ny = 1 makes every TURB_ICE_* call a one-point call, so the
+ * LG15 form drag uses the record's own ice concentration).
+ *   rho_zt .. (:350, not returned); SIQ = q_sat(SIT, SLP, l_ice) (:362); theta_zt = t_zt + gamma_moist(t_zt, q_zt) zt (:371);
+ *   RiB_zt = Ri_bulk(zt, SIT, theta_zt, SIQ, q_zt, MAX(W10, wspd_thrshld_ice)) (:380); Qsw = (1 - rice_alb0) rad_sw (:384);
+ *   only where SIC > 0.01 (:388): TURB_ICE_<nemo|an05|lu12|lg15> (:392-411), RiB_zu (:427),
+ *   BULK_FORMULA(l_ice, pEvap, prhoa) (:430-433), Qlw = qlw_net(rad_lw, SIT, l_ice) (:436), QNS = QH + QL + Qlw (:439).
+ * Records without ice are skipped by the program (its arrays keep whatever ALLOCATE left there); here they read 0.
+ * hum_kind 0 q, 1 dew-point [K], 2 RH [%] (:194-207).  out[21] (NULL = skip):
+ *   0 rho_zu 1 QL 2 QH 3 Qlw 4 QNS 5 Qsw 6 TAU 7 SBLM [kg/m^2/s] 8 Cd_i 9 Ch_i 10 Ce_i 11 z0 12 RiB_zt 13 RiB_zu 14 CdN
+ *   15 u_star 16 L 17 UN10 18 theta_zu 19 q_zu 20 Ublk
+ */
+static const double rice_alb0 = 0.8;    /* mod_const.f90:51 */
+static const double emiss_i = 0.996;    /* mod_const.f90:56 */
+
+int abo_series_ice(abo_session *s, const char *calgo, double zt, double zu, long n, const double *sic, const double *sit,
+                   const double *t_zt, const double *hum_zt, int hum_kind, const double *wnd, const double *slp,
+                   const double *rad_sw, const double *rad_lw, double *const *out)
+{
+    init_consts();
+    s->errmsg[0] = 0;
+    int ialgo = ice_algo_id(calgo);
+    if (ialgo != ABO_ICE_NEMO && ialgo != ABO_ICE_AN05 && ialgo != ABO_ICE_LU12 && ialgo != ABO_ICE_LG15) {
+        snprintf(s->errmsg, sizeof(s->errmsg), "UNKNOWN algo: %s !!!", calgo);   /* :413-415 */
+        return ABO_ERR_ALGO;
+    }
+    long bad = n;
+    int badtau = 0;
+    const int nb_iter = s->nb_iter;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(s->nthreads) schedule(static) reduction(min:bad) reduction(|:badtau)
+#endif
+    for (long i = 0; i < n; i++) {
+        const double T = t_zt[i], P = slp[i];
+        double q;
+        if (hum_kind == 2) q = q_air_rh(hum_zt[i], T, P);
+        else if (hum_kind == 1) q = q_air_dp(hum_zt[i], P);
+        else q = hum_zt[i];
+        const double siq = q_sat_ice(sit[i], P);
+        const double tha = T + gamma_moist(T, q) * zt;
+        double v[21];
+        for (int k = 0; k < 21; k++) v[k] = 0.;
+        v[12] = Ri_bulk(zt, sit[i], tha, siq, q, MAX(wnd[i], wspd_thrshld_ice));
+        v[5] = (1. - rice_alb0) * rad_sw[i];
+        if (sic[i] > 0.01) {
+            ice_out o;
+            memset(&o, 0, sizeof(o));
+            if (ice_point(ialgo, nb_iter, zt, zu, sit[i], tha, siq, q, wnd[i], sic[i], sic[i], NULL, &o) && i < bad) bad = i;
+            double tau, qh, ql, ev;
+            bulk_formula_ice(zu, sit[i], siq, o.t_zu, o.q_zu, o.Cd, o.Ch, o.Ce, wnd[i], o.Ub, P, &tau, &qh, &ql, &ev);
+            if (tau > 10.) badtau = 1;
+            /* prhoa of BULK_FORMULA: the density before its MAX(., 1) */
+            const double zta = o.t_zu - rgamma_dry * zu;
+            double rho = rho_air(zta, o.q_zu, P);
+            rho = rho_air(zta, o.q_zu, P - rho * grav * zu);
+            const double zt2 = sit[i] * sit[i];
+            const double qlw = emiss_i * (rad_lw[i] - stefan * zt2 * zt2);   /* qlw_net_sclr with l_ice, mod_phymbl.f90:1306-1312 */
+            v[0] = rho; v[1] = ql; v[2] = qh; v[3] = qlw; v[4] = qh + ql + qlw; v[6] = tau; v[7] = ev;
+            v[8] = o.Cd; v[9] = o.Ch; v[10] = o.Ce; v[11] = o.z0;
+            v[13] = Ri_bulk(zu, sit[i], o.t_zu, siq, o.q_zu, o.Ub);
+            v[14] = o.CdN; v[15] = o.us; v[16] = o.L; v[17] = o.UN10; v[18] = o.t_zu; v[19] = o.q_zu; v[20] = o.Ub;
+        }
+        for (int k = 0; k < 21; k++)
+            if (out[k]) out[k][i] = v[k];
+    }
+    if (bad < n) {
+        snprintf(s->errmsg, sizeof(s->errmsg), " rough_leng_tq@mod_blk_ice_an05.f90 => something wrong with zsmoot, ztrans, zrough! (point %ld)", bad + 1);
+        return ABO_ERR_ICE_ROUGH;
+    }
+    if (badtau) { snprintf(s->errmsg, sizeof(s->errmsg), "wind stress too strong"); return ABO_ERR_TAU; }
+    return ABO_OK;
+}
+
 /* ------------------------------------------------------------------ */
 /* building blocks for unit tests                                      */
 /* ------------------------------------------------------------------ */

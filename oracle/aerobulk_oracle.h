@@ -149,6 +149,11 @@ int abo_oce_ice(abo_session *s, const char *calgo_ice, const char *calgo_oce, do
                 const double *wnd, const double *slp, const double *frice, const double *cxn, int per_point_form_drag,
                 double *const *out);
 
+/* sea-ice station series of src/ice/test_aerobulk_buoy_series_ice.f90 on n records; out[21], see .c */
+int abo_series_ice(abo_session *s, const char *calgo, double zt, double zu, long n, const double *sic, const double *sit,
+                   const double *t_zt, const double *hum_zt, int hum_kind, const double *wnd, const double *slp,
+                   const double *rad_sw, const double *rad_lw, double *const *out);
+
 /* test-only: reproduce the pre-drift COARE 3.0 viscosity line (see .c) */
 void abo_debug_coare3p0_visc_at_tzu(int on);
 

@@ -83,6 +83,9 @@ def lib():
         L.abo_turb_ice.restype = C.c_int
         L.abo_turb_ice.argtypes = ([C.c_void_p, C.c_char_p, C.c_double, C.c_double, C.c_long] + [_dp] * 7 + [C.c_int] +
                                    [_dp] * 6 + [C.POINTER(_dp)])
+        L.abo_series_ice.restype = C.c_int
+        L.abo_series_ice.argtypes = ([C.c_void_p, C.c_char_p, C.c_double, C.c_double, C.c_long] + [_dp] * 4 + [C.c_int] +
+                                     [_dp] * 4 + [C.POINTER(_dp)])
         L.abo_oce_ice.restype = C.c_int
         L.abo_oce_ice.argtypes = ([C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_long] + [_dp] * 4 +
                                   [C.c_int] + [_dp] * 4 + [C.c_int, C.POINTER(_dp)])
@@ -247,6 +250,22 @@ class OracleSession:
         rc = self._L.abo_oce_ice(self._s, calgo_ice.encode(), None if calgo_oce is None else calgo_oce.encode(), float(zt),
                                  float(zu), n, _ptr(ins[0]), _ptr(ins[1]), _ptr(ins[2]), _ptr(ins[3]), int(hum_kind),
                                  _ptr(ins[4]), _ptr(ins[5]), _ptr(ins[6]), _ptr(cx), int(bool(per_point_form_drag)), arr)
+        if rc != 0:
+            raise OracleError(rc, self._L.abo_errmsg(self._s).decode())
+        return outs
+
+    SERIES_ICE_OUT = ("rho_zu", "QL", "QH", "Qlw", "QNS", "Qsw", "TAU", "SBLM", "Cd_i", "Ch_i", "Ce_i", "z0", "RiB_zt", "RiB_zu",
+                      "CdN", "u_star", "L", "UN10", "theta_zu", "q_zu", "Ublk")
+
+    def series_ice(self, calgo, zt, zu, sic, sit, t_zt, hum_zt, wind, slp, rad_sw, rad_lw, hum_kind=0):
+        """Sea-ice station series (abo_series_ice); returns the 21 series of SERIES_ICE_OUT, flattened."""
+        f = lambda a: np.ascontiguousarray(np.ravel(a), dtype=np.float64)
+        ins = [f(a) for a in (sic, sit, t_zt, hum_zt, wind, slp, rad_sw, rad_lw)]
+        n = ins[0].size
+        outs = {k: np.zeros(n) for k in self.SERIES_ICE_OUT}
+        arr = (_dp * 21)(*[_ptr(outs[k]) for k in self.SERIES_ICE_OUT])
+        rc = self._L.abo_series_ice(self._s, calgo.encode(), float(zt), float(zu), n, *[_ptr(a) for a in ins[:4]],
+                                    int(hum_kind), *[_ptr(a) for a in ins[4:]], arr)
         if rc != 0:
             raise OracleError(rc, self._L.abo_errmsg(self._s).decode())
         return outs

@@ -83,6 +83,7 @@ def test_compute_fails_loudly_without_device(ab):
     for call in (lambda: ab.series("ncar", 2.0, 10.0, **d),
                  lambda: ab.oce_ice("nemo", None, 2.0, 10.0, **synth.ice_fields(4)),
                  lambda: ab.turb_ice("nemo", 2.0, 10.0, one * 270, one * 271, one * 1e-3, one * 1e-3, one * 3),
+                 lambda: ab.series_ice("nemo", 2.0, 10.0, one * 0.9, one * 265, one * 266, one * 1e-3, one * 4, one * 1e5, one * 50, one * 200),
                  lambda: ab.turb("ncar", 1, 2.0, 10.0, one * 290, one * 289, one * 1e-2, one * 8e-3, one * 5),
                  lambda: ab.flux_diagnostics({"QL": one})):
         with pytest.raises(ab.AerobulkError) as e:

@@ -178,3 +178,52 @@ def test_ice_errors(ab):
     with pytest.raises(ab.AerobulkError) as e:
         ab.oce_ice("nemo", None, 2.0, 10.0, **f)
     assert e.value.code == 8
+
+
+@pytest.mark.parametrize("algo,zt,hum", [("nemo", 2.0, "q"), ("an05", 2.0, "rh"), ("lu12", 10.0, "dp"), ("lg15", 2.0, "q"),
+                                         ("lg15", 10.0, "rh"), ("an05", 10.0, "q")])
+def test_series_ice_matches_oracle(ab, algo, zt, hum):
+    """aerobulk_gpu_series_ice against the oracle's restatement of src/ice/test_aerobulk_buoy_series_ice.f90:326-470:
+    all 21 series, records without ice read 0 on both sides."""
+    from oracle.oracle import OracleSession, OracleError
+    n = 40000
+    f = synth.ice_fields(n, seed=314, humidity=hum)
+    rng = np.random.default_rng(7)
+    f = dict(sic=f["frice"], sit=f["sit"], t_zt=f["t_zt"], hum_zt=f["hum_zt"], wind=f["wind"], slp=f["slp"],
+             rad_sw=np.maximum(0.0, 400.0 * rng.random(n) - 80.0), rad_lw=170.0 + 140.0 * rng.random(n))
+    ab.reset()
+    ab.set_nb_iter(20)                 # src/ice/test_aerobulk_buoy_series_ice.f90:77
+    o = OracleSession(threads=8)
+    o.set_nb_iter(20)
+    hk = {"q": 0, "dp": 1, "rh": 2}[hum]
+    got, ref, f = _both(lambda d: ab.series_ice(algo, zt, 10.0, **d, hum_kind=hum),
+                        lambda d: o.series_ice(algo, zt, 10.0, **d, hum_kind=hk), f, ab.AerobulkError, OracleError)
+    ice = f["sic"] > 0.01
+    assert 0 < (~ice).sum() < n
+    ren = {"Cd_i": "Cd", "Ch_i": "Ch", "Ce_i": "Ce", "TAU": "Tau", "SBLM": "Evap", "Ublk": "Ub", "RiB_zt": "RiB", "RiB_zu": "RiB",
+           "Qlw": "QH", "QNS": "QH", "Qsw": "QH"}
+    worst = 0.0
+    for k in ab.SERIES_ICE_OUT:
+        g, r = got[k], ref[k]
+        assert np.all(np.isfinite(g)), k
+        if k not in ("Qsw", "RiB_zt"):
+            assert np.all(g[~ice] == 0.0) and np.all(r[~ice] == 0.0), k
+        base = ren.get(k, k)
+        if base == "L":
+            g, r = 1.0 / np.where(ice, g, 1.0), 1.0 / np.where(ice, r, 1.0)
+        e = np.abs(g - r) / (np.abs(r) + SCALE[base])
+        if k == "Ch_i":
+            e = np.where(np.abs(ref["QH"]) > 1.0, e, 0.0)
+        if k == "Ce_i":
+            e = np.where(np.abs(ref["QL"]) > 1.0, e, 0.0)
+        bad = int((e > TOL).sum())
+        assert bad <= max(1, int(2e-5 * n)), (algo, k, bad, float(e.max()))
+        assert float(e.max()) <= 1e-6, (algo, k, float(e.max()))
+        worst = max(worst, float(np.sort(e)[-2]))
+    assert worst <= TOL
+    # a subset of outputs gives the same bits
+    part = ab.series_ice(algo, zt, 10.0, **f, hum_kind=hum, want=("QNS", "TAU"))
+    assert np.array_equal(part["QNS"], got["QNS"]) and np.array_equal(part["TAU"], got["TAU"])
+    with pytest.raises(ab.AerobulkError) as e:
+        ab.series_ice("easy", zt, 10.0, **f, hum_kind=hum)
+    assert e.value.code == 7

@@ -85,6 +85,15 @@ def test_turb_ice_and_oce_ice_large_pageable_arrays(ab):
             assert np.array_equal(whole[k], np.concatenate([lo[k], hi[k]])), (oce, k)
         if oce is None:   # no leads: the over-water outputs are left as the caller passed them
             assert np.all(whole["QH_w"] == 0.0) and np.all(whole["Tau_w"] == 0.0)
+
+    rng = np.random.default_rng(1)
+    d = dict(sic=f["frice"], sit=f["sit"], t_zt=f["t_zt"], hum_zt=f["hum_zt"], wind=f["wind"], slp=f["slp"],
+             rad_sw=300.0 * rng.random(n), rad_lw=180.0 + 100.0 * rng.random(n))
+    whole = ab.series_ice("lg15", 2.0, 10.0, **d)
+    lo = ab.series_ice("lg15", 2.0, 10.0, **{k: v[:h].copy() for k, v in d.items()})
+    hi = ab.series_ice("lg15", 2.0, 10.0, **{k: v[h:].copy() for k, v in d.items()})
+    for k in whole:
+        assert np.array_equal(whole[k], np.concatenate([lo[k], hi[k]])), k
     ab.reset()
 
 

@@ -127,3 +127,46 @@ def test_ice_all_algorithms_finite_and_ordered():
         assert np.all(r["QH_w"] == 0)          # leads skipped
     with pytest.raises(oracle.OracleError):
         o.oce_ice("best", None, 2.0, 10.0, f["sit"], None, f["t_zt"], f["hum_zt"], f["wind"], f["slp"], f["frice"])
+
+
+def test_series_ice_restatement_against_its_building_blocks():
+    """abo_series_ice (src/ice/test_aerobulk_buoy_series_ice.f90:326-470): the bulk part coincides with the ice half of
+    abo_oce_ice evaluated with each record's own concentration; the radiative terms, the gate at SIC = 0.01 and RiB at zt
+    are checked against hand evaluations of the source formulas."""
+    n = 4000
+    f = synth.ice_fields(n, seed=21)
+    rng = np.random.default_rng(5)
+    rsw, rlw = np.maximum(0.0, 400.0 * rng.random(n) - 80.0), 170.0 + 140.0 * rng.random(n)
+    sic = f["frice"].copy()
+    sic[:8] = [0.0, 0.005, 0.01, 0.0100001, 0.02, 0.5, 1.0, 0.009999]
+    o = OracleSession(threads=4)
+    o.set_nb_iter(20)
+    L = oracle.lib()
+    ice = sic > 0.01
+    assert not ice[2] and ice[3]
+    for algo in ("nemo", "an05", "lu12", "lg15"):
+        r = o.series_ice(algo, 2.0, 10.0, sic, f["sit"], f["t_zt"], f["hum_zt"], f["wind"], f["slp"], rsw, rlw)
+        b = o.oce_ice(algo, None, 2.0, 10.0, f["sit"], None, f["t_zt"], f["hum_zt"], f["wind"], f["slp"], sic, per_point_form_drag=True)
+        for a, c in (("QH", "QH_i"), ("QL", "QL_i"), ("TAU", "Tau_i"), ("SBLM", "Evap_i"), ("Cd_i", "Cd_i"), ("Ch_i", "Ch_i"),
+                     ("Ce_i", "Ce_i"), ("z0", "z0_i"), ("RiB_zu", "RiB_i"), ("u_star", "u_star_i"), ("L", "L_i"),
+                     ("UN10", "UN10_i"), ("theta_zu", "theta_zu_i"), ("q_zu", "q_zu_i"), ("Ublk", "Ub_i")):
+            assert np.array_equal(r[a][ice], b[c][ice]), (algo, a)
+        for k in o.SERIES_ICE_OUT:
+            if k not in ("Qsw", "RiB_zt"):
+                assert np.all(r[k][~ice] == 0.0), (algo, k)
+        assert np.array_equal(r["Qsw"], (1.0 - 0.8) * rsw)
+        qlw = 0.996 * (rlw - 5.67e-8 * (f["sit"] * f["sit"]) * (f["sit"] * f["sit"]))
+        assert np.allclose(r["Qlw"][ice], qlw[ice], rtol=1e-15, atol=0)
+        assert np.array_equal(r["QNS"][ice], (r["QH"] + r["QL"] + r["Qlw"])[ice])
+        for i in (0, 3, 100, 2000):
+            tha = f["t_zt"][i] + L.abo_gamma_moist(f["t_zt"][i], f["hum_zt"][i]) * 2.0
+            siq = L.abo_q_sat_ice(f["sit"][i], f["slp"][i])
+            ref = L.abo_Ri_bulk(2.0, f["sit"][i], tha, siq, f["hum_zt"][i], max(f["wind"][i], 0.2))
+            assert r["RiB_zt"][i] == ref
+        # prhoa of BULK_FORMULA: air density at zu from theta_zu - gamma_dry zu, with the pressure lowered by rho g zu
+        i = 5
+        ta = r["theta_zu"][i] - 9.8 / 1005.0 * 10.0
+        rho = L.abo_rho_air(ta, r["q_zu"][i], f["slp"][i])
+        assert r["rho_zu"][i] == pytest.approx(L.abo_rho_air(ta, r["q_zu"][i], f["slp"][i] - rho * 9.8 * 10.0), rel=1e-13)
+    with pytest.raises(oracle.OracleError):
+        o.series_ice("easy", 2.0, 10.0, sic, f["sit"], f["t_zt"], f["hum_zt"], f["wind"], f["slp"], rsw, rlw)
