@@ -137,6 +137,11 @@ def test_series_cli_arguments():
     r = subprocess.run([sys.executable, "-m", "aerobulk_b200.series_cli", "a.csv", "b.csv", "--algo", "coare9"], cwd=ROOT,
                        capture_output=True, text=True)
     assert r.returncode == 2 and "invalid choice" in r.stderr
+    # ocean and sea-ice algorithms do not mix
+    for args, word in ((["--ice", "--algo", "ncar"], "does not go with"), (["--algo", "lg15"], "needs --ice")):
+        r = subprocess.run([sys.executable, "-m", "aerobulk_b200.series_cli", "a.csv", "b.csv"] + args, cwd=ROOT,
+                           capture_output=True, text=True)
+        assert r.returncode == 2 and word in r.stderr, r.stderr
 
 
 def test_host_copy_threads_selftest(ab):

@@ -227,3 +227,39 @@ def test_series_ice_matches_oracle(ab, algo, zt, hum):
     with pytest.raises(ab.AerobulkError) as e:
         ab.series_ice("easy", zt, 10.0, **f, hum_kind=hum)
     assert e.value.code == 7
+
+
+def test_series_cli_ice(ab, tmp_path):
+    """python -m aerobulk_b200.series_cli --ice: CSV with the ERA5 column names of test_aerobulk_buoy_series_ice.f90:179-211
+    (deg C temperatures, RH, u10/v10) -> the program's 14 series, equal to a direct aerobulk_gpu_series_ice call."""
+    import os, subprocess, sys
+    n = 48
+    f = synth.ice_fields(n, seed=8, humidity="rh")
+    rng = np.random.default_rng(2)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    u10, v10 = f["wind"] * np.cos(ang), f["wind"] * np.sin(ang)
+    rsw, rlw = 250.0 * rng.random(n), 180.0 + 90.0 * rng.random(n)
+    fin, fout = tmp_path / "ice.csv", tmp_path / "out.csv"
+    with open(fin, "w") as fh:
+        fh.write("# synthetic ice station\ntime, siconc, istl1, t2m, rh_air, u10, v10, msl, ssrd, strd\n")
+        for i in range(n):
+            row = [f["frice"][i], f["sit"][i] - 273.15, f["t_zt"][i] - 273.15, f["hum_zt"][i], u10[i], v10[i], f["slp"][i], rsw[i], rlw[i]]
+            fh.write(f"2019-02-{1 + i // 24:02d} {i % 24:02d}:00," + ",".join(repr(float(x)) for x in row) + "\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "aerobulk_b200.series_cli", str(fin), str(fout), "--ice", "--algo", "lu12"],
+                       cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = open(fout).read().strip().splitlines()
+    hdr = lines[0].split(",")
+    assert hdr[:5] == ["time", "Wind", "A", "rho_a", "Qlat"] and len(lines) == n + 1
+    got = np.array([[float(x) for x in l.split(",")[1:]] for l in lines[1:]])
+    ab.reset()
+    ab.set_nb_iter(20)
+    # the CLI converted the temperatures back to K and u10, v10 to a speed: feed the API the same values
+    ref = ab.series_ice("lu12", 2.0, 10.0, f["frice"], (f["sit"] - 273.15) + 273.15, (f["t_zt"] - 273.15) + 273.15, f["hum_zt"],
+                        np.hypot(u10, v10), f["slp"], rsw, rlw, hum_kind="rh")
+    for j, k in enumerate(("rho_zu", "QL", "QH", "Qlw", "QNS", "Qsw", "TAU", "SBLM", "Cd_i", "Ch_i", "z0", "RiB_zt", "RiB_zu", "CdN")):
+        assert np.array_equal(got[:, 2 + j], ref[k]), k
+    r = subprocess.run([sys.executable, "-m", "aerobulk_b200.series_cli", str(fin), str(fout), "--ice", "--algo", "ncar"],
+                       cwd=root, capture_output=True, text=True)
+    assert r.returncode == 2
