@@ -1,4 +1,4 @@
-"""Regression fixtures of the ORACLE for the paths the reference holds no fixture for (sea ice, station series, TURB_*
+"""Regression fixtures of the ORACLE for the paths the reference holds no fixture for (sea ice, station series, sea-ice series, TURB_*
 optional outputs).  NOT reference outputs: they freeze today's restatement so that a later edit of oracle/ that changes
 a number is noticed (tests/test_oracle_golden.py::test_oracle_regression_fixtures).  Re-run only when such a change
 is intended:  python tests/golden/make_regression.py"""
@@ -29,6 +29,15 @@ def cases():
         r = o.oce_ice(ice, "ncar", 2.0, 10.0, one(268.15), one(271.35), one(258.15), one(0.0009), one(9.0), one(100500.0),
                       one(0.35))
         out[f"ice_unstable/{ice}"] = {k: float(v[0]) for k, v in r.items()}
+    # sea-ice station series (src/ice/test_aerobulk_buoy_series_ice.f90): the test_ice.sh point with radiation, a record
+    # below the SIC gate, an unstable one
+    sic, sit = np.array([0.8, 0.005, 0.35]), np.array([270.15, 270.15, 268.15])
+    tair, qa = np.array([276.15, 276.15, 258.15]), np.array([0.004, 0.004, 0.0009])
+    wnd, slp = np.array([3.0, 3.0, 9.0]), np.array([101000.0, 101000.0, 100500.0])
+    rsw, rlw = np.array([120.0, 120.0, 0.0]), np.array([250.0, 250.0, 190.0])
+    for ice in ("nemo", "an05", "lu12", "lg15"):
+        r = o.series_ice(ice, 2.0, 10.0, sic, sit, tair, qa, wnd, slp, rsw, rlw)
+        out[f"series_ice/{ice}"] = {k: [float(x) for x in v] for k, v in r.items()}
     # station series: 30 records of 3 stations, two algorithms; the last record and two mid-series values per output
     d = synth.station_series(30, 3)
     for algo in ("coare3p6", "ecmwf"):
