@@ -66,7 +66,9 @@ def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "")
         if job.wait() != 0:
             raise subprocess.CalledProcessError(job.returncode, cmd)
     if force or _stale(lib, objs):
-        cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + ARCH + ["-shared", "-o", lib] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"]
+        # -z nodelete: the copy threads of ab_copy_pool.hpp must outlive any dlclose of the library
+        cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + ARCH + ["-shared", "-o", lib] + objs + [
+            "-cudart", "static", "-Xlinker", "--exclude-libs,ALL", "-Xlinker", "-z", "-Xlinker", "nodelete"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
