@@ -145,7 +145,8 @@ def test_pageable_path_knobs_do_not_change_results():
     hashes = {}
     for tag, env in {"default": {}, "no bounce": {"AEROBULK_GPU_BOUNCE": "0"}, "slab budget 1 MB": {"AEROBULK_GPU_BOUNCE_MAX_MB": "1"},
                      "1 thread, plain stores": {"AEROBULK_GPU_HOST_THREADS": "1", "AEROBULK_GPU_COPY_STREAMING": "0"},
-                     "small chunks, 3 threads": {"AEROBULK_GPU_BOUNCE_CHUNK_POINTS": "20000", "AEROBULK_GPU_HOST_THREADS": "3"}}.items():
+                     "small chunks, 3 threads": {"AEROBULK_GPU_BOUNCE_CHUNK_POINTS": "20000", "AEROBULK_GPU_HOST_THREADS": "3"},
+                     "equal chunks": {"AEROBULK_GPU_BOUNCE_CHUNK_POINTS": "50000", "AEROBULK_GPU_BOUNCE_SHAPE": "0"}}.items():
         r = subprocess.run([sys.executable, "-c", _KNOB_SCRIPT], cwd=root, env={**os.environ, **env}, capture_output=True,
                            text=True, timeout=600)
         assert r.returncode == 0, (tag, r.stderr[-2000:])
