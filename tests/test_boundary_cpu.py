@@ -37,6 +37,14 @@ def test_library_exports_every_declared_symbol(ab):
         assert hasattr(L, s), f"{s} is declared in include/aerobulk_gpu.h but not exported"
 
 
+def test_header_is_plain_c_and_cxx():
+    """include/aerobulk_gpu.h is what a C (cgo, ctypes generators ...) or C++ caller includes: strict C99 and C++11."""
+    for comp, std, lang in (("gcc", "-std=c99", "c"), ("g++", "-std=c++11", "c++")):
+        r = subprocess.run([comp, std, "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", lang, HDR],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
 def test_no_unexpected_exports(ab):
     """Only the declared C ABI and the aerobulk:: C++ API are exported (-fvisibility=hidden)."""
     from aerobulk_b200.model import _SO
