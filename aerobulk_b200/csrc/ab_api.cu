@@ -699,6 +699,38 @@ int check_bad_flag(const double *h_taux, const double *h_tauy)
                 sqrt(tx * tx + ty * ty), (long long)(bad % Ni) + 1, (long long)(bad / Ni) + 1);
 }
 
+// Row-block chunk plan of a host-array call: cstart[0..nchunks], boundaries on multiples of 2048 points (whole sort
+// windows / thread blocks).  kind 0: one chunk (device arrays, zero-copy on pinned arrays); 1: staged H2D | kernel | D2H
+// pipeline (sizes decrease linearly by default: short exposed tail); 2: pageable arrays through the pinned slab (small
+// first and last chunks by default: short fill and drain).
+int plan_chunks(long long n, int kind, long long *cstart)
+{
+    int nchunks = 1;
+    if (kind == 2) {
+        nchunks = (int)((n + bounce_chunk_points() - 1) / bounce_chunk_points());
+        nchunks = nchunks < 1 ? 1 : (nchunks > MAX_CHUNKS ? MAX_CHUNKS : nchunks);
+    } else if (kind == 1) {
+        nchunks = (int)(n / min_chunk_points());
+        nchunks = nchunks < 1 ? 1 : (nchunks > chunk_limit() ? chunk_limit() : nchunks);
+    }
+    double w[MAX_CHUNKS], wsum = 0.;
+    for (int c = 0; c < nchunks; ++c) {
+        if (kind == 2) w[c] = bounce_shape() == 1 ? (double)((c + 1 < nchunks - c) ? c + 1 : nchunks - c) : 1.;
+        else w[c] = chunk_shape() == 0 ? (double)(nchunks - c) : (chunk_shape() == 2 && c == 0 ? 0.5 : 1.);
+        wsum += w[c];
+    }
+    double acc = 0.;
+    cstart[0] = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        acc += w[c];
+        long long s0 = (long long)((double)n * acc / wsum);
+        s0 = (s0 + 2047) / 2048 * 2048;
+        cstart[c + 1] = s0 > n ? n : s0;
+    }
+    cstart[nchunks] = n;
+    return nchunks;
+}
+
 // ---------------------------------------------------------------------------
 // AEROBULK_MODEL (mod_aerobulk.f90:176-269) + aerobulk_compute dispatch
 // ---------------------------------------------------------------------------
@@ -783,31 +815,8 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         for (int k = 0; k < 6; ++k) out_alias[k] = out_h[k] ? g.hb_dev + (long long)(8 + k) * g.cap_hb : nullptr;
         zc_in = zc_out = true;
     }
-    int nchunks = 1;
-    if (bounce) {
-        nchunks = (int)((n + bounce_chunk_points() - 1) / bounce_chunk_points());
-        nchunks = nchunks > MAX_CHUNKS ? MAX_CHUNKS : nchunks;
-    } else if (!device_ptrs && !zc_in) {
-        nchunks = (int)(n / min_chunk_points());
-        nchunks = nchunks < 1 ? 1 : (nchunks > chunk_limit() ? chunk_limit() : nchunks);
-    }
     long long cstart[MAX_CHUNKS + 1];
-    {
-        double w[MAX_CHUNKS], wsum = 0.;
-        for (int c = 0; c < nchunks; ++c) {
-            w[c] = bounce ? (bounce_shape() == 1 ? (double)((c + 1 < nchunks - c) ? c + 1 : nchunks - c) : 1.) : chunk_shape() == 0 ? (double)(nchunks - c) : (chunk_shape() == 2 && c == 0 ? 0.5 : 1.);
-            wsum += w[c];
-        }
-        double acc = 0.;
-        cstart[0] = 0;
-        for (int c = 0; c < nchunks; ++c) {
-            acc += w[c];
-            long long s0 = (long long)((double)n * acc / wsum);
-            s0 = (s0 + 2047) / 2048 * 2048;   // whole sort windows / thread blocks
-            cstart[c + 1] = s0 > n ? n : s0;
-        }
-        cstart[nchunks] = n;
-    }
+    const int nchunks = plan_chunks(n, bounce ? 2 : ((!device_ptrs && !zc_in) ? 1 : 0), cstart);
 
     if (device_ptrs) {
         for (int k = 0; k < 8; ++k) in_d[k] = in_h[k];
@@ -1944,6 +1953,12 @@ int aerobulk_gpu_flux_diagnostics(long long n, const double *QL, const double *Q
 }
 
 int aerobulk_gpu_diag_reduce_op(int i) { return (i <= 0 || i >= abk::NDIAG) ? 0 : (i - 1) % 3; }
+
+int aerobulk_gpu_chunk_plan(long long n, int kind, long long *cstart)
+{
+    if (n < 0 || kind < 0 || kind > 2 || !cstart) return -1;
+    return plan_chunks(n, kind, cstart);
+}
 
 int aerobulk_gpu_selftest_host_copy(long long n, int rounds)
 {

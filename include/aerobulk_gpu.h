@@ -256,6 +256,10 @@ int aerobulk_gpu_host_unregister(void *ptr);
 /* Self-test of the host copy threads used for PAGEABLE caller arrays (needs no device): copies n doubles through the
  * thread pool and back, `rounds` times; returns the number of rounds whose data came back changed (0 = pass). */
 int aerobulk_gpu_selftest_host_copy(long long n, int rounds);
+/* The row-block chunk plan aerobulk_gpu_model uses for n points (needs no device; for tests and tuning): kind 0 device or
+ * pinned arrays (one chunk), 1 staged pipeline, 2 pageable arrays through the pinned slab.  Writes the nchunks + 1
+ * boundaries into cstart (room for 17) and returns nchunks, or -1 for bad arguments. */
+int aerobulk_gpu_chunk_plan(long long n, int kind, long long *cstart);
 
 /* ---- optional global flux diagnostics for sharded grids ---------------------------------------------- */
 #define AEROBULK_GPU_NDIAG 19

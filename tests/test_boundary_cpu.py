@@ -172,3 +172,36 @@ def test_host_copy_pool_under_thread_sanitizer(tmp_path):
     for args in ([], ["streaming-stores"]):
         r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "bad=0" in r.stdout and "ThreadSanitizer" not in r.stderr, r.stderr[-2000:]
+
+
+def test_chunk_plan_of_host_array_calls(ab):
+    """The row-block plans of aerobulk_gpu_model (pure host logic): boundaries start at 0, end at n, never decrease, fall on
+    whole 2048-point windows, stay within the chunk limits; the staged pipeline shrinks its chunks, the pageable path
+    ramps them up and down."""
+    L = ab.lib()
+    L.aerobulk_gpu_chunk_plan.restype = C.c_int
+    L.aerobulk_gpu_chunk_plan.argtypes = [C.c_longlong, C.c_int, C.POINTER(C.c_longlong)]
+
+    def plan(n, kind):
+        cs = (C.c_longlong * 17)()
+        m = L.aerobulk_gpu_chunk_plan(n, kind, cs)
+        return m, [cs[i] for i in range(m + 1)]
+
+    rng = np.random.default_rng(0)
+    sizes = [0, 1, 5, 2047, 2048, 2049, 65535, 65536, 199999, 200000, 400001, 1036800, 9331200, 83980800] + \
+        [int(x) for x in rng.integers(1, 20_000_000, 40)]
+    for n in sizes:
+        for kind in (0, 1, 2):
+            m, cs = plan(n, kind)
+            assert 1 <= m <= 16 and cs[0] == 0 and cs[-1] == n, (n, kind, cs)
+            assert all(b >= a for a, b in zip(cs, cs[1:])), (n, kind, cs)
+            assert all(c % 2048 == 0 for c in cs[:-1]), (n, kind, cs)
+            if kind == 0:
+                assert m == 1
+    m, cs = plan(1036800, 1)
+    sz = [b - a for a, b in zip(cs, cs[1:])]
+    assert m == 5 and sz == sorted(sz, reverse=True)                 # K..1 weights: short exposed tail
+    m, cs = plan(1036800, 2)
+    sz = [b - a for a, b in zip(cs, cs[1:])]
+    assert m == 6 and sz[0] < sz[1] < sz[2] and sz[3] > sz[4] > sz[5] and abs(sz[0] - sz[5]) <= 4096
+    assert L.aerobulk_gpu_chunk_plan(-1, 0, (C.c_longlong * 17)()) == -1 and L.aerobulk_gpu_chunk_plan(10, 3, (C.c_longlong * 17)()) == -1
