@@ -171,6 +171,8 @@ def test_host_copy_pool_under_thread_sanitizer(tmp_path):
         pytest.skip("no ThreadSanitizer runtime here: " + r.stderr[-200:])
     for args in ([], ["streaming-stores"]):
         r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+        if "unexpected memory mapping" in r.stderr:   # the sanitizer runtime cannot start under this kernel's ASLR settings
+            pytest.skip("ThreadSanitizer runtime cannot run here")
         assert r.returncode == 0 and "bad=0" in r.stdout and "ThreadSanitizer" not in r.stderr, r.stderr[-2000:]
 
 
