@@ -3,7 +3,7 @@
     python -m aerobulk_b200.build [--force]
 
 The shared library lands next to this file (git-ignored, shipped to the GPU box by
-gpurun).  No JIT cache, no torch extension machinery: five translation units,
+gpurun).  No JIT cache, no torch extension machinery: six translation units,
 one link step.
 """
 from __future__ import annotations
@@ -23,7 +23,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 # -fmad=true (default): FMA contraction is part of the documented GPU arithmetic
 
-SOURCES = ["ab_kernels.cu", "ab_series.cu", "ab_ice.cu", "ab_api.cu", "aerobulk.cpp"]
+SOURCES = ["ab_kernels.cu", "ab_series.cu", "ab_ice.cu", "ab_probe.cu", "ab_api.cu", "aerobulk.cpp"]
 HEADERS = [os.path.join(CSRC, h) for h in ("ab_device.cuh", "ab_ice.cuh", "ab_kernels.cuh", "ab_math.cuh", "ab_math_tables.cuh", "ab_copy_pool.hpp")] + [
     os.path.join(ROOT, "include", h) for h in ("aerobulk_gpu.h", "aerobulk.hpp")]
 

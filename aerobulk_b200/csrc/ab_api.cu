@@ -2215,6 +2215,27 @@ double aerobulk_gpu_bytes_per_point(const char *calgo, int skin)
     return a == abd::ECMWF ? 128. : 176.;
 }
 
-const char *aerobulk_gpu_version(void) { return "aerobulk-b200 0.1 (sm_100a, FP64)"; }
+const char *aerobulk_gpu_version(void) { return "aerobulk-b200 0.2 (sm_100a, FP64)"; }
+
+int aerobulk_gpu_probe(int func, long long n, int nargs, const double *args, double *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (n < 0 || nargs < 1 || nargs > 6 || !args || !out) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_probe: bad argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (n == 0) return 0;
+    rc = ensure_turb_slab(n * (nargs + 1));
+    if (rc) return rc;
+    cudaStream_t cs_ = compute_stream();
+    CUDA_TRY(cudaMemcpyAsync(g.d_turb, args, sizeof(double) * (size_t)n * nargs, cudaMemcpyHostToDevice, cs_));
+    double *d_out = g.d_turb + n * nargs;
+    CUDA_TRY(abk::launch_probe(func, n, nargs, g.d_turb, d_out, cs_));
+    g.launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, cs_));
+    CUDA_TRY(cudaStreamSynchronize(cs_));
+    return 0;
+}
 
 }  // extern "C"

@@ -144,4 +144,17 @@ int stats_max_blocks();
 double measure_fp64_peak(cudaStream_t s);
 cudaError_t flux_kernel_attributes(int algo, bool skin, bool zt_eq_zu, cudaFuncAttributes *attr);
 
+// probe_kernel (ab_probe.cu): one __device__ building block per launch, for the per-function GPU unit tests.
+// The numbering is part of the C ABI (aerobulk_gpu_probe, include/aerobulk_gpu.h).
+enum ProbeFunc {
+    PROBE_E_SAT = 1, PROBE_Q_SAT, PROBE_THETA, PROBE_RHO_AIR, PROBE_VISC_AIR, PROBE_L_VAP, PROBE_CP_AIR, PROBE_GAMMA_MOIST,
+    PROBE_ALPHA_SW, PROBE_QLW_NET, PROBE_ONE_ON_L, PROBE_RI_BULK, PROBE_Q_AIR_RH, PROBE_Q_AIR_DP,
+    PROBE_PSI_M_NCAR = 20, PROBE_PSI_H_NCAR, PROBE_PSI_M_COARE, PROBE_PSI_H_COARE, PROBE_PSI_M_ECMWF, PROBE_PSI_H_ECMWF,
+    PROBE_PSI_M_ANDREAS, PROBE_PSI_H_ANDREAS,
+    PROBE_Z0TQ_LKB = 30, PROBE_CD_N10_NCAR, PROBE_CHARN_COARE3P0, PROBE_CHARN_COARE3P6, PROBE_CS_COARE, PROBE_CS_ECMWF,
+    PROBE_EXP = 40, PROBE_EXP10, PROBE_LOG, PROBE_ATAN, PROBE_SQRT, PROBE_RSQRT, PROBE_CBRT, PROBE_RCBRT, PROBE_POW075,
+    PROBE_RCP, PROBE_POWR
+};
+cudaError_t launch_probe(int func, long long n, int nargs, const double *args, double *out, cudaStream_t s);
+
 }  // namespace abk

@@ -96,6 +96,8 @@ def lib():
                                       [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int])
     L.aerobulk_gpu_series_csv.restype = C.c_int
     L.aerobulk_gpu_series_csv.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_int]
+    L.aerobulk_gpu_probe.restype = C.c_int
+    L.aerobulk_gpu_probe.argtypes = [C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]
     L.aerobulk_cxx_skin.restype = None
     L.aerobulk_cxx_no_skin.restype = None
     # language bindings get return codes instead of the reference's fail-stop
@@ -111,11 +113,31 @@ def _check(rc: int):
 
 
 def _f64(a, shape=None):
+    """float64 array in the ONE layout the library indexes: column-major (Fortran) for 2-D fields -- the flat index
+    ji + Ni*jj of the reference's (Ni,Nj) arrays -- and contiguous for 1-D.  A C-ordered 2-D array (numpy's default)
+    is copied; arrays already in that layout (pinned slabs, views of torch tensors) pass through untouched."""
     a = np.asarray(a, dtype=np.float64)
-    if not (a.flags.f_contiguous or a.flags.c_contiguous):
-        a = np.asfortranarray(a)
+    if a.ndim >= 2:
+        if not a.flags.f_contiguous:
+            a = np.asfortranarray(a)
+    elif not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a)
     if shape is not None and a.shape != shape:
         raise AerobulkError(101, f"AEROBULK_INIT => arrays do not agree in shape: {a.shape} vs {shape}")
+    return a
+
+
+def _check_out(name, a, shape):
+    """A caller-supplied output array must be exactly what the library writes: float64, the grid's shape, column-major
+    (2-D) or contiguous (1-D), writeable -- anything else would silently pair different grid points across fields."""
+    if not isinstance(a, np.ndarray) or a.dtype != np.float64:
+        raise AerobulkError(101, f"out['{name}'] must be a float64 numpy array")
+    if a.shape != shape:
+        raise AerobulkError(101, f"out['{name}'] has shape {a.shape}, the fields have {shape}")
+    if not (a.flags.f_contiguous if a.ndim >= 2 else a.flags.c_contiguous):
+        raise AerobulkError(101, f"out['{name}'] must be {'column-major (order=F)' if a.ndim >= 2 else 'contiguous'}")
+    if not a.flags.writeable:
+        raise AerobulkError(101, f"out['{name}'] is read-only")
     return a
 
 
@@ -142,14 +164,13 @@ def aerobulk_model(jt: int, Nt: int, calgo: str, zt: float, zu: float, sst, t_zt
     ins = [sst] + [_f64(a, shape) for a in (t_zt, hum_zt, U_zu, V_zu, slp)]
     rs = None if rad_sw is None else _f64(rad_sw, shape)
     rl = None if rad_lw is None else _f64(rad_lw, shape)
-    order = "F" if sst.flags.f_contiguous else "C"
     names = ["QL", "QH", "Tau_x", "Tau_y", "Evap"] + (["T_s"] if (rs is not None and rl is not None) else [])
     res = {}
     for k in names:
         if out is not None and k in out:
-            res[k] = out[k]
+            res[k] = _check_out(k, out[k], shape)
         else:
-            res[k] = np.empty(shape, dtype=np.float64, order=order)
+            res[k] = np.empty(shape, dtype=np.float64, order="F")
     ni = None if Niter is None else C.byref(C.c_int(int(Niter)))
     ls = None if l_use_skin is None else C.byref(C.c_int(int(bool(l_use_skin))))
     ptr = lambda a: None if a is None else a.ctypes.data
@@ -372,7 +393,7 @@ def turb_ice(calgo: str, zt: float, zu: float, Ts_i, t_zt, qs_i, q_zt, U_zu, fri
     """Direct TURB_ICE_<calgo> call on HOST (numpy) arrays (src/ice/mod_blk_ice_*.f90).
     Returns {"Cd","Ch","Ce","t_zu","q_zu","Ubzu"} plus the optional outputs named in `want`."""
     L = lib()
-    Ts = _f64(Ts_i, np.shape(Ts_i))
+    Ts = _f64(Ts_i)
     shape = Ts.shape
     Ni, Nj = _shape2(shape)
     ins = [Ts] + [_f64(a, shape) for a in (t_zt, qs_i, q_zt, U_zu)] + [None if frice is None else _f64(frice, shape)]
@@ -479,6 +500,25 @@ def diagnostics_summary(st: np.ndarray) -> dict:
         if hi >= lo:
             out[k] = {"mean": float(s_ / max(st[0], 1.0)), "min": float(lo), "max": float(hi)}
     return out
+
+
+PROBE = {"e_sat": 1, "q_sat": 2, "theta_from_z_P0_T_q": 3, "rho_air": 4, "visc_air": 5, "L_vap": 6, "cp_air": 7,
+         "gamma_moist": 8, "alpha_sw": 9, "qlw_net": 10, "one_on_L": 11, "Ri_bulk": 12, "q_air_rh": 13, "q_air_dp": 14,
+         "psi_m_ncar": 20, "psi_h_ncar": 21, "psi_m_coare": 22, "psi_h_coare": 23, "psi_m_ecmwf": 24, "psi_h_ecmwf": 25,
+         "psi_m_andreas": 26, "psi_h_andreas": 27, "z0tq_LKB": 30, "cd_n10_ncar": 31, "charn_coare3p0": 32,
+         "charn_coare3p6": 33, "cs_coare": 34, "cs_ecmwf": 35, "exp": 40, "exp10": 41, "log": 42, "atan": 43, "sqrt": 44,
+         "rsqrt": 45, "cbrt": 46, "rcbrt": 47, "pow075": 48, "rcp": 49, "powr": 50}
+
+
+def probe(func: str, *args) -> np.ndarray:
+    """One __device__ building block of the hot path evaluated on the GPU for arrays of arguments
+    (aerobulk_gpu_probe; the per-function unit tests of tests/test_gpu_functions.py)."""
+    cols = np.broadcast_arrays(*[np.asarray(a, dtype=np.float64) for a in args])
+    n = cols[0].size
+    packed = np.ascontiguousarray(np.stack([c.ravel() for c in cols], axis=0))
+    out = np.empty(n, dtype=np.float64)
+    _check(lib().aerobulk_gpu_probe(PROBE[func], n, len(cols), packed.ctypes.data, out.ctypes.data))
+    return out.reshape(cols[0].shape)
 
 
 def host_register(a: np.ndarray):

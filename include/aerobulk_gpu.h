@@ -339,6 +339,20 @@ double aerobulk_gpu_work_per_point(const char *calgo, int skin, int nb_iter);
 double aerobulk_gpu_bytes_per_point(const char *calgo, int skin);
 const char *aerobulk_gpu_version(void);
 
+/* ---- per-function probe (test support) ---------------------------------------
+ * Evaluates ONE device building block of the hot path on n argument tuples (host arrays: args is
+ * [nargs][n], argument-major; out is [n]) so that each can be checked against the CPU restatement of the
+ * reference function it replaces.  func:
+ *    1 e_sat(T)  2 q_sat(T,p)  3 Theta_from_z_P0_T_q(z,slp,T,q)  4 rho_air(T,q,p)  5 visc_air(T)  6 L_vap(T)
+ *    7 cp_air(q)  8 gamma_moist(T,q)  9 alpha_sw(T)  10 qlw_net(rlw,Ts)  11 One_on_L(tha,qa,us,ts,qs)
+ *    12 Ri_bulk(z,sst,tha,ssq,qa,ub)  13 q_air_rh(rh,T,p)  14 q_air_dp(dp,p)        (src/mod_phymbl.f90)
+ *    20/21 psi_m/psi_h NCAR  22/23 COARE  24/25 ECMWF  26/27 ANDREAS  (zeta)
+ *    30 z0tq_LKB(iflag,Rer,z0)  31 cd_n10_ncar(w)  32 charn_coare3p0(w)  33 charn_coare3p6(w)
+ *    34 dT_cs of CS_COARE(alpha,Qsw,Qnsol,us,Qlat)  35 dT_cs of CS_ECMWF(alpha,Qsw,Qnsol,us)
+ *    40 exp  41 exp10  42 log  43 atan  44 sqrt  45 x**-1/2  46 cbrt  47 x**-1/3  48 x**0.75  49 1/x  50 x**y
+ * Returns 0, or an AEROBULK_GPU_ERR_* code. */
+int aerobulk_gpu_probe(int func, long long n, int nargs, const double *args, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -207,3 +207,36 @@ def test_chunk_plan_of_host_array_calls(ab):
     sz = [b - a for a, b in zip(cs, cs[1:])]
     assert m == 6 and sz[0] < sz[1] < sz[2] and sz[3] > sz[4] > sz[5] and abs(sz[0] - sz[5]) <= 4096
     assert L.aerobulk_gpu_chunk_plan(-1, 0, (C.c_longlong * 17)()) == -1 and L.aerobulk_gpu_chunk_plan(10, 3, (C.c_longlong * 17)()) == -1
+
+
+def test_python_mirror_normalises_layout_and_validates_out(ab):
+    """ADVICE r1 (model.py:127): every 2-D field reaches the library column-major, whatever layout the caller used, and a
+    caller-supplied output array of another dtype / shape / layout is refused instead of being written with a flat index
+    that pairs different grid points across fields."""
+    from aerobulk_b200 import model
+    c = np.arange(12, dtype=np.float64).reshape(3, 4)                 # numpy default: C order
+    f = model._f64(c)
+    assert f.flags.f_contiguous and np.array_equal(f, c)
+    assert np.array_equal(f.ravel(order="K"), c.ravel(order="F"))     # memory order == the reference's ji + Ni*jj
+    fo = np.asfortranarray(c)
+    assert model._f64(fo) is fo                                       # already right: no copy (pinned slabs stay pinned)
+    v = np.arange(10.0)[::2]
+    assert model._f64(v).flags.c_contiguous
+    assert model._f64(np.arange(6, dtype=np.float32).reshape(2, 3)).dtype == np.float64
+    with pytest.raises(ab.AerobulkError):
+        model._f64(c, (4, 3))
+    good = np.empty((3, 4), order="F")
+    assert model._check_out("QL", good, (3, 4)) is good
+    for bad in (np.empty((3, 4)), np.empty((3, 4), dtype=np.float32, order="F"), np.empty((4, 3), order="F"), [0.0] * 12,
+                np.empty(24)[::2]):
+        with pytest.raises(ab.AerobulkError):
+            model._check_out("QL", bad, (3, 4) if not (isinstance(bad, np.ndarray) and bad.ndim == 1) else (12,))
+    ro = np.empty((3, 4), order="F")
+    ro.flags.writeable = False
+    with pytest.raises(ab.AerobulkError):
+        model._check_out("QL", ro, (3, 4))
+    # the public entry validates before anything is computed (no device needed to be refused)
+    z = np.full((3, 4), 290.0)
+    with pytest.raises(ab.AerobulkError) as e:
+        ab.aerobulk_model(1, 1, "ncar", 2.0, 10.0, z, z, z * 0 + 0.01, z * 0 + 5, z * 0, z * 0 + 101000.0, out={"QL": np.empty((3, 4))})
+    assert e.value.code == 101

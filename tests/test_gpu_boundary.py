@@ -111,6 +111,31 @@ def test_empty_and_tiny_inputs(ab):
     assert np.isfinite(o["QH"]).all()
 
 
+def test_c_ordered_2d_inputs_give_the_same_fields(ab):
+    """numpy's default C-ordered 2-D arrays, mixed with Fortran-ordered ones, give index-for-index the same
+    result as all-Fortran inputs (the mirror normalises the layout; outputs come back (Ni,Nj) column-major)."""
+    Ni, Nj = 37, 23
+    f = synth.fields(Ni, Nj)
+    kw = dict(Niter=5, l_use_skin=True)
+    ab.reset()
+    want = ab.aerobulk_model(1, 1, "coare3p6", 2.0, 10.0, *_ins(f), rad_sw=f["rad_sw"], rad_lw=f["rad_lw"], **kw)
+    c = {k: np.ascontiguousarray(v) for k, v in f.items()}
+    assert c["sst"].flags.c_contiguous and not c["sst"].flags.f_contiguous
+    ab.reset()
+    got = ab.aerobulk_model(1, 1, "coare3p6", 2.0, 10.0, c["sst"], f["t_zt"], c["hum_zt"], c["U_zu"], f["V_zu"], c["slp"],
+                            rad_sw=c["rad_sw"], rad_lw=f["rad_lw"], **kw)
+    for k in want:
+        assert got[k].shape == (Ni, Nj) and np.array_equal(got[k], want[k]), k
+    # the TURB_* mirror too
+    ab.reset()
+    qs = np.full((Ni, Nj), 0.015)
+    a = ab.turb("ncar", 1, 2.0, 10.0, f["sst"], f["t_zt"], qs, f["hum_zt"], np.hypot(f["U_zu"], f["V_zu"]))
+    b = ab.turb("ncar", 1, 2.0, 10.0, c["sst"], c["t_zt"], np.ascontiguousarray(qs), c["hum_zt"],
+                np.ascontiguousarray(np.hypot(f["U_zu"], f["V_zu"])))
+    for k in ("Cd", "Ch", "Ce", "t_zu", "q_zu", "Ubzu"):
+        assert np.array_equal(a[k], b[k]), k
+
+
 def test_calm_points_have_zero_stress(ab):
     f = synth.fields(512, 256)
     calm = (f["U_zu"] == 0) & (f["V_zu"] == 0)
