@@ -28,6 +28,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <fstream>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -58,11 +59,12 @@ int chunk_limit()
     return v;
 }
 // AEROBULK_GPU_TRACE=1: GPU timeline of every host-array call (H2D / kernel / D2H end of each chunk) on stderr
-bool trace_on()
+bool trace_env()
 {
     static bool v = [] { const char *e = getenv("AEROBULK_GPU_TRACE"); return e && atoi(e) != 0; }();
     return v;
 }
+bool trace_on();   // + "the calling thread drives session 0" (the trace events live on its device), defined below
 cudaEvent_t tr_t0 = nullptr, tr_in[MAX_CHUNKS] = {}, tr_k[MAX_CHUNKS] = {}, tr_out[MAX_CHUNKS] = {};
 void trace_init()
 {
@@ -159,6 +161,14 @@ CopyPool &copy_pool()
     static CopyPool *p = new CopyPool(host_threads(), [] { const char *e = getenv("AEROBULK_GPU_COPY_STREAMING"); return e ? atoi(e) != 0 : AEROBULK_GPU_COPY_STREAMING_DEFAULT != 0; }());   // never destroyed: its threads outlive static destructors
     return *p;
 }
+// CopyPool::run has ONE caller at a time; the device threads of a split call take turns (the copies are bound by the
+// host memory system, which they share anyway)
+void pool_run(const CopyPiece *pieces, int np)
+{
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    copy_pool().run(pieces, np);
+}
 bool bounce_on()
 {
     static int v = [] { const char *e = getenv("AEROBULK_GPU_BOUNCE"); return e ? atoi(e) : 1; }();
@@ -241,15 +251,75 @@ struct Session {
     double *d_partials = nullptr, *d_stats = nullptr;
     unsigned long long *d_bad = nullptr, *h_bad = nullptr;   // h_bad: pinned
     bool bad_pending = false;
+    int pend_launches = 0;        // model calls whose flag has not been looked at yet
     int last_Ni = 0;
     const double *last_taux = nullptr, *last_tauy = nullptr;   // device pointers of the last launch
     long launches = 0;
+    // ---- aerobulk_gpu_set_devices(n): this session's share of a call that the library split over several GPUs
+    int shard = 0;                 // index of this session among the devices of the split
+    long long flat_offset = 0;     // global flat index of the shard's first point (error messages, tau > 10 report)
+    int report_Ni = 0, report_Nj = 0;   // the caller's (Ni,Nj): banner and (ji,jj) of error messages
+    struct StatsHook *stats_hook = nullptr;   // jt == 1: row-block statistics -> global (AEROBULK_INIT sees the whole field)
 };
 
-Session g;
+// One session per GPU.  sess[0] is THE session of the single-device library (every entry point); with
+// aerobulk_gpu_set_devices(n > 1) the host-array aerobulk_gpu_model call splits its points over sess[0..n-1], each
+// driven by its own host thread whose `cur` points at its session.  `g` is "the session of the calling thread".
+constexpr int MAX_DEVICES = 16;
+Session sess[MAX_DEVICES];
+thread_local Session *cur = &sess[0];
+#define g (*cur)
+int n_devices = 1;
 std::mutex g_mu;
+bool trace_on() { return trace_env() && cur == &sess[0]; }
 
 const char *HUM_NAMES[3] = {"sh", "dp", "rh"};
+
+// Rendezvous of the per-device statistics of one split jt == 1 call (the reference computes AEROBULK_INIT's sums, minima
+// and maxima over the WHOLE field, src/mod_aerobulk.f90:104-153): every shard contributes its 64-double vector, the last
+// arrival combines them in shard order (deterministic), all leave with the global vector.  A shard that failed before
+// reaching the rendezvous arrives with ok = false and everybody leaves with an error instead of waiting for ever.
+struct StatsHook {
+    std::mutex mu;
+    std::condition_variable cv;
+    int expected = 0, arrived = 0;
+    bool failed = false;
+    bool seen[MAX_DEVICES] = {};
+    double part[MAX_DEVICES][abk::NSTATS];
+    double global[abk::NSTATS];
+    void reset(int n)
+    {
+        expected = n;
+        arrived = 0;
+        failed = false;
+        for (int k = 0; k < MAX_DEVICES; ++k) seen[k] = false;
+    }
+    // returns false when some shard failed
+    bool combine(int shard, const double *st, bool ok, double *out)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        if (seen[shard]) return !failed;   // a shard arrives once (the failure path may call again)
+        seen[shard] = true;
+        if (ok) memcpy(part[shard], st, sizeof(double) * abk::NSTATS);
+        else failed = true;
+        if (++arrived == expected) {
+            if (!failed) {
+                for (int k = 0; k < abk::NSTATS; ++k) {
+                    const int op = aerobulk_gpu_stats_reduce_op(k);
+                    double r = part[0][k];
+                    for (int d = 1; d < expected; ++d)
+                        r = (op == 0) ? r + part[d][k] : (op == 1) ? fmin(r, part[d][k]) : fmax(r, part[d][k]);
+                    global[k] = r;
+                }
+            }
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return arrived == expected; });
+        }
+        if (!failed && out) memcpy(out, global, sizeof(double) * abk::NSTATS);
+        return !failed;
+    }
+};
 
 // ---------------------------------------------------------------------------
 // errors: ctl_stop semantics (mod_const.f90:238-278) or return codes
@@ -456,7 +526,7 @@ void bounce_copy(int nf, double *const *user, int row0, long long s0, long long 
             pieces.push_back(to_slab ? CopyPiece{b, u, sizeof(double) * (size_t)m} : CopyPiece{u, b, sizeof(double) * (size_t)m});
         }
     }
-    copy_pool().run(pieces.data(), (int)pieces.size());
+    pool_run(pieces.data(), (int)pieces.size());
 }
 
 
@@ -484,7 +554,7 @@ void bounce_run(const HostBounce &hb, unsigned char which, bool to_slab)
             pieces.push_back(to_slab ? CopyPiece{b, u, sizeof(double) * (size_t)m} : CopyPiece{u, b, sizeof(double) * (size_t)m});
         }
     }
-    copy_pool().run(pieces.data(), (int)pieces.size());
+    pool_run(pieces.data(), (int)pieces.size());
 }
 // 0: use the staged path of the entry point; 1: d = aliases of the caller's pinned arrays; 2: d = aliases of slab rows
 // holding copies of the inputs (call bounce_finish after the launch); < 0: -error code
@@ -680,23 +750,39 @@ abd::Uniform make_uniform(double zt, double zu)
 int check_bad_flag(const double *h_taux, const double *h_tauy)
 {
     if (!g.bad_pending) return 0;
+    // the flag copy of an asynchronous device-pointer call may still be in flight (entry points that did not wait)
+    cudaEventSynchronize(g.ev_bad);
     g.bad_pending = false;
+    const int flagged_launches = g.pend_launches;
+    g.pend_launches = 0;
     const unsigned long long bad = *g.h_bad;
     if (bad == ~0ull) return 0;
     *g.h_bad = ~0ull;
-    cudaMemset(g.d_bad, 0xFF, sizeof(unsigned long long));
+    // ordered after every kernel that may still be updating the word, unlike a memset on the legacy stream
+    cudaMemsetAsync(g.d_bad, 0xFF, sizeof(unsigned long long), compute_stream());
+    // (ji, jj) of the CALLER's grid: a shard of a split call reports through its global flat index
+    const long long Ni = g.report_Ni > 0 ? g.report_Ni : (g.last_Ni > 0 ? g.last_Ni : 1);
+    const long long idx = (long long)bad + g.flat_offset;
     double tx = 0., ty = 0.;
+    bool have_tau = false;
     if (h_taux && h_tauy) {
         tx = h_taux[bad];
         ty = h_tauy[bad];
-    } else if (g.last_taux && g.last_tauy) {
-        cudaMemcpy(&tx, g.last_taux + bad, sizeof(double), cudaMemcpyDeviceToHost);
-        cudaMemcpy(&ty, g.last_tauy + bad, sizeof(double), cudaMemcpyDeviceToHost);
+        have_tau = true;
+    } else if (g.last_taux && g.last_tauy && flagged_launches == 1) {
+        // the buffers of the ONE call the flag can come from; with several asynchronous calls behind the flag the
+        // offending call (and its output arrays and shape) is not known any more and only the index is reported
+        have_tau = cudaMemcpy(&tx, g.last_taux + bad, sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess &&
+                   cudaMemcpy(&ty, g.last_tauy + bad, sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
     }
-    const int Ni = g.last_Ni > 0 ? g.last_Ni : 1;
+    if (have_tau)
+        return fail(AEROBULK_GPU_ERR_TAU,
+                    "BULK_FORMULA_VCTR()@mod_phymbl: wind stress too strong!\n  => %8.2f N/m^2 ! At ji, jj = %04lld, %04lld",
+                    sqrt(tx * tx + ty * ty), idx % Ni + 1, idx / Ni + 1);
     return fail(AEROBULK_GPU_ERR_TAU,
-                "BULK_FORMULA_VCTR()@mod_phymbl: wind stress too strong!\n  => %8.2f N/m^2 ! At ji, jj = %04lld, %04lld",
-                sqrt(tx * tx + ty * ty), (long long)(bad % Ni) + 1, (long long)(bad / Ni) + 1);
+                "BULK_FORMULA_VCTR()@mod_phymbl: wind stress too strong!\n  => above 10 N/m^2 in one of the last %d asynchronous "
+                "calls, first at flat index %lld of that call",
+                flagged_launches, idx);
 }
 
 // Row-block chunk plan of a host-array call: cstart[0..nchunks], boundaries on multiples of 2048 points (whole sort
@@ -858,7 +944,10 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
             } else {
                 memset(st, 0, sizeof(st));
             }
-            rc = init_from_stats(Nt, calgo, lskin, lsrad, st, Ni, Nj);
+            // aerobulk_gpu_set_devices(n): this session holds one shard; AEROBULK_INIT judges the whole field
+            if (g.stats_hook && !g.stats_hook->combine(g.shard, st, true, st))
+                return fail(AEROBULK_GPU_ERR_STATE, "AEROBULK_INIT => another device of the split call failed");
+            rc = init_from_stats(Nt, calgo, lskin, lsrad, st, g.report_Ni > 0 ? g.report_Ni : Ni, g.report_Ni > 0 ? g.report_Nj : Nj);
             if (rc) return rc;
         }
     }
@@ -979,6 +1068,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     CUDA_TRY(cudaMemcpyAsync(g.h_bad, g.d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaEventRecord(g.ev_bad, cs));
     g.bad_pending = true;
+    g.pend_launches += 1;
     g.last_Ni = Ni;
     g.last_taux = out_d[2];
     g.last_tauy = out_d[3];
@@ -1016,6 +1106,201 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------
+// aerobulk_gpu_set_devices(n): ONE aerobulk_model call split over n GPUs inside the library.
+// The caller makes the reference's call -- whole (Ni,Nj) fields, host arrays, src/mod_aerobulk.f90:176-269 -- and the
+// library partitions the flat point range into n contiguous shards (boundaries on multiples of 2048 points; for a
+// 2-D field these are latitude row blocks up to that rounding), one per GPU, each with its own session: streams,
+// staging, pinned bounce slab, warm-layer state, tau > 10 flag.  Points are independent, so there is no data-path
+// exchange; the only combine is AEROBULK_INIT's field statistics at jt == 1 (StatsHook, in host memory: the devices
+// belong to one process).  Device 0's shard runs on the calling thread, the others on persistent host threads.
+// ---------------------------------------------------------------------------
+class DeviceThreads
+{
+  public:
+    // runs job(d) for d = 1 .. n-1 on the worker of session d and job(0) on the caller; returns when all are done
+    template <class F>
+    void run(int n, F &&job)
+    {
+        while ((int)started_ < n - 1) {
+            const int d = ++started_;
+            std::thread([this, d] { work(d); }).detach();   // never joined: the library is linked -z nodelete
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = [&job](int d) { job(d); };
+            active_ = n;
+            pending_ = n - 1;
+            ++gen_;
+        }
+        cv_.notify_all();
+        job(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+  private:
+    void work(int d)
+    {
+        cur = &sess[d];
+        unsigned long long seen = 0;
+        for (;;) {
+            std::function<void(int)> job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (d >= active_) continue;
+                job = job_;
+            }
+            job(d);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                --pending_;
+            }
+            done_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::function<void(int)> job_;
+    unsigned long long gen_ = 0;
+    int active_ = 0, pending_ = 0;
+    int started_ = 0;
+};
+DeviceThreads &device_threads()
+{
+    static DeviceThreads *t = new DeviceThreads();   // never destroyed, like the copy threads
+    return *t;
+}
+
+// shard boundaries of the last split call (state get / set, tests)
+int split_nd = 1;
+long long split_start[MAX_DEVICES + 1] = {0, 0};
+
+int plan_shards(long long n, int nd_max, long long *start)
+{
+    int nd = nd_max < 1 ? 1 : (nd_max > MAX_DEVICES ? MAX_DEVICES : nd_max);
+    long long per = (n + nd - 1) / nd;
+    per = (per + 2047) / 2048 * 2048;
+    if (per < 2048) per = 2048;
+    nd = (int)((n + per - 1) / per);
+    if (nd < 1) nd = 1;
+    for (int d = 0; d <= nd; ++d) start[d] = (long long)d * per < n ? (long long)d * per : n;
+    start[nd] = n;
+    return nd;
+}
+
+int model_multi(int jt, int Nt, const char *calgo, double zt, double zu, int Ni, int Nj, const double *sst,
+                const double *t_zt, const double *hum_zt, const double *U_zu, const double *V_zu, const double *slp,
+                double *QL, double *QH, double *Tau_x, double *Tau_y, double *Evap, const int *Niter,
+                const int *l_use_skin, const double *rad_sw, const double *rad_lw, double *T_s)
+{
+    Session &s0 = sess[0];
+    s0.errcode = 0;
+    s0.errmsg[0] = 0;
+    if (!calgo || !sst || !t_zt || !hum_zt || !U_zu || !V_zu || !slp || !QL || !QH || !Tau_x || !Tau_y || !Evap)
+        return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_model: NULL mandatory argument");
+    if (Ni < 0 || Nj < 0) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_model: negative shape %d x %d", Ni, Nj);
+    if (jt < 1) return fail(AEROBULK_GPU_ERR_JT, "AEROBULK_MODEL => jt < 1 !??\n we are in a Fortran world here...");
+    int rc = ensure_device();   // session 0: resolves its device id
+    if (rc) return rc;
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    const long long n = (long long)Ni * Nj;
+    long long start[MAX_DEVICES + 1];
+    const int nd = plan_shards(n, n_devices < count ? n_devices : count, start);
+    for (int d = 0; d < nd; ++d)
+        if (start[d + 1] - start[d] > 0x7fffffffLL) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_model: shard %d has more than 2^31 points", d);
+    if (s0.use_user_stream)
+        return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_set_devices(n > 1) and aerobulk_gpu_set_stream are exclusive: each device runs on a stream of the library");
+    // a session keeps the shard it was given at jt == 1
+    if (jt > 1 && (s0.n_coare || s0.n_ecmwf) && nd != split_nd)
+        return fail(AEROBULK_GPU_ERR_STATE, "the number of devices changed inside a warm-layer session");
+    // session-wide settings (the SAVEd module variables of mod_const.f90:22-33 exist once) follow session 0
+    for (int d = 1; d < nd; ++d) {
+        Session &sd = sess[d];
+        const int want = (s0.device + d) % count;
+        if (sd.device_ready && sd.device != want)
+            return fail(AEROBULK_GPU_ERR_ARG, "device %d of the split is bound to GPU %d, not %d: call aerobulk_gpu_reset()", d, sd.device, want);
+        sd.device = want;
+        sd.nb_iter = s0.nb_iter; sd.nitend = s0.nitend; sd.l_use_skin_schemes = s0.l_use_skin_schemes; sd.ihum = s0.ihum;
+        sd.rdt = s0.rdt; sd.gdept = s0.gdept; sd.error_mode = s0.error_mode; sd.verbose = 0; sd.sort_points = s0.sort_points;
+        sd.preinit_done = s0.preinit_done;
+    }
+    static StatsHook hook;
+    const bool need_stats = (jt == 1) && !s0.preinit_done;
+    if (need_stats) hook.reset(nd);
+    int rcs[MAX_DEVICES] = {};
+    device_threads().run(nd, [&](int d) {
+        Session &sd = sess[d];
+        sd.shard = d;
+        sd.flat_offset = start[d];
+        sd.report_Ni = Ni;
+        sd.report_Nj = Nj;
+        sd.stats_hook = need_stats ? &hook : nullptr;
+        const long long o = start[d];
+        const int len = (int)(start[d + 1] - o);
+        rcs[d] = model_impl(false, jt, Nt, calgo, zt, zu, len, 1, sst + o, t_zt + o, hum_zt + o, U_zu + o, V_zu + o, slp + o,
+                            QL + o, QH + o, Tau_x + o, Tau_y + o, Evap + o, Niter, l_use_skin, rad_sw ? rad_sw + o : nullptr,
+                            rad_lw ? rad_lw + o : nullptr, T_s ? T_s + o : nullptr);
+        if (need_stats && rcs[d]) hook.combine(d, nullptr, false, nullptr);   // failed before the rendezvous: release the others
+        sd.stats_hook = nullptr;
+    });
+    split_nd = nd;
+    for (int d = 0; d <= nd; ++d) split_start[d] = start[d];
+    // the reference would have stopped at the first error: report the one of the lowest shard that is not the echo of another's
+    int first = -1;
+    for (int d = 0; d < nd && first < 0; ++d)
+        if (rcs[d] && !(rcs[d] == AEROBULK_GPU_ERR_STATE && strstr(sess[d].errmsg, "another device of the split call failed"))) first = d;
+    for (int d = 0; d < nd && first < 0; ++d)
+        if (rcs[d]) first = d;
+    for (int d = 0; d < nd; ++d) {
+        sess[d].report_Ni = sess[d].report_Nj = 0;
+        sess[d].flat_offset = 0;
+    }
+    if (first < 0) return 0;
+    if (first != 0) {
+        memcpy(s0.errmsg, sess[first].errmsg, sizeof(s0.errmsg));
+        s0.errcode = sess[first].errcode;
+    }
+    return rcs[first];
+}
+
+
+// Return-code mode only (the default fail-stop mode never gets here: fail() has ended the process).  The reference
+// would have STOPped: whatever session was open is over.  The warm-layer state is released on every device and a skin
+// flag switched on by the failed jt == 1 call is rolled back, so that the next jt == 1 call starts clean.
+void end_session_after_error(int jt, bool skin_before)
+{
+    for (int d = 0; d < MAX_DEVICES; ++d) {
+        sess[d].n_coare = sess[d].n_ecmwf = 0;
+        sess[d].preinit_done = false;
+        if (jt == 1) sess[d].l_use_skin_schemes = skin_before;
+    }
+}
+
+// host-array AEROBULK_MODEL: one device, or split over aerobulk_gpu_set_devices(n) of them
+int model_host(int jt, int Nt, const char *calgo, double zt, double zu, int Ni, int Nj, const double *sst,
+               const double *t_zt, const double *hum_zt, const double *U_zu, const double *V_zu, const double *slp,
+               double *QL, double *QH, double *Tau_x, double *Tau_y, double *Evap, const int *Niter,
+               const int *l_use_skin, const double *rad_sw, const double *rad_lw, double *T_s)
+{
+    const bool skin_before = sess[0].l_use_skin_schemes;
+    int rc;
+    if (n_devices > 1) {
+        rc = model_multi(jt, Nt, calgo, zt, zu, Ni, Nj, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y, Evap,
+                         Niter, l_use_skin, rad_sw, rad_lw, T_s);
+    } else {
+        split_nd = 1;
+        rc = model_impl(false, jt, Nt, calgo, zt, zu, Ni, Nj, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y, Evap,
+                        Niter, l_use_skin, rad_sw, rad_lw, T_s);
+    }
+    if (rc) end_session_after_error(jt, skin_before);
+    return rc;
+}
 
 // ---------------------------------------------------------------------------
 // TURB_* 
@@ -1219,7 +1504,7 @@ int series_impl(const char *calgo, int Nt, long long S, double zt, double zu, co
     const unsigned long long bad = *g.h_bad;
     if (bad != ~0ull) {
         *g.h_bad = ~0ull;
-        cudaMemset(g.d_bad, 0xFF, sizeof(unsigned long long));
+        cudaMemsetAsync(g.d_bad, 0xFF, sizeof(unsigned long long), cs_);
         return fail(AEROBULK_GPU_ERR_TAU,
                     "BULK_FORMULA_VCTR()@mod_phymbl: wind stress too strong!\n  => at record %lld, station %lld",
                     (long long)(bad / (unsigned long long)S) + 1, (long long)(bad % (unsigned long long)S) + 1);
@@ -1436,7 +1721,7 @@ int finish_ice_call(cudaStream_t cs_, const char *what)
     const unsigned long long bad_tau = g.h_bad[0], bad_rough = g.h_bad[1];
     if (bad_tau != ~0ull || bad_rough != ~0ull) {
         g.h_bad[0] = g.h_bad[1] = ~0ull;
-        cudaMemset(g.d_bad, 0xFF, 2 * sizeof(unsigned long long));
+        cudaMemsetAsync(g.d_bad, 0xFF, 2 * sizeof(unsigned long long), cs_);
         if (bad_rough != ~0ull)
             return fail(AEROBULK_GPU_ERR_ICE_ROUGH,
                         " rough_leng_tq@mod_blk_ice_an05.f90 => something wrong with zsmoot, ztrans, zrough!\n  (%s, point %lld)",
@@ -1730,7 +2015,7 @@ int aerobulk_gpu_model(int jt, int Nt, const char *calgo, double zt, double zu, 
                        const int *Niter, const int *l_use_skin, const double *rad_sw, const double *rad_lw, double *T_s)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    return model_impl(false, jt, Nt, calgo, zt, zu, Ni, Nj, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y,
+    return model_host(jt, Nt, calgo, zt, zu, Ni, Nj, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y,
                       Evap, Niter, l_use_skin, rad_sw, rad_lw, T_s);
 }
 
@@ -1741,8 +2026,11 @@ int aerobulk_gpu_model_device(int jt, int Nt, const char *calgo, double zt, doub
                               const double *rad_sw, const double *rad_lw, double *T_s)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    return model_impl(true, jt, Nt, calgo, zt, zu, Ni, Nj, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y,
-                      Evap, Niter, l_use_skin, rad_sw, rad_lw, T_s);
+    const bool skin_before = sess[0].l_use_skin_schemes;
+    const int rc = model_impl(true, jt, Nt, calgo, zt, zu, Ni, Nj, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y,
+                              Evap, Niter, l_use_skin, rad_sw, rad_lw, T_s);
+    if (rc) end_session_after_error(jt, skin_before);
+    return rc;
 }
 
 static void copy_algo(char *dst, size_t cap, const char *calgo, int l)
@@ -1765,7 +2053,7 @@ void aerobulk_cxx_skin(const int *jt, const int *Nt, const char *calgo, const do
     copy_algo(algo, sizeof(algo), calgo, *l);
     const int lskin = (*(const unsigned char *)l_skin) != 0;
     std::lock_guard<std::mutex> lk(g_mu);
-    model_impl(false, *jt, *Nt, algo, *zt, *zu, *m, 1, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y, Evap,
+    model_host(*jt, *Nt, algo, *zt, *zu, *m, 1, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y, Evap,
                Niter, &lskin, rad_sw, rad_lw, T_s);
 }
 
@@ -1777,7 +2065,7 @@ void aerobulk_cxx_no_skin(const int *jt, const int *Nt, const char *calgo, const
     char algo[64];
     copy_algo(algo, sizeof(algo), calgo, *l);
     std::lock_guard<std::mutex> lk(g_mu);
-    model_impl(false, *jt, *Nt, algo, *zt, *zu, *m, 1, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y, Evap,
+    model_host(*jt, *Nt, algo, *zt, *zu, *m, 1, sst, t_zt, hum_zt, U_zu, V_zu, slp, QL, QH, Tau_x, Tau_y, Evap,
                Niter, nullptr, nullptr, nullptr, nullptr);
 }
 
@@ -2021,11 +2309,46 @@ void aerobulk_gpu_set_nitend(int nitend) { std::lock_guard<std::mutex> lk(g_mu);
 int aerobulk_gpu_synchronize(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
+    for (int d = MAX_DEVICES - 1; d >= 1; --d) {   // the other devices of a split call (their calls are blocking: nothing pending)
+        if (!sess[d].device_ready) continue;
+        CUDA_TRY(cudaSetDevice(sess[d].device));
+        CUDA_TRY(cudaStreamSynchronize(sess[d].own_stream));
+        CUDA_TRY(cudaStreamSynchronize(sess[d].out_stream));
+    }
     if (!g.device_ready) return 0;
     CUDA_TRY(cudaSetDevice(g.device));
     CUDA_TRY(cudaStreamSynchronize(compute_stream()));
     CUDA_TRY(cudaStreamSynchronize(g.out_stream));
     return check_bad_flag(nullptr, nullptr);
+}
+
+int aerobulk_gpu_set_devices(int n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (n < 1 || n > MAX_DEVICES) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_set_devices(%d): 1 .. %d devices", n, MAX_DEVICES);
+    for (int d = 0; d < MAX_DEVICES; ++d)
+        if (sess[d].n_coare || sess[d].n_ecmwf)
+            return fail(AEROBULK_GPU_ERR_STATE, "aerobulk_gpu_set_devices(%d): a warm-layer session is open (finish it at jt == Nt or call aerobulk_gpu_reset)", n);
+    if (n > 1) {
+        int count = 0;
+        const cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count <= 0)
+            return fail(AEROBULK_GPU_ERR_CUDA, "no CUDA device available (%s): libaerobulk_gpu has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        if (n > count) return fail(AEROBULK_GPU_ERR_CUDA, "aerobulk_gpu_set_devices(%d): only %d device(s) visible", n, count);
+    }
+    n_devices = n;
+    if (n == 1) split_nd = 1;
+    return 0;
+}
+int aerobulk_gpu_get_devices(void) { return n_devices; }
+
+int aerobulk_gpu_shard_plan(long long n, int n_dev, long long *start)
+{
+    if (n < 0 || n_dev < 1 || !start) return -1;
+    return plan_shards(n, n_dev, start);
 }
 
 int aerobulk_gpu_init_local_stats(int Ni, int Nj, const double *sst, const double *t_zt, const double *hum_zt,
@@ -2098,9 +2421,8 @@ void aerobulk_gpu_set_sort(int mode) { g.sort_points = mode < 0 ? 0 : (mode > 2 
 const char *aerobulk_gpu_last_error(void) { return g.errmsg; }
 int aerobulk_gpu_last_error_code(void) { return g.errcode; }
 
-void aerobulk_gpu_reset(void)
+static void reset_session()   // the session of `cur`
 {
-    std::lock_guard<std::mutex> lk(g_mu);
     if (g.device_ready) {
         cudaSetDevice(g.device);
         cudaDeviceSynchronize();
@@ -2120,6 +2442,7 @@ void aerobulk_gpu_reset(void)
         if (g.h_bad) g.h_bad[0] = g.h_bad[1] = ~0ull;
         if (g.d_bad) cudaMemset(g.d_bad, 0xFF, 2 * sizeof(unsigned long long));
     }
+    g.n_coare = g.n_ecmwf = 0;
     g.ice_form_per_point = 0;
     g.pitched_ok = true;
     g.nb_iter = 5;
@@ -2130,58 +2453,115 @@ void aerobulk_gpu_reset(void)
     g.gdept = 1.;
     g.preinit_done = false;
     g.bad_pending = false;
+    g.pend_launches = 0;
     g.errcode = 0;
     g.errmsg[0] = 0;
+    g.shard = 0;
+    g.flat_offset = 0;
+    g.report_Ni = g.report_Nj = 0;
+    g.stats_hook = nullptr;
 }
 
-static double *state_ptr(int which, long long *n)
+void aerobulk_gpu_reset(void)
 {
-    if (g.n_coare) {
-        *n = g.n_coare;
-        return (which >= 0 && which < 4) ? g.c_state[which] : nullptr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Session *const mine = cur;
+    for (int d = MAX_DEVICES - 1; d >= 0; --d) {   // session 0 last: its device stays the thread's current one
+        cur = &sess[d];
+        reset_session();
     }
-    if (g.n_ecmwf) {
+    cur = mine;
+    split_nd = 1;
+}
+
+// Warm-layer state of the session of `cur`.  which 0..3: dT_wl, Hz_wl, Qnt_ac, Tau_ac of the COARE scheme when a COARE
+// session is open, else dT_wl (0) and the constant Hz_wl (1) of the ECMWF scheme; which 4 / 5 name the ECMWF pair
+// explicitly (both schemes can hold a session at the same time, as the module arrays of the reference can).
+static double *state_ptr(int which, long long *n, bool *const_hz)
+{
+    *const_hz = false;
+    if (which >= 0 && which < 4 && g.n_coare) {
+        *n = g.n_coare;
+        return g.c_state[which];
+    }
+    if (g.n_ecmwf && (which == 0 || which == 1 || which == 4 || which == 5) && !(which < 4 && g.n_coare)) {
         *n = g.n_ecmwf;
-        return which == 0 ? g.e_dT_wl : nullptr;
+        if (which == 1 || which == 5) {
+            *const_hz = true;
+            return nullptr;
+        }
+        return g.e_dT_wl;
     }
     *n = 0;
     return nullptr;
 }
 
+// get (dir 0) or set (dir 1) the state of every session that took part in the last (possibly split) call
+static long state_io(int which, double *host, long n, int dir)
+{
+    if (!host) return 0;
+    Session *const mine = cur;
+    long long total = 0;
+    for (int d = 0; d < split_nd; ++d) {
+        cur = &sess[d];
+        long long have = 0;
+        bool chz = false;
+        state_ptr(which, &have, &chz);
+        total += have;
+    }
+    long done = 0;
+    if (total == n && total > 0) {
+        long long off = 0;
+        for (int d = 0; d < split_nd; ++d) {
+            cur = &sess[d];
+            long long have = 0;
+            bool chz = false;
+            double *p = state_ptr(which, &have, &chz);
+            if (have == 0) continue;
+            cudaSetDevice(g.device);
+            cudaStreamSynchronize(compute_stream());
+            if (chz) {   // Hz_wl of the ECMWF scheme is the constant rd0 = 3 m (mod_skin_ecmwf.f90:57): nothing stored
+                if (dir == 0)
+                    for (long long i = 0; i < have; ++i) host[off + i] = 3.;
+            } else if (!p) {
+                off = -1;
+                break;
+            } else if (cudaMemcpy(dir == 0 ? (void *)(host + off) : (void *)p, dir == 0 ? (const void *)p : (const void *)(host + off),
+                                  sizeof(double) * (size_t)have, dir == 0 ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice) != cudaSuccess) {
+                off = -1;
+                break;
+            }
+            off += have;
+        }
+        done = (off == total) ? n : 0;
+    }
+    cur = mine;
+    if (mine->device_ready) cudaSetDevice(mine->device);
+    return done;
+}
+
 long aerobulk_gpu_get_state(int which, double *host_out, long n)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    long long have = 0;
-    double *p = state_ptr(which, &have);
-    if (!host_out || n != have || have == 0) return 0;
-    cudaSetDevice(g.device);
-    cudaStreamSynchronize(compute_stream());
-    if (!p) {
-        if (g.n_ecmwf && which == 1) {   // Hz_wl of the ECMWF scheme is the constant rd0 = 3 m
-            for (long i = 0; i < n; ++i) host_out[i] = 3.;
-            return n;
-        }
-        return 0;
-    }
-    if (cudaMemcpy(host_out, p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
-    return n;
+    return state_io(which, host_out, n, 0);
 }
 
 long aerobulk_gpu_set_state(int which, const double *host_in, long n)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    long long have = 0;
-    double *p = state_ptr(which, &have);
-    if (host_in && !p && g.n_ecmwf && which == 1 && n == have) return n;   // Hz_wl of ECMWF is the constant 3 m: nothing to restore
-    if (!host_in || !p || n != have) return 0;
-    cudaSetDevice(g.device);
-    cudaStreamSynchronize(compute_stream());
-    if (cudaMemcpy(p, host_in, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) return 0;
-    return n;
+    return state_io(which, const_cast<double *>(host_in), n, 1);
 }
 
-long aerobulk_gpu_launch_count(void) { return g.launches; }
-void aerobulk_gpu_reset_launch_count(void) { g.launches = 0; }
+long aerobulk_gpu_launch_count(void)
+{
+    long t = 0;
+    for (int d = 0; d < MAX_DEVICES; ++d) t += sess[d].launches;
+    return t;
+}
+void aerobulk_gpu_reset_launch_count(void)
+{
+    for (int d = 0; d < MAX_DEVICES; ++d) sess[d].launches = 0;
+}
 
 double aerobulk_gpu_measure_fp64_peak(void)
 {

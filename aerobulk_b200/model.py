@@ -54,6 +54,11 @@ def lib():
     L.aerobulk_gpu_set_nb_iter.argtypes = [C.c_int]
     L.aerobulk_gpu_get_humidity_type.restype = C.c_char_p
     L.aerobulk_gpu_set_device.argtypes = [C.c_int]
+    L.aerobulk_gpu_set_devices.restype = C.c_int
+    L.aerobulk_gpu_set_devices.argtypes = [C.c_int]
+    L.aerobulk_gpu_get_devices.restype = C.c_int
+    L.aerobulk_gpu_shard_plan.restype = C.c_int
+    L.aerobulk_gpu_shard_plan.argtypes = [C.c_longlong, C.c_int, C.POINTER(C.c_longlong)]
     L.aerobulk_gpu_set_stream.argtypes = [C.c_void_p]
     L.aerobulk_gpu_set_error_mode.argtypes = [C.c_int]
     L.aerobulk_gpu_set_verbose.argtypes = [C.c_int]
@@ -249,6 +254,24 @@ def set_stream(cuda_stream_handle: Optional[int]):
 
 def set_device(device: int):
     _check(lib().aerobulk_gpu_set_device(int(device)))
+
+
+def set_devices(n: int):
+    """Split every host-array aerobulk_model call over n GPUs inside the library (aerobulk_gpu_set_devices)."""
+    _check(lib().aerobulk_gpu_set_devices(int(n)))
+
+
+def get_devices() -> int:
+    return lib().aerobulk_gpu_get_devices()
+
+
+def shard_plan(n: int, n_dev: int) -> list:
+    """Shard boundaries (flat point indices) of an n-point field on n_dev devices."""
+    start = (C.c_longlong * 17)()
+    k = lib().aerobulk_gpu_shard_plan(int(n), int(n_dev), start)
+    if k < 0:
+        raise ValueError("shard_plan: bad arguments")
+    return [int(start[i]) for i in range(k + 1)]
 
 
 def set_rdt(v: float): lib().aerobulk_gpu_set_rdt(float(v))

@@ -305,10 +305,28 @@ const char *aerobulk_gpu_get_humidity_type(void); /* "sh" | "rh" | "dp" */
 /* ---- session plumbing ------------------------------------------------------ */
 int aerobulk_gpu_set_device(int device);         /* default: $LOCAL_RANK or 0; before first compute call */
 int aerobulk_gpu_get_device(void);
+/* Multi-GPU inside ONE process.  After aerobulk_gpu_set_devices(n), every host-array
+ * AEROBULK_MODEL call (aerobulk_gpu_model, aerobulk_cxx_skin / _no_skin and the Fortran / C++ APIs on top of them) is
+ * split by the library over GPUs device .. device+n-1: the flat point range of the caller's (Ni,Nj) fields is cut into
+ * n contiguous shards (latitude row blocks, boundaries on multiples of 2048 points: aerobulk_gpu_shard_plan), each GPU
+ * keeps the warm-layer state of its shard for the whole jt = 1..Nt session, and the field statistics AEROBULK_INIT needs
+ * at jt == 1 (src/mod_aerobulk.f90:104-153) are combined over the shards inside the library.  Results are bit-identical
+ * to the single-GPU call.  The caller still makes ONE call per time step, exactly as with the reference
+ * (src/mod_aerobulk.f90:176-269).  Not combinable with aerobulk_gpu_set_stream; the device-pointer entry points and
+ * the other entry points (turb, series, sea ice) stay on the first device.  n cannot change while a warm-layer session
+ * is open.  aerobulk_gpu_get_state / _set_state gather / scatter the shards in point order. */
+int aerobulk_gpu_set_devices(int n);             /* default 1 */
+int aerobulk_gpu_get_devices(void);
+/* The shard boundaries used for n points on n_dev devices (needs no device): writes the nshards + 1 boundaries into
+ * start (room for 17) and returns nshards (<= n_dev: a tiny grid uses fewer devices), or -1 for bad arguments. */
+int aerobulk_gpu_shard_plan(long long n, int n_dev, long long *start);
 /* Run on a caller-owned cudaStream_t.  NULL selects the library's own non-blocking stream; to use the
  * legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1), cudaStreamPerThread is (cudaStream_t)0x2. */
 int aerobulk_gpu_set_stream(void *cuda_stream);
-void aerobulk_gpu_set_error_mode(int return_codes); /* 0: fail-stop like the reference (default), 1: return codes */
+/* 0: fail-stop like the reference (default), 1: return codes.  With return codes an error ENDS the session, as the
+ * STOP of the reference ends the process: the warm-layer state is released and a skin flag set by the failed jt == 1
+ * call is rolled back, so the next jt == 1 call starts clean (no aerobulk_gpu_reset needed). */
+void aerobulk_gpu_set_error_mode(int return_codes);
 /* Grouping of points of equal stability class into the same thread blocks (performance only; results
  * are bit-identical either way): 0 never, 1 (default) where it measured faster, 2 always. */
 void aerobulk_gpu_set_sort(int mode);
@@ -321,8 +339,14 @@ void aerobulk_gpu_reset(void);
 
 /* Persistent warm-layer state, device-resident between jt==1 and jt==Nt
  * (src/mod_skin_coare.f90:31-36, src/mod_skin_ecmwf.f90:52-55).
- * which: 0 dT_wl, 1 Hz_wl, 2 Qnt_ac, 3 Tau_ac.  Returns the number of points
- * copied (0 when the state does not exist). */
+ * which: 0 dT_wl, 1 Hz_wl, 2 Qnt_ac, 3 Tau_ac of the COARE scheme while a COARE session is open, else dT_wl (0) and
+ * the constant Hz_wl = 3 m (1) of the ECMWF scheme; 4 / 5 name the ECMWF pair explicitly (a COARE and an ECMWF session
+ * can be open together, like the module arrays of the reference).  Returns the number of points copied (0 when the
+ * state does not exist or n is not its size).
+ * Restart protocol: the checkpoint holds the warm-layer arrays only.  The session globals set at jt == 1 (humidity type,
+ * skin flag, nitend, nb_iter) are rebuilt by re-running the jt == 1 call with the step-1 inputs (or
+ * aerobulk_gpu_init_from_stats), then aerobulk_gpu_set_state restores the arrays and the run continues at jt+1
+ * (tests/test_gpu_checkpoint.py). */
 long aerobulk_gpu_get_state(int which, double *host_out, long n);
 long aerobulk_gpu_set_state(int which, const double *host_in, long n);
 

@@ -240,3 +240,21 @@ def test_python_mirror_normalises_layout_and_validates_out(ab):
     with pytest.raises(ab.AerobulkError) as e:
         ab.aerobulk_model(1, 1, "ncar", 2.0, 10.0, z, z, z * 0 + 0.01, z * 0 + 5, z * 0, z * 0 + 101000.0, out={"QL": np.empty((3, 4))})
     assert e.value.code == 101
+
+
+def test_shard_plan_of_split_calls(ab):
+    """aerobulk_gpu_set_devices(n): contiguous shards covering [0, n), inner boundaries on multiples of 2048 points (whole
+    sort windows / thread blocks), never more shards than devices, fewer for tiny grids (needs no device)."""
+    for n, nd in ((1036800, 8), (83980800, 8), (64800, 2), (5000, 8), (1, 4), (2048 * 3 + 1, 3)):
+        plan = ab.shard_plan(n, nd)
+        k = len(plan) - 1
+        assert 1 <= k <= nd and plan[0] == 0 and plan[-1] == n
+        assert all(b > a for a, b in zip(plan[:-1], plan[1:]))
+        assert all(b % 2048 == 0 for b in plan[1:-1])
+        sizes = [b - a for a, b in zip(plan[:-1], plan[1:])]
+        assert max(sizes) - min(sizes[:-1] or sizes) <= 0 or max(sizes[:-1]) == min(sizes[:-1])   # equal shards but the last
+        assert max(sizes) <= -(-n // k) + 2048
+    assert ab.shard_plan(83980800, 8) == [i * 10498048 if i < 8 else 83980800 for i in range(9)]   # C5: 810 rows rounded up to 2048 points
+    with pytest.raises(ValueError):
+        ab.shard_plan(-1, 2)
+    assert ab.get_devices() == 1

@@ -39,8 +39,11 @@ CASES = {
     "qlw_net": (lambda L: L.abo_qlw_net, (U(150.0, 500.0), T_SEA), 1e-13, 10.0, "mod_phymbl.f90:1291-1314"),
     "one_on_L": (lambda L: L.abo_one_on_L, (T_AIR, Q_AIR, 10.0 ** U(-4, 0.3), U(-1.0, 1.0), U(-1e-3, 1e-3)), 2e-14, 1e-3,
                  "mod_phymbl.f90:666-693"),
-    "Ri_bulk": (lambda L: L.abo_Ri_bulk, (U(2.0, 30.0), T_SEA, T_SEA + U(-8.0, 4.0), Q_AIR, Q_AIR * 0.8, U(0.2, 30.0)), 1e-13,
-                1e-3, "mod_phymbl.f90:712-747"),
+    # Ri_b = g z dtheta_v / (Tv Ub^2) with dtheta_v a DIFFERENCE of two ~300 K virtual temperatures: its rounding error is
+    # ~1 ulp(300 K) whatever its size, so the error is measured against Ri_b of a unit virtual-temperature difference
+    # (floor = g z / (280 Ub^2), filled in per point by the test)
+    "Ri_bulk": (lambda L: L.abo_Ri_bulk, (U(2.0, 30.0), T_SEA, T_SEA + U(-8.0, 4.0), Q_AIR, Q_AIR * 0.8, U(0.2, 30.0)), 1e-12,
+                "ri_bulk_scale", "mod_phymbl.f90:712-747"),
     "q_air_rh": (lambda L: L.abo_q_air_rh, (U(5.0, 100.0), T_AIR, P), 2e-14, 1e-6, "mod_phymbl.f90:963-985"),
     "q_air_dp": (lambda L: L.abo_q_air_dp, (T_AIR - 3.0, P), 2e-14, 1e-6, "mod_phymbl.f90:990-1000"),
     "cd_n10_ncar": (lambda L: L.abo_cd_n10_ncar, (np.concatenate([WIND, [32.999999, 33.0, 33.000001, 0.5]]),), 1e-14, 1e-4,
@@ -79,6 +82,8 @@ def test_device_function_matches_oracle(ab, OL, name):
     got = ab.probe(name, *cols)
     ref = _oracle_eval(get(OL), cols)
     assert np.all(np.isfinite(got)), name
+    if floor == "ri_bulk_scale":
+        floor = 9.8 * cols[0] / (280.0 * cols[5] ** 2)
     err = np.abs(got - ref) / np.maximum(np.abs(ref), floor)
     print(f"[function] {name:22s} ({where}): max rel err {err.max():.2e} over {ref.size} points")
     assert err.max() <= rel, (name, float(err.max()), [float(c[err.argmax()]) for c in cols])
