@@ -249,6 +249,14 @@ struct Session {
     int ice_form_per_point = 0;   // 0: LG15 form drag from the LAST point's ice fraction (reference), 1: per point
     // ---- statistics + deferred wind-stress flag
     double *d_partials = nullptr, *d_stats = nullptr;
+    // ---- asynchronous AEROBULK_INIT of device-resident sessions: the stats-dependent verdict lives on the device
+    // (d_init = {humidity type, error flag}, d_gstats = the combined statistics) until the host next synchronises
+    int *d_init = nullptr;
+    double *d_gstats = nullptr;
+    bool init_pending = false;
+    int pend_Nt = 0, pend_Ni = 0, pend_Nj = 0;
+    bool pend_lsrad = false;
+    char pend_algo[32] = {0};
     unsigned long long *d_bad = nullptr, *h_bad = nullptr;   // h_bad: pinned
     bool bad_pending = false;
     int pend_launches = 0;        // model calls whose flag has not been looked at yet
@@ -377,6 +385,9 @@ int ensure_device()
     CUDA_TRY(cudaEventCreateWithFlags(&g.ev_bad, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&g.d_partials, sizeof(double) * abk::NSTATS * abk::stats_max_blocks()));
     CUDA_TRY(cudaMalloc(&g.d_stats, sizeof(double) * abk::NSTATS));
+    CUDA_TRY(cudaMalloc(&g.d_gstats, sizeof(double) * abk::NSTATS));
+    CUDA_TRY(cudaMalloc(&g.d_init, 2 * sizeof(int)));
+    CUDA_TRY(cudaMemset(g.d_init, 0, 2 * sizeof(int)));
     // word 0: wind stress > 10 N/m^2; word 1 (sea-ice calls only): rough_leng_tq fail-stop
     CUDA_TRY(cudaMalloc(&g.d_bad, 2 * sizeof(unsigned long long)));
     CUDA_TRY(cudaHostAlloc(&g.h_bad, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -637,7 +648,8 @@ int check_units(const char *name, const char *unit, double zmin, double zmax, co
     return 0;
 }
 
-int init_from_stats(int Nt, const char *calgo, bool lskin, bool lsrad, const double *st, int Ni, int Nj)
+// AEROBULK_INIT, first half (mod_aerobulk.f90:56-99): what depends on the ARGUMENTS only -- skin flag, nitend
+int init_flags(int Nt, const char *calgo, bool lskin, bool lsrad)
 {
     if (g.verbose) {
         printf(" \n ===================================================================\n");
@@ -657,6 +669,12 @@ int init_from_stats(int Nt, const char *calgo, bool lskin, bool lsrad, const dou
         printf("     *** Cool-skin & Warm-layer schemes will NOT be used!\n");
     }
     g.nitend = Nt;   // :99
+    return 0;
+}
+
+// AEROBULK_INIT, second half (mod_aerobulk.f90:100-160): what depends on the field STATISTICS -- mask, humidity type, units
+int init_checks(bool lsrad, const double *st, int Ni, int Nj)
+{
     if (g.verbose) {
         if (Ni > 0) printf("     *** Computational domain shape: Ni x Nj = %05d x %05d\n", Ni, Nj);
         printf("     *** Number of time records that will be treated: %11d\n", g.nitend);
@@ -704,18 +722,62 @@ int init_from_stats(int Nt, const char *calgo, bool lskin, bool lsrad, const dou
     return 0;
 }
 
-int local_stats(long long n, const double *sst, const double *t_zt, const double *hum, const double *U,
-                const double *V, const double *slp, const double *rad_lw, cudaStream_t s, double *host_stats)
+int init_from_stats(int Nt, const char *calgo, bool lskin, bool lsrad, const double *st, int Ni, int Nj)
+{
+    const int rc = init_flags(Nt, calgo, lskin, lsrad);
+    return rc ? rc : init_checks(lsrad, st, Ni, Nj);
+}
+
+// Asynchronous AEROBULK_INIT (device-resident sessions, banners off): the argument-only half runs now, the statistics
+// are combined and judged by init_decide_kernel on the compute stream, and the kernels that follow read the humidity
+// type (and the stop flag) from device memory.  The host catches up in resolve_init() at its next synchronisation.
+int init_async(int Nt, const char *calgo, bool lskin, bool lsrad, const double *d_all, int nranks, int Ni, int Nj, cudaStream_t s)
+{
+    int rc = init_flags(Nt, calgo, lskin, lsrad);
+    if (rc) return rc;
+    CUDA_TRY(abk::launch_init_decide(d_all, nranks, lsrad ? 1 : 0, g.d_gstats, g.d_init, s));
+    g.launches += 1;
+    g.init_pending = true;
+    g.pend_Nt = Nt;
+    g.pend_Ni = Ni;
+    g.pend_Nj = Nj;
+    g.pend_lsrad = lsrad;
+    snprintf(g.pend_algo, sizeof(g.pend_algo), "%s", calgo);
+    return 0;
+}
+
+// The host half of an asynchronous AEROBULK_INIT: waits for the stream, reads the combined statistics back and runs the
+// reference's checks on them (same verdict as the device, with the reference's messages).  Cheap no-op otherwise.
+int resolve_init()
+{
+    if (!g.init_pending) return 0;
+    g.init_pending = false;
+    double st[abk::NSTATS];
+    CUDA_TRY(cudaMemcpyAsync(st, g.d_gstats, sizeof(st), cudaMemcpyDeviceToHost, compute_stream()));
+    CUDA_TRY(cudaStreamSynchronize(compute_stream()));
+    return init_checks(g.pend_lsrad, st, g.pend_Ni, g.pend_Nj);
+}
+
+// stats_kernel + stats_final on stream s; the 64-double vector lands in `d_out` (device memory)
+int launch_local_stats(long long n, const double *sst, const double *t_zt, const double *hum, const double *U,
+                       const double *V, const double *slp, const double *rad_lw, cudaStream_t s, double *d_out)
 {
     abk::StatsArgs a;
     a.sst = sst; a.t_zt = t_zt; a.hum_zt = hum; a.U_zu = U; a.V_zu = V; a.slp = slp; a.rad_lw = rad_lw;
     a.n = n;
     a.partials = g.d_partials;
-    a.out = g.d_stats;
+    a.out = d_out;
     long long want = (n + 255) / 256;
     int nblocks = (int)(want < 1 ? 1 : (want > abk::stats_max_blocks() ? abk::stats_max_blocks() : want));
     CUDA_TRY(abk::launch_stats(a, nblocks, s));
     g.launches += 2;
+    return 0;
+}
+int local_stats(long long n, const double *sst, const double *t_zt, const double *hum, const double *U,
+                const double *V, const double *slp, const double *rad_lw, cudaStream_t s, double *host_stats)
+{
+    const int rc = launch_local_stats(n, sst, t_zt, hum, U, V, slp, rad_lw, s, g.d_stats);
+    if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(host_stats, g.d_stats, sizeof(double) * abk::NSTATS, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return 0;
@@ -785,6 +847,13 @@ int check_bad_flag(const double *h_taux, const double *h_tauy)
                 flagged_launches, idx);
 }
 
+// entry points other than aerobulk_gpu_model*: everything an earlier asynchronous call still owes the caller
+int deferred_errors()
+{
+    const int rc = resolve_init();
+    return rc ? rc : check_bad_flag(nullptr, nullptr);
+}
+
 // Row-block chunk plan of a host-array call: cstart[0..nchunks], boundaries on multiples of 2048 points (whole sort
 // windows / thread blocks).  kind 0: one chunk (device arrays, zero-copy on pinned arrays); 1: staged H2D | kernel | D2H
 // pipeline (sizes decrease linearly by default: short exposed tail); 2: pageable arrays through the pinned slab (small
@@ -841,6 +910,10 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     if (rc) return rc;
     const long long n = (long long)Ni * (long long)Nj;
     cudaStream_t cs = compute_stream();
+    if (g.init_pending && !device_ptrs) {   // a host-array call is blocking anyway: catch up with an asynchronous AEROBULK_INIT
+        rc = resolve_init();
+        if (rc) return rc;
+    }
 
     // a deferred wind-stress error of earlier asynchronous launches surfaces as soon as its flag
     // copy has landed (no synchronisation here: device-resident calls stay asynchronous)
@@ -937,6 +1010,14 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         } else {
             double st[abk::NSTATS];
             if (!device_ptrs) CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_in[nchunks - 1], 0));
+            if (device_ptrs && !g.verbose && !g.stats_hook && n > 0) {
+                // device-resident session, banners off: no host round trip -- the statistics stay on the device, are judged
+                // there, and the flux kernel reads the verdict from device memory (init_async / resolve_init)
+                rc = launch_local_stats(n, in_d[0], in_d[1], in_d[2], in_d[3], in_d[4], in_d[5], lsrad ? in_d[6] : nullptr, cs, g.d_stats);
+                if (rc) return rc;
+                rc = init_async(Nt, calgo, lskin, lsrad, g.d_stats, 1, Ni, Nj, cs);
+                if (rc) return rc;
+            } else {
             if (n > 0) {
                 // :248 -- prsw=rad_lw: rad_lw is checked against both radiation ranges, rad_sw never
                 rc = local_stats(n, in_d[0], in_d[1], in_d[2], in_d[3], in_d[4], in_d[5], lsrad ? in_d[6] : nullptr, cs, st);
@@ -949,6 +1030,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
                 return fail(AEROBULK_GPU_ERR_STATE, "AEROBULK_INIT => another device of the split call failed");
             rc = init_from_stats(Nt, calgo, lskin, lsrad, st, g.report_Ni > 0 ? g.report_Ni : Ni, g.report_Ni > 0 ? g.report_Nj : Nj);
             if (rc) return rc;
+            }
         }
     }
 
@@ -1004,6 +1086,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     memset(&a, 0, sizeof(a));
     a.u = make_uniform(zt, zu);
     a.ihum = g.ihum;
+    a.init_dev = g.init_pending ? g.d_init : nullptr;
     a.first_step = (jt == 1);
     a.bad_index = g.d_bad;
     const bool zteq = fabs(zu - zt) < 0.01;
@@ -1074,11 +1157,12 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     g.last_tauy = out_d[3];
 
     const bool last = (jt == g.nitend);
-    if (!device_ptrs || last || jt == 1) {
+    if (!device_ptrs || last || (jt == 1 && !g.init_pending)) {
         CUDA_TRY(cudaStreamSynchronize(cs));
         if (!device_ptrs) CUDA_TRY(cudaStreamSynchronize(g.out_stream));
         if (bounce_first) bounce_copy(6, user_out, 8, 0, n, false);
-        rc = check_bad_flag(device_ptrs ? nullptr : Tau_x, device_ptrs ? nullptr : Tau_y);
+        rc = resolve_init();   // an asynchronous AEROBULK_INIT of this session reports first, as in the reference
+        if (!rc) rc = check_bad_flag(device_ptrs ? nullptr : Tau_x, device_ptrs ? nullptr : Tau_y);
         if (!device_ptrs && trace_on()) {
             fprintf(stderr, "[aerobulk_gpu trace] jt=%d chunks=%d  (ms since the first H2D: in | kernel | out)\n", jt, nchunks);
             for (int c = 0; c < nchunks; ++c) {
@@ -1278,6 +1362,7 @@ void end_session_after_error(int jt, bool skin_before)
     for (int d = 0; d < MAX_DEVICES; ++d) {
         sess[d].n_coare = sess[d].n_ecmwf = 0;
         sess[d].preinit_done = false;
+        sess[d].init_pending = false;
         if (jt == 1) sess[d].l_use_skin_schemes = skin_before;
     }
 }
@@ -1328,6 +1413,8 @@ int turb_impl(const char *calgo, int kt, double zt, double zu, int Ni, int Nj, d
         return fail(AEROBULK_GPU_ERR_SKIN_NORAD,
                     "[turb_%s] => you need to provide Qsw, rad_lw, slp, isecday_utc & plong to use warm-layer param!", calgo);
     int rc = ensure_device();
+    if (rc) return rc;
+    rc = resolve_init();
     if (rc) return rc;
     const long long n = (long long)Ni * Nj;
     cudaStream_t cs_ = compute_stream();
@@ -1438,7 +1525,7 @@ int series_impl(const char *calgo, int Nt, long long S, double zt, double zu, co
     const long long n = (long long)Nt * S;
     if (n == 0) return 0;
     cudaStream_t cs_ = compute_stream();
-    rc = check_bad_flag(nullptr, nullptr);   // a deferred error of earlier aerobulk_gpu_model_device calls
+    rc = deferred_errors();   // of earlier asynchronous aerobulk_gpu_model_device calls
     if (rc) return rc;
 
     double *const hout[abk::NSERIES_OUT] = {
@@ -1764,7 +1851,7 @@ int turb_ice_impl(const char *calgo, double zt, double zu, int Ni, int Nj, const
     const long long n = (long long)Ni * Nj;
     if (n == 0) return 0;
     cudaStream_t cs_ = compute_stream();
-    rc = check_bad_flag(nullptr, nullptr);
+    rc = deferred_errors();
     if (rc) return rc;
 
     double *optp[8] = {nullptr};
@@ -1829,7 +1916,7 @@ int oce_ice_impl(const char *calgo_ice, const char *calgo_oce, double zt, double
     if (rc) return rc;
     if (n == 0) return 0;
     cudaStream_t cs_ = compute_stream();
-    rc = check_bad_flag(nullptr, nullptr);
+    rc = deferred_errors();
     if (rc) return rc;
 
     double *const hout[abk::NOCEICE_OUT] = {
@@ -1917,7 +2004,7 @@ int series_ice_impl(const char *calgo, double zt, double zu, long long n, const 
     if (rc) return rc;
     if (n == 0) return 0;
     cudaStream_t cs_ = compute_stream();
-    rc = check_bad_flag(nullptr, nullptr);
+    rc = deferred_errors();
     if (rc) return rc;
 
     static_assert(sizeof(aerobulk_gpu_series_ice_out) == abk::NICESERIES_OUT * sizeof(double *), "21 output pointers");
@@ -2319,7 +2406,11 @@ int aerobulk_gpu_synchronize(void)
     CUDA_TRY(cudaSetDevice(g.device));
     CUDA_TRY(cudaStreamSynchronize(compute_stream()));
     CUDA_TRY(cudaStreamSynchronize(g.out_stream));
-    return check_bad_flag(nullptr, nullptr);
+    const bool skin_before = g.l_use_skin_schemes;
+    int rc = resolve_init();
+    if (!rc) rc = check_bad_flag(nullptr, nullptr);
+    if (rc) end_session_after_error(0, skin_before);
+    return rc;
 }
 
 int aerobulk_gpu_set_devices(int n)
@@ -2390,12 +2481,59 @@ int aerobulk_gpu_init_from_stats(int Nt, const char *calgo, const int *l_use_ski
     return 0;
 }
 
+int aerobulk_gpu_init_local_stats_device(int Ni, int Nj, const double *sst, const double *t_zt, const double *hum_zt,
+                                         const double *U_zu, const double *V_zu, const double *slp, const double *rad_lw,
+                                         double *d_stats)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!d_stats || !sst || !t_zt || !hum_zt || !U_zu || !V_zu || !slp)
+        return fail(AEROBULK_GPU_ERR_ARG, "init_local_stats_device: NULL argument");
+    const long long n = (long long)Ni * Nj;
+    if (n <= 0) return fail(AEROBULK_GPU_ERR_ARG, "init_local_stats_device: empty row block (give it the identity vector instead)");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return launch_local_stats(n, sst, t_zt, hum_zt, U_zu, V_zu, slp, rad_lw, compute_stream(), d_stats);
+}
+
+int aerobulk_gpu_init_from_gathered_stats(int Nt, const char *calgo, const int *l_use_skin, int have_rad,
+                                          const double *d_all, int nranks)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!calgo || !d_all || nranks < 1) return fail(AEROBULK_GPU_ERR_ARG, "init_from_gathered_stats: bad argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const bool lskin = l_use_skin ? (*l_use_skin != 0) : false;
+    const int verbose = g.verbose;
+    g.verbose = 0;   // the banner needs the statistics on the host: this path never brings them back in time
+    rc = init_async(Nt, calgo, lskin, have_rad != 0, d_all, nranks, 0, 0, compute_stream());
+    g.verbose = verbose;
+    if (rc) return rc;
+    g.preinit_done = true;
+    return 0;
+}
+
 void aerobulk_gpu_set_rdt(double v) { std::lock_guard<std::mutex> lk(g_mu); g.rdt = v; }
 void aerobulk_gpu_set_gdept(double v) { std::lock_guard<std::mutex> lk(g_mu); g.gdept = v; }
 void aerobulk_gpu_set_nb_iter(int v) { std::lock_guard<std::mutex> lk(g_mu); g.nb_iter = v; }
 int aerobulk_gpu_get_nb_iter(void) { return g.nb_iter; }
 int aerobulk_gpu_get_use_skin(void) { return g.l_use_skin_schemes ? 1 : 0; }
-const char *aerobulk_gpu_get_humidity_type(void) { return HUM_NAMES[g.ihum]; }
+const char *aerobulk_gpu_get_humidity_type(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.init_pending && g.device_ready && cudaSetDevice(g.device) == cudaSuccess) {
+        // asynchronous AEROBULK_INIT: the device has decided, the host has not caught up -- read the device's verdict
+        // (the checks and their error, if any, still surface at the next synchronising call, where they belong)
+        int v[2] = {g.ihum, 0};
+        if (cudaStreamSynchronize(compute_stream()) == cudaSuccess &&
+            cudaMemcpy(v, g.d_init, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess && v[0] >= 0 && v[0] <= 2)
+            return HUM_NAMES[v[0]];
+    }
+    return HUM_NAMES[g.ihum];
+}
 
 int aerobulk_gpu_set_device(int device)
 {
@@ -2452,6 +2590,7 @@ static void reset_session()   // the session of `cur`
     g.rdt = 3600.;
     g.gdept = 1.;
     g.preinit_done = false;
+    g.init_pending = false;
     g.bad_pending = false;
     g.pend_launches = 0;
     g.errcode = 0;

@@ -31,10 +31,10 @@ static constexpr int FLUX_BLOCK = AB_FLUX_BLOCK;
 // Cheap proxy of the sign of the air-sea virtual potential temperature difference, i.e. of the
 // stability class every psi_m/psi_h evaluation branches on.  Only used to GROUP points (performance);
 // the physics below never sees it.
-__device__ __forceinline__ bool stable_proxy(const FluxArgs &a, long long i)
+__device__ __forceinline__ bool stable_proxy(const FluxArgs &a, int ihum, long long i)
 {
     const double sst = __ldg(a.sst + i), ta = __ldg(a.t_zt + i) + RGAMMA_DRY * a.u.zt;
-    if (a.ihum != 0) return ta >= sst;
+    if (ihum != 0) return ta >= sst;
     const double q = __ldg(a.hum_zt + i), p = __ldg(a.slp + i);
     const double tc = sst - 273.15;
     const double es = 611.2 * abm::dexp(17.67 * tc * abm::fast_rcp(tc + 243.5));     // Magnus
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) classify_kernel(const FluxArgs a, 
     abm::load_tables();
     const long long base = (long long)blockIdx.x * SORT_WIN;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int ihum = a.init_dev ? __ldg(a.init_dev) : a.ihum;
     constexpr int NW = SORT_BLOCK / 32;
     int cls[SORT_ITEMS];
     unsigned m0[SORT_ITEMS], m1[SORT_ITEMS];
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) classify_kernel(const FluxArgs a, 
     for (int k = 0; k < SORT_ITEMS; ++k) {
         const long long i = base + k * SORT_BLOCK + tid;
         cls[k] = 2;
-        if (i < a.n) cls[k] = stable_proxy(a, i) ? 0 : 1;
+        if (i < a.n) cls[k] = stable_proxy(a, ihum, i) ? 0 : 1;
         m0[k] = __ballot_sync(0xffffffffu, cls[k] == 0);
         m1[k] = __ballot_sync(0xffffffffu, cls[k] == 1);
         if (lane == 0) {
@@ -108,6 +109,11 @@ __global__ void __launch_bounds__(FLUX_BLOCK, AB_MIN_BLOCKS) flux_kernel(const F
     long long i = (long long)blockIdx.x * FLUX_BLOCK + threadIdx.x;
     if (a.perm) i = (i / SORT_WIN) * SORT_WIN + a.perm[i];   // slot -> point (perm is padded to whole windows)
     if (i >= a.n) return;
+    int ihum = a.ihum;
+    if (a.init_dev) {   // asynchronous AEROBULK_INIT: its verdict is on the device, the host has not seen it yet
+        if (__ldg(a.init_dev + 1) != 0) return;   // the reference would have stopped: nothing is computed
+        ihum = __ldg(a.init_dev);
+    }
 
     // ---- coalesced loads of the 6 (8) input fields
     const double sst = __ldg(a.sst + i);
@@ -121,8 +127,8 @@ __global__ void __launch_bounds__(FLUX_BLOCK, AB_MIN_BLOCKS) flux_kernel(const F
     p.sst = sst;
     p.slp = slp;
     // humidity -> specific humidity (mod_aerobulk_compute.f90:99-108); slp floored at 5e4 Pa by the caller
-    if (a.ihum == 0) p.q_zt = hum;
-    else if (a.ihum == 1) p.q_zt = q_air_dp(hum, abm::dmax(slp, 50000.));
+    if (ihum == 0) p.q_zt = hum;
+    else if (ihum == 1) p.q_zt = q_air_dp(hum, abm::dmax(slp, 50000.));
     else p.q_zt = q_air_rh(hum, t_air, abm::dmax(slp, 50000.));
     // :111 -- no FMA contraction here: U*U+V*V must not depend on the order of the components
     p.wnd = sqrt(__dadd_rn(__dmul_rn(U, U), __dmul_rn(V, V)));
@@ -475,6 +481,56 @@ cudaError_t launch_stats(const StatsArgs &a, int nblocks, cudaStream_t s)
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     stats_final<<<NSTATS * 32 / 256, 256, 0, s>>>(a.partials, nblocks, a.out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// init_decide_kernel: the stats-dependent half of AEROBULK_INIT on the device, so that jt == 1 of a device-resident
+// session needs no host round trip (the host re-derives the same verdict, with its messages, when it next synchronises)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(NSTATS) init_decide_kernel(const double *all, int nranks, int have_rad, double *gstats, int *init)
+{
+    __shared__ double st[NSTATS];
+    const int k = threadIdx.x;
+    const int op = stat_op(k);
+    double r = all[k];
+    for (int d = 1; d < nranks; ++d) {
+        const double w = all[(long long)d * NSTATS + k];
+        r = (op == 0) ? r + w : (op == 1) ? fmin(r, w) : fmax(r, w);
+    }
+    st[k] = r;
+    gstats[k] = r;
+    __syncthreads();
+    if (k != 0) return;
+    const double np = st[0];
+    int ihum = 0, err = 0;
+    if (!(np > 0.)) {
+        err = 4;   // AEROBULK_GPU_ERR_ALL_MASKED
+    } else {
+        // type_of_humidity, mod_phymbl.f90:1957-2007
+        const double *h = st + 2 + 5 * 6;
+        const double zmean = h[0] / np, zmin = h[1], zmax = h[2];
+        double hlo = 0., hhi = 0.08;
+        if (zmean >= 0. && zmean < 0.08 && zmin >= 0. && zmax < 0.08) { ihum = 0; }
+        else if (zmean >= 150. && zmean < 330. && zmin >= 150. && zmax < 330.) { ihum = 1; hlo = 150.; hhi = 330.; }
+        else if (zmean >= 0. && zmean <= 100. && zmin >= 0. && zmax <= 100.) { ihum = 2; hlo = 0.; hhi = 100.; }
+        else err = 5;   // AEROBULK_GPU_ERR_HUMIDITY
+        // check_unit_consistency, mod_phymbl.f90:1851-1954; field order of the statistics vector
+        const double lo[9] = {270., 180., 80000., -50., -50., 0., hlo, 0., 0.};
+        const double hi[9] = {320., 330., 110000., 50., 50., 50., hhi, 1500., 750.};
+        for (int f = 0; f < (have_rad ? 9 : 7) && !err; ++f) {
+            const double *s5 = st + 2 + 5 * f;
+            const double m = s5[0] / np;
+            if (s5[2] > hi[f] || s5[1] < lo[f] || m < lo[f] || m > hi[f]) err = 6;   // AEROBULK_GPU_ERR_UNITS
+        }
+    }
+    init[0] = ihum;
+    init[1] = err;
+}
+
+cudaError_t launch_init_decide(const double *all, int nranks, int have_rad, double *gstats, int *init, cudaStream_t s)
+{
+    init_decide_kernel<<<1, NSTATS, 0, s>>>(all, nranks, have_rad, gstats, init);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,9 @@ struct FluxArgs {
     long long n;
     abd::Uniform u;
     int ihum;          // 0 'sh', 1 'dp', 2 'rh'   (mod_aerobulk_compute.f90:99-108)
+    // device-side AEROBULK_INIT still in flight (asynchronous jt == 1 of a device-resident session): {humidity type,
+    // error flag} written by init_decide_kernel earlier on the same stream; NULL: `ihum` above is final
+    const int *init_dev;
     int first_step;    // kt == nit000: state starts from its *_INIT values, not from memory
     // first linear index whose wind stress exceeds 10 N/m^2 (mod_phymbl.f90:1250-1253), else ~0ull
     unsigned long long *bad_index;
@@ -139,6 +142,11 @@ int sort_window();
 // fills perm[] (ceil(n / sort_window()) * sort_window() entries) for the launch described by `a`
 cudaError_t launch_classify(const FluxArgs &a, unsigned short *perm, cudaStream_t s);
 cudaError_t launch_stats(const StatsArgs &a, int nblocks, cudaStream_t s);
+// AEROBULK_INIT's stats-dependent decisions on the device (src/mod_aerobulk.f90:104-153, src/mod_phymbl.f90:1851-2007):
+// combines the statistics vectors of `nranks` row blocks (all[r][NSTATS], rank order: deterministic) into gstats[NSTATS]
+// and writes init[0] = humidity type (0 'sh', 1 'dp', 2 'rh'), init[1] = 0 or the AEROBULK_GPU_ERR_* code the host will
+// raise when it next synchronises (all masked / unknown humidity / unit check).
+cudaError_t launch_init_decide(const double *all, int nranks, int have_rad, double *gstats, int *init, cudaStream_t s);
 int stats_max_blocks();
 // DFMA-chain microbenchmark: returns FP64 FMA instructions per second, <0 on error
 double measure_fp64_peak(cudaStream_t s);

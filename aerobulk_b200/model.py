@@ -49,6 +49,10 @@ def lib():
     L.aerobulk_gpu_stats_reduce_op.argtypes = [C.c_int]
     L.aerobulk_gpu_init_from_stats.restype = C.c_int
     L.aerobulk_gpu_init_from_stats.argtypes = [C.c_int, C.c_char_p, _ip, C.c_int, _dp]
+    L.aerobulk_gpu_init_local_stats_device.restype = C.c_int
+    L.aerobulk_gpu_init_local_stats_device.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 8
+    L.aerobulk_gpu_init_from_gathered_stats.restype = C.c_int
+    L.aerobulk_gpu_init_from_gathered_stats.argtypes = [C.c_int, C.c_char_p, _ip, C.c_int, C.c_void_p, C.c_int]
     L.aerobulk_gpu_set_rdt.argtypes = [C.c_double]
     L.aerobulk_gpu_set_gdept.argtypes = [C.c_double]
     L.aerobulk_gpu_set_nb_iter.argtypes = [C.c_int]
@@ -237,6 +241,29 @@ def init_from_stats(Nt: int, calgo: str, l_use_skin: Optional[bool], have_rad: b
     st = np.ascontiguousarray(stats, dtype=np.float64)
     ls = None if l_use_skin is None else C.byref(C.c_int(int(bool(l_use_skin))))
     _check(L.aerobulk_gpu_init_from_stats(int(Nt), calgo.encode(), ls, int(bool(have_rad)), st.ctypes.data_as(_dp)))
+
+
+def init_local_stats_device(sst, t_zt, hum_zt, U_zu, V_zu, slp, rad_lw=None, out=None):
+    """Row-block statistics of AEROBULK_INIT written to DEVICE memory (`out`: 64-double CUDA tensor, created if None) on
+    the session stream -- no host copy, no synchronisation (aerobulk_gpu_init_local_stats_device)."""
+    import torch
+    L = lib()
+    if out is None:
+        out = torch.empty(NSTATS, dtype=torch.float64, device=sst.device)
+    ptr = lambda t: None if t is None else t.data_ptr()
+    _check(L.aerobulk_gpu_init_local_stats_device(sst.numel(), 1, ptr(sst), ptr(t_zt), ptr(hum_zt), ptr(U_zu), ptr(V_zu),
+                                                  ptr(slp), ptr(rad_lw), ptr(out)))
+    return out
+
+
+def init_from_gathered_stats(Nt: int, calgo: str, l_use_skin: Optional[bool], have_rad: bool, gathered, nranks: int):
+    """AEROBULK_INIT from the all-gathered [nranks, 64] DEVICE tensor of row-block statistics: combined and judged on the
+    device, asynchronously (aerobulk_gpu_init_from_gathered_stats)."""
+    L = lib()
+    if (not gathered.is_cuda) or str(gathered.dtype) != "torch.float64" or not gathered.is_contiguous() or gathered.numel() != nranks * NSTATS:
+        raise AerobulkError(101, "init_from_gathered_stats needs a contiguous float64 CUDA tensor of nranks * 64 values")
+    ls = None if l_use_skin is None else C.byref(C.c_int(int(bool(l_use_skin))))
+    _check(L.aerobulk_gpu_init_from_gathered_stats(int(Nt), calgo.encode(), ls, int(bool(have_rad)), gathered.data_ptr(), int(nranks)))
 
 
 def synchronize():

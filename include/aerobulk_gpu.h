@@ -294,6 +294,23 @@ int aerobulk_gpu_stats_reduce_op(int i);
 int aerobulk_gpu_init_from_stats(int Nt, const char *calgo, const int *l_use_skin, int have_rad,
                                  const double *stats);
 
+/* The same split WITHOUT a host round trip, for device-resident sessions (one collective, nothing copied to the host,
+ * no synchronisation).  aerobulk_gpu_init_local_stats_device writes the row-block vector into DEVICE memory d_stats
+ * (AEROBULK_GPU_NSTATS doubles) on the session stream.  The caller gathers the vectors of all ranks with ONE collective
+ * (ncclAllGather / MPI_Allgather of 64 doubles per rank on that stream) into d_all[nranks][AEROBULK_GPU_NSTATS] and calls
+ * aerobulk_gpu_init_from_gathered_stats: the argument-only decisions of AEROBULK_INIT (skin flag, nitend and their
+ * errors) are taken at once; the statistics are combined in rank order and judged ON THE DEVICE (mask count, humidity
+ * type, unit checks), and the flux kernels that follow read the verdict from device memory.  The host catches up -- and
+ * raises an AEROBULK_INIT error with the reference's message -- at its next synchronisation (aerobulk_gpu_synchronize,
+ * the jt == Nt call, any host-array call): the deferred-error rule the tau > 10 N/m^2 check already follows.  A kernel
+ * launched after a failed device-side init computes nothing.  aerobulk_gpu_model_device(jt == 1) uses the same mechanism
+ * on its own when the banners are off (aerobulk_gpu_set_verbose(0)). */
+int aerobulk_gpu_init_local_stats_device(int Ni, int Nj, const double *sst, const double *t_zt, const double *hum_zt,
+                                         const double *U_zu, const double *V_zu, const double *slp,
+                                         const double *rad_lw, double *d_stats /* device, AEROBULK_GPU_NSTATS */);
+int aerobulk_gpu_init_from_gathered_stats(int Nt, const char *calgo, const int *l_use_skin, int have_rad,
+                                          const double *d_all /* device, [nranks][AEROBULK_GPU_NSTATS] */, int nranks);
+
 /* ---- module globals of src/mod_const.f90:22-33 that callers may overwrite ------ */
 void aerobulk_gpu_set_rdt(double rdt_seconds);   /* default 3600 */
 void aerobulk_gpu_set_gdept(double depth_m);     /* default 1    */

@@ -125,17 +125,24 @@ def test_split_init_sees_the_whole_field(ab):
     assert ab.humidity_type() == h1 == "rh"
     for k in one:
         assert np.array_equal(one[k], two[k]), k
-    # a Celsius SST block in the SECOND shard only: check_unit_consistency fails for the whole call (error 6: units)
-    sst = f["sst"].copy()
-    sst[:, Nj // 2:] -= 273.15
-    ab.reset()
-    with pytest.raises(ab.AerobulkError) as e:
-        ab.aerobulk_model(1, 1, "coare3p6", 2.0, 10.0, sst, f["t_zt"], f["hum_zt"], f["U_zu"], f["V_zu"], f["slp"])
-    ab.set_devices(1)
-    ab.reset()
-    with pytest.raises(ab.AerobulkError) as e1:
-        ab.aerobulk_model(1, 1, "coare3p6", 2.0, 10.0, sst, f["t_zt"], f["hum_zt"], f["U_zu"], f["V_zu"], f["slp"])
-    assert e.value.code == e1.value.code
+    # specific humidity in the first shard, dew points in the second: EACH shard alone is a valid field ('sh', 'dp'), the
+    # whole is neither -> the reference's type_of_humidity stops (error 5), and so must the split call
+    hum2 = hum.copy()
+    hum2[:, Nj // 2:] = 280.0
+    codes = []
+    for nd in (2, 1):
+        ab.set_devices(1)
+        ab.reset()
+        ab.set_devices(nd)
+        with pytest.raises(ab.AerobulkError) as e:
+            ab.aerobulk_model(1, 1, "coare3p6", 2.0, 10.0, f["sst"], f["t_zt"], hum2, f["U_zu"], f["V_zu"], f["slp"])
+        codes.append((e.value.code, e.value.message))
+    assert codes[0][0] == codes[1][0] == 5
+    assert codes[0][1] == codes[1][1]
+    # and the error ended the session cleanly on every device: the next call works
+    ab.set_devices(2)
+    ok = ab.aerobulk_model(1, 1, "coare3p6", 2.0, 10.0, f["sst"], f["t_zt"], hum, f["U_zu"], f["V_zu"], f["slp"])
+    assert np.array_equal(ok["QL"], one["QL"])
 
 
 def test_split_reports_wind_stress_error_with_global_indices(ab):
@@ -146,14 +153,14 @@ def test_split_reports_wind_stress_error_with_global_indices(ab):
     f = synth.fields(Ni, Nj)
     U = f["U_zu"].copy()
     V = f["V_zu"].copy()
-    U[100, 50], V[100, 50] = 49.0, 0.0       # 49 m/s: inside the sanity range, tau ~ 11 N/m2 with NCAR
+    U[100, 50], V[100, 50] = 48.0, 0.0       # 48 m/s: inside the sanity range (<= 50), tau > 10 N/m2 with COARE 3.6
     msgs = []
     for nd in (1, 2):
         ab.set_devices(1)
         ab.reset()
         ab.set_devices(nd)
         with pytest.raises(ab.AerobulkError) as e:
-            ab.aerobulk_model(1, 1, "ncar", 2.0, 10.0, f["sst"], f["t_zt"], f["hum_zt"], U, V, f["slp"])
+            ab.aerobulk_model(1, 1, "coare3p6", 2.0, 10.0, f["sst"], f["t_zt"], f["hum_zt"], U, V, f["slp"])
         assert e.value.code == 8
         msgs.append(e.value.message)
     assert "ji, jj = 0101, 0051" in msgs[0], msgs[0]
