@@ -263,6 +263,13 @@ struct Session {
     int last_Ni = 0;
     const double *last_taux = nullptr, *last_tauy = nullptr;   // device pointers of the last launch
     long launches = 0;
+    // ---- opt-in: device-pointer calls never synchronise, not even at jt == Nt (aerobulk_gpu_set_async)
+    bool async_device = false;
+    // ---- opt-in: CUDA events around every flux launch (aerobulk_gpu_set_kernel_timing): the roofline denominators of
+    // bench.py are durations of the flux kernel ALONE, measured on the stream it runs on
+    bool time_kernels = false;
+    std::vector<cudaEvent_t> kt_ev;   // pairs
+    size_t kt_used = 0;
     // ---- aerobulk_gpu_set_devices(n): this session's share of a call that the library split over several GPUs
     int shard = 0;                 // index of this session among the devices of the split
     long long flat_offset = 0;     // global flat index of the shard's first point (error messages, tau > 10 report)
@@ -1122,8 +1129,23 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
             g.launches += 1;
             a.perm = perm;
         }
+        cudaEvent_t kt0 = nullptr, kt1 = nullptr;
+        if (g.time_kernels) {
+            if (g.kt_used + 2 > g.kt_ev.size()) {
+                cudaEvent_t e0, e1;
+                CUDA_TRY(cudaEventCreate(&e0));
+                CUDA_TRY(cudaEventCreate(&e1));
+                g.kt_ev.push_back(e0);
+                g.kt_ev.push_back(e1);
+            }
+            kt0 = g.kt_ev[g.kt_used];
+            kt1 = g.kt_ev[g.kt_used + 1];
+            g.kt_used += 2;
+            CUDA_TRY(cudaEventRecord(kt0, cs));
+        }
         CUDA_TRY(abk::launch_flux(ialgo, use_skin, zteq, a, cs));
         g.launches += 1;
+        if (kt1) CUDA_TRY(cudaEventRecord(kt1, cs));
         if (!device_ptrs) {
             CUDA_TRY(cudaEventRecord(g.ev_k[c], cs));
             if (trace_on()) cudaEventRecord(tr_k[c], cs);
@@ -1157,7 +1179,8 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     g.last_tauy = out_d[3];
 
     const bool last = (jt == g.nitend);
-    if (!device_ptrs || last || (jt == 1 && !g.init_pending)) {
+    const bool never_sync = device_ptrs && g.async_device;   // the caller collects errors with aerobulk_gpu_synchronize()
+    if (!never_sync && (!device_ptrs || last || (jt == 1 && !g.init_pending))) {
         CUDA_TRY(cudaStreamSynchronize(cs));
         if (!device_ptrs) CUDA_TRY(cudaStreamSynchronize(g.out_stream));
         if (bounce_first) bounce_copy(6, user_out, 8, 0, n, false);
@@ -2593,6 +2616,9 @@ static void reset_session()   // the session of `cur`
     g.init_pending = false;
     g.bad_pending = false;
     g.pend_launches = 0;
+    g.async_device = false;
+    g.time_kernels = false;
+    g.kt_used = 0;
     g.errcode = 0;
     g.errmsg[0] = 0;
     g.shard = 0;
@@ -2689,6 +2715,56 @@ long aerobulk_gpu_set_state(int which, const double *host_in, long n)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     return state_io(which, const_cast<double *>(host_in), n, 1);
+}
+
+void aerobulk_gpu_new_session(void)
+{
+    // what a NEW PROCESS of the reference would start with: the SAVEd module variables of mod_const.f90:22-33 at their
+    // initial values and no warm-layer arrays -- without giving the device buffers back (aerobulk_gpu_reset does that
+    // too, at the price of a device synchronisation and re-allocation).  Settings of this library (device(s), stream,
+    // error mode, verbosity, sort policy, rdt / gdept, async mode) are kept.  Deferred errors of earlier asynchronous
+    // calls are NOT cleared: they still surface at the next synchronising call.
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int d = 0; d < MAX_DEVICES; ++d) {
+        sess[d].nb_iter = 5;
+        sess[d].nitend = 1;
+        sess[d].l_use_skin_schemes = false;
+        if (!sess[d].init_pending) sess[d].ihum = 0;
+        sess[d].preinit_done = false;
+        sess[d].n_coare = sess[d].n_ecmwf = 0;
+    }
+}
+
+void aerobulk_gpu_set_async(int on)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.async_device = on != 0;
+}
+
+void aerobulk_gpu_set_kernel_timing(int on)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.time_kernels = on != 0;
+    g.kt_used = 0;
+}
+
+int aerobulk_gpu_kernel_times(double *ms, int max)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.device_ready || !ms) return 0;
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(compute_stream());
+    int k = 0;
+    for (size_t i = 0; i + 1 < g.kt_used && k < max; i += 2) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, g.kt_ev[i], g.kt_ev[i + 1]) != cudaSuccess) {
+            cudaGetLastError();
+            break;
+        }
+        ms[k++] = (double)t;
+    }
+    g.kt_used = 0;
+    return k;
 }
 
 long aerobulk_gpu_launch_count(void)

@@ -53,6 +53,10 @@ def lib():
     L.aerobulk_gpu_init_local_stats_device.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 8
     L.aerobulk_gpu_init_from_gathered_stats.restype = C.c_int
     L.aerobulk_gpu_init_from_gathered_stats.argtypes = [C.c_int, C.c_char_p, _ip, C.c_int, C.c_void_p, C.c_int]
+    L.aerobulk_gpu_set_async.argtypes = [C.c_int]
+    L.aerobulk_gpu_set_kernel_timing.argtypes = [C.c_int]
+    L.aerobulk_gpu_kernel_times.restype = C.c_int
+    L.aerobulk_gpu_kernel_times.argtypes = [_dp, C.c_int]
     L.aerobulk_gpu_set_rdt.argtypes = [C.c_double]
     L.aerobulk_gpu_set_gdept.argtypes = [C.c_double]
     L.aerobulk_gpu_set_nb_iter.argtypes = [C.c_int]
@@ -301,6 +305,17 @@ def shard_plan(n: int, n_dev: int) -> list:
     return [int(start[i]) for i in range(k + 1)]
 
 
+def set_async(on: bool): lib().aerobulk_gpu_set_async(int(bool(on)))
+def set_kernel_timing(on: bool): lib().aerobulk_gpu_set_kernel_timing(int(bool(on)))
+
+
+def kernel_times(max_n: int = 65536) -> np.ndarray:
+    """Durations [ms] of the flux-kernel launches recorded since the last call (set_kernel_timing(True))."""
+    buf = np.zeros(max_n, dtype=np.float64)
+    k = lib().aerobulk_gpu_kernel_times(buf.ctypes.data_as(_dp), max_n)
+    return buf[:k].copy()
+
+
 def set_rdt(v: float): lib().aerobulk_gpu_set_rdt(float(v))
 def set_gdept(v: float): lib().aerobulk_gpu_set_gdept(float(v))
 def set_nb_iter(v: int): lib().aerobulk_gpu_set_nb_iter(int(v))
@@ -311,6 +326,7 @@ def use_skin() -> bool: return bool(lib().aerobulk_gpu_get_use_skin())
 def humidity_type() -> str: return lib().aerobulk_gpu_get_humidity_type().decode()
 def last_error() -> str: return lib().aerobulk_gpu_last_error().decode(errors="replace")
 def reset(): lib().aerobulk_gpu_reset()
+def new_session(): lib().aerobulk_gpu_new_session()
 def launch_count() -> int: return lib().aerobulk_gpu_launch_count()
 def reset_launch_count(): lib().aerobulk_gpu_reset_launch_count()
 def measure_fp64_peak() -> float: return lib().aerobulk_gpu_measure_fp64_peak()

@@ -158,3 +158,26 @@ def ice_fields(n: int, seed: int = SEED, humidity: str = "q") -> dict:
     a = u("rsw")
     frice = np.where(a < 0.02, 0.0, np.where(a > 0.9, 1.0, (a - 0.02) / 0.88))
     return dict(sit=sit, sst=sst, t_zt=t_zt, hum_zt=hum, wind=wind, slp=slp, frice=frice)
+
+
+def fields_parallel(Ni: int, Nj: int, j0: int = 0, j1: int | None = None, threads: int = 8, rows_per_task: int = 32,
+                    out: dict | None = None, **kw) -> dict:
+    """:func:`fields` for big row blocks: the rows are generated in independent chunks on a thread pool (numpy releases the
+    GIL inside its loops) and written straight into (Ni, j1-j0) Fortran-ordered arrays -- `out` may supply them (e.g.
+    views of pinned memory).  Bit-identical to :func:`fields` (the generator is counter-based)."""
+    from concurrent.futures import ThreadPoolExecutor
+    j1 = Nj if j1 is None else j1
+    nj = j1 - j0
+    keys = ("sst", "t_zt", "hum_zt", "U_zu", "V_zu", "slp", "rad_sw", "rad_lw")
+    res = out if out is not None else {k: np.empty((Ni, nj), dtype=np.float64, order="F") for k in keys}
+
+    def task(a):
+        b = min(nj, a + rows_per_task)
+        f = fields(Ni, Nj, j0=j0 + a, j1=j0 + b, **kw)
+        for k in keys:
+            if k in res:
+                res[k][:, a:b] = f[k]
+
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+        list(ex.map(task, range(0, nj, rows_per_task)))
+    return res

@@ -353,6 +353,11 @@ int aerobulk_gpu_last_error_code(void);
 /* Drops every piece of session state (sticky globals, warm-layer arrays, buffers):
  * the equivalent of restarting the reference process. */
 void aerobulk_gpu_reset(void);
+/* The same for the reference-visible state only -- sticky nb_iter / skin flag / humidity type / nitend back to their
+ * initial values, warm-layer arrays gone -- keeping the device buffers and this library's settings: what a program
+ * that runs several independent AEROBULK_MODEL sessions in one process calls between them (the reference cannot:
+ * its skin flag is sticky for the life of the process, src/mod_aerobulk.f90:74).  No device synchronisation. */
+void aerobulk_gpu_new_session(void);
 
 /* Persistent warm-layer state, device-resident between jt==1 and jt==Nt
  * (src/mod_skin_coare.f90:31-36, src/mod_skin_ecmwf.f90:52-55).
@@ -367,7 +372,17 @@ void aerobulk_gpu_reset(void);
 long aerobulk_gpu_get_state(int which, double *host_out, long n);
 long aerobulk_gpu_set_state(int which, const double *host_in, long n);
 
+/* Fully asynchronous device-pointer calls (default off).  By default aerobulk_gpu_model_device synchronises at jt == Nt
+ * (and at jt == 1 when the banners are on) so that a fail-stop caller sees every error before its session ends.  With
+ * aerobulk_gpu_set_async(1) it never does: the caller collects deferred errors with aerobulk_gpu_synchronize(). */
+void aerobulk_gpu_set_async(int on);
+
 /* ---- measurement helpers --------------------------------------------------- */
+/* CUDA events around every flux-kernel launch of aerobulk_gpu_model* on the stream it runs on (default off).
+ * aerobulk_gpu_kernel_times waits for the stream, writes the durations [ms] of the launches recorded since the last call
+ * (oldest first, at most max) and returns their number. */
+void aerobulk_gpu_set_kernel_timing(int on);
+int aerobulk_gpu_kernel_times(double *ms, int max);
 /* Number of kernels this library has launched since load / reset of the counter. */
 long aerobulk_gpu_launch_count(void);
 void aerobulk_gpu_reset_launch_count(void);

@@ -34,7 +34,7 @@ elif os.environ.get("KBENCH_QUICK"):
     cases = [("ncar", False, None), ("andreas", False, None), ("coare3p6", False, None), ("coare3p6", True, "night"), ("coare3p6", True, "day"), ("ecmwf", True, "day")]
 for algo, skin, rad in cases:
     ab.reset(); ab.set_stream(st.cuda_stream)
-    kw = dict(Niter=5)
+    kw = dict(Niter=int(os.environ.get("KBENCH_NITER", "5")))
     o = {k: out[k] for k in OUT[:5]}
     if skin:
         kw.update(l_use_skin=True, rad_sw=rsw_day if rad == "day" else rsw_night, rad_lw=dev["rad_lw"])

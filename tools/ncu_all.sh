@@ -10,9 +10,11 @@ NI=${2:-1440}
 NJ=${3:-720}
 KEEP_REP=${KEEP_REP:-"coare3p6_skin_day andreas"}
 mkdir -p gpurun_out
-for c in "ncar,0,-" "andreas,0,-" "coare3p0,0,-" "coare3p6,0,-" "ecmwf,0,-" "coare3p6,1,night" "coare3p6,1,day" "ecmwf,1,night" "ecmwf,1,day" "coare3p0,1,day"; do
-  IFS=, read algo skin rad <<< "$c"
-  name=${algo}$([ "$skin" = 1 ] && echo "_skin_${rad}")
+for c in "ncar,0,-" "andreas,0,-" "coare3p0,0,-" "coare3p6,0,-" "ecmwf,0,-" "coare3p6,1,night" "coare3p6,1,day" "ecmwf,1,night" "ecmwf,1,day" "coare3p0,1,day" "andreas,0,-,30" "coare3p0,0,-,30"; do
+  IFS=, read algo skin rad nb <<< "$c"
+  name=${algo}$([ "$skin" = 1 ] && echo "_skin_${rad}")$([ -n "$nb" ] && echo "_nb${nb}")
+  export KBENCH_NITER=${nb:-5}
+  c="$algo,$skin,$rad"
   rep=gpurun_out/prof_${TAG}_${name}
   KBENCH_ONE=$c timeout 600 ncu --set full --clock-control none --import-source on -k regex:flux_kernel -s 5 -c 1 -f -o $rep \
       python tools/kbench.py $NI $NJ > gpurun_out/ncu_${TAG}_${name}.log 2>&1
