@@ -253,6 +253,10 @@ struct Session {
     // (d_init = {humidity type, error flag}, d_gstats = the combined statistics) until the host next synchronises
     int *d_init = nullptr;
     double *d_gstats = nullptr;
+    // speculative AEROBULK_INIT of the staged host-array pipeline (see model_impl): per-chunk statistics, the running
+    // combination after each chunk, and the running verdicts
+    double *d_cstats = nullptr, *d_cgstats = nullptr;
+    int *d_cinit = nullptr;
     bool init_pending = false;
     int pend_Nt = 0, pend_Ni = 0, pend_Nj = 0;
     bool pend_lsrad = false;
@@ -395,6 +399,9 @@ int ensure_device()
     CUDA_TRY(cudaMalloc(&g.d_gstats, sizeof(double) * abk::NSTATS));
     CUDA_TRY(cudaMalloc(&g.d_init, 2 * sizeof(int)));
     CUDA_TRY(cudaMemset(g.d_init, 0, 2 * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&g.d_cstats, sizeof(double) * abk::NSTATS * MAX_CHUNKS));
+    CUDA_TRY(cudaMalloc(&g.d_cgstats, sizeof(double) * abk::NSTATS * MAX_CHUNKS));
+    CUDA_TRY(cudaMalloc(&g.d_cinit, 2 * sizeof(int) * MAX_CHUNKS));
     // word 0: wind stress > 10 N/m^2; word 1 (sea-ice calls only): rough_leng_tq fail-stop
     CUDA_TRY(cudaMalloc(&g.d_bad, 2 * sizeof(unsigned long long)));
     CUDA_TRY(cudaHostAlloc(&g.h_bad, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -983,6 +990,16 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     }
     long long cstart[MAX_CHUNKS + 1];
     const int nchunks = plan_chunks(n, bounce ? 2 : ((!device_ptrs && !zc_in) ? 1 : 0), cstart);
+    // Speculative AEROBULK_INIT (jt == 1 of a staged host-array call with >= 2 chunks).  The reference judges the WHOLE
+    // fields before it computes anything, which would hold the first flux launch -- and every byte of D2H -- back until the
+    // last input byte has arrived: H2D and D2H one after the other.  Instead each chunk's statistics are taken as it lands,
+    // combined with those of the chunks before it and judged on the device (init_decide_kernel), and the chunk's flux
+    // launch runs on that RUNNING verdict (humidity type; stop flag).  When the last chunk is in, the verdict is the
+    // reference's; the few chunks (normally none) whose running verdict differed from it are recomputed from the staged
+    // inputs, and an AEROBULK_INIT error is raised exactly as before -- the arrays the reference would never have
+    // written are then undefined.  Same results, H2D and D2H overlapped: C5 end to end 0.54 -> ~1 Gpt/s.
+    static const bool spec_env = [] { const char *e = getenv("AEROBULK_GPU_SPEC_INIT"); return e ? atoi(e) != 0 : true; }();
+    const bool spec_init = spec_env && jt == 1 && !g.preinit_done && !device_ptrs && !zc_in && !bounce && !g.stats_hook && nchunks >= 2;
 
     if (device_ptrs) {
         for (int k = 0; k < 8; ++k) in_d[k] = in_h[k];
@@ -1016,6 +1033,11 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
             g.preinit_done = false;   // aerobulk_gpu_init_from_stats() already ran the global init
         } else {
             double st[abk::NSTATS];
+            if (spec_init) {
+                // staged host-array pipeline: see the chunk loop -- only the argument-dependent half runs here
+                rc = init_flags(Nt, calgo, lskin, lsrad);
+                if (rc) return rc;
+            } else {
             if (!device_ptrs) CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_in[nchunks - 1], 0));
             if (device_ptrs && !g.verbose && !g.stats_hook && n > 0) {
                 // device-resident session, banners off: no host round trip -- the statistics stay on the device, are judged
@@ -1037,6 +1059,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
                 return fail(AEROBULK_GPU_ERR_STATE, "AEROBULK_INIT => another device of the split call failed");
             rc = init_from_stats(Nt, calgo, lskin, lsrad, st, g.report_Ni > 0 ? g.report_Ni : Ni, g.report_Ni > 0 ? g.report_Nj : Nj);
             if (rc) return rc;
+            }
             }
         }
     }
@@ -1122,10 +1145,19 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         a.index_offset = s0;
         if (bounce) bounce_copy(8, const_cast<double *const *>(in_h), 0, s0, len, true);
         if (!device_ptrs) CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_in[c], 0));
+        if (spec_init) {
+            rc = launch_local_stats(len, a.sst, a.t_zt, a.hum_zt, a.U_zu, a.V_zu, a.slp, lsrad ? a.rad_lw : nullptr, cs,
+                                    g.d_cstats + (long long)c * abk::NSTATS);
+            if (rc) return rc;
+            CUDA_TRY(abk::launch_init_decide(g.d_cstats, c + 1, lsrad ? 1 : 0, g.d_cgstats + (long long)c * abk::NSTATS,
+                                             g.d_cinit + 2 * c, cs));
+            g.launches += 1;
+            a.init_dev = g.d_cinit + 2 * c;
+        }
         a.perm = nullptr;
         if (do_sort) {
             unsigned short *perm = g.d_perm + s0 + (long long)c * abk::sort_window();
-            CUDA_TRY(abk::launch_classify(a, perm, cs));
+            CUDA_TRY(abk::launch_classify(a, perm, use_skin, cs));
             g.launches += 1;
             a.perm = perm;
         }
@@ -1162,6 +1194,57 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
                     CUDA_TRY(cudaEventSynchronize(g.ev_k[h]));
                     bounce_copy(6, out_h, 8, cstart[h], cstart[h + 1] - cstart[h], false);
                 }
+            }
+        }
+    }
+    if (spec_init) {
+        // the reference's verdict (all chunks), then the chunks that ran on a different running verdict once more
+        int cinit[2 * MAX_CHUNKS];
+        double st[abk::NSTATS];
+        CUDA_TRY(cudaMemcpyAsync(cinit, g.d_cinit, 2 * sizeof(int) * nchunks, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(st, g.d_cgstats + (long long)(nchunks - 1) * abk::NSTATS, sizeof(st), cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaStreamSynchronize(cs));
+        rc = init_checks(lsrad, st, g.report_Ni > 0 ? g.report_Ni : Ni, g.report_Ni > 0 ? g.report_Nj : Nj);
+        if (rc) {
+            cudaStreamSynchronize(g.out_stream);   // nothing may still be writing the caller's arrays when the call returns
+            return rc;
+        }
+        a.init_dev = nullptr;
+        a.ihum = g.ihum;
+        for (int c = 0; c < nchunks; ++c) {
+            const long long s0 = cstart[c], len = cstart[c + 1] - s0;
+            if (len <= 0 || (cinit[2 * c] == g.ihum && cinit[2 * c + 1] == 0)) continue;
+            a.sst = in_d[0] + s0; a.t_zt = in_d[1] + s0; a.hum_zt = in_d[2] + s0;
+            a.U_zu = in_d[3] + s0; a.V_zu = in_d[4] + s0; a.slp = in_d[5] + s0;
+            a.rad_lw = in_d[6] ? in_d[6] + s0 : nullptr;
+            a.rad_sw = in_d[7] ? in_d[7] + s0 : nullptr;
+            a.QL = out_d[0] + s0; a.QH = out_d[1] + s0; a.Tau_x = out_d[2] + s0; a.Tau_y = out_d[3] + s0;
+            a.Evap = out_d[4] + s0;
+            a.T_s = out_d[5] ? out_d[5] + s0 : nullptr;
+            if (use_skin) {
+                if (ialgo == abd::ECMWF) {
+                    a.dT_wl = g.e_dT_wl + s0;
+                } else {
+                    a.dT_wl = g.c_state[0] + s0; a.Hz_wl = g.c_state[1] + s0;
+                    a.Qnt_ac = g.c_state[2] + s0; a.Tau_ac = g.c_state[3] + s0;
+                }
+            }
+            a.n = len;
+            a.index_offset = s0;
+            a.perm = nullptr;
+            if (do_sort) {
+                unsigned short *perm = g.d_perm + s0 + (long long)c * abk::sort_window();
+                CUDA_TRY(abk::launch_classify(a, perm, use_skin, cs));
+                g.launches += 1;
+                a.perm = perm;
+            }
+            CUDA_TRY(abk::launch_flux(ialgo, use_skin, zteq, a, cs));
+            g.launches += 1;
+            CUDA_TRY(cudaEventRecord(g.ev_k[c], cs));
+            CUDA_TRY(cudaStreamWaitEvent(g.out_stream, g.ev_k[c], 0));
+            if (!zc_out) {
+                rc = copy_fields(6, g.d_out, out_h, g.cap, s0, len, false, g.out_stream);
+                if (rc) return rc;
             }
         }
     }

@@ -28,76 +28,100 @@ using namespace abd;
 #endif
 static constexpr int FLUX_BLOCK = AB_FLUX_BLOCK;
 
-// Cheap proxy of the sign of the air-sea virtual potential temperature difference, i.e. of the
-// stability class every psi_m/psi_h evaluation branches on.  Only used to GROUP points (performance);
-// the physics below never sees it.
-__device__ __forceinline__ bool stable_proxy(const FluxArgs &a, int ihum, long long i)
+// Cheap proxy of the air-sea virtual potential temperature difference [K], whose sign is the stability class every
+// psi_m / psi_h evaluation branches on.  Only used to GROUP points (performance); the physics never sees it.
+// `skin_off`: what the skin schemes will do to the surface temperature before the first psi is evaluated (T_s starts at
+// sst - 0.25 K, mod_blk_coare3p6.f90:254; plus the warm-layer increment carried from the previous step).
+#ifndef AB_SORT_BAND
+#define AB_SORT_BAND 0.25    // |proxy| below this [K]: class "uncertain" (own group, between the two sure ones)
+#endif
+#ifndef AB_SORT_BAND_NOQ
+#define AB_SORT_BAND_NOQ 1.0 // the same when the humidity is rh / dp (the proxy ignores it)
+#endif
+__device__ __forceinline__ double stability_proxy(const FluxArgs &a, int ihum, double skin_off, long long i)
 {
-    const double sst = __ldg(a.sst + i), ta = __ldg(a.t_zt + i) + RGAMMA_DRY * a.u.zt;
-    if (ihum != 0) return ta >= sst;
+    const double sst = __ldg(a.sst + i) + skin_off, ta = __ldg(a.t_zt + i) + RGAMMA_DRY * a.u.zt;
+    if (ihum != 0) return ta - sst;
     const double q = __ldg(a.hum_zt + i), p = __ldg(a.slp + i);
     const double tc = sst - 273.15;
     const double es = 611.2 * abm::dexp(17.67 * tc * abm::fast_rcp(tc + 243.5));     // Magnus
     const double qs = 0.98 * 0.622 * es * abm::fast_rcp(p - 0.378 * es);
-    return ta * (1. + 0.608 * q) >= sst * (1. + 0.608 * qs);
+    return ta * (1. + 0.608 * q) - sst * (1. + 0.608 * qs);
 }
 
 // ---------------------------------------------------------------------------
 // classify_kernel: stability sort inside windows of SORT_WIN consecutive points.
-// The iteration branches on the stability class in every psi function (and the two sides differ a
-// lot in cost); where stability is not spatially coherent a warp would execute both sides (23/32
-// active lanes in the round-1 profile).  One block per window writes perm[] such that slots
-// [0,n_stable) of the window hold its stable points and the rest the unstable ones; flux_kernel
-// then runs 256 consecutive SLOTS per block, so all but one block per window are homogeneous --
-// and a homogeneous block retires as a whole (sorting inside a block left its fast warps idle
-// behind the slow ones and was slower).  Accesses stay inside the window's 16 KB of each field.
+// The iteration branches on the stability class in every psi function (and the two sides differ a lot in cost); where
+// stability is not spatially coherent a warp would execute both sides (23/32 active lanes in the round-1 profile).
+// One block per window writes perm[] such that the window's slots hold, in this order, its surely-stable points, the
+// uncertain ones (|proxy| < band: a misjudged point makes its whole warp run both sides, so the doubtful ones are kept
+// to themselves) and the surely-unstable ones; flux_kernel then runs 256 consecutive SLOTS per block, so that all but two
+// blocks per window are homogeneous -- and a homogeneous block retires as a whole (sorting inside a block left its fast
+// warps idle behind the slow ones and was slower).  Accesses stay inside the window's 16 KB of each field.
 // ---------------------------------------------------------------------------
 static constexpr int SORT_WIN = 2048;
 static constexpr int SORT_BLOCK = 256;
 static constexpr int SORT_ITEMS = SORT_WIN / SORT_BLOCK;
+static constexpr int SORT_CLASSES = 3;
 
-__global__ void __launch_bounds__(SORT_BLOCK) classify_kernel(const FluxArgs a, unsigned short *perm)
+__global__ void __launch_bounds__(SORT_BLOCK) classify_kernel(const FluxArgs a, unsigned short *perm, int skin)
 {
-    __shared__ unsigned short s_c0[SORT_ITEMS * SORT_BLOCK / 32], s_c1[SORT_ITEMS * SORT_BLOCK / 32];
+    constexpr int NW = SORT_BLOCK / 32, NG = SORT_ITEMS * NW;
+    __shared__ unsigned short s_c[SORT_CLASSES][NG];
     abm::load_tables();
     const long long base = (long long)blockIdx.x * SORT_WIN;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int ihum = a.init_dev ? __ldg(a.init_dev) : a.ihum;
-    constexpr int NW = SORT_BLOCK / 32;
+    const double band = (ihum != 0) ? AB_SORT_BAND_NOQ : AB_SORT_BAND;
+    const bool wl = skin && !a.first_step && a.dT_wl != nullptr;
     int cls[SORT_ITEMS];
-    unsigned m0[SORT_ITEMS], m1[SORT_ITEMS];
+    unsigned m[SORT_ITEMS][SORT_CLASSES];
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; ++k) {
         const long long i = base + k * SORT_BLOCK + tid;
-        cls[k] = 2;
-        if (i < a.n) cls[k] = stable_proxy(a, ihum, i) ? 0 : 1;
-        m0[k] = __ballot_sync(0xffffffffu, cls[k] == 0);
-        m1[k] = __ballot_sync(0xffffffffu, cls[k] == 1);
-        if (lane == 0) {
-            s_c0[k * NW + w] = (unsigned short)__popc(m0[k]);
-            s_c1[k * NW + w] = (unsigned short)__popc(m1[k]);
+        cls[k] = SORT_CLASSES;   // padding beyond n
+        if (i < a.n) {
+            const double off = skin ? (-0.25 + (wl ? a.dT_wl[i] : 0.)) : 0.;
+            const double d = stability_proxy(a, ihum, off, i);
+            cls[k] = (d >= band) ? 0 : (d > -band) ? 1 : 2;
+        }
+#pragma unroll
+        for (int c = 0; c < SORT_CLASSES; ++c) {
+            m[k][c] = __ballot_sync(0xffffffffu, cls[k] == c);
+            if (lane == 0) s_c[c][k * NW + w] = (unsigned short)__popc(m[k][c]);
         }
     }
     __syncthreads();
-    int tot0 = 0, tot1 = 0;
-    for (int g = 0; g < SORT_ITEMS * NW; ++g) {
-        tot0 += s_c0[g];
-        tot1 += s_c1[g];
+    int tot[SORT_CLASSES];
+#pragma unroll
+    for (int c = 0; c < SORT_CLASSES; ++c) tot[c] = 0;
+    for (int g = 0; g < NG; ++g) {
+#pragma unroll
+        for (int c = 0; c < SORT_CLASSES; ++c) tot[c] += s_c[c][g];
     }
     const unsigned lt = (1u << lane) - 1u;
-    int off0 = 0, off1 = 0, g = 0;
+    int off[SORT_CLASSES];
+#pragma unroll
+    for (int c = 0; c < SORT_CLASSES; ++c) off[c] = 0;
+    int g = 0;
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; ++k) {
         // counts of the groups (k', w') that precede (k, w)
         for (; g < k * NW + w; ++g) {
-            off0 += s_c0[g];
-            off1 += s_c1[g];
+#pragma unroll
+            for (int c = 0; c < SORT_CLASSES; ++c) off[c] += s_c[c][g];
         }
         const int item = k * SORT_BLOCK + tid;
-        int slot;
-        if (cls[k] == 0) slot = off0 + __popc(m0[k] & lt);
-        else if (cls[k] == 1) slot = tot0 + off1 + __popc(m1[k] & lt);
-        else slot = tot0 + tot1 + (item - (off0 + off1 + __popc((m0[k] | m1[k]) & lt)));
+        int slot = 0, before = 0, all_off = 0;
+        unsigned any = 0u;
+#pragma unroll
+        for (int c = 0; c < SORT_CLASSES; ++c) {
+            if (cls[k] == c) slot = before + off[c] + __popc(m[k][c] & lt);
+            before += tot[c];
+            all_off += off[c];
+            any |= m[k][c];
+        }
+        if (cls[k] == SORT_CLASSES) slot = before + (item - (all_off + __popc(any & lt)));
         perm[base + slot] = (unsigned short)item;
     }
 }
@@ -332,11 +356,11 @@ int flux_block_size() { return FLUX_BLOCK; }
 
 int sort_window() { return SORT_WIN; }
 
-cudaError_t launch_classify(const FluxArgs &a, unsigned short *perm, cudaStream_t s)
+cudaError_t launch_classify(const FluxArgs &a, unsigned short *perm, bool skin, cudaStream_t s)
 {
     if (a.n <= 0) return cudaSuccess;
     const long long nwin = (a.n + SORT_WIN - 1) / SORT_WIN;
-    classify_kernel<<<(unsigned)nwin, SORT_BLOCK, 0, s>>>(a, perm);
+    classify_kernel<<<(unsigned)nwin, SORT_BLOCK, 0, s>>>(a, perm, skin ? 1 : 0);
     return cudaGetLastError();
 }
 

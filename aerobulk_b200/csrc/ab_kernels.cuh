@@ -140,7 +140,7 @@ cudaError_t launch_flux(int algo, bool skin, bool zt_eq_zu, const FluxArgs &a, c
 int flux_block_size();
 int sort_window();
 // fills perm[] (ceil(n / sort_window()) * sort_window() entries) for the launch described by `a`
-cudaError_t launch_classify(const FluxArgs &a, unsigned short *perm, cudaStream_t s);
+cudaError_t launch_classify(const FluxArgs &a, unsigned short *perm, bool skin, cudaStream_t s);
 cudaError_t launch_stats(const StatsArgs &a, int nblocks, cudaStream_t s);
 // AEROBULK_INIT's stats-dependent decisions on the device (src/mod_aerobulk.f90:104-153, src/mod_phymbl.f90:1851-2007):
 // combines the statistics vectors of `nranks` row blocks (all[r][NSTATS], rank order: deterministic) into gstats[NSTATS]

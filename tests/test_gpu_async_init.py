@@ -116,3 +116,58 @@ def test_gathered_stats_init_on_device(ab):
         assert ab.humidity_type() == "rh"
         for k in out:
             assert np.array_equal(out[k].cpu().numpy(), want[k][:, a:b].ravel(order="F")), (a, b, k)
+
+
+def _device_call(ab, algo, f, Ni, Nj, skin):
+    """The non-speculative route to the same numbers: device tensors, asynchronous init over the whole field."""
+    import torch
+    d = _dev(f)
+    keys = OUT_KEYS if skin else OUT_KEYS[:5]
+    out = {k: torch.empty(Ni * Nj, dtype=torch.float64, device="cuda") for k in keys}
+    kw = dict(l_use_skin=True, rad_sw=d["rad_sw"], rad_lw=d["rad_lw"]) if skin else {}
+    ab.aerobulk_model_device(1, 1, algo, 2.0, 10.0, *[d[k] for k in IN_KEYS], out=out, Niter=5, shape=(Ni, Nj), **kw)
+    ab.synchronize()
+    return {k: v.cpu().numpy().reshape((Ni, Nj), order="F") for k, v in out.items()}
+
+
+@pytest.mark.parametrize("algo,skin", [("coare3p6", True), ("ecmwf", False)])
+def test_speculative_init_of_the_staged_pipeline(ab, algo, skin):
+    """jt == 1 of a host-array call with several pipeline chunks: each chunk's flux launch runs on the RUNNING verdict of
+    AEROBULK_INIT (statistics of the chunks so far) and is recomputed if the final verdict differs.  Three fields:
+    (a) ordinary; (b) relative humidity whose first chunk alone reads as specific humidity (wrong running verdict ->
+    recomputed); (c) a first chunk that is entirely masked (running verdict 'whole domain masked' -> nothing computed ->
+    recomputed).  All equal the single-verdict device path bit for bit."""
+    Ni, Nj = 1440, 720                       # 1 036 800 points: 5 chunks
+    assert ab.lib().aerobulk_gpu_chunk_plan(Ni * Nj, 1, (__import__("ctypes").c_longlong * 17)()) >= 2
+    cases = {"plain": synth.fields(Ni, Nj)}
+    rh = synth.fields(Ni, Nj, humidity="rh")
+    rh["hum_zt"][:, :300] = 0.02
+    cases["rh with an sh-like first chunk"] = rh
+    cold = synth.fields(Ni, Nj)
+    cold["sst"][:, :330] -= 273.15           # degrees Celsius: masked out by the sanity range, the rest is fine
+    cases["first chunk masked"] = cold
+    for name, f in cases.items():
+        ab.reset()
+        ab.set_verbose(False)
+        kw = dict(l_use_skin=True, rad_sw=f["rad_sw"], rad_lw=f["rad_lw"]) if skin else {}
+        got = ab.aerobulk_model(1, 1, algo, 2.0, 10.0, *[f[k] for k in IN_KEYS], Niter=5, **kw)
+        hum = ab.humidity_type()
+        ab.reset()
+        ab.set_verbose(False)
+        want = _device_call(ab, algo, f, Ni, Nj, skin)
+        assert ab.humidity_type() == hum, name
+        for k in want:
+            assert np.array_equal(got[k], want[k], equal_nan=True), (name, k)
+
+
+def test_speculative_init_raises_the_final_verdict(ab):
+    """A humidity field that only becomes unidentifiable with its LAST chunk: the error of the reference (code 5)."""
+    Ni, Nj = 1440, 720
+    f = synth.fields(Ni, Nj)
+    f["hum_zt"][:, 700:] = 280.0             # dew points in the last rows of a specific-humidity field
+    with pytest.raises(ab.AerobulkError) as e:
+        ab.aerobulk_model(1, 1, "ncar", 2.0, 10.0, *[f[k] for k in IN_KEYS])
+    assert e.value.code == 5
+    g = synth.fields(Ni, Nj)
+    ok = ab.aerobulk_model(1, 1, "ncar", 2.0, 10.0, *[g[k] for k in IN_KEYS])     # and the next session is clean
+    assert np.isfinite(ok["QL"]).all()
