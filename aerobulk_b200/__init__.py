@@ -13,7 +13,8 @@ from .model import (AerobulkError, aerobulk_model, aerobulk_model_device, get_st
                     set_nitend, turb, series, series_csv, series_device, SERIES_OUT, turb_ice, oce_ice,
                     set_ice_form_drag_per_point, ICE_ALGORITHMS, OCE_ICE_OUT, set_sort, flux_diagnostics,
                     diag_reduce_ops, diagnostics_summary, host_register, host_unregister, series_ice, SERIES_ICE_OUT, probe, set_devices, get_devices, shard_plan, init_local_stats_device,
-                    init_from_gathered_stats, new_session, set_async, set_kernel_timing, kernel_times)
+                    init_from_gathered_stats, new_session, set_async, set_kernel_timing, kernel_times, aerobulk_init,
+                    aerobulk_bye)
 
 ALGORITHMS = ("coare3p0", "coare3p6", "ncar", "ecmwf", "andreas")
 __all__ = ["ALGORITHMS", "AerobulkError", "aerobulk_model", "aerobulk_model_device", "get_state", "set_state", "humidity_type",
@@ -22,4 +23,4 @@ __all__ = ["ALGORITHMS", "AerobulkError", "aerobulk_model", "aerobulk_model_devi
            "set_nitend", "turb", "series", "series_csv", "series_device", "SERIES_OUT", "turb_ice", "oce_ice",
            "set_ice_form_drag_per_point", "ICE_ALGORITHMS", "OCE_ICE_OUT", "set_sort", "flux_diagnostics",
            "diag_reduce_ops", "diagnostics_summary", "host_register", "host_unregister", "series_ice", "SERIES_ICE_OUT", "probe", "set_devices", "get_devices", "shard_plan", "init_local_stats_device",
-           "init_from_gathered_stats", "new_session", "set_async", "set_kernel_timing", "kernel_times"]
+           "init_from_gathered_stats", "new_session", "set_async", "set_kernel_timing", "kernel_times", "aerobulk_init", "aerobulk_bye"]

@@ -1093,13 +1093,13 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
             return fail(AEROBULK_GPU_ERR_STATE, "warm-layer state missing or of another size at jt=%d (no jt==1 call for this session?)", jt);
     }
 
-    // Stability sort (classify_kernel).  Measured on B200 (tools/kbench.py, round 1): a gain for ANDREAS
-    // and the COARE / ECMWF kernels without skin schemes, a loss for NCAR (too little work per point)
-    // and for the skin kernels (instruction-cache bound: homogeneous blocks run different code regions)
-    // auto policy = where it measured faster (tools/kbench.py, KBENCH_SORT=0/2): not NCAR (+10 %), not ECMWF + skin (+1 %);
-    // COARE + skin: -7 % at night, neutral by day
+    // Stability sort (classify_kernel).  Auto policy = where it measured faster on B200 (tools/exp_sort.sh, KBENCH_SORT=1/2,
+    // profiles/exp_sort_r02d.txt, 4320x2160): everything but NCAR (too little work per point: 0.97 -> 1.06 ms).  Since the
+    // proxy follows the skin temperature (T_s starts 0.25 K below the SST and carries the warm-layer increment) and keeps
+    // the doubtful points to themselves, ECMWF + skin gains the most (5.01 -> 4.54 ms by day, 4.46 -> 3.88 ms by night;
+    // with the round-1 proxy it lost 1 %).
     // (never with zero-copy inputs: the gather through the permutation would cross PCIe at sector granularity)
-    const bool do_sort = !zc_in && !zc_out && (g.sort_points == 2 || (g.sort_points == 1 && ialgo != abd::NCAR && !(use_skin && ialgo == abd::ECMWF)));
+    const bool do_sort = !zc_in && !zc_out && (g.sort_points == 2 || (g.sort_points == 1 && ialgo != abd::NCAR));
     if (do_sort) {
         // every chunk is padded to whole sort windows
         const long long need = n + (long long)(nchunks + 1) * abk::sort_window();
@@ -2585,6 +2585,51 @@ int aerobulk_gpu_init_from_stats(int Nt, const char *calgo, const int *l_use_ski
     if (rc) return rc;
     g.preinit_done = true;
     return 0;
+}
+
+int aerobulk_gpu_init(int Nt, const char *calgo, int Ni, int Nj, const double *sst, const double *t_zt, const double *hum_zt,
+                      const double *U_zu, const double *V_zu, const double *slp, const int *l_use_skin, const double *rad_sw,
+                      const double *rad_lw)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    if (!calgo || !sst || !t_zt || !hum_zt || !U_zu || !V_zu || !slp) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_init: NULL mandatory argument");
+    if (Ni < 0 || Nj < 0) return fail(AEROBULK_GPU_ERR_ARG, "aerobulk_gpu_init: negative shape %d x %d", Ni, Nj);
+    int rc = ensure_device();
+    if (rc) return rc;
+    rc = resolve_init();
+    if (rc) return rc;
+    const long long n = (long long)Ni * Nj;
+    const bool lskin = l_use_skin ? (*l_use_skin != 0) : false;
+    const bool lsrad = rad_sw && rad_lw;
+    double st[abk::NSTATS];
+    memset(st, 0, sizeof(st));
+    if (n > 0) {
+        rc = ensure_staging(n);
+        if (rc) return rc;
+        cudaStream_t cs = compute_stream();
+        const double *h[7] = {sst, t_zt, hum_zt, U_zu, V_zu, slp, lsrad ? rad_lw : nullptr};
+        for (int k = 0; k < 7; ++k)
+            if (h[k]) CUDA_TRY(cudaMemcpyAsync(g.d_in[k], h[k], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs));
+        rc = local_stats(n, g.d_in[0], g.d_in[1], g.d_in[2], g.d_in[3], g.d_in[4], g.d_in[5], lsrad ? g.d_in[6] : nullptr, cs, st);
+        if (rc) return rc;
+    }
+    const bool skin_before = g.l_use_skin_schemes;
+    rc = init_from_stats(Nt, calgo, lskin, lsrad, st, Ni, Nj);
+    if (rc) end_session_after_error(1, skin_before);
+    return rc;
+}
+
+void aerobulk_gpu_bye(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.verbose) {
+        printf(" ===================================================================\n");
+        printf("                    ----- AeroBulk_bye -----\n");
+        printf(" ===================================================================\n \n");
+        fflush(stdout);
+    }
 }
 
 int aerobulk_gpu_init_local_stats_device(int Ni, int Nj, const double *sst, const double *t_zt, const double *hum_zt,

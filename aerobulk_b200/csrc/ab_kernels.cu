@@ -32,8 +32,15 @@ static constexpr int FLUX_BLOCK = AB_FLUX_BLOCK;
 // psi_m / psi_h evaluation branches on.  Only used to GROUP points (performance); the physics never sees it.
 // `skin_off`: what the skin schemes will do to the surface temperature before the first psi is evaluated (T_s starts at
 // sst - 0.25 K, mod_blk_coare3p6.f90:254; plus the warm-layer increment carried from the previous step).
+// |proxy| below the band [K]: class "uncertain" (own group, between the two sure ones).  Measured on B200 at 4320x2160
+// (profiles/exp_sort_r02d.txt; band 0 / 0.1 / 0.25 / 0.5): COARE 3.6 2.146 / 2.080 / 2.099 / 2.136 ms, ECMWF 2.318 /
+// 2.233 / 2.248 / 2.306 ms, COARE 3.6 + skin by day 4.495 / 4.459 / 4.411 / 4.377 ms and by night 3.635 / 3.538 / 3.449 /
+// 3.419 ms, ECMWF + skin 4.731 / 4.631 / 4.555 / 4.535 ms: the skin schemes move T_s by a few tenths of a kelvin more.
 #ifndef AB_SORT_BAND
-#define AB_SORT_BAND 0.25    // |proxy| below this [K]: class "uncertain" (own group, between the two sure ones)
+#define AB_SORT_BAND 0.15
+#endif
+#ifndef AB_SORT_BAND_SKIN
+#define AB_SORT_BAND_SKIN 0.5
 #endif
 #ifndef AB_SORT_BAND_NOQ
 #define AB_SORT_BAND_NOQ 1.0 // the same when the humidity is rh / dp (the proxy ignores it)
@@ -72,7 +79,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) classify_kernel(const FluxArgs a, 
     const long long base = (long long)blockIdx.x * SORT_WIN;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int ihum = a.init_dev ? __ldg(a.init_dev) : a.ihum;
-    const double band = (ihum != 0) ? AB_SORT_BAND_NOQ : AB_SORT_BAND;
+    const double band = (ihum != 0) ? AB_SORT_BAND_NOQ : (skin ? AB_SORT_BAND_SKIN : AB_SORT_BAND);
     const bool wl = skin && !a.first_step && a.dT_wl != nullptr;
     int cls[SORT_ITEMS];
     unsigned m[SORT_ITEMS][SORT_CLASSES];
@@ -386,7 +393,7 @@ cudaError_t flux_kernel_attributes(int algo, bool skin, bool zteq, cudaFuncAttri
 // AEROBULK_INIT statistics (src/mod_aerobulk.f90:104-153, src/mod_phymbl.f90:1851-2007)
 // ---------------------------------------------------------------------------
 static constexpr int STATS_BLOCK = 256;
-static constexpr int STATS_MAX_BLOCKS = 148 * 2;
+static constexpr int STATS_MAX_BLOCKS = 148 * 8;   // x 256 threads: enough warps to hide the 7 loads per point (HBM-bound pass)
 
 // sanity ranges, src/mod_const.f90:138-146
 __device__ __forceinline__ bool point_unmasked(double sst, double ta, double slp, double wnd, bool rad, double rlw)
@@ -452,13 +459,14 @@ __global__ void __launch_bounds__(STATS_BLOCK) stats_kernel(const StatsArgs a)
         acc[1] += 1.;
 #pragma unroll
         for (int f = 0; f < NFIELDS; ++f) {
+            // (v < acc ? v : acc) keeps acc when v is a NaN, like fmin / fmax, in 3 instructions instead of their 8-9
             if (m) {
                 acc[2 + 5 * f + 0] += v[f];
-                acc[2 + 5 * f + 1] = fmin(acc[2 + 5 * f + 1], v[f]);
-                acc[2 + 5 * f + 2] = fmax(acc[2 + 5 * f + 2], v[f]);
+                acc[2 + 5 * f + 1] = abm::dmin(v[f], acc[2 + 5 * f + 1]);
+                acc[2 + 5 * f + 2] = abm::dmax(v[f], acc[2 + 5 * f + 2]);
             }
-            acc[2 + 5 * f + 3] = fmin(acc[2 + 5 * f + 3], v[f]);
-            acc[2 + 5 * f + 4] = fmax(acc[2 + 5 * f + 4], v[f]);
+            acc[2 + 5 * f + 3] = abm::dmin(v[f], acc[2 + 5 * f + 3]);
+            acc[2 + 5 * f + 4] = abm::dmax(v[f], acc[2 + 5 * f + 4]);
         }
     }
     __shared__ double sm[STATS_BLOCK / 32][2 + 5 * NFIELDS];

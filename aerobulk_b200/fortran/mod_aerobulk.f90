@@ -32,20 +32,56 @@ MODULE mod_aerobulk
 CONTAINS
 
    SUBROUTINE AEROBULK_INIT( Nt, calgo, psst, pta, pha, pU, pV, pslp,  l_use_skin, prsw, prlw )
-      !! Kept for interface compatibility (reference src/mod_aerobulk.f90:24-48).  The checks themselves run
-      !! inside the library when AEROBULK_MODEL is called with jt==1; calling this routine directly only
-      !! records the number of time records, as the reference does at :99.
+      !! Same interface and behaviour as the reference (src/mod_aerobulk.f90:24-160): skin flag and its two errors,
+      !! nitend = Nt, sanity mask, humidity type, unit checks -- done by the library on the GPU (aerobulk_gpu_init),
+      !! with the reference's messages and fail-stop.  As in the reference, AEROBULK_MODEL(jt==1) runs the same
+      !! initialisation again on its own arguments, so calling this routine first is never required.
       INTEGER,                  INTENT(in)  :: Nt
       CHARACTER(len=*),         INTENT(in)  :: calgo
-      REAL(wp), DIMENSION(:,:), INTENT(in)  :: psst, pta, pha, pU, pV, pslp
+      REAL(wp), DIMENSION(:,:), INTENT(in), TARGET :: psst, pta, pha, pU, pV, pslp
       LOGICAL,                  INTENT(in), OPTIONAL :: l_use_skin
-      REAL(wp), DIMENSION(:,:), INTENT(in), OPTIONAL :: prsw, prlw
+      REAL(wp), DIMENSION(:,:), INTENT(in), OPTIONAL, TARGET :: prsw, prlw
+      !!
+      INTEGER :: Ni, Nj, ierr
+      INTEGER(c_int), TARGET :: iskin
+      TYPE(c_ptr) :: pskin, p_rsw, p_rlw
+      CHARACTER(KIND=c_char, LEN=LEN_TRIM(calgo)+1) :: calgo_c
+      !! contiguous copies (AEROBULK_INIT is called once per run: always copied, no IS_CONTIGUOUS case analysis)
+      REAL(wp), DIMENSION(:,:), ALLOCATABLE, TARGET :: c_sst, c_ta, c_ha, c_U, c_V, c_slp, c_rsw, c_rlw
+      Ni = SIZE(psst,1)
+      Nj = SIZE(psst,2)
+      IF( ANY( (/ SIZE(pta,1),SIZE(pha,1),SIZE(pU,1),SIZE(pV,1),SIZE(pslp,1) /) /= Ni ) .OR. &
+         &ANY( (/ SIZE(pta,2),SIZE(pha,2),SIZE(pU,2),SIZE(pV,2),SIZE(pslp,2) /) /= Nj ) )    &
+         &  STOP 'AEROBULK_INIT => SST, t_air, hum, U, V and SLP arrays do not agree in shape!'   ! reference :85-92
+      ALLOCATE( c_sst(Ni,Nj), c_ta(Ni,Nj), c_ha(Ni,Nj), c_U(Ni,Nj), c_V(Ni,Nj), c_slp(Ni,Nj) )
+      c_sst = psst ; c_ta = pta ; c_ha = pha ; c_U = pU ; c_V = pV ; c_slp = pslp
+      pskin = C_NULL_PTR
+      IF( PRESENT(l_use_skin) ) THEN
+         iskin = 0_c_int
+         IF( l_use_skin ) iskin = 1_c_int
+         pskin = C_LOC(iskin)
+      END IF
+      p_rsw = C_NULL_PTR
+      p_rlw = C_NULL_PTR
+      IF( PRESENT(prsw) .AND. PRESENT(prlw) ) THEN
+         ALLOCATE( c_rsw(Ni,Nj), c_rlw(Ni,Nj) )
+         c_rsw = prsw ; c_rlw = prlw
+         p_rsw = C_LOC(c_rsw)
+         p_rlw = C_LOC(c_rlw)
+      END IF
+      calgo_c = TRIM(calgo)//C_NULL_CHAR
+      ierr = aerobulk_gpu_init( INT(Nt,c_int), calgo_c, INT(Ni,c_int), INT(Nj,c_int), C_LOC(c_sst), C_LOC(c_ta),       &
+         &                      C_LOC(c_ha), C_LOC(c_U), C_LOC(c_V), C_LOC(c_slp), pskin, p_rsw, p_rlw )
+      IF( ierr /= 0 ) STOP 'AEROBULK_INIT (GPU): the library reported an error'
+      !! mirror the session globals the reference keeps in mod_const
       nitend = Nt
+      l_use_skin_schemes = ( aerobulk_gpu_get_use_skin() /= 0_c_int )
    END SUBROUTINE AEROBULK_INIT
 
 
    SUBROUTINE AEROBULK_BYE()
-      !! The library prints the `AeroBulk_bye` banner itself at jt==Nt (reference :164-170).
+      !! reference :162-170 (AEROBULK_MODEL prints the same banner itself at jt==Nt)
+      CALL aerobulk_gpu_bye()
    END SUBROUTINE AEROBULK_BYE
 
 

@@ -16,6 +16,7 @@ MODULE mod_aerobulk_gpu
    PRIVATE
 
    PUBLIC :: aerobulk_gpu_model, aerobulk_gpu_synchronize,                       &
+      &      aerobulk_gpu_init, aerobulk_gpu_bye, aerobulk_gpu_set_devices, aerobulk_gpu_get_devices, aerobulk_gpu_new_session, &
       &      aerobulk_gpu_turb, aerobulk_gpu_turb_optional, aerobulk_gpu_set_nitend, &
       &      aerobulk_gpu_series, aerobulk_gpu_series_out, aerobulk_gpu_series_csv,  &
       &      aerobulk_gpu_turb_ice, aerobulk_gpu_turb_ice_optional,                  &
@@ -93,6 +94,37 @@ MODULE mod_aerobulk_gpu
          TYPE(c_ptr),            VALUE                     :: rad_sw, rad_lw, T_s    !: double*, NULL if absent
          INTEGER(c_int)                                    :: ierr
       END FUNCTION aerobulk_gpu_model
+
+      !! int aerobulk_gpu_init(int Nt, const char *calgo, int Ni, int Nj, 6 x const double*, const int *l_use_skin,
+      !!                       const double *rad_sw, const double *rad_lw)   -- AEROBULK_INIT on host arrays
+      FUNCTION aerobulk_gpu_init( Nt, calgo, Ni, Nj, sst, t_zt, hum_zt, U_zu, V_zu, slp, l_use_skin, rad_sw, rad_lw ) &
+         &     BIND(C, NAME='aerobulk_gpu_init') RESULT(ierr)
+         IMPORT :: c_int, c_char, c_ptr
+         INTEGER(c_int),         VALUE                     :: Nt
+         CHARACTER(KIND=c_char), DIMENSION(*), INTENT(in)  :: calgo
+         INTEGER(c_int),         VALUE                     :: Ni, Nj
+         TYPE(c_ptr),            VALUE                     :: sst, t_zt, hum_zt, U_zu, V_zu, slp
+         TYPE(c_ptr),            VALUE                     :: l_use_skin, rad_sw, rad_lw
+         INTEGER(c_int)                                    :: ierr
+      END FUNCTION aerobulk_gpu_init
+
+      SUBROUTINE aerobulk_gpu_bye() BIND(C, NAME='aerobulk_gpu_bye')
+      END SUBROUTINE aerobulk_gpu_bye
+
+      !! Split every AEROBULK_MODEL call over n GPUs inside the library (row blocks; include/aerobulk_gpu.h)
+      FUNCTION aerobulk_gpu_set_devices( n ) BIND(C, NAME='aerobulk_gpu_set_devices') RESULT(ierr)
+         IMPORT :: c_int
+         INTEGER(c_int), VALUE :: n
+         INTEGER(c_int)        :: ierr
+      END FUNCTION aerobulk_gpu_set_devices
+
+      FUNCTION aerobulk_gpu_get_devices() BIND(C, NAME='aerobulk_gpu_get_devices') RESULT(n)
+         IMPORT :: c_int
+         INTEGER(c_int) :: n
+      END FUNCTION aerobulk_gpu_get_devices
+
+      SUBROUTINE aerobulk_gpu_new_session() BIND(C, NAME='aerobulk_gpu_new_session')
+      END SUBROUTINE aerobulk_gpu_new_session
 
       !! Direct TURB_COARE3P0 / TURB_COARE3P6 / TURB_ECMWF / TURB_NCAR / TURB_ANDREAS (selected by calgo);
       !! pt_zt: POTENTIAL temperature, pQsw: NET solar flux, pT_s/pq_s in-out; popt: C_LOC of a

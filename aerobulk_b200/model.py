@@ -53,6 +53,9 @@ def lib():
     L.aerobulk_gpu_init_local_stats_device.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 8
     L.aerobulk_gpu_init_from_gathered_stats.restype = C.c_int
     L.aerobulk_gpu_init_from_gathered_stats.argtypes = [C.c_int, C.c_char_p, _ip, C.c_int, C.c_void_p, C.c_int]
+    L.aerobulk_gpu_init.restype = C.c_int
+    L.aerobulk_gpu_init.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int] + [C.c_void_p] * 6 + [_ip, C.c_void_p, C.c_void_p]
+    L.aerobulk_gpu_bye.restype = None
     L.aerobulk_gpu_set_async.argtypes = [C.c_int]
     L.aerobulk_gpu_set_kernel_timing.argtypes = [C.c_int]
     L.aerobulk_gpu_kernel_times.restype = C.c_int
@@ -245,6 +248,25 @@ def init_from_stats(Nt: int, calgo: str, l_use_skin: Optional[bool], have_rad: b
     st = np.ascontiguousarray(stats, dtype=np.float64)
     ls = None if l_use_skin is None else C.byref(C.c_int(int(bool(l_use_skin))))
     _check(L.aerobulk_gpu_init_from_stats(int(Nt), calgo.encode(), ls, int(bool(have_rad)), st.ctypes.data_as(_dp)))
+
+
+def aerobulk_init(Nt: int, calgo: str, psst, pta, pha, pU, pV, pslp, l_use_skin: Optional[bool] = None, prsw=None, prlw=None):
+    """AEROBULK_INIT on HOST (numpy) arrays -- the reference's public routine of the same name
+    (src/mod_aerobulk.f90:24-160): flags, mask, humidity type and unit checks; raises AerobulkError where it STOPs."""
+    L = lib()
+    sst = _f64(psst)
+    shape = sst.shape
+    Ni, Nj = _shape2(shape)
+    ins = [sst] + [_f64(a, shape) for a in (pta, pha, pU, pV, pslp)]
+    rs = None if prsw is None else _f64(prsw, shape)
+    rl = None if prlw is None else _f64(prlw, shape)
+    ls = None if l_use_skin is None else C.byref(C.c_int(int(bool(l_use_skin))))
+    ptr = lambda a: None if a is None else a.ctypes.data
+    _check(L.aerobulk_gpu_init(int(Nt), calgo.encode(), Ni, Nj, *[ptr(a) for a in ins], ls, ptr(rs), ptr(rl)))
+
+
+def aerobulk_bye():
+    lib().aerobulk_gpu_bye()
 
 
 def init_local_stats_device(sst, t_zt, hum_zt, U_zu, V_zu, slp, rad_lw=None, out=None):

@@ -274,6 +274,17 @@ int aerobulk_gpu_flux_diagnostics(long long n, const double *QL, const double *Q
                                   int on_device);
 int aerobulk_gpu_diag_reduce_op(int i);
 
+/* ---- the reference's other two PUBLIC routines (src/mod_aerobulk.f90:20) ---------------------------------- */
+/* AEROBULK_INIT (src/mod_aerobulk.f90:24-160) on HOST arrays, for callers that invoke it themselves: skin flag and its
+ * two errors, nitend = Nt, the sanity mask, the humidity type and the unit checks -- with the reference's messages and
+ * fail-stop.  As in the reference, AEROBULK_MODEL(jt == 1) runs the same initialisation again on its own arguments
+ * (:255-262), so calling this first is never required.  rad_sw / rad_lw may be NULL (no radiation given). */
+int aerobulk_gpu_init(int Nt, const char *calgo, int Ni, int Nj, const double *sst, const double *t_zt,
+                      const double *hum_zt, const double *U_zu, const double *V_zu, const double *slp,
+                      const int *l_use_skin, const double *rad_sw, const double *rad_lw);
+/* AEROBULK_BYE (:162-170): prints the closing banner (AEROBULK_MODEL does it itself at jt == Nt). */
+void aerobulk_gpu_bye(void);
+
 /* ---- AEROBULK_INIT split for row-block sharded grids (one process per GPU) ---- */
 
 #define AEROBULK_GPU_NSTATS 64

@@ -96,6 +96,30 @@ def test_fail_stop_conditions(ab):
     ab.reset()
 
 
+def test_public_aerobulk_init(ab):
+    """AEROBULK_INIT called directly (it is PUBLIC in the reference, src/mod_aerobulk.f90:20): same decisions and
+    fail-stops as the initialisation AEROBULK_MODEL runs at jt == 1."""
+    f = synth.fields(64, 32, humidity="dp")
+    ab.reset()
+    ab.aerobulk_init(7, "ecmwf", *_ins(f), l_use_skin=True, prsw=f["rad_sw"], prlw=f["rad_lw"])
+    assert ab.use_skin() and ab.humidity_type() == "dp"
+    o = ab.aerobulk_model(7, 7, "ecmwf", 2.0, 10.0, *_ins(f), rad_sw=f["rad_sw"], rad_lw=f["rad_lw"])   # nitend = 7: BYE at jt == 7
+    assert "T_s" in o
+    ab.reset()
+    with pytest.raises(ab.AerobulkError) as e:
+        ab.aerobulk_init(1, "ncar", *_ins(f), l_use_skin=True, prsw=f["rad_sw"], prlw=f["rad_lw"])
+    assert e.value.code == 2                                # skin asked for an algorithm without skin schemes
+    with pytest.raises(ab.AerobulkError) as e:
+        ab.aerobulk_init(1, "coare3p6", *_ins(f), l_use_skin=True)
+    assert e.value.code == 3 and not ab.use_skin()          # no radiation given; the flag was rolled back
+    g = dict(f)
+    g["slp"] = f["slp"] / 100.0                             # hPa: every point masked
+    with pytest.raises(ab.AerobulkError) as e:
+        ab.aerobulk_init(1, "coare3p6", *_ins(g))
+    assert e.value.code == 4
+    ab.aerobulk_bye()
+
+
 def test_empty_and_tiny_inputs(ab):
     ab.reset()
     z = np.zeros((0,), dtype=np.float64)

@@ -40,21 +40,61 @@ def _err(a, b, k, S):
     return e.max(axis=0)
 
 
-def _compare(tag, got, ref, S):
-    """Scaled error of every series per STATION (the warm-layer state carries a perturbation forward in time).
-    At least 97 % of the stations must be within TOL on every series and record; the others -- near-calm stable
-    records, where the iteration amplifies rounding noise: the ORACLE itself moves by up to 1e-8 when its inputs move
-    by a relative 1e-15, tests/test_oracle_series.py::test_series_conditioning -- within 1e-5.
-    Returns the worst error over the stations within TOL."""
+SERIES_IN = ("sst", "t_zt", "hum_zt", "wind", "slp", "rad_sw", "rad_lw")
+NUDGES = (1, 4, 16, 64)
+
+
+def _nudge(a, ulps):
+    out = np.array(a, dtype=np.float64, copy=True)
+    step = np.inf if ulps > 0 else -np.inf
+    for _ in range(abs(ulps)):
+        out = np.where(out != 0.0, np.nextafter(out, step), out)
+    return out
+
+
+def _station_errors(got, ref, S):
     emax = np.zeros(S)
     for k in SCALE:
-        assert np.all(np.isfinite(got[k])), (tag, k)
-        e = _err(got, ref, k, S)
-        assert float(e.max()) <= 1e-5, (tag, k, float(e.max()))
-        emax = np.maximum(emax, e)
-    bad = emax > TOL
-    assert int(bad.sum()) <= max(1, int(0.03 * S)), (tag, int(bad.sum()), S, float(emax.max()))
-    return float(emax[~bad].max()) if (~bad).any() else 0.0
+        assert np.all(np.isfinite(got[k])), k
+        emax = np.maximum(emax, _err(got, ref, k, S))
+    return emax
+
+
+def _compare(tag, got, ref, S, d=None, run_oracle=None):
+    """Scaled error of every series per STATION (the warm-layer state carries a perturbation forward in time).
+    Gate: every series of every record within TOL = 1e-10, except at stations PROVEN ill-conditioned: the time loop
+    amplifies rounding noise at near-calm stable records, so for each station above TOL the ORACLE is re-run on that
+    station with its inputs nudged by 1, 4, 16, 64 ulp (each field alone and all together, both directions) and must
+    itself move by at least a tenth of the GPU's deviation.  A station whose oracle series stays put is a real mismatch
+    and fails; proven stations must stay below 3 % of the fleet.  Returns the worst error over the stations within TOL."""
+    emax = _station_errors(got, ref, S)
+    bad = np.flatnonzero(emax > TOL)
+    print(f"[series] {tag}: worst {emax.max():.3e}, stations above 1e-10: {bad.size} of {S}")
+    assert bad.size <= max(1, int(0.03 * S)), (tag, int(bad.size), S, float(emax.max()))
+    if bad.size:
+        assert d is not None and run_oracle is not None, (tag, "stations above 1e-10 and no proof machinery", float(emax.max()))
+        sub = {k: np.ascontiguousarray(d[k][:, bad]) for k in SERIES_IN}
+        lon = np.ascontiguousarray(d["lon"][bad])
+        base = run_oracle(lon, sub)
+        proven = np.zeros(bad.size, dtype=bool)
+        best = np.zeros(bad.size)
+        for ulps in NUDGES:
+            for sgn in (+1, -1):
+                variants = [{k: (_nudge(v, sgn * ulps) if k == f else v) for k, v in sub.items()} for f in SERIES_IN]
+                variants.append({k: _nudge(v, sgn * ulps) for k, v in sub.items()})
+                for var in variants:
+                    spread = _station_errors(run_oracle(lon, var), base, bad.size)
+                    best = np.maximum(best, spread)
+                    proven |= spread >= 0.1 * emax[bad]
+            if proven.all():
+                break
+        for i, s_ in enumerate(bad):
+            print(f"[series-proof] {tag} station {int(s_)}: gpu-oracle {emax[s_]:.3e}, oracle moves by {best[i]:.3e} under "
+                  f"<= 64 ulp input nudges -> {'PROVEN' if proven[i] else 'NOT PROVEN'}")
+        assert proven.all(), (tag, "stations off by more than 1e-10 where the oracle is NOT sensitive to ulp-level nudges",
+                              bad[~proven].tolist(), emax[bad][~proven].tolist())
+    ok = emax <= TOL
+    return float(emax[ok].max()) if ok.any() else 0.0
 
 
 @pytest.mark.parametrize("algo,hum", [("coare3p6", "q"), ("coare3p6", "rh"), ("coare3p0", "dp"), ("ecmwf", "q"),
@@ -70,7 +110,13 @@ def test_series_matches_oracle(ab, algo, hum):
     o.set_nb_iter(20)
     hk = {"q": 0, "dp": 1, "rh": 2}[hum]
     ref = o.series(algo, 2.0, 10.0, **d, hum_kind=hk)
-    worst = _compare(f"series {algo} {hum}", got, ref, S)
+
+    def rerun(lon, sub):
+        oo = OracleSession(threads=8)
+        oo.set_nb_iter(20)
+        return oo.series(algo, 2.0, 10.0, d["isecday_utc"], lon, **sub, hum_kind=hk)
+
+    worst = _compare(f"series {algo} {hum}", got, ref, S, d, rerun)
     assert worst <= TOL
     if algo.startswith("coare"):
         assert ref["dT_wl"].max() > 0.3   # the warm layer is exercised (and its dawn reset, see the CPU test)
@@ -92,7 +138,14 @@ def test_series_variants(ab, algo, nb_iter, zt, skin):
     o.set_nb_iter(nb_iter)
     o.set_rdt(1800.0)
     ref = o.series(algo, zt, 10.0, **d, l_use_skin=skin)
-    assert _compare(f"series {algo} n{nb_iter} zt{zt}", got, ref, S) <= TOL
+
+    def rerun(lon, sub):
+        oo = OracleSession(threads=8)
+        oo.set_nb_iter(nb_iter)
+        oo.set_rdt(1800.0)
+        return oo.series(algo, zt, 10.0, d["isecday_utc"], lon, **sub, l_use_skin=skin)
+
+    assert _compare(f"series {algo} n{nb_iter} zt{zt}", got, ref, S, d, rerun) <= TOL
     ab.reset()
 
 

@@ -10,9 +10,11 @@ VARIANTS = {
     "b256x4": ["AB_FLUX_BLOCK=256", "AB_MIN_BLOCKS=4"],
     "b256x2": ["AB_FLUX_BLOCK=256", "AB_MIN_BLOCKS=2"],
     "b128x5": ["AB_FLUX_BLOCK=128", "AB_MIN_BLOCKS=5"],
-    "band0": ["AB_SORT_BAND=0.0", "AB_SORT_BAND_NOQ=0.0"],
-    "band05": ["AB_SORT_BAND=0.5"],
+    "band0": ["AB_SORT_BAND=0.0", "AB_SORT_BAND_SKIN=0.0", "AB_SORT_BAND_NOQ=0.0"],
+    "sband075": ["AB_SORT_BAND_SKIN=0.75"],
+    "sband1": ["AB_SORT_BAND_SKIN=1.0"],
     "band01": ["AB_SORT_BAND=0.1"],
+    "band02": ["AB_SORT_BAND=0.2"],
     "ser64x1": ["AB_SERIES_MIN_BLOCKS=1"],
     "ser64x8": ["AB_SERIES_MIN_BLOCKS=8"],
     "ser128x6": ["AB_SERIES_BLOCK=128", "AB_SERIES_MIN_BLOCKS=6"],
