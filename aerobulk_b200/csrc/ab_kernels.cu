@@ -443,30 +443,51 @@ __global__ void __launch_bounds__(STATS_BLOCK) stats_kernel(const StatsArgs a)
     }
     const bool rad = (a.rad_lw != nullptr);
     const long long stride = (long long)gridDim.x * STATS_BLOCK;
-    for (long long i = (long long)blockIdx.x * STATS_BLOCK + threadIdx.x; i < a.n; i += stride) {
-        double v[NFIELDS];
-        v[0] = __ldg(a.sst + i);
-        v[1] = __ldg(a.t_zt + i);
-        v[2] = __ldg(a.slp + i);
-        v[3] = __ldg(a.U_zu + i);
-        v[4] = __ldg(a.V_zu + i);
-        v[5] = sqrt(__dadd_rn(__dmul_rn(v[3], v[3]), __dmul_rn(v[4], v[4])));
-        v[6] = __ldg(a.hum_zt + i);
-        v[7] = rad ? __ldg(a.rad_lw + i) : 0.;
-        v[8] = v[7];
-        const bool m = point_unmasked(v[0], v[1], v[2], v[5], rad, v[7]);
-        acc[0] += m ? 1. : 0.;
-        acc[1] += 1.;
+    // STATS_UNROLL points per trip with all their loads issued first: the pass is bound by memory latency, not by its
+    // arithmetic (one point per trip ran at 1.5 TB/s: ~47 accumulators leave room for 2 blocks per SM only)
+    constexpr int STATS_UNROLL = 4;
+    for (long long i0 = (long long)blockIdx.x * STATS_BLOCK + threadIdx.x; i0 < a.n; i0 += stride * STATS_UNROLL) {
+        double in[STATS_UNROLL][7];
 #pragma unroll
-        for (int f = 0; f < NFIELDS; ++f) {
-            // (v < acc ? v : acc) keeps acc when v is a NaN, like fmin / fmax, in 3 instructions instead of their 8-9
-            if (m) {
-                acc[2 + 5 * f + 0] += v[f];
-                acc[2 + 5 * f + 1] = abm::dmin(v[f], acc[2 + 5 * f + 1]);
-                acc[2 + 5 * f + 2] = abm::dmax(v[f], acc[2 + 5 * f + 2]);
+        for (int u = 0; u < STATS_UNROLL; ++u) {
+            const long long i = i0 + u * stride;
+            const bool ok = i < a.n;
+            const long long j = ok ? i : i0;
+            in[u][0] = __ldg(a.sst + j);
+            in[u][1] = __ldg(a.t_zt + j);
+            in[u][2] = __ldg(a.slp + j);
+            in[u][3] = __ldg(a.U_zu + j);
+            in[u][4] = __ldg(a.V_zu + j);
+            in[u][5] = __ldg(a.hum_zt + j);
+            in[u][6] = rad ? __ldg(a.rad_lw + j) : 0.;
+        }
+#pragma unroll
+        for (int u = 0; u < STATS_UNROLL; ++u) {
+            if (i0 + u * stride >= a.n) break;
+            double v[NFIELDS];
+            v[0] = in[u][0];
+            v[1] = in[u][1];
+            v[2] = in[u][2];
+            v[3] = in[u][3];
+            v[4] = in[u][4];
+            v[5] = sqrt(__dadd_rn(__dmul_rn(v[3], v[3]), __dmul_rn(v[4], v[4])));
+            v[6] = in[u][5];
+            v[7] = in[u][6];
+            v[8] = v[7];
+            const bool m = point_unmasked(v[0], v[1], v[2], v[5], rad, v[7]);
+            acc[0] += m ? 1. : 0.;
+            acc[1] += 1.;
+#pragma unroll
+            for (int f = 0; f < NFIELDS; ++f) {
+                // (v < acc ? v : acc) keeps acc when v is a NaN, like fmin / fmax, in 3 instructions instead of their 8-9
+                if (m) {
+                    acc[2 + 5 * f + 0] += v[f];
+                    acc[2 + 5 * f + 1] = abm::dmin(v[f], acc[2 + 5 * f + 1]);
+                    acc[2 + 5 * f + 2] = abm::dmax(v[f], acc[2 + 5 * f + 2]);
+                }
+                acc[2 + 5 * f + 3] = abm::dmin(v[f], acc[2 + 5 * f + 3]);
+                acc[2 + 5 * f + 4] = abm::dmax(v[f], acc[2 + 5 * f + 4]);
             }
-            acc[2 + 5 * f + 3] = abm::dmin(v[f], acc[2 + 5 * f + 3]);
-            acc[2 + 5 * f + 4] = abm::dmax(v[f], acc[2 + 5 * f + 4]);
         }
     }
     __shared__ double sm[STATS_BLOCK / 32][2 + 5 * NFIELDS];
@@ -486,23 +507,30 @@ __global__ void __launch_bounds__(STATS_BLOCK) stats_kernel(const StatsArgs a)
     }
 }
 
-// fixed-order final reduction (one warp per statistic) -> results do not depend on scheduling
-__global__ void __launch_bounds__(256) stats_final(const double *partials, int nblocks, double *out)
+// fixed-order final reduction (one block of 128 threads per statistic) -> results do not depend on scheduling
+static constexpr int FINAL_BLOCK = 128;
+__global__ void __launch_bounds__(FINAL_BLOCK) stats_final(const double *partials, int nblocks, double *out)
 {
-    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (k >= NSTATS) return;
+    const int k = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (k >= 2 + 5 * NFIELDS) {
-        if (lane == 0) out[k] = 0.;
+        if (threadIdx.x == 0) out[k] = 0.;
         return;
     }
     const int op = stat_op(k);
     double r = (op == 0) ? 0. : (op == 1) ? DBL_MAX : -DBL_MAX;
-    for (int b = lane; b < nblocks; b += 32) {
-        const double w = partials[(long long)b * NSTATS + k];
-        r = (op == 0) ? r + w : (op == 1) ? fmin(r, w) : fmax(r, w);
+    for (int b = threadIdx.x; b < nblocks; b += FINAL_BLOCK) {
+        const double x = partials[(long long)b * NSTATS + k];
+        r = (op == 0) ? r + x : (op == 1) ? fmin(r, x) : fmax(r, x);
     }
     r = warp_reduce(r, op);
-    if (lane == 0) out[k] = r;
+    __shared__ double sm[FINAL_BLOCK / 32];
+    if (lane == 0) sm[w] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = sm[0];
+        for (int j = 1; j < FINAL_BLOCK / 32; ++j) t = (op == 0) ? t + sm[j] : (op == 1) ? fmin(t, sm[j]) : fmax(t, sm[j]);
+        out[k] = t;
+    }
 }
 
 int stats_max_blocks() { return STATS_MAX_BLOCKS; }
@@ -512,7 +540,7 @@ cudaError_t launch_stats(const StatsArgs &a, int nblocks, cudaStream_t s)
     stats_kernel<<<nblocks, STATS_BLOCK, 0, s>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    stats_final<<<NSTATS * 32 / 256, 256, 0, s>>>(a.partials, nblocks, a.out);
+    stats_final<<<NSTATS, FINAL_BLOCK, 0, s>>>(a.partials, nblocks, a.out);
     return cudaGetLastError();
 }
 

@@ -101,10 +101,12 @@ def test_public_aerobulk_init(ab):
     fail-stops as the initialisation AEROBULK_MODEL runs at jt == 1."""
     f = synth.fields(64, 32, humidity="dp")
     ab.reset()
-    ab.aerobulk_init(7, "ecmwf", *_ins(f), l_use_skin=True, prsw=f["rad_sw"], prlw=f["rad_lw"])
+    ab.aerobulk_init(2, "ecmwf", *_ins(f), l_use_skin=True, prsw=f["rad_sw"], prlw=f["rad_lw"])
     assert ab.use_skin() and ab.humidity_type() == "dp"
-    o = ab.aerobulk_model(7, 7, "ecmwf", 2.0, 10.0, *_ins(f), rad_sw=f["rad_sw"], rad_lw=f["rad_lw"])   # nitend = 7: BYE at jt == 7
-    assert "T_s" in o
+    for jt in (1, 2):     # AEROBULK_MODEL(jt == 1) initialises again on its own arguments, as in the reference
+        o = ab.aerobulk_model(jt, 2, "ecmwf", 2.0, 10.0, *_ins(f), l_use_skin=True, rad_sw=f["rad_sw"], rad_lw=f["rad_lw"])
+        assert "T_s" in o and np.isfinite(o["T_s"]).all()
+    assert ab.get_state(0, 64 * 32) is None                 # the session ended at jt == nitend
     ab.reset()
     with pytest.raises(ab.AerobulkError) as e:
         ab.aerobulk_init(1, "ncar", *_ins(f), l_use_skin=True, prsw=f["rad_sw"], prlw=f["rad_lw"])

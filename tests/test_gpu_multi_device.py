@@ -189,3 +189,25 @@ def test_cxx_bridge_symbol_is_split_too(ab):
         outs[nd] = o
     for a, b in zip(outs[1], outs[2]):
         assert np.array_equal(a, b)
+
+
+def test_split_call_with_speculative_init_per_shard(ab):
+    """Shards big enough for several pipeline chunks each (>= 400 000 points): every shard runs its chunks on its LOCAL
+    running AEROBULK_INIT verdict and recomputes what the GLOBAL verdict (statistics of all devices) overrules.  A
+    relative-humidity field whose first rows -- the whole first chunk of shard 0 -- read as specific humidity."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    Ni, Nj = 1440, 720
+    f = synth.fields(Ni, Nj, humidity="rh")
+    f["hum_zt"][:, :150] = 0.02
+    kw = dict(Niter=5, l_use_skin=True, rad_sw=f["rad_sw"], rad_lw=f["rad_lw"])
+    ab.set_devices(1)
+    ab.reset()
+    one = ab.aerobulk_model(1, 1, "ecmwf", 2.0, 10.0, *[f[k] for k in IN_KEYS], **kw)
+    assert ab.humidity_type() == "rh"
+    ab.reset()
+    ab.set_devices(2)
+    two = ab.aerobulk_model(1, 1, "ecmwf", 2.0, 10.0, *[f[k] for k in IN_KEYS], **kw)
+    assert ab.humidity_type() == "rh"
+    for k in one:
+        assert np.array_equal(one[k], two[k]), k
