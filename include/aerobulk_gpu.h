@@ -33,7 +33,7 @@
  * AEROBULK_GPU_TRACE=1 GPU timeline of every staged call on stderr; pageable arrays: AEROBULK_GPU_BOUNCE=0 driver-staged
  * copies, AEROBULK_GPU_HOST_THREADS copy threads (default: half the CPUs the process may run on, at most 8),
  * AEROBULK_GPU_BOUNCE_CHUNK_POINTS, AEROBULK_GPU_COPY_STREAMING=0 plain instead of non-temporal stores,
- * AEROBULK_GPU_BOUNCE_MAX_MB largest pinned slab the library may allocate for them (default 4096; beyond it, or when the
+ * AEROBULK_GPU_BOUNCE_MAX_MB largest pinned slab the library may allocate for them (default 12288; beyond it, or when the
  * host refuses the allocation, the driver-staged copies are used).
  */
 #ifndef AEROBULK_GPU_H
@@ -258,7 +258,8 @@ int aerobulk_gpu_host_unregister(void *ptr);
 int aerobulk_gpu_selftest_host_copy(long long n, int rounds);
 /* The row-block chunk plan aerobulk_gpu_model uses for n points (needs no device; for tests and tuning): kind 0 device or
  * pinned arrays (one chunk), 1 staged pipeline, 2 pageable arrays through the pinned slab.  Writes the nchunks + 1
- * boundaries into cstart (room for 17) and returns nchunks, or -1 for bad arguments. */
+ * boundaries into cstart (room for 17) and returns nchunks, or -1 for bad arguments.  kind 3: the staged pipeline of a
+ * jt == 1 call (speculative AEROBULK_INIT: H2D and D2H overlap). */
 int aerobulk_gpu_chunk_plan(long long n, int kind, long long *cstart);
 
 /* ---- optional global flux diagnostics for sharded grids ---------------------------------------------- */

@@ -193,7 +193,7 @@ def test_chunk_plan_of_host_array_calls(ab):
     sizes = [0, 1, 5, 2047, 2048, 2049, 65535, 65536, 199999, 200000, 400001, 1036800, 9331200, 83980800] + \
         [int(x) for x in rng.integers(1, 20_000_000, 40)]
     for n in sizes:
-        for kind in (0, 1, 2):
+        for kind in (0, 1, 2, 3):
             m, cs = plan(n, kind)
             assert 1 <= m <= 16 and cs[0] == 0 and cs[-1] == n, (n, kind, cs)
             assert all(b >= a for a, b in zip(cs, cs[1:])), (n, kind, cs)
@@ -206,7 +206,10 @@ def test_chunk_plan_of_host_array_calls(ab):
     m, cs = plan(1036800, 2)
     sz = [b - a for a, b in zip(cs, cs[1:])]
     assert m == 6 and sz[0] < sz[1] < sz[2] and sz[3] > sz[4] > sz[5] and abs(sz[0] - sz[5]) <= 4096
-    assert L.aerobulk_gpu_chunk_plan(-1, 0, (C.c_longlong * 17)()) == -1 and L.aerobulk_gpu_chunk_plan(10, 3, (C.c_longlong * 17)()) == -1
+    m, cs = plan(83980800, 3)                                        # jt == 1 with the speculative AEROBULK_INIT: both
+    sz = [b - a for a, b in zip(cs, cs[1:])]                         # PCIe directions busy -> equal pieces, half-size ends
+    assert m == 12 and max(sz[1:-1]) - min(sz[1:-1]) <= 4096 and sz[0] < 0.6 * sz[1] and sz[-1] < 0.6 * sz[1]
+    assert L.aerobulk_gpu_chunk_plan(-1, 0, (C.c_longlong * 17)()) == -1 and L.aerobulk_gpu_chunk_plan(10, 4, (C.c_longlong * 17)()) == -1
 
 
 def test_python_mirror_normalises_layout_and_validates_out(ab):
