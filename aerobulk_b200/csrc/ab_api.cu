@@ -784,7 +784,7 @@ int launch_local_stats(long long n, const double *sst, const double *t_zt, const
     long long want = (n + 255) / 256;
     int nblocks = (int)(want < 1 ? 1 : (want > abk::stats_max_blocks() ? abk::stats_max_blocks() : want));
     CUDA_TRY(abk::launch_stats(a, nblocks, s));
-    g.launches += 2;
+    g.launches += 3;   // stats_fast_kernel, stats_fix_kernel, stats_final
     return 0;
 }
 int local_stats(long long n, const double *sst, const double *t_zt, const double *hum, const double *U,

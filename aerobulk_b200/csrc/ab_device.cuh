@@ -123,7 +123,7 @@ constexpr double INV_GRAV = 1. / GRAV;
 // ---------------------------------------------------------------------------
 // thermodynamics, reference src/mod_phymbl.f90
 // ---------------------------------------------------------------------------
-ABD double virt_temp(double T, double q) { return T * (1. + RCTV0 * q); }           // :247-269
+ABD double virt_temp(double T, double q) { return T * (1. + KC(RCTV0) * q); }           // :247-269
 
 // Goff (1957) saturation vapour pressure [Pa], :777-800 (rt0, not the triple point)
 ABD_HEAVY double e_sat(double T)
@@ -187,8 +187,8 @@ ABD double ri_bulk(double z, double sst, double tha, double ssq, double qa, doub
 {
     const double sstv = virt_temp(sst, ssq);
     const double dthv = virt_temp(tha, qa) - sstv;
-    const double tv = 0.5 * (sstv + virt_temp(tha - RGAMMA_DRY * z, qa));
-    return fdiv(GRAV * dthv * z, tv * ub * ub);
+    const double tv = 0.5 * (sstv + virt_temp(tha - KC(RGAMMA_DRY) * z, qa));
+    return fdiv(KC(GRAV) * dthv * z, tv * ub * ub);
 }
 
 ABD double q_air_rh(double rh, double T, double p)  // :963-985
@@ -244,8 +244,8 @@ ABD_HEAVY void update_qnsol_tau(const AirZu &air, double Ts, double qs, double t
                                 double qst, double wnd, double Ub, double rlw,
                                 double &Qns, double &Tau, double &Qlat)
 {
-    const double dt = floor_abs(tha - Ts, 1.E-09);
-    const double dq = floor_abs(qa - qs, 1.E-12);
+    const double dt = floor_abs(tha - Ts, KC(1.E-09));
+    const double dq = floor_abs(qa - qs, KC(1.E-12));
     const double z0 = fdiv(us, Ub);
     const Flux f = bulk_formula(air, Ts, qs, tha, qa, z0 * z0, fdiv(z0 * ts, dt), fdiv(z0 * qst, dq), wnd, Ub);
     Qns = f.qlat + f.qsen + qlw_net(rlw, Ts);
@@ -285,17 +285,17 @@ struct PsiMH {
 // Large & Yeager, src/mod_blk_ncar.f90:333-407
 ABD PsiMH psi_mh_ncar_unstable(double z)
 {
-    const double x2 = abm::dmax(abm::fast_sqrt(fabs(1. - 16. * z)), 1.);
-    const double x = abm::fast_sqrt(x2);
+    const double x2 = abm::dmax(abm::fast_sqrt_pos(fabs(1. - 16. * z)), 1.);
+    const double x = abm::fast_sqrt_pos(x2);
     const double l2 = abm::dlog((1. + x2) * 0.5);
     PsiMH r;
-    r.m = 2. * abm::dlog((1. + x) * 0.5) + l2 - 2. * abm::datan(x) + RPI * 0.5;
+    r.m = 2. * abm::dlog((1. + x) * 0.5) + l2 - 2. * abm::datan_ge1(x) + RPI * 0.5;
     r.h = 2. * l2;
     return r;
 }
 ABD double psi_h_ncar_unstable(double z)
 {
-    const double x2 = abm::dmax(abm::fast_sqrt(fabs(1. - 16. * z)), 1.);
+    const double x2 = abm::dmax(abm::fast_sqrt_pos(fabs(1. - 16. * z)), 1.);
     return 2. * abm::dlog(0.5 * (1. + x2));
 }
 ABD double psi_m_ncar(double z) { return nonneg(z) ? -5. * z : psi_mh_ncar_unstable(z).m; }
@@ -305,7 +305,7 @@ ABD double psi_h_ncar(double z) { return nonneg(z) ? -5. * z : psi_h_ncar_unstab
 // SIGN(0.5,+0.) selects the stable branch and the truncated literals do not cancel.
 ABD double psi_coare_convective(double phi_c)
 {
-    return 1.5 * abm::dlog((1. + phi_c + phi_c * phi_c) * KC(1. / 3.)) - KC(1.7320508) * abm::datan((1. + 2. * phi_c) * KC(1. / 1.7320508)) + KC(1.813799447);
+    return 1.5 * abm::dlog((1. + phi_c + phi_c * phi_c) * KC(1. / 3.)) - KC(1.7320508) * abm::datan_ge1((1. + 2. * phi_c) * KC(1. / 1.7320508)) + KC(1.813799447);
 }
 ABD PsiMH psi_mh_coare_stable(double z)
 {
@@ -313,22 +313,22 @@ ABD PsiMH psi_mh_coare_stable(double z)
     const double a = fabs(1. + 2. * z * KC(1. / 3.));
     PsiMH r;
     r.m = -(1. + 1. * z + KC(0.6667) * (z - KC(14.28)) * e + KC(8.525));
-    r.h = -(a * abm::fast_sqrt(a) + KC(.6667) * (z - KC(14.28)) * e + KC(8.525));                      // **1.5
+    r.h = -(a * abm::fast_sqrt_pos(a) + KC(.6667) * (z - KC(14.28)) * e + KC(8.525));                      // **1.5
     return r;
 }
 ABD double psi_h_coare_stable(double z)
 {
     const double e = abm::dexp_b(-abm::dmin(50., KC(0.35) * z));   // stable branch: z >= 0
     const double a = fabs(1. + 2. * z * KC(1. / 3.));
-    return -(a * abm::fast_sqrt(a) + KC(.6667) * (z - KC(14.28)) * e + KC(8.525));
+    return -(a * abm::fast_sqrt_pos(a) + KC(.6667) * (z - KC(14.28)) * e + KC(8.525));
 }
 ABD PsiMH psi_mh_coare_unstable(double z)
 {
-    const double phi_h = abm::fast_sqrt(fabs(1. - 15. * z));                               // **.5
-    const double phi_m = abm::fast_sqrt(phi_h);                                            // **.25
+    const double phi_h = abm::fast_sqrt_pos(fabs(1. - 15. * z));                               // **.5
+    const double phi_m = abm::fast_sqrt_pos(phi_h);                                            // **.25
     double f = z * z;
     f = fdiv(f, 1. + f);
-    const double km = 2. * abm::dlog((1. + phi_m) * 0.5) + abm::dlog((1. + phi_m * phi_m) * 0.5) - 2. * abm::datan(phi_m) + 0.5 * RPI;
+    const double km = 2. * abm::dlog((1. + phi_m) * 0.5) + abm::dlog((1. + phi_m * phi_m) * 0.5) - 2. * abm::datan_ge1(phi_m) + 0.5 * RPI;
     const double kh = 2. * abm::dlog((1. + phi_h) * 0.5);
     const double cm = psi_coare_convective(powr(fabs(1. - KC(10.15) * z), KC(.3333)));
     const double ch = psi_coare_convective(powr(fabs(1. - KC(34.15) * z), KC(.3333)));
@@ -339,7 +339,7 @@ ABD PsiMH psi_mh_coare_unstable(double z)
 }
 ABD double psi_h_coare_unstable(double z)
 {
-    const double phi_h = abm::fast_sqrt(fabs(1. - 15. * z));
+    const double phi_h = abm::fast_sqrt_pos(fabs(1. - 15. * z));
     double f = z * z;
     f = fdiv(f, 1. + f);
     const double kh = 2. * abm::dlog((1. + phi_h) * 0.5);
@@ -368,23 +368,23 @@ ABD void psi3_coare(double zeta_u, double zeta_t, double &m_u, double &h_u, doub
 ABD double cap_zeta(double zeta) { return abm::dmin(abm::dmax(zeta, -50.), 5.); }
 ABD PsiMH psi_mh_ecmwf_stable(double zeta)
 {
-    const double zc = 5. / 0.35;
+    constexpr double zc = 5. / 0.35;
     const double z = cap_zeta(zeta);
-    const double t = 2. / 3. * (z - zc) * abm::dexp_b(-0.35 * z);   // zeta is capped to [-50, 5]
-    const double a = fabs(1. + 2. / 3. * z);
+    const double t = KC(2. / 3.) * (z - KC(zc)) * abm::dexp_b(KC(-0.35) * z);   // zeta is capped to [-50, 5]
+    const double a = fabs(1. + KC(2. / 3.) * z);
     PsiMH r;
-    r.m = -t - z - 2. / 3. * zc;
-    r.h = -t - a * abm::fast_sqrt(a) - 2. / 3. * zc + 1.;
+    r.m = -t - z - KC(2. / 3. * zc);
+    r.h = -t - a * abm::fast_sqrt_pos(a) - KC(2. / 3. * zc) + 1.;
     return r;
 }
 ABD PsiMH psi_mh_ecmwf_unstable(double zeta)
 {
     const double z = cap_zeta(zeta);
-    const double x2 = abm::fast_sqrt(fabs(1. - 16. * z));
-    const double x = abm::fast_sqrt(x2);
+    const double x2 = abm::fast_sqrt_pos(fabs(1. - 16. * z));
+    const double x = abm::fast_sqrt_pos(x2);
     const double t = 1. + x;
     PsiMH r;
-    r.m = abm::dlog(0.125 * t * t * (1. + x2)) - 2. * abm::datan(x) + 0.5 * RPI;
+    r.m = abm::dlog(0.125 * t * t * (1. + x2)) - 2. * abm::datan_ge1(x) + KC(0.5 * RPI);
     r.h = 2. * abm::dlog(0.5 * (1. + x2));
     return r;
 }
@@ -393,7 +393,7 @@ ABD double psi_h_ecmwf_stable(double zeta) { return psi_mh_ecmwf_stable(zeta).h;
 ABD double psi_m_ecmwf_unstable(double zeta) { return psi_mh_ecmwf_unstable(zeta).m; }
 ABD double psi_h_ecmwf_unstable(double zeta)
 {
-    const double x2 = abm::fast_sqrt(fabs(1. - 16. * cap_zeta(zeta)));
+    const double x2 = abm::fast_sqrt_pos(fabs(1. - 16. * cap_zeta(zeta)));
     return 2. * abm::dlog(0.5 * (1. + x2));
 }
 
@@ -407,7 +407,7 @@ ABD double psi_m_andreas_stable(double zeta)
            + zam * ZBBM_A / (2. * ZBM_A)
                  * (2. * abm::dlog(fabs((x + ZBBM_A) * (1. / (1. + ZBBM_A))))
                     - abm::dlog(fabs((x * x - x * ZBBM_A + ZBBM_A * ZBBM_A) * (1. / (1. - ZBBM_A + ZBBM_A * ZBBM_A))))
-                    + 2. * SR3 * (abm::datan((2. * x - ZBBM_A) * (1. / (SR3 * ZBBM_A))) - abm::datan((2. - ZBBM_A) / (SR3 * ZBBM_A))));
+                    + 2. * SR3 * (abm::datan_ge1((2. * x - ZBBM_A) * (1. / (SR3 * ZBBM_A))) - abm::datan_ge1((2. - ZBBM_A) / (SR3 * ZBBM_A))));
 }
 ABD double psi_h_andreas_stable(double zeta)
 {
@@ -421,16 +421,16 @@ ABD double psi_h_andreas_stable(double zeta)
 ABD PsiMH psi_mh_andreas_unstable(double zeta)
 {
     const double z = abm::dmin(zeta, 15.);
-    const double x2 = abm::dmax(abm::fast_sqrt(fabs(1. - 16. * z)), 1.);
-    const double x = abm::fast_sqrt(x2);
+    const double x2 = abm::dmax(abm::fast_sqrt_pos(fabs(1. - 16. * z)), 1.);
+    const double x = abm::fast_sqrt_pos(x2);
     PsiMH r;
-    r.m = 2. * abm::dlog(fabs((1. + x) * 0.5)) + abm::dlog(fabs((1. + x2) * 0.5)) - 2. * abm::datan(x) + RPI * 0.5;
+    r.m = 2. * abm::dlog(fabs((1. + x) * 0.5)) + abm::dlog(fabs((1. + x2) * 0.5)) - 2. * abm::datan_ge1(x) + RPI * 0.5;
     r.h = 2. * abm::dlog(0.5 * (1. + x2));
     return r;
 }
 ABD double psi_h_andreas_unstable(double zeta)
 {
-    const double x2 = abm::dmax(abm::fast_sqrt(fabs(1. - 16. * abm::dmin(zeta, 15.))), 1.);
+    const double x2 = abm::dmax(abm::fast_sqrt_pos(fabs(1. - 16. * abm::dmin(zeta, 15.))), 1.);
     return 2. * abm::dlog(0.5 * (1. + x2));
 }
 
@@ -534,8 +534,10 @@ ABD double cool_skin_dT(double alpha, double Qsw, double Qnsol, double us, doubl
     auto delta = [&](double Qd) -> double {
         const double zQd = COARE_FORM ? Qd + q_lat_term : Qd;
         if (nonneg(zQd)) return d_warm;                                  // warming of the viscous layer
-        const double x = abm::dmax(c_lamb * zQd, 0.);
-        const double x75 = abm::pow075(x);                               // **0.75
+        // floored at 1e-30 instead of 0: x**0.75 < 4e-23 vanishes against the 1 it is added to (bit-identical), and
+        // the root needs no zero guard
+        const double x = abm::dmax(c_lamb * zQd, KC(1.e-30));
+        const double x75 = abm::pow075_pos(x);                           // **0.75
         return 6. * abm::fast_rcbrt(1. + x75) * nu_o_usw;                 // **(-1./3.)
     };
 
@@ -690,17 +692,17 @@ ABD void wl_ecmwf(WarmLayer &w, const WlEcmwfCtx &c, double alpha, double Qsw, d
     const double usw2 = usw * usw;
     const bool warming = nonneg(Qabs);
 
-    const double cst1 = VKARMN * GRAV * alpha;
+    const double cst1 = KC(VKARMN * GRAV) * alpha;
     const double L2 = fdiv(cst1 * Qabs, RhoCp_w * usw2 * usw);
     const double cst2 = fdiv(cst1, 5. * H * usw2);
     const double cst0 = fdiv(rdt * (rNuwl0 + 1.), H);
-    const double A = cst0 * Qabs * (1. / (rNuwl0 * RhoCp_w));
-    const double cst3 = -cst0 * VKARMN * usw * FLA_ECMWF;
+    const double A = cst0 * Qabs * KC(1. / (rNuwl0 * RhoCp_w));
+    const double cst3 = -cst0 * KC(VKARMN) * usw * KC(FLA_ECMWF);
 
     // while the layer warms zeta = H L2 does not depend on dT: B is the same in all ten passes
     const double B_warm = warming ? fdiv(cst3, phi_takaya(H * L2)) : 0.;
     double dT_n = dT_b;
-#pragma unroll 1
+#pragma unroll 2
     for (int jc = 0; jc < 10; ++jc) {
         const double prev = dT_n;
         dT_n = 0.5 * (dT_n + dT_b);
@@ -746,7 +748,7 @@ ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p, Diag &dg)
     const double Ub = abm::dmax(0.5, p.wnd);
     const bool stable0 = nonneg(virt_temp(p.theta_zt, p.q_zt) - virt_temp(p.sst, p.ssq));
     double CdN = cd_n10_ncar(Ub);
-    double sqrt_CdN = abm::fast_sqrt(CdN);
+    double sqrt_CdN = abm::fast_sqrt_pos(CdN);
     double Cd = CdN;
     double Ce = abm::dmax(1.e-3 * (34.6 * sqrt_CdN), CX_MIN);
     double Ch = abm::dmax(1.e-3 * sqrt_CdN * (stable0 ? 18. : 32.7), CX_MIN);
@@ -786,10 +788,10 @@ ABD Coeffs solve_ncar(const Uniform &u, const PointIn &p, Diag &dg)
         // z0 = zu EXP(-(k/SQRT(Cd) + psi_m)) only enters as LOG(10/z0) = k/SQRT(Cd) + psi_m - LOG(zu/10)
         Un10 = abm::dmax(0.25, sqrt_Cd * Ub * INV_VKARMN * (VKARMN * r_sqrt_Cd + psi_m - u.log_zu10));
         CdN = cd_n10_ncar(Un10);
-        sqrt_CdN = abm::fast_sqrt(CdN);
+        sqrt_CdN = abm::fast_sqrt_pos(CdN);
         double tmp = 1. + sqrt_CdN * INV_VKARMN * (u.log_zu10 - psi_m);
         Cd = abm::dmax(fdiv(CdN, tmp * tmp), CX_MIN);
-        sqrt_Cd = abm::fast_sqrt(Cd);
+        sqrt_Cd = abm::fast_sqrt_pos(Cd);
         const double r_sqrt_CdN = abm::fast_rcp(sqrt_CdN);
         tmp = (u.log_zu10 - psi_h_u) * INV_VKARMN * r_sqrt_CdN;
         const double tmp2 = sqrt_Cd * r_sqrt_CdN;
@@ -946,7 +948,7 @@ template <bool CS, bool WL, bool ZTEQ>
 ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &dg)
 {
     constexpr bool SKIN = CS || WL;
-    const double charn0 = 0.018, zi0 = 1000., Beta0 = 1., alpha_M = 0.11, alpha_H = 0.40, alpha_Q = 0.62;
+    constexpr double charn0 = 0.018, zi0 = 1000., Beta0 = 1., alpha_M = 0.11, alpha_H = 0.40, alpha_Q = 0.62;
 
     double Ts = p.sst, qs_ = p.ssq;
     double alpha = 0.;
@@ -1010,16 +1012,16 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
 
         Fm = u.log_zu - log_z0 - psi_m_u + psi_m_z0old;
 
-        us = fdiv(Ub * VKARMN, Fm);
+        us = fdiv(Ub * KC(VKARMN), Fm);
         const double us2 = us * us;
         double tmp0 = fdiv(nu_a, us);
-        z0 = abm::dmin(fabs(alpha_M * tmp0 + charn0 * us2 * INV_GRAV), 0.001);
-        z0t = abm::dmin(fabs(alpha_H * tmp0), 0.001);
-        const double z0q = abm::dmin(fabs(alpha_Q * tmp0), 0.001);
+        z0 = abm::dmin(fabs(KC(alpha_M) * tmp0 + KC(charn0) * us2 * KC(INV_GRAV)), KC(0.001));
+        z0t = abm::dmin(fabs(KC(alpha_H) * tmp0), KC(0.001));
+        const double z0q = abm::dmin(fabs(KC(alpha_Q) * tmp0), KC(0.001));
         log_z0 = abm::dlog(z0);
         const double log_t0 = abm::dlog(fabs(tmp0));          // LOG(alpha nu/u*) = LOG(alpha) + LOG(nu/u*)
-        log_z0t = abm::dmin(LOG_0P40 + log_t0, LOG_1EM3);
-        log_z0q = abm::dmin(LOG_0P62 + log_t0, LOG_1EM3);
+        log_z0t = abm::dmin(KC(LOG_0P40) + log_t0, KC(LOG_1EM3));
+        log_z0q = abm::dmin(KC(LOG_0P62) + log_t0, KC(LOG_1EM3));
 
         double psi_m_z0, psi_h_z0t;
         if (stable) {
@@ -1034,10 +1036,10 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
 
         const double cv = abm::fast_cbrt(abm::dmax(-zi0 * r1oL * INV_VKARMN, 0.));
         tmp0 = Beta0 * Beta0 * us2 * (cv * cv);
-        Ub = abm::dmax(abm::fast_sqrt(p.wnd * p.wnd + tmp0), 0.2);
+        Ub = abm::dmax(abm::fast_sqrt(p.wnd * p.wnd + tmp0), KC(0.2));
 
         tmp0 = psi_h_u - psi_h_z0t;
-        double tmp1 = fdiv(VKARMN, u.log_zu - log_z0t - tmp0);
+        double tmp1 = fdiv(KC(VKARMN), u.log_zu - log_z0t - tmp0);
         ts = dt * tmp1;
         if (!ZTEQ) {
             tmp1 = u.log_ztu + tmp0 - psi_h_t + psi_h_z0t;
@@ -1046,7 +1048,7 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
             t_zu = p.theta_zt;
         }
         tmp0 = psi_h_u - psi_h_z0q;
-        tmp1 = fdiv(VKARMN, u.log_zu - log_z0q - tmp0);
+        tmp1 = fdiv(KC(VKARMN), u.log_zu - log_z0q - tmp0);
         qst = dq * tmp1;
         if (!ZTEQ) {
             tmp1 = u.log_ztu + tmp0 - psi_h_t + psi_h_z0q;
@@ -1074,11 +1076,11 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
                     Ts = p.sst + wl.dT;
                     if (CS) Ts = Ts + dT_cs;
                 }
-                qs_ = RDCT_QSAT_SALT * q_sat(abm::dmax(Ts, 200.), p.slp);
+                qs_ = KC(RDCT_QSAT_SALT) * q_sat(abm::dmax(Ts, 200.), p.slp);
             }
         }
-        dt = floor_abs(t_zu - Ts, 1.E-09);
-        dq = floor_abs(q_zu - qs_, 1.E-12);
+        dt = floor_abs(t_zu - Ts, KC(1.E-09));
+        dq = floor_abs(q_zu - qs_, KC(1.E-12));
     }
     Coeffs c;
     const double Fq = u.log_zu - log_z0q - psi_h_u + psi_h_z0q;
@@ -1117,7 +1119,7 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p, Diag &dg)
     for (int jit = 1; jit <= u.nb_iter; ++jit) {
         if (RiB < rRi_max) {
             const double za = UN10 - KC(8.271);
-            u_star = KC(0.239) + KC(0.0433) * (za + abm::fast_sqrt(KC(0.12) * za * za + KC(0.181)));   // :275-293
+            u_star = KC(0.239) + KC(0.0433) * (za + abm::fast_sqrt_pos(KC(0.12) * za * za + KC(0.181)));   // :275-293
         } else {
             u_star = abm::fast_sqrt(CX_MIN) * Ub;
         }

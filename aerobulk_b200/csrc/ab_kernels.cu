@@ -45,15 +45,19 @@ static constexpr int FLUX_BLOCK = AB_FLUX_BLOCK;
 #ifndef AB_SORT_BAND_NOQ
 #define AB_SORT_BAND_NOQ 1.0 // the same when the humidity is rh / dp (the proxy ignores it)
 #endif
-__device__ __forceinline__ double stability_proxy(const FluxArgs &a, int ihum, double skin_off, long long i)
+// The proxy only groups points, so it runs in FP32 (FP32 pipe and MUFU, both idle in this FP64 path): the temperature
+// difference is taken in FP64 first (exact to 1e-13 K), the humidity correction 0.608 (T_a q - T_s q_s) ~ 1 K is good to
+// 1e-6 K in FP32 -- against a band of 0.15 K.  classify_kernel is then bound by its 34 bytes per point.
+__device__ __forceinline__ float stability_proxy(const FluxArgs &a, int ihum, double skin_off, long long i)
 {
     const double sst = __ldg(a.sst + i) + skin_off, ta = __ldg(a.t_zt + i) + RGAMMA_DRY * a.u.zt;
-    if (ihum != 0) return ta - sst;
-    const double q = __ldg(a.hum_zt + i), p = __ldg(a.slp + i);
-    const double tc = sst - 273.15;
-    const double es = 611.2 * abm::dexp(17.67 * tc * abm::fast_rcp(tc + 243.5));     // Magnus
-    const double qs = 0.98 * 0.622 * es * abm::fast_rcp(p - 0.378 * es);
-    return ta * (1. + 0.608 * q) - sst * (1. + 0.608 * qs);
+    const float d0 = (float)(ta - sst);
+    if (ihum != 0) return d0;
+    const float q = (float)__ldg(a.hum_zt + i), p = (float)__ldg(a.slp + i);
+    const float tc = (float)(sst - 273.15);
+    const float es = 611.2f * __expf(17.67f * tc * __frcp_rn(tc + 243.5f));     // Magnus
+    const float qs = 0.98f * 0.622f * es * __frcp_rn(p - 0.378f * es);
+    return d0 + 0.608f * ((float)ta * q - (float)sst * qs);
 }
 
 // ---------------------------------------------------------------------------
@@ -74,61 +78,72 @@ static constexpr int SORT_CLASSES = 3;
 __global__ void __launch_bounds__(SORT_BLOCK) classify_kernel(const FluxArgs a, unsigned short *perm, int skin)
 {
     constexpr int NW = SORT_BLOCK / 32, NG = SORT_ITEMS * NW;
-    __shared__ unsigned short s_c[SORT_CLASSES][NG];
-    abm::load_tables();
+    __shared__ unsigned short s_c[SORT_CLASSES][NG], s_off[SORT_CLASSES][NG];
+    __shared__ int s_tot[SORT_CLASSES];
     const long long base = (long long)blockIdx.x * SORT_WIN;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int ihum = a.init_dev ? __ldg(a.init_dev) : a.ihum;
-    const double band = (ihum != 0) ? AB_SORT_BAND_NOQ : (skin ? AB_SORT_BAND_SKIN : AB_SORT_BAND);
+    const float band = (ihum != 0) ? (float)AB_SORT_BAND_NOQ : (skin ? (float)AB_SORT_BAND_SKIN : (float)AB_SORT_BAND);
     const bool wl = skin && !a.first_step && a.dT_wl != nullptr;
     int cls[SORT_ITEMS];
-    unsigned m[SORT_ITEMS][SORT_CLASSES];
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; ++k) {
         const long long i = base + k * SORT_BLOCK + tid;
         cls[k] = SORT_CLASSES;   // padding beyond n
         if (i < a.n) {
             const double off = skin ? (-0.25 + (wl ? a.dT_wl[i] : 0.)) : 0.;
-            const double d = stability_proxy(a, ihum, off, i);
+            const float d = stability_proxy(a, ihum, off, i);
             cls[k] = (d >= band) ? 0 : (d > -band) ? 1 : 2;
         }
-#pragma unroll
-        for (int c = 0; c < SORT_CLASSES; ++c) {
-            m[k][c] = __ballot_sync(0xffffffffu, cls[k] == c);
-            if (lane == 0) s_c[c][k * NW + w] = (unsigned short)__popc(m[k][c]);
-        }
     }
-    __syncthreads();
-    int tot[SORT_CLASSES];
-#pragma unroll
-    for (int c = 0; c < SORT_CLASSES; ++c) tot[c] = 0;
-    for (int g = 0; g < NG; ++g) {
-#pragma unroll
-        for (int c = 0; c < SORT_CLASSES; ++c) tot[c] += s_c[c][g];
-    }
+    // (the votes in a loop of their own: all 8 x 4 loads of a thread are in flight together)
+    // group (k, w) = the 32 items warp w holds in round k, in item order g = k NW + w; per group and class: the count
+    // (shared), and per thread its rank among the lanes of its class (`rank`) and among all real points (`real_rank`)
     const unsigned lt = (1u << lane) - 1u;
-    int off[SORT_CLASSES];
-#pragma unroll
-    for (int c = 0; c < SORT_CLASSES; ++c) off[c] = 0;
-    int g = 0;
+    int rank[SORT_ITEMS], real_rank[SORT_ITEMS];
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; ++k) {
-        // counts of the groups (k', w') that precede (k, w)
-        for (; g < k * NW + w; ++g) {
-#pragma unroll
-            for (int c = 0; c < SORT_CLASSES; ++c) off[c] += s_c[c][g];
-        }
-        const int item = k * SORT_BLOCK + tid;
-        int slot = 0, before = 0, all_off = 0;
         unsigned any = 0u;
+        rank[k] = 0;
 #pragma unroll
         for (int c = 0; c < SORT_CLASSES; ++c) {
-            if (cls[k] == c) slot = before + off[c] + __popc(m[k][c] & lt);
-            before += tot[c];
-            all_off += off[c];
-            any |= m[k][c];
+            const unsigned b = __ballot_sync(0xffffffffu, cls[k] == c);
+            if (lane == 0) s_c[c][k * NW + w] = (unsigned short)__popc(b);
+            if (cls[k] == c) rank[k] = __popc(b & lt);
+            any |= b;
         }
-        if (cls[k] == SORT_CLASSES) slot = before + (item - (all_off + __popc(any & lt)));
+        real_rank[k] = __popc(any & lt);
+    }
+    __syncthreads();
+    // exclusive prefix of the counts over the NG = 64 groups, one warp per class (two groups per lane)
+    static_assert(NG == 64 && SORT_CLASSES * 32 <= SORT_BLOCK, "prefix layout");
+    if (w < SORT_CLASSES) {
+        const int a0 = s_c[w][2 * lane], a1 = s_c[w][2 * lane + 1];
+        int incl = a0 + a1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int excl = incl - (a0 + a1);
+        s_off[w][2 * lane] = (unsigned short)excl;
+        s_off[w][2 * lane + 1] = (unsigned short)(excl + a0);
+        if (lane == 31) s_tot[w] = incl;
+    }
+    __syncthreads();
+    const int tot0 = s_tot[0], tot1 = s_tot[1], tot2 = s_tot[2];
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        const int g = k * NW + w, item = k * SORT_BLOCK + tid;
+        int slot;
+        if (cls[k] < SORT_CLASSES) {
+            const int before = (cls[k] > 0 ? tot0 : 0) + (cls[k] > 1 ? tot1 : 0);
+            slot = before + s_off[cls[k]][g] + rank[k];
+        } else {
+            // padding: after all real points, in item order (item - number of real items before it)
+            const int real_before = s_off[0][g] + s_off[1][g] + s_off[2][g] + real_rank[k];
+            slot = tot0 + tot1 + tot2 + (item - real_before);
+        }
         perm[base + slot] = (unsigned short)item;
     }
 }
@@ -428,8 +443,124 @@ __host__ __device__ inline int stat_op(int k)   // 0 sum, 1 min, 2 max
     return (r == 0) ? 0 : (r == 1 || r == 3) ? 1 : 2;
 }
 
-__global__ void __launch_bounds__(STATS_BLOCK) stats_kernel(const StatsArgs a)
+// Slot of a block's partials row that tells stats_fix_kernel to redo the block (rows have NSTATS = 64 slots, 47 used).
+static constexpr int STATS_REDO_SLOT = NSTATS - 1;
+
+// stats_fast_kernel: the pass every jt == 1 call pays.  Where no point of a block is masked -- the normal case: the mask
+// only removes values outside the sanity ranges of mod_const.f90:138-146 -- the masked statistics ARE the raw ones, so the
+// fast pass keeps sum / min / max per field (27 accumulators instead of 47, no per-point mask tests) and derives "was any
+// point of this block masked?" from the block's own raw minima and maxima at the end.  A block that may hold a masked
+// point raises its redo flag and stats_fix_kernel recomputes that block's row with the full accumulator set (same points,
+// same order: the row is bit-identical to what the one-kernel version produced).  NaNs: `x < lo || x > hi` is false for a
+// NaN (the reference does not mask it) and the (v < acc ? v : acc) min / max skip it -- the derived test agrees.
+// rad_lw is held against both radiation ranges (the reference's prsw=rad_lw slip): fields 7 and 8 are the same values.
+template <int UNROLL>
+__device__ __forceinline__ void stats_fast_body(const StatsArgs &a, double (&sum)[8], double (&mn)[8], double (&mx)[8], double &cnt)
 {
+    const bool rad = (a.rad_lw != nullptr);
+    const long long stride = (long long)gridDim.x * STATS_BLOCK;
+    // UNROLL points per trip with all their loads issued first; a thread meets its points (base + k stride) in the same
+    // order as in stats_fix_kernel whatever the unroll factor: the sums add up identically
+    for (long long i0 = (long long)blockIdx.x * STATS_BLOCK + threadIdx.x; i0 < a.n; i0 += stride * UNROLL) {
+        double in[UNROLL][7];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long i = i0 + u * stride;
+            const long long j = (i < a.n) ? i : i0;
+            in[u][0] = __ldg(a.sst + j);
+            in[u][1] = __ldg(a.t_zt + j);
+            in[u][2] = __ldg(a.slp + j);
+            in[u][3] = __ldg(a.U_zu + j);
+            in[u][4] = __ldg(a.V_zu + j);
+            in[u][5] = __ldg(a.hum_zt + j);
+            in[u][6] = rad ? __ldg(a.rad_lw + j) : 0.;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (i0 + u * stride >= a.n) break;
+            double v[8];
+            v[0] = in[u][0];
+            v[1] = in[u][1];
+            v[2] = in[u][2];
+            v[3] = in[u][3];
+            v[4] = in[u][4];
+            v[5] = sqrt(__dadd_rn(__dmul_rn(v[3], v[3]), __dmul_rn(v[4], v[4])));
+            v[6] = in[u][5];
+            v[7] = in[u][6];
+            cnt += 1.;
+#pragma unroll
+            for (int f = 0; f < 8; ++f) {
+                sum[f] += v[f];
+                mn[f] = abm::dmin(v[f], mn[f]);
+                mx[f] = abm::dmax(v[f], mx[f]);
+            }
+        }
+    }
+}
+
+#ifndef AB_STATS_UNROLL
+#define AB_STATS_UNROLL 3   // 120 registers, no spills, 2 blocks/SM x 21 loads in flight per thread
+#endif
+__global__ void __launch_bounds__(STATS_BLOCK, 2) stats_fast_kernel(const StatsArgs a)
+{
+    double sum[8], mn[8], mx[8], cnt = 0.;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        sum[f] = 0.;
+        mn[f] = DBL_MAX;
+        mx[f] = -DBL_MAX;
+    }
+    stats_fast_body<AB_STATS_UNROLL>(a, sum, mn, mx, cnt);   // a thread meets its points in the same order for any unroll
+    // block reduction in the order of the one-kernel version: lanes by shuffle, then the warps in index order
+    __shared__ double sm[STATS_BLOCK / 32][1 + 3 * 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        const double r = warp_reduce(cnt, 0);
+        if (lane == 0) sm[warp][0] = r;
+    }
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        const double s = warp_reduce(sum[f], 0), lo = warp_reduce(mn[f], 1), hi = warp_reduce(mx[f], 2);
+        if (lane == 0) {
+            sm[warp][1 + 3 * f + 0] = s;
+            sm[warp][1 + 3 * f + 1] = lo;
+            sm[warp][1 + 3 * f + 2] = hi;
+        }
+    }
+    __syncthreads();
+    double *row = a.partials + (long long)blockIdx.x * NSTATS;
+    if (threadIdx.x < 1 + 3 * 8) {
+        const int k = threadIdx.x, op = (k == 0) ? 0 : (k - 1) % 3;
+        double r = sm[0][k];
+        for (int w = 1; w < STATS_BLOCK / 32; ++w)
+            r = (op == 0) ? r + sm[w][k] : (op == 1) ? fmin(r, sm[w][k]) : fmax(r, sm[w][k]);
+        sm[0][k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double *b = sm[0];
+        const bool rad = (a.rad_lw != nullptr);
+        // min / max of field f: b[2 + 3 f], b[3 + 3 f]; field order sst t_zt slp U V wnd hum rad_lw
+        bool masked = b[2] < 270. || b[3] > 320. || b[5] < 180. || b[6] > 330. || b[8] < 80000. || b[9] > 110000. || b[18] > 50.;
+        if (rad) masked = masked || b[23] < 0. || b[24] > 750.;
+        row[STATS_REDO_SLOT] = masked ? 1. : 0.;
+        row[0] = b[0];
+        row[1] = b[0];
+        for (int f = 0; f < NFIELDS; ++f) {
+            const int g = (f < 8) ? f : 7;   // field 8 = rad_lw again (checked against the short-wave range)
+            row[2 + 5 * f + 0] = b[1 + 3 * g];
+            row[2 + 5 * f + 1] = b[2 + 3 * g];
+            row[2 + 5 * f + 2] = b[3 + 3 * g];
+            row[2 + 5 * f + 3] = b[2 + 3 * g];
+            row[2 + 5 * f + 4] = b[3 + 3 * g];
+        }
+    }
+}
+
+// the full accumulator set (masked and raw statistics side by side), for the blocks stats_fast_kernel flagged
+__global__ void __launch_bounds__(STATS_BLOCK) stats_fix_kernel(const StatsArgs a)
+{
+    if (a.partials[(long long)blockIdx.x * NSTATS + STATS_REDO_SLOT] == 0.) return;
     double acc[2 + 5 * NFIELDS];
     acc[0] = 0.;
     acc[1] = 0.;
@@ -537,8 +668,11 @@ int stats_max_blocks() { return STATS_MAX_BLOCKS; }
 
 cudaError_t launch_stats(const StatsArgs &a, int nblocks, cudaStream_t s)
 {
-    stats_kernel<<<nblocks, STATS_BLOCK, 0, s>>>(a);
+    stats_fast_kernel<<<nblocks, STATS_BLOCK, 0, s>>>(a);
     cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    stats_fix_kernel<<<nblocks, STATS_BLOCK, 0, s>>>(a);   // returns at once in every block that holds no masked point
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     stats_final<<<NSTATS, FINAL_BLOCK, 0, s>>>(a.partials, nblocks, a.out);
     return cudaGetLastError();

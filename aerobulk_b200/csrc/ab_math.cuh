@@ -129,6 +129,8 @@ ABM_FN double fast_sqrt(double x)
     const double r = fast_rsqrt(x);
     return (hi_word(x) >= 0x03d00000) ? x * r : 0.;   // x >= 2^-962
 }
+// the same for callers whose argument is provably positive and normal (no zero guard: 1 compare and 2 selects less)
+ABM_FN double fast_sqrt_pos(double x) { return x * fast_rsqrt(x); }
 ABM_FN double fast_rcbrt(double x)              // x**(-1/3), x in the normal FP32 range
 {
     const double y = pow_seed(x, -1.0f / 3.0f);
@@ -146,6 +148,7 @@ ABM_FN double fast_r4rt(double x)               // x**(-1/4), x in the normal FP
 // the callers add it to 1 (delta_skin_layer) or to a squared wind speed (gustiness)
 // (the guards compare the high word: x > 2^-100 without an FP64 compare or a 64-bit literal)
 ABM_FN double pow075(double x) { return (hi_word(x) >= 0x39b00000) ? x * fast_r4rt(x) : 0.; }
+ABM_FN double pow075_pos(double x) { return x * fast_r4rt(x); }   // x inside the normal FP32 range (caller's guarantee)
 ABM_FN double fast_cbrt(double x)
 {
     if (hi_word(x) < 0x39b00000) return 0.;
@@ -328,6 +331,16 @@ ABM_FN double dlog(double x) { return dlog_table(x); }
 
 ABM_FN double dlog10(double x) { return dlog(x) * MATH_K[K_LOG10E]; }
 
+// atan(t) for |t| <= tan(pi/8) (Estrin)
+ABM_FN double atan_core(double t)
+{
+    const double z = t * t;
+    const double z2 = z * z, z4 = z2 * z2;
+    const double a0 = fma(ATAN_C[1], z, ATAN_C[0]), a1 = fma(ATAN_C[3], z, ATAN_C[2]), a2 = fma(ATAN_C[5], z, ATAN_C[4]);
+    const double a3 = fma(ATAN_C[7], z, ATAN_C[6]), a4 = fma(ATAN_C[9], z, ATAN_C[8]);
+    const double q = fma(fma(ATAN_C[10], z2, a4), z4 * z4, fma(fma(a3, z2, a2), z4, fma(a1, z2, a0)));
+    return fma(t * z, q, t);
+}
 // atan: |x| <= tan(pi/8): poly; <= tan(3pi/8): pi/4 + atan((x-1)/(x+1)); else pi/2 - atan(1/x)
 ABM_BIG double datan(double x)
 {
@@ -338,17 +351,23 @@ ABM_BIG double datan(double x)
     } else if (ax > MATH_K[K_TANPIO8]) {
         num = ax - 1.0; den = ax + 1.0; bhi = MATH_K[K_PIO4_HI]; blo = MATH_K[K_PIO4_LO];
     }
-    const double t = num * fast_rcp(den);
-    const double z = t * t;
-    const double z2 = z * z, z4 = z2 * z2;
-    const double a0 = fma(ATAN_C[1], z, ATAN_C[0]), a1 = fma(ATAN_C[3], z, ATAN_C[2]), a2 = fma(ATAN_C[5], z, ATAN_C[4]);
-    const double a3 = fma(ATAN_C[7], z, ATAN_C[6]), a4 = fma(ATAN_C[9], z, ATAN_C[8]);
-    const double q = fma(fma(ATAN_C[10], z2, a4), z4 * z4, fma(fma(a3, z2, a2), z4, fma(a1, z2, a0)));
-    const double a = fma(t * z, q, t);          // atan(t)
+    const double a = atan_core(num * fast_rcp(den));
     return copysign(bhi + (a + blo), x);
+}
+// atan(x) for x >= 1 -- every atan of the stability functions: its argument is a root of (1 - g zeta) >= 1 or
+// (1 + 2 phi) / sqrt(3) with phi >= 1.  With c = tan(3 pi/8), atan(x) = atan(c) + atan((x - c) / (1 + c x)) and the
+// inner argument stays inside [-tan(pi/8), tan(pi/8)] for ALL x in [1, inf): the polynomial's range, one formula, no
+// range selection (the three-way selection of datan cost 2 compares and ~10 predicated moves per call: 18 % of the
+// register moves the COARE + skin kernel executed) and no sign handling.
+ABM_BIG double datan_ge1(double x)
+{
+    const double c = MATH_K[K_TAN3PIO8];
+    const double a = atan_core((x - c) * fast_rcp(fma(c, x, 1.0)));
+    return MATH_K[K_ATANC_HI] + (a + MATH_K[K_ATANC_LO]);
 }
 
 // x**y, x >= 0
-ABM_FN double dpowr(double x, double y) { return (x > 0.) ? dexp(y * dlog(x)) : 0.; }
+// (|y log x| <= 0.8 * 745 for the exponents of this path, all below 0.8 in magnitude: the bounded exp)
+ABM_FN double dpowr(double x, double y) { return (x > 0.) ? dexp_b(y * dlog(x)) : 0.; }
 
 }  // namespace abm

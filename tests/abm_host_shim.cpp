@@ -22,6 +22,9 @@ void abm_eval(int fn, const double *x, const double *y, double *out, long n)
         case 13: out[i] = abm::pow075(x[i]); break;
         case 14: out[i] = abm::fast_cbrt(x[i]); break;
         case 15: out[i] = abm::fast_sqrt(x[i]); break;
+        case 16: out[i] = abm::datan_ge1(x[i]); break;
+        case 17: out[i] = abm::fast_sqrt_pos(x[i]); break;
+        case 18: out[i] = abm::pow075_pos(x[i]); break;
         }
     }
 }

@@ -295,6 +295,54 @@ def test_sharded_init_on_device(ab):
     ab.reset()
 
 
+@pytest.mark.parametrize("rad", [True, False])
+def test_stats_vector_with_masked_points_matches_numpy(ab, rad):
+    """The AEROBULK_INIT statistics pass (stats_fast_kernel + stats_fix_kernel + stats_final): blocks without a masked
+    point take the 27-accumulator fast path, blocks with one are redone with the full set -- the 64-double vector must be
+    what numpy computes from the mask of src/mod_aerobulk.f90:104-124 (counts and extrema exactly, sums to rounding),
+    whichever blocks the masked points fall in."""
+    import torch
+    from aerobulk_b200 import model as abm
+    Ni, Nj = 700, 301                                   # 210 700 points: 824 blocks, the last one ragged
+    f = synth.fields(Ni, Nj)
+    rng = np.random.default_rng(5)
+    flat = {k: np.ravel(v, order="F").copy() for k, v in f.items()}
+    n = Ni * Nj
+    hit = rng.choice(n, size=12, replace=False)
+    flat["sst"][hit[0:3]] -= 273.15                     # deg C
+    flat["t_zt"][hit[3]] = 400.0
+    flat["slp"][hit[4:6]] /= 100.0                      # hPa
+    flat["U_zu"][hit[6]], flat["V_zu"][hit[6]] = 40.0, 40.0   # |U| = 56.6 > 50
+    flat["rad_lw"][hit[7]] = 900.0                      # inside the long-wave range, outside the short-wave one (prsw=rad_lw)
+    flat["rad_lw"][hit[8]] = -1.0
+    flat["sst"][n - 1] = 100.0                          # the ragged last block
+    dev = {k: torch.from_numpy(v).cuda() for k, v in flat.items()}
+    got = abm.init_local_stats(*[dev[k] for k in IN_KEYS], rad_lw=dev["rad_lw"] if rad else None)
+    wnd = np.sqrt(flat["U_zu"] * flat["U_zu"] + flat["V_zu"] * flat["V_zu"])
+    lw = flat["rad_lw"] if rad else np.zeros(n)
+    m = (flat["sst"] >= 270.) & (flat["sst"] <= 320.) & (flat["t_zt"] >= 180.) & (flat["t_zt"] <= 330.) \
+        & (flat["slp"] >= 80000.) & (flat["slp"] <= 110000.) & (wnd <= 50.)
+    if rad:
+        m &= (lw >= 0.) & (lw <= 750.)
+    assert got[0] == m.sum() and got[1] == n and m.sum() == n - (10 if rad else 8)
+    fields = [flat["sst"], flat["t_zt"], flat["slp"], flat["U_zu"], flat["V_zu"], wnd, flat["hum_zt"], lw, lw]
+    for k, v in enumerate(fields):
+        b = 2 + 5 * k
+        assert got[b] == pytest.approx(v[m].sum(), rel=1e-12, abs=1e-9), k
+        assert got[b + 1] == v[m].min() and got[b + 2] == v[m].max(), k
+        assert got[b + 3] == v.min() and got[b + 4] == v.max(), k
+    # no masked point at all: the same numbers from the fast path alone
+    clean = {k: torch.from_numpy(np.ravel(v, order="F").copy()).cuda() for k, v in f.items()}
+    got = abm.init_local_stats(*[clean[k] for k in IN_KEYS], rad_lw=clean["rad_lw"] if rad else None)
+    assert got[0] == n and got[1] == n
+    for k, key in enumerate(("sst", "t_zt", "slp", "U_zu", "V_zu")):
+        v = np.ravel(f[key], order="F")
+        b = 2 + 5 * k
+        assert got[b] == pytest.approx(v.sum(), rel=1e-12)
+        assert got[b + 1] == got[b + 3] == v.min() and got[b + 2] == got[b + 4] == v.max()
+    ab.reset()
+
+
 def test_deferred_wind_stress_error_on_device_api(ab):
     """Device-resident calls are asynchronous for jt>1: tau > 10 N/m2 surfaces at synchronize()."""
     import torch
@@ -415,10 +463,11 @@ def test_pinned_arrays_take_the_zero_copy_path_and_agree(ab):
     for jt in range(Nt):
         for k in names:
             assert np.array_equal(a[jt][k], b[jt][k]), (jt, k)
-    # jt == 1 is staged either way (AEROBULK_INIT needs the statistics): two statistics kernels, classify, flux.
+    # jt == 1 is staged either way (AEROBULK_INIT needs the statistics): three statistics kernels (fast pass, fix-up of
+    # the blocks with masked points, final reduction), classify, flux.
     # Afterwards no classify: pinned arrays are used in place (ONE flux launch), pageable ones of this size go through
     # the library's pinned slab in row-block chunks (one flux launch per chunk; one chunk here)
-    assert la[1:] == [1] * (Nt - 1) and lb[1:] == [1] * (Nt - 1) and la[0] == lb[0] == 4
+    assert la[1:] == [1] * (Nt - 1) and lb[1:] == [1] * (Nt - 1) and la[0] == lb[0] == 5
     ab.reset()
 
 

@@ -86,6 +86,24 @@ def test_atan(abm):
     assert np.signbit(abm(4, np.array([-0.0]))[0])
 
 
+def test_atan_of_arguments_from_one_up(abm):
+    """datan_ge1: the one-range atan the stability functions use (their arguments are >= 1): atan(c) + atan((x-c)/(1+cx))
+    with c = tan(3 pi/8) keeps the inner argument inside the polynomial's range for every x in [1, inf)."""
+    x = np.concatenate([RNG.uniform(1.0, 6.0, N), 1.0 + np.exp(RNG.uniform(-36, 3, N)), np.exp(RNG.uniform(0, 40, N)),
+                        [1.0, np.nextafter(1.0, 2.0), 2.414213562373095, 2.4142135623730954, 1.7320508, 1e30]])
+    assert _relerr(abm(16, x), x, mp.atan) <= 3 * ULP
+    # and it agrees with the general-purpose version to rounding
+    assert np.abs(abm(16, x) - abm(4, x)).max() <= 4 * ULP
+
+
+def test_guard_free_roots(abm):
+    x = np.concatenate([np.exp(RNG.uniform(-60, 60, N)), RNG.uniform(1.0, 30.0, N), [1.0, 1e-30, 1e30]])
+    mp.mp.dps = 50
+    assert _relerr(abm(17, x), x, mp.sqrt) <= 2 * ULP
+    assert _relerr(abm(18, x), x, lambda v: v ** mp.mpf(0.75)) <= 3 * ULP
+    assert (abm(17, x) == abm(15, x)).all() and (abm(18, x) == abm(13, x)).all()    # the guarded versions, bit for bit
+
+
 def test_powr_and_rcp(abm):
     x = np.exp(RNG.uniform(-12, 12, N))
     y = RNG.choice([0.25, 0.3333, 0.5, 0.6, 0.72, 0.75, 0.79, 1.5, -0.599, -3.935, 0.929, 2.0 / 3.0, 0.0], N)
