@@ -26,6 +26,10 @@
 
 namespace abd {
 
+#ifndef AB_CS_UNROLL
+#define AB_CS_UNROLL 1   // cool-skin passes rolled: the delta code exists once (instruction-cache footprint)
+#endif
+constexpr int CS_UNROLL = AB_CS_UNROLL;
 #define ABD __device__ __forceinline__
 // heavy helpers can be kept out of line (one shared body instead of 2-5 inlined copies) to shrink the
 // instruction footprint: -DAB_NOINLINE=1
@@ -544,7 +548,7 @@ ABD double cool_skin_dT(double alpha, double Qsw, double Qnsol, double us, doubl
     // delta(Qnsol), then 4 x { solar absorption fr(delta) -> Qabs -> delta(Qabs) }: one rolled loop so that
     // the delta code exists once (instruction-cache footprint)
     double Qabs = Qnsol, d = 0.;
-#pragma unroll 1
+#pragma unroll CS_UNROLL
     for (int jc = 0; jc < 5; ++jc) {
         const double d_prev = d;
         if (jc > 0) {

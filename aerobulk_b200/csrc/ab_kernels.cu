@@ -23,8 +23,16 @@ using namespace abd;
 #ifndef AB_FLUX_BLOCK
 #define AB_FLUX_BLOCK 256
 #endif
+// Resident blocks per SM (x 256 threads).  Skin kernels: 3 (24 warps/SM, <= 85 registers: the ~28 doubles they carry across
+// the bulk iteration do not fit 64 registers without spilling into the loop).  Kernels without skin: 4 (32 warps/SM, 64
+// registers; their few spills sit outside the loop).  Measured at 4320x2160 (profiles/exp_variants_r02i.txt, 256x3 ->
+// 256x4): NCAR 0.900 -> 0.877 ms, ANDREAS 1.372 -> 1.322, COARE 3.6 1.900 -> 1.842; COARE 3.6 + skin 3.147 -> 3.204 (night),
+// ECMWF + skin 4.126 -> 4.226.  128 x 7 (73 registers) loses everywhere but ANDREAS.
 #ifndef AB_MIN_BLOCKS
-#define AB_MIN_BLOCKS 3   // 256 x 3 = 24 warps/SM, <= 85 registers: measured best (tools/build_variants.py, round 1)
+#define AB_MIN_BLOCKS 3
+#endif
+#ifndef AB_MIN_BLOCKS_NOSKIN
+#define AB_MIN_BLOCKS_NOSKIN 4
 #endif
 static constexpr int FLUX_BLOCK = AB_FLUX_BLOCK;
 
@@ -149,7 +157,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) classify_kernel(const FluxArgs a, 
 }
 
 template <int ALGO, bool SKIN, bool ZTEQ>
-__global__ void __launch_bounds__(FLUX_BLOCK, AB_MIN_BLOCKS) flux_kernel(const FluxArgs a)
+__global__ void __launch_bounds__(FLUX_BLOCK, SKIN ? AB_MIN_BLOCKS : AB_MIN_BLOCKS_NOSKIN) flux_kernel(const FluxArgs a)
 {
     abm::load_tables();
     long long i = (long long)blockIdx.x * FLUX_BLOCK + threadIdx.x;

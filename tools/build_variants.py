@@ -8,8 +8,12 @@ VARIANTS = {
     "b128x7": ["AB_FLUX_BLOCK=128", "AB_MIN_BLOCKS=7"],
     "b128x8": ["AB_FLUX_BLOCK=128", "AB_MIN_BLOCKS=8"],
     "b256x4": ["AB_FLUX_BLOCK=256", "AB_MIN_BLOCKS=4"],
+    "ns3": ["AB_MIN_BLOCKS_NOSKIN=3"],
+    "ns5": ["AB_MIN_BLOCKS_NOSKIN=5"],
     "b256x2": ["AB_FLUX_BLOCK=256", "AB_MIN_BLOCKS=2"],
     "b128x5": ["AB_FLUX_BLOCK=128", "AB_MIN_BLOCKS=5"],
+    "cs2": ["AB_CS_UNROLL=2"],
+    "cs5": ["AB_CS_UNROLL=5"],
     "band0": ["AB_SORT_BAND=0.0", "AB_SORT_BAND_SKIN=0.0", "AB_SORT_BAND_NOQ=0.0"],
     "sband075": ["AB_SORT_BAND_SKIN=0.75"],
     "sband1": ["AB_SORT_BAND_SKIN=1.0"],
