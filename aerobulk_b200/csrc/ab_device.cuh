@@ -402,25 +402,29 @@ ABD double psi_h_ecmwf_unstable(double zeta)
 }
 
 // Andreas et al. 2015 (Paulson unstable / Grachev 2007 stable), src/mod_blk_andreas.f90:307-410
+// the two terms of the stable functions that do not depend on zeta, as glibc evaluates them (the reference computes them
+// at run time): ATAN((2 - b)/(SQRT(3) b)) and LOG(ABS((c - SQRT(5))/(c + SQRT(5)))), :353 / :384
+constexpr double ATAN_A_STABLE = 0x1.b53ea749504d7p-1;
+constexpr double LOG_A_STABLE = -0x1.ecc2caec5160ap+0;
 ABD double psi_m_andreas_stable(double zeta)
 {
     const double z = abm::dmin(zeta, 15.);
-    const double zam = 5.;
+    constexpr double zam = 5.;
     const double x = abm::fast_cbrt(fabs(1. + z));
-    return -(3. * zam / ZBM_A * (x - 1.))
-           + zam * ZBBM_A / (2. * ZBM_A)
-                 * (2. * abm::dlog(fabs((x + ZBBM_A) * (1. / (1. + ZBBM_A))))
-                    - abm::dlog(fabs((x * x - x * ZBBM_A + ZBBM_A * ZBBM_A) * (1. / (1. - ZBBM_A + ZBBM_A * ZBBM_A))))
-                    + 2. * SR3 * (abm::datan_ge1((2. * x - ZBBM_A) * (1. / (SR3 * ZBBM_A))) - abm::datan_ge1((2. - ZBBM_A) / (SR3 * ZBBM_A))));
+    return -(KC(3. * zam / ZBM_A) * (x - 1.))
+           + KC(zam * ZBBM_A / (2. * ZBM_A))
+                 * (2. * abm::dlog(fabs((x + KC(ZBBM_A)) * KC(1. / (1. + ZBBM_A))))
+                    - abm::dlog(fabs((x * x - x * KC(ZBBM_A) + KC(ZBBM_A * ZBBM_A)) * KC(1. / (1. - ZBBM_A + ZBBM_A * ZBBM_A))))
+                    + KC(2. * SR3) * (abm::datan_ge1((2. * x - KC(ZBBM_A)) * KC(1. / (SR3 * ZBBM_A))) - KC(ATAN_A_STABLE)));
 }
 ABD double psi_h_andreas_stable(double zeta)
 {
     const double z = abm::dmin(zeta, 15.);
-    const double zah = 5., zbh = 5., zch = 3.;
+    constexpr double zah = 5., zbh = 5., zch = 3.;
     const double zz = 2. * z + zch;
-    return -(0.5 * zbh * abm::dlog(fabs(1. + zch * z + z * z)))
-           + (-zah / SR5 + 0.5 * zbh * zch / SR5)
-                 * (abm::dlog(fabs(fdiv(zz - SR5, zz + SR5))) - abm::dlog(fabs((zch - SR5) / (zch + SR5))));
+    return -(KC(0.5 * zbh) * abm::dlog(fabs(1. + zch * z + z * z)))
+           + KC(-zah / SR5 + 0.5 * zbh * zch / SR5)
+                 * (abm::dlog(fabs(fdiv(zz - KC(SR5), zz + KC(SR5)))) - KC(LOG_A_STABLE));
 }
 ABD PsiMH psi_mh_andreas_unstable(double zeta)
 {
@@ -1125,7 +1129,7 @@ ABD Coeffs solve_andreas(const Uniform &u, const PointIn &p, Diag &dg)
             const double za = UN10 - KC(8.271);
             u_star = KC(0.239) + KC(0.0433) * (za + abm::fast_sqrt_pos(KC(0.12) * za * za + KC(0.181)));   // :275-293
         } else {
-            u_star = abm::fast_sqrt(CX_MIN) * Ub;
+            u_star = KC(0x1.47ae147ae147bp-7) * Ub;   // SQRT(Cx_min) = 0.01
         }
         zeta_u = u.zu * one_on_L(t_zu, q_zu, u_star, t_star, q_star);
         const double r = u_star * r_Ub;
