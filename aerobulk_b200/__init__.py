@@ -9,7 +9,7 @@ library raises, and every compute call fails without a CUDA device.
 """
 from .model import (AerobulkError, aerobulk_model, aerobulk_model_device, get_state, set_state, humidity_type,
                     last_error, launch_count, lib, measure_fp64_peak, nb_iter, reset, set_gdept, set_nb_iter,
-                    set_rdt, set_stream, set_verbose, synchronize, use_skin, work_per_point, bytes_per_point,
+                    set_rdt, set_stream, set_verbose, synchronize, use_skin, work_per_point, bytes_per_point, kernel_info,
                     set_nitend, turb, series, series_csv, series_device, SERIES_OUT, turb_ice, oce_ice,
                     set_ice_form_drag_per_point, ICE_ALGORITHMS, OCE_ICE_OUT, set_sort, flux_diagnostics,
                     diag_reduce_ops, diagnostics_summary, host_register, host_unregister, series_ice, SERIES_ICE_OUT, probe, set_devices, get_devices, shard_plan, init_local_stats_device,
@@ -19,7 +19,7 @@ from .model import (AerobulkError, aerobulk_model, aerobulk_model_device, get_st
 ALGORITHMS = ("coare3p0", "coare3p6", "ncar", "ecmwf", "andreas")
 __all__ = ["ALGORITHMS", "AerobulkError", "aerobulk_model", "aerobulk_model_device", "get_state", "set_state", "humidity_type",
            "last_error", "launch_count", "lib", "measure_fp64_peak", "nb_iter", "reset", "set_gdept", "set_nb_iter",
-           "set_rdt", "set_stream", "set_verbose", "synchronize", "use_skin", "work_per_point", "bytes_per_point",
+           "set_rdt", "set_stream", "set_verbose", "synchronize", "use_skin", "work_per_point", "bytes_per_point", "kernel_info",
            "set_nitend", "turb", "series", "series_csv", "series_device", "SERIES_OUT", "turb_ice", "oce_ice",
            "set_ice_form_drag_per_point", "ICE_ALGORITHMS", "OCE_ICE_OUT", "set_sort", "flux_diagnostics",
            "diag_reduce_ops", "diagnostics_summary", "host_register", "host_unregister", "series_ice", "SERIES_ICE_OUT", "probe", "set_devices", "get_devices", "shard_plan", "init_local_stats_device",

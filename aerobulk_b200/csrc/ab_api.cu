@@ -2959,6 +2959,25 @@ double aerobulk_gpu_bytes_per_point(const char *calgo, int skin)
     return a == abd::ECMWF ? 128. : 176.;
 }
 
+int aerobulk_gpu_kernel_info(const char *calgo, int skin, int zt_eq_zu, int *registers, int *local_bytes, int *blocks_per_sm)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.errcode = 0;
+    g.errmsg[0] = 0;
+    const int a = calgo ? algo_id(calgo) : 0;
+    if (!a) return fail(AEROBULK_GPU_ERR_ALGO, "aerobulk_gpu_kernel_info: bulk algorithm %s is unknown!!!", calgo ? calgo : "(null)");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const bool sk = skin && (a == abd::COARE3P0 || a == abd::COARE3P6 || a == abd::ECMWF);
+    cudaFuncAttributes at;
+    int blocks = 0;
+    CUDA_TRY(abk::flux_kernel_attributes(a, sk, zt_eq_zu != 0, &at, &blocks));
+    if (registers) *registers = at.numRegs;
+    if (local_bytes) *local_bytes = (int)at.localSizeBytes;
+    if (blocks_per_sm) *blocks_per_sm = blocks;
+    return 0;
+}
+
 const char *aerobulk_gpu_version(void) { return "aerobulk-b200 0.2 (sm_100a, FP64)"; }
 
 int aerobulk_gpu_probe(int func, long long n, int nargs, const double *args, double *out)

@@ -332,8 +332,11 @@ ABD PsiMH psi_mh_coare_unstable(double z)
     const double phi_m = abm::fast_sqrt_pos(phi_h);                                            // **.25
     double f = z * z;
     f = fdiv(f, 1. + f);
-    const double km = 2. * abm::dlog((1. + phi_m) * 0.5) + abm::dlog((1. + phi_m * phi_m) * 0.5) - 2. * abm::datan_ge1(phi_m) + 0.5 * RPI;
-    const double kh = 2. * abm::dlog((1. + phi_h) * 0.5);
+    // LOG((1 + phi_m**2)/2) of psi_m is LOG((1 + phi_h)/2) of psi_h up to the rounding of phi_m**2 (phi_m = SQRT(phi_h)):
+    // one logarithm serves both (the argument differs by <= 1 ulp: 1e-16 in the logarithm)
+    const double lh = abm::dlog((1. + phi_h) * 0.5);
+    const double km = 2. * abm::dlog((1. + phi_m) * 0.5) + lh - 2. * abm::datan_ge1(phi_m) + KC(0.5 * RPI);
+    const double kh = 2. * lh;
     const double cm = psi_coare_convective(powr(fabs(1. - KC(10.15) * z), KC(.3333)));
     const double ch = psi_coare_convective(powr(fabs(1. - KC(34.15) * z), KC(.3333)));
     PsiMH r;
@@ -432,8 +435,9 @@ ABD PsiMH psi_mh_andreas_unstable(double zeta)
     const double x2 = abm::dmax(abm::fast_sqrt_pos(fabs(1. - 16. * z)), 1.);
     const double x = abm::fast_sqrt_pos(x2);
     PsiMH r;
-    r.m = 2. * abm::dlog(fabs((1. + x) * 0.5)) + abm::dlog(fabs((1. + x2) * 0.5)) - 2. * abm::datan_ge1(x) + RPI * 0.5;
-    r.h = 2. * abm::dlog(0.5 * (1. + x2));
+    const double l2 = abm::dlog(0.5 * (1. + x2));   // x, x2 >= 1: the ABS of the reference is the identity
+    r.m = 2. * abm::dlog((1. + x) * 0.5) + l2 - 2. * abm::datan_ge1(x) + KC(RPI * 0.5);
+    r.h = 2. * l2;
     return r;
 }
 ABD double psi_h_andreas_unstable(double zeta)

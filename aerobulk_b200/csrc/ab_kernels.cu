@@ -281,7 +281,7 @@ cudaError_t launch_flux(int algo, bool skin, bool zteq, const FluxArgs &a, cudaS
 // turb_kernel<ALGO,CS,WL,ZTEQ>: the direct TURB_* entry on the same solvers
 // ---------------------------------------------------------------------------
 template <int ALGO, bool CS, bool WL, bool ZTEQ>
-__global__ void __launch_bounds__(FLUX_BLOCK, AB_MIN_BLOCKS) turb_kernel(const TurbArgs a)
+__global__ void __launch_bounds__(FLUX_BLOCK, (CS || WL) ? AB_MIN_BLOCKS : AB_MIN_BLOCKS_NOSKIN) turb_kernel(const TurbArgs a)
 {
     abm::load_tables();
     const long long i = (long long)blockIdx.x * FLUX_BLOCK + threadIdx.x;
@@ -394,20 +394,26 @@ cudaError_t launch_classify(const FluxArgs &a, unsigned short *perm, bool skin, 
     return cudaGetLastError();
 }
 
-template <int ALGO, bool SKIN>
-static cudaError_t attr_zt(bool zteq, cudaFuncAttributes *attr)
+template <int ALGO, bool SKIN, bool ZTEQ>
+static cudaError_t attr_one(cudaFuncAttributes *attr, int *blocks_per_sm)
 {
-    return zteq ? cudaFuncGetAttributes(attr, flux_kernel<ALGO, SKIN, true>)
-                : cudaFuncGetAttributes(attr, flux_kernel<ALGO, SKIN, false>);
+    cudaError_t e = cudaFuncGetAttributes(attr, flux_kernel<ALGO, SKIN, ZTEQ>);
+    if (e != cudaSuccess || !blocks_per_sm) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, flux_kernel<ALGO, SKIN, ZTEQ>, FLUX_BLOCK, 0);
 }
-cudaError_t flux_kernel_attributes(int algo, bool skin, bool zteq, cudaFuncAttributes *attr)
+template <int ALGO, bool SKIN>
+static cudaError_t attr_zt(bool zteq, cudaFuncAttributes *attr, int *blocks_per_sm)
+{
+    return zteq ? attr_one<ALGO, SKIN, true>(attr, blocks_per_sm) : attr_one<ALGO, SKIN, false>(attr, blocks_per_sm);
+}
+cudaError_t flux_kernel_attributes(int algo, bool skin, bool zteq, cudaFuncAttributes *attr, int *blocks_per_sm)
 {
     switch (algo) {
-    case COARE3P0: return skin ? attr_zt<COARE3P0, true>(zteq, attr) : attr_zt<COARE3P0, false>(zteq, attr);
-    case COARE3P6: return skin ? attr_zt<COARE3P6, true>(zteq, attr) : attr_zt<COARE3P6, false>(zteq, attr);
-    case ECMWF: return skin ? attr_zt<ECMWF, true>(zteq, attr) : attr_zt<ECMWF, false>(zteq, attr);
-    case NCAR: return attr_zt<NCAR, false>(zteq, attr);
-    case ANDREAS: return attr_zt<ANDREAS, false>(zteq, attr);
+    case COARE3P0: return skin ? attr_zt<COARE3P0, true>(zteq, attr, blocks_per_sm) : attr_zt<COARE3P0, false>(zteq, attr, blocks_per_sm);
+    case COARE3P6: return skin ? attr_zt<COARE3P6, true>(zteq, attr, blocks_per_sm) : attr_zt<COARE3P6, false>(zteq, attr, blocks_per_sm);
+    case ECMWF: return skin ? attr_zt<ECMWF, true>(zteq, attr, blocks_per_sm) : attr_zt<ECMWF, false>(zteq, attr, blocks_per_sm);
+    case NCAR: return attr_zt<NCAR, false>(zteq, attr, blocks_per_sm);
+    case ANDREAS: return attr_zt<ANDREAS, false>(zteq, attr, blocks_per_sm);
     default: return cudaErrorInvalidValue;
     }
 }

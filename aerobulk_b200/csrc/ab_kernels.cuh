@@ -150,7 +150,8 @@ cudaError_t launch_init_decide(const double *all, int nranks, int have_rad, doub
 int stats_max_blocks();
 // DFMA-chain microbenchmark: returns FP64 FMA instructions per second, <0 on error
 double measure_fp64_peak(cudaStream_t s);
-cudaError_t flux_kernel_attributes(int algo, bool skin, bool zt_eq_zu, cudaFuncAttributes *attr);
+// blocks_per_sm (may be NULL): resident blocks per SM at the launch configuration
+cudaError_t flux_kernel_attributes(int algo, bool skin, bool zt_eq_zu, cudaFuncAttributes *attr, int *blocks_per_sm);
 
 // probe_kernel (ab_probe.cu): one __device__ building block per launch, for the per-function GPU unit tests.
 // The numbering is part of the C ABI (aerobulk_gpu_probe, include/aerobulk_gpu.h).

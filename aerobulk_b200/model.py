@@ -84,6 +84,8 @@ def lib():
     L.aerobulk_gpu_work_per_point.argtypes = [C.c_char_p, C.c_int, C.c_int]
     L.aerobulk_gpu_bytes_per_point.restype = C.c_double
     L.aerobulk_gpu_bytes_per_point.argtypes = [C.c_char_p, C.c_int]
+    L.aerobulk_gpu_kernel_info.restype = C.c_int
+    L.aerobulk_gpu_kernel_info.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.aerobulk_gpu_version.restype = C.c_char_p
     L.aerobulk_gpu_turb.restype = C.c_int
     L.aerobulk_gpu_turb.argtypes = ([C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int] + [C.c_void_p] * 5 +
@@ -354,6 +356,14 @@ def reset_launch_count(): lib().aerobulk_gpu_reset_launch_count()
 def measure_fp64_peak() -> float: return lib().aerobulk_gpu_measure_fp64_peak()
 def work_per_point(calgo: str, skin: bool, nb: int) -> float: return lib().aerobulk_gpu_work_per_point(calgo.encode(), int(skin), int(nb))
 def bytes_per_point(calgo: str, skin: bool) -> float: return lib().aerobulk_gpu_bytes_per_point(calgo.encode(), int(skin))
+
+
+def kernel_info(calgo: str, skin: bool = False, zt_eq_zu: bool = False) -> dict:
+    """Registers per thread, local (spill) bytes per thread and resident blocks per SM of the flux kernel that a call
+    with (algo, skin, zt == zu) launches (aerobulk_gpu_kernel_info)."""
+    r, l, b = C.c_int(0), C.c_int(0), C.c_int(0)
+    _check(lib().aerobulk_gpu_kernel_info(calgo.encode(), int(skin), int(zt_eq_zu), C.byref(r), C.byref(l), C.byref(b)))
+    return {"registers": r.value, "local_bytes": l.value, "blocks_per_sm": b.value, "warps_per_sm": b.value * 8}
 
 
 def get_state(which: int, n: int) -> Optional[np.ndarray]:

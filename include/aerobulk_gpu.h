@@ -405,6 +405,10 @@ double aerobulk_gpu_measure_fp64_peak(void);
  * algorithmic bytes per point for (algo, skin). */
 double aerobulk_gpu_work_per_point(const char *calgo, int skin, int nb_iter);
 double aerobulk_gpu_bytes_per_point(const char *calgo, int skin);
+/* Resources of the flux kernel a call with (algo, skin, zt == zu) launches, on the session device: registers per thread,
+ * local-memory (spill) bytes per thread, resident blocks per SM at the launch configuration (256 threads).  For reports
+ * and regression tests: the skin kernels are built for 3 blocks/SM, the others for 4.  0 on success. */
+int aerobulk_gpu_kernel_info(const char *calgo, int skin, int zt_eq_zu, int *registers, int *local_bytes, int *blocks_per_sm);
 const char *aerobulk_gpu_version(void);
 
 /* ---- per-function probe (test support) ---------------------------------------

@@ -343,6 +343,23 @@ def test_stats_vector_with_masked_points_matches_numpy(ab, rad):
     ab.reset()
 
 
+def test_flux_kernels_keep_their_occupancy(ab):
+    """The launch configuration DESIGN.md 3.1 measured: kernels without skin 4 blocks of 256 threads per SM (<= 64
+    registers), skin kernels 3 (<= 85 registers) -- a change that silently costs a resident block fails here."""
+    for algo in ("ncar", "andreas", "coare3p0", "coare3p6", "ecmwf"):
+        for zteq in (False, True):
+            k = ab.kernel_info(algo, False, zteq)
+            assert k["registers"] <= 64 and k["blocks_per_sm"] == 4, (algo, zteq, k)
+    for algo in ("coare3p0", "coare3p6", "ecmwf"):
+        for zteq in (False, True):
+            k = ab.kernel_info(algo, True, zteq)
+            assert k["registers"] <= 85 and k["blocks_per_sm"] == 3, (algo, zteq, k)
+            assert k["local_bytes"] <= 160, (algo, zteq, k)          # a few spilled doubles outside the loop, no more
+    assert ab.kernel_info("ncar", True) == ab.kernel_info("ncar", False)    # no skin variant of NCAR
+    with pytest.raises(ab.AerobulkError):
+        ab.kernel_info("lg15")
+
+
 def test_deferred_wind_stress_error_on_device_api(ab):
     """Device-resident calls are asynchronous for jt>1: tau > 10 N/m2 surfaces at synchronize()."""
     import torch
