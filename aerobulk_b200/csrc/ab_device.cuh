@@ -30,6 +30,10 @@ namespace abd {
 #define AB_CS_UNROLL 1   // cool-skin passes rolled: the delta code exists once (instruction-cache footprint)
 #endif
 constexpr int CS_UNROLL = AB_CS_UNROLL;
+#ifndef AB_PASS_UNROLL
+#define AB_PASS_UNROLL 1   // cool-skin pass and warm-layer pass rolled: UPDATE_QNSOL_TAU and q_sat exist once in the loop body
+#endif
+constexpr int PASS_UNROLL = AB_PASS_UNROLL;
 #define ABD __device__ __forceinline__
 // heavy helpers can be kept out of line (one shared body instead of 2-5 inlined copies) to shrink the
 // instruction footprint: -DAB_NOINLINE=1
@@ -912,7 +916,7 @@ ABD Coeffs solve_coare(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
             // iwait = MOD(nb_iter, jit) == 0 (mod_blk_coare3p6.f90:370), from a host-computed bit mask: the integer
             // division cost 1.2 % of the kernel
             const bool commit = (jit < 64) ? ((u.wl_commit_mask >> jit) & 1ull) != 0ull : (u.nb_iter % jit) == 0;
-#pragma unroll 1
+#pragma unroll PASS_UNROLL
             for (int pass = CS ? 0 : 1; pass < (WL ? 2 : 1); ++pass) {
                 const double Ts_q = Ts;
                 if (CS && pass == 0) {
@@ -1075,7 +1079,7 @@ ABD Coeffs solve_ecmwf(const Uniform &u, const PointIn &p, WarmLayer &wl, Diag &
         if (SKIN) {
             // pass 0: cool skin, pass 1: warm layer -- advanced at every iteration
             const AirZu air = air_at_zu(u.zu, t_zu, q_zu, p.slp);
-#pragma unroll 1
+#pragma unroll PASS_UNROLL
             for (int pass = CS ? 0 : 1; pass < (WL ? 2 : 1); ++pass) {
                 double Qns, Tau, Qlat;
                 update_qnsol_tau(air, Ts, qs_, t_zu, q_zu, us, ts, qst, p.wnd, Ub, p.rlw, Qns, Tau, Qlat);

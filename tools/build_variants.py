@@ -8,6 +8,8 @@ VARIANTS = {
     "b128x7": ["AB_FLUX_BLOCK=128", "AB_MIN_BLOCKS=7"],
     "b128x8": ["AB_FLUX_BLOCK=128", "AB_MIN_BLOCKS=8"],
     "b256x4": ["AB_FLUX_BLOCK=256", "AB_MIN_BLOCKS=4"],
+    "pass2": ["AB_PASS_UNROLL=2"],
+    "sband035": ["AB_SORT_BAND_SKIN=0.35"],
     "ns3": ["AB_MIN_BLOCKS_NOSKIN=3"],
     "ns5": ["AB_MIN_BLOCKS_NOSKIN=5"],
     "b256x2": ["AB_FLUX_BLOCK=256", "AB_MIN_BLOCKS=2"],
