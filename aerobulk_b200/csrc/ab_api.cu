@@ -131,7 +131,7 @@ long long min_chunk_points()
 // 14 GB/s).  Instead a few persistent host threads move each row-block chunk between the caller's arrays and a pinned
 // slab owned by the library, and the flux kernel works on that slab zero-copy: chunk c+1 is copied in and chunk c-1
 // copied out while the kernel runs on chunk c.  AEROBULK_GPU_BOUNCE=0 restores the driver-staged copies,
-// AEROBULK_GPU_HOST_THREADS sets the number of copy threads (default: half the hardware threads, at most 8).
+// AEROBULK_GPU_HOST_THREADS sets the number of copy threads (default: 3/4 of the CPUs of the affinity mask, at most 12).
 // ---------------------------------------------------------------------------
 using abpool::CopyPiece;
 using abpool::CopyPool;
@@ -149,8 +149,11 @@ int host_threads()
             cpu_set_t set;
             if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
 #endif
-            k = cpus / 2;
-            if (k > 8) k = 8;
+            // three quarters of them, at most 12: measured on the 16-core GPU box (tools/pageable_jt1_probe.py, 9.3 M-point
+            // jt == 1 skin call) 4 / 8 / 12 / 16 threads -> 32.1 / 25.4 / 23.1 / 22.2 ms; the 1 M-point jt > 1 call
+            // (tools/pin_probe.py) 2.32 / 2.27 / 2.30 / 2.35 ms with 6 / 8 / 12 / 16
+            k = cpus * 3 / 4;
+            if (k > 12) k = 12;
         }
         return k < 1 ? 1 : (k > 64 ? 64 : k);
     }();
@@ -217,7 +220,7 @@ struct Session {
     bool device_ready = false;
     cudaStream_t own_stream = nullptr, user_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
     bool use_user_stream = false;
-    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {}, ev_bad = nullptr;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {}, ev_out[MAX_CHUNKS] = {}, ev_bad = nullptr;
     int error_mode = 0;
     int verbose = 1;
     char errmsg[1024] = {0};
@@ -392,6 +395,7 @@ int ensure_device()
     for (int i = 0; i < MAX_CHUNKS; ++i) {
         CUDA_TRY(cudaEventCreateWithFlags(&g.ev_in[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&g.ev_k[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&g.ev_out[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreateWithFlags(&g.ev_bad, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&g.d_partials, sizeof(double) * abk::NSTATS * abk::stats_max_blocks()));
@@ -956,17 +960,19 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     double *out_h[6] = {QL, QH, Tau_x, Tau_y, Evap, lsrad ? T_s : nullptr};
     double *out_d[6];
 
-    // jt == 1 with PAGEABLE arrays (AEROBULK_INIT wants the statistics of the whole fields on the device before any flux
-    // is computed, so the chunk-by-chunk bounce below does not apply): the copy threads bring the inputs into the pinned
-    // slab in one go, the staged pipeline then runs from / to the slab, and the results go home at the end
+    // jt == 1 with PAGEABLE arrays: the staged pipeline (with its speculative AEROBULK_INIT) runs from / to the library's
+    // pinned slab, and the copy threads feed it chunk by chunk -- chunk c+1 of the 8 inputs goes into the slab while the
+    // GPU receives / computes chunk c, and the results of the chunks whose D2H has landed go home meanwhile.  (Round 1
+    // copied the whole inputs in first and the whole outputs out last: three phases one after the other.)
     double *user_out[6] = {};
+    const double *user_in[8] = {};
     bool bounce_first = false;
     if (!device_ptrs && jt == 1 && !g.preinit_done && bounce_on() && zerocopy_mode() == 3 && n >= BOUNCE_MIN_POINTS) {
         bool pinned = true;
         for (int k = 0; k < 8 && pinned; ++k) pinned = !in_h[k] || device_alias(in_h[k]);
         for (int k = 0; k < 6 && pinned; ++k) pinned = !out_h[k] || device_alias(out_h[k]);
         if (!pinned && ensure_bounce(n)) {
-            bounce_copy(8, const_cast<double *const *>(in_h), 0, 0, n, true);
+            for (int k = 0; k < 8; ++k) user_in[k] = in_h[k];
             for (int k = 0; k < 8; ++k) in_h[k] = in_h[k] ? g.hb + (long long)k * g.cap_hb : nullptr;
             for (int k = 0; k < 6; ++k) {
                 user_out[k] = out_h[k];
@@ -1030,15 +1036,28 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
             trace_init();
             cudaEventRecord(tr_t0, g.in_stream);
         }
-        // H2D, chunk by chunk, on the copy-in stream
-        for (int c = 0; c < nchunks; ++c) {
-            const long long s0 = cstart[c], len = cstart[c + 1] - s0;
-            if (len > 0 && !zc_in) {
-                rc = copy_fields(8, g.d_in, const_cast<double *const *>(in_h), g.cap, s0, len, true, g.in_stream);
-                if (rc) return rc;
-            }
-            CUDA_TRY(cudaEventRecord(g.ev_in[c], g.in_stream));
-            if (trace_on()) cudaEventRecord(tr_in[c], g.in_stream);
+    }
+    // pageable arrays at jt == 1: chunk-wise through the slab if the pipeline is chunk-wise (speculative init), else whole
+    const bool pipe_bounce = bounce_first && spec_init;
+    if (bounce_first && !pipe_bounce) bounce_copy(8, const_cast<double *const *>(user_in), 0, 0, n, true);
+    // H2D of chunk c on the copy-in stream (preceded by its way into the slab on the copy threads where that applies)
+    auto enqueue_h2d = [&](int c) -> int {
+        const long long s0 = cstart[c], len = cstart[c + 1] - s0;
+        if (len > 0 && !zc_in) {
+            if (pipe_bounce) bounce_copy(8, const_cast<double *const *>(user_in), 0, s0, len, true);
+            const int r = copy_fields(8, g.d_in, const_cast<double *const *>(in_h), g.cap, s0, len, true, g.in_stream);
+            if (r) return r;
+        }
+        CUDA_TRY(cudaEventRecord(g.ev_in[c], g.in_stream));
+        if (trace_on()) cudaEventRecord(tr_in[c], g.in_stream);
+        return 0;
+    };
+    int h2d_next = 0;   // first chunk whose H2D is not enqueued yet
+    if (!device_ptrs) {
+        // all of them up front, except where the copy threads feed the slab: there chunk c + 1 follows the launch of chunk c
+        for (; h2d_next < (pipe_bounce ? 1 : nchunks); ++h2d_next) {
+            rc = enqueue_h2d(h2d_next);
+            if (rc) return rc;
         }
     }
 
@@ -1137,6 +1156,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     const bool zteq = fabs(zu - zt) < 0.01;
 
     int launched[MAX_CHUNKS], n_launched = 0, n_home = 0;
+    bool home[MAX_CHUNKS] = {};   // pageable jt == 1: chunk already copied back to the caller's arrays
     for (int c = 0; c < nchunks; ++c) {
         const long long s0 = cstart[c], len = cstart[c + 1] - s0;
         if (len <= 0) continue;
@@ -1159,6 +1179,10 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
         a.n = len;
         a.index_offset = s0;
         if (bounce) bounce_copy(8, const_cast<double *const *>(in_h), 0, s0, len, true);
+        while (pipe_bounce && h2d_next <= c) {   // (normally enqueued one iteration ahead, below)
+            rc = enqueue_h2d(h2d_next++);
+            if (rc) return rc;
+        }
         if (!device_ptrs) CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_in[c], 0));
         if (spec_init) {
             rc = launch_local_stats(len, a.sst, a.t_zt, a.hum_zt, a.U_zu, a.V_zu, a.slp, lsrad ? a.rad_lw : nullptr, cs,
@@ -1202,6 +1226,21 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
                 if (rc) return rc;
             }
             if (trace_on()) cudaEventRecord(tr_out[c], g.out_stream);
+            if (pipe_bounce) {
+                CUDA_TRY(cudaEventRecord(g.ev_out[c], g.out_stream));
+                launched[n_launched++] = c;
+                // the next chunk goes into the slab (and on to the device) while the GPU works on this one ...
+                while (h2d_next < nchunks && h2d_next <= c + 1) {
+                    rc = enqueue_h2d(h2d_next++);
+                    if (rc) return rc;
+                }
+                // ... and the chunks whose results have landed in the slab go home
+                while (n_home < n_launched && cudaEventQuery(g.ev_out[launched[n_home]]) == cudaSuccess) {
+                    const int h = launched[n_home++];
+                    bounce_copy(6, user_out, 8, cstart[h], cstart[h + 1] - cstart[h], false);
+                    home[h] = true;
+                }
+            }
             if (bounce) {   // results of an earlier chunk go home while the GPU has bounce_lag() chunks queued
                 launched[n_launched++] = c;
                 if (n_launched - n_home > bounce_lag()) {
@@ -1267,6 +1306,7 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
                 rc = copy_fields(6, g.d_out, out_h, g.cap, s0, len, false, g.out_stream);
                 if (rc) return rc;
             }
+            home[c] = false;   // recomputed: what went home earlier is stale
         }
     }
     while (bounce && n_home < n_launched) {
@@ -1287,7 +1327,12 @@ int model_impl(bool device_ptrs, int jt, int Nt, const char *calgo, double zt, d
     if (!never_sync && (!device_ptrs || last || (jt == 1 && !g.init_pending))) {
         CUDA_TRY(cudaStreamSynchronize(cs));
         if (!device_ptrs) CUDA_TRY(cudaStreamSynchronize(g.out_stream));
-        if (bounce_first) bounce_copy(6, user_out, 8, 0, n, false);
+        if (bounce_first) {   // what is not home yet (everything, without the chunk-wise feed)
+            for (int c = 0; c < nchunks; ++c) {
+                const long long s0 = cstart[c], len = cstart[c + 1] - s0;
+                if (len > 0 && !(pipe_bounce && home[c])) bounce_copy(6, user_out, 8, s0, len, false);
+            }
+        }
         rc = resolve_init();   // an asynchronous AEROBULK_INIT of this session reports first, as in the reference
         if (!rc) rc = check_bad_flag(device_ptrs ? nullptr : Tau_x, device_ptrs ? nullptr : Tau_y);
         if (!device_ptrs && trace_on()) {

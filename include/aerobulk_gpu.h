@@ -31,7 +31,7 @@
  * Environment: AEROBULK_GPU_DEVICE (or LOCAL_RANK) device ordinal; AEROBULK_GPU_ZEROCOPY=0 staged copies even for pinned
  * arrays; AEROBULK_GPU_MAX_CHUNKS / AEROBULK_GPU_MIN_CHUNK_POINTS / AEROBULK_GPU_CHUNK_SHAPE pipeline tuning;
  * AEROBULK_GPU_TRACE=1 GPU timeline of every staged call on stderr; pageable arrays: AEROBULK_GPU_BOUNCE=0 driver-staged
- * copies, AEROBULK_GPU_HOST_THREADS copy threads (default: half the CPUs the process may run on, at most 8),
+ * copies, AEROBULK_GPU_HOST_THREADS copy threads (default: 3/4 of the CPUs the process may run on, at most 12),
  * AEROBULK_GPU_BOUNCE_CHUNK_POINTS, AEROBULK_GPU_COPY_STREAMING=0 plain instead of non-temporal stores,
  * AEROBULK_GPU_BOUNCE_MAX_MB largest pinned slab the library may allocate for them (default 12288; beyond it, or when the
  * host refuses the allocation, the driver-staged copies are used).
