@@ -1,7 +1,7 @@
 """Regenerates the measured tables of DESIGN.md (the blocks between <!-- BEGIN:x --> / <!-- END:x --> markers) from the
 committed evidence files, so that the document always quotes the files it names.
 
-    python tools/design_numbers.py <tag> [--check]
+    python tools/design_numbers.py <tag> [--bench-tag <tag2>] [--check]
 
 reads profiles/bench_<tag>.json, profiles/launches_<tag>_summary.txt, profiles/traffic.json,
 profiles/kbench_1440x720_<tag>.txt, profiles/kbench_4320x2160_<tag>.txt; --check only reports whether DESIGN.md is current."""
@@ -9,8 +9,9 @@ import json, os, re, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
+btag = sys.argv[sys.argv.index("--bench-tag") + 1] if "--bench-tag" in sys.argv else tag   # bench line of a later checkpoint
 P = lambda *a: os.path.join(ROOT, "profiles", *a)
-bench = json.loads(open(P(f"bench_{tag}.json")).read().strip().splitlines()[-1])
+bench = json.loads(open(P(f"bench_{btag}.json")).read().strip().splitlines()[-1])
 traffic = json.load(open(P("traffic.json")))
 NAMES = {"ncar": "NCAR", "andreas": "ANDREAS", "coare3p0": "COARE 3.0", "coare3p6": "COARE 3.6", "ecmwf": "ECMWF",
          "coare3p0+skin": "COARE 3.0 + skin", "coare3p6+skin": "COARE 3.6 + skin", "ecmwf+skin": "ECMWF + skin"}
