@@ -776,7 +776,7 @@ int resolve_init()
     return init_checks(g.pend_lsrad, st, g.pend_Ni, g.pend_Nj);
 }
 
-// stats_kernel + stats_final on stream s; the 64-double vector lands in `d_out` (device memory)
+// stats_fast_kernel + stats_fix_kernel + stats_final on stream s; the 64-double vector lands in `d_out` (device memory)
 int launch_local_stats(long long n, const double *sst, const double *t_zt, const double *hum, const double *U,
                        const double *V, const double *slp, const double *rad_lw, cudaStream_t s, double *d_out)
 {

@@ -6,8 +6,11 @@
 //       vector -- reference src/mod_aerobulk_compute.f90:22-213 fused into one launch.
 //       All iteration state lives in registers; global memory is touched once per field
 //       (6-8 coalesced 8-byte loads, 5-6 stores, 1-4 state words R+W).
-//   stats_kernel / stats_final   the field statistics AEROBULK_INIT needs
-//       (src/mod_aerobulk.f90:104-153): mask, per-field masked sum/min/max, raw min/max.
+//   classify_kernel              stability sort inside 2048-point windows (FP32 proxy, warp-scan prefix): whole thread
+//       blocks of flux_kernel see one stability class.
+//   stats_fast_kernel / stats_fix_kernel / stats_final   the field statistics AEROBULK_INIT needs
+//       (src/mod_aerobulk.f90:104-153): mask, per-field masked sum/min/max, raw min/max; init_decide_kernel judges them
+//       on the device (humidity type, unit checks) for asynchronous jt == 1 calls.
 //   dfma_peak_kernel             dependent-chain DFMA microbenchmark (FP64 roofline denominator).
 //
 // The path is FP64-pipe bound (no contraction -> no tensor cores): see DESIGN.md.
