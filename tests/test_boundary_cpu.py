@@ -261,3 +261,12 @@ def test_shard_plan_of_split_calls(ab):
     with pytest.raises(ValueError):
         ab.shard_plan(-1, 2)
     assert ab.get_devices() == 1
+
+
+def test_design_tables_quote_the_committed_evidence():
+    """The measured tables of DESIGN.md are exactly what tools/design_numbers.py generates from the evidence files
+    profiles/CURRENT.json names (bench line, ncu counters, launch list, kbench) -- the document cannot drift from them."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "design_numbers.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -1,16 +1,21 @@
 """Regenerates the measured tables of DESIGN.md (the blocks between <!-- BEGIN:x --> / <!-- END:x --> markers) from the
 committed evidence files, so that the document always quotes the files it names.
 
-    python tools/design_numbers.py <tag> [--bench-tag <tag2>] [--check]
+    python tools/design_numbers.py [<tag> [--bench-tag <tag2>]] [--check]        (no tag: profiles/CURRENT.json)
 
 reads profiles/bench_<tag>.json, profiles/launches_<tag>_summary.txt, profiles/traffic.json,
 profiles/kbench_1440x720_<tag>.txt, profiles/kbench_4320x2160_<tag>.txt; --check only reports whether DESIGN.md is current."""
 import json, os, re, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1]
-btag = sys.argv[sys.argv.index("--bench-tag") + 1] if "--bench-tag" in sys.argv else tag   # bench line of a later checkpoint
 P = lambda *a: os.path.join(ROOT, "profiles", *a)
+pos = [a for i, a in enumerate(sys.argv[1:], 1) if not a.startswith("--") and sys.argv[i - 1] != "--bench-tag"]
+if pos:
+    tag = pos[0]
+    btag = sys.argv[sys.argv.index("--bench-tag") + 1] if "--bench-tag" in sys.argv else tag   # bench line of a later checkpoint
+else:                                    # the checkpoint DESIGN.md currently quotes
+    cur = json.load(open(P("CURRENT.json")))
+    tag, btag = cur["tag"], cur["bench_tag"]
 bench = json.loads(open(P(f"bench_{btag}.json")).read().strip().splitlines()[-1])
 traffic = json.load(open(P("traffic.json")))
 NAMES = {"ncar": "NCAR", "andreas": "ANDREAS", "coare3p0": "COARE 3.0", "coare3p6": "COARE 3.6", "ecmwf": "ECMWF",
