@@ -57,6 +57,8 @@ head = "\n".join([
     "| flux kernels, ms per 84 M-point launch | " + " · ".join(f"{NAMES[k['variant']]} {k['avg_launch_ms']:.2f}" for k in K) + " |",
     "| FP64 roofline fraction per kernel (executed) | " + " · ".join(f"{f:.2f}" for f in fr) +
     f" -- `roofline.frac` = **{bench['roofline']['frac']:.2f}** ({NAMES[bench['roofline']['variant']]}, the longest) |",
+    "| the same counting only active lanes (fraction × lanes per instruction / 32, ncu) | " + " · ".join(
+        f"{k['fp64_frac'] * (k.get('ncu_lanes') or traffic[k['variant']]['lanes_per_inst']) / 32:.2f}" for k in K) + " |",
     f"| not flux: statistics ×7, classify ×6, small launches | {gap:.1f} ms of the step (round 1 code: 15.6 ms) |",
     f"| `e2e` pinned / pageable | {bench['e2e']['value'] / 1e9:.2f} / {bench['e2e_pageable']['value'] / 1e9:.2f} Gpt/s (PCIe-bound: 94.9 B per point evaluation) |",
     f"| CPU port, {cb['cores']} threads / 1 thread | {cb['value'] / 1e6:.2f} / {cb['serial_value'] / 1e6:.3f} Mpt/s → `e2e` ≈ {bench['e2e']['value'] / cb['value']:.0f}× the {cb['cores']}-thread figure, `value` ≈ {bench['value'] / cb['value']:.0f}× |",
